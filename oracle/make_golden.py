@@ -1,0 +1,348 @@
+"""Generate ``tests/golden/*.npz`` by running the UNMODIFIED reference in the build container.
+
+TEST INFRASTRUCTURE.  Run here (``python oracle/make_golden.py``); it needs ``/root/reference`` and
+therefore cannot run on the GPU box -- the fixtures it writes are committed and travel instead.
+Every case is seeded; inputs and the reference's outputs are stored side by side, so that
+``tests/test_oracle_golden.py`` can pin ``oracle/cluster_oracle.py`` to the reference and the
+``-m gpu`` tests can compare the CUDA path with the reference's own numbers.
+
+Cases
+-----
+fitfunc_*   residual / jacobian values of ``FitFunctions.get_residual`` (fitfunc.py:421-489)
+pixels_*    ``prepare_subimage`` pixel sets (refine.py:28-58) and ``slices_multiple`` boxes
+clusters_*  ``find_clusters`` labels (find.py:132-163)
+refine_*    ``refine_leastsq`` end to end (refine.py:82-452), default ``tol`` and ``tol=1e-12``
+"""
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+import pandas as pd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_loader  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote %-40s %7.1f KiB" % (name + ".npz", os.path.getsize(path) / 1024.))
+
+
+def frame_to_arrays(prefix, df):
+    out = {prefix + "columns": np.array(list(df.columns)), prefix + "index": df.index.values}
+    for col in df.columns:
+        out[prefix + "col_" + col] = df[col].values
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def golden_fitfunc(ct):
+    from clustertracking.fitfunc import FitFunctions, vect_from_params
+    rng = np.random.RandomState(11)
+    cases = [
+        ("gauss", 2, True, 1, {}), ("gauss", 2, False, 1, {}), ("gauss", 3, True, 1, {}),
+        ("gauss", 3, False, 1, {}), ("ring", 2, True, 1, {}), ("ring", 3, False, 2, {}),
+        ("gauss", 2, True, 2, {}), ("gauss", 2, True, 3, dict(signal='cluster')),
+        ("gauss", 2, True, 4, dict(size='cluster')), ("disc", 2, True, 2, {}),
+        ("disc", 3, False, 1, {}),
+    ]
+    n_pix = 100
+    for k, (family, ndim, iso, n, custom) in enumerate(cases):
+        ff = FitFunctions(family, ndim, iso)
+        param_mode = {p: 'var' for p in ff.params}
+        param_mode['background'] = 'cluster'
+        param_mode.update(custom)
+        ff = FitFunctions(family, ndim, iso, param_mode=param_mode)
+        params = rng.random_sample((n, len(ff.params))) * 10
+        if family != 'gauss':
+            params[:, -1] = rng.uniform(0.2, 0.8, n)
+        image = rng.random_sample(n_pix) * 200
+        mesh = rng.random_sample((ndim, n_pix)) * 10
+        masks = rng.random_sample((n, n_pix)) > 0.5
+        norm = 3.7
+        residual, jacobian = ff.get_residual([image], [mesh], [masks], params, None, norm)
+        vect = vect_from_params(params, ff.modes, None, operation=np.mean)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            fun = residual(vect)
+            jac = jacobian(vect) if jacobian is not None else np.zeros(0)
+        save("fitfunc_%02d" % k, family=np.array(family), ndim=ndim, isotropic=iso, n=n,
+             param_mode=np.array(json.dumps(param_mode)), params=params, image=image, mesh=mesh,
+             masks=masks, norm=norm, vect=vect, fun=fun, jac=jac, modes=np.array(ff.modes),
+             param_names=np.array(ff.params))
+
+
+def golden_pixels(ct):
+    from clustertracking.refine import prepare_subimage
+    from clustertracking.masks import slices_multiple
+    rng = np.random.RandomState(5)
+    # bounding boxes, incl. edges / out of image / half-integer coordinates (round-half-even)
+    boxes = []
+    for shape, radius in (((9, 9), 2), ((20, 31), (3, 5)), ((9, 9, 9), 2), ((12, 20, 20), (2, 4, 4))):
+        ndim = len(shape)
+        for _ in range(12):
+            n = rng.randint(1, 5)
+            coords = rng.uniform(-4, max(shape) + 4, (n, ndim))
+            if rng.rand() < 0.4:
+                coords = np.round(coords * 2) / 2.         # exact .5 values
+            slices, origin = slices_multiple(coords, shape, radius)
+            lo = [-1] * ndim if origin is None else list(origin)
+            hi = [-1] * ndim if origin is None else [s.stop for s in slices]
+            boxes.append((shape, radius, coords, lo, hi))
+    save("pixels_boxes", n_cases=len(boxes),
+         **{"shape_%d" % i: np.array(b[0]) for i, b in enumerate(boxes)},
+         **{"radius_%d" % i: np.array(b[1]) for i, b in enumerate(boxes)},
+         **{"coords_%d" % i: b[2] for i, b in enumerate(boxes)},
+         **{"lo_%d" % i: np.array(b[3]) for i, b in enumerate(boxes)},
+         **{"hi_%d" % i: np.array(b[4]) for i, b in enumerate(boxes)})
+    # pixel sets; integer-valued coordinates put pixels exactly on the mask boundary
+    k = 0
+    for shape, radius in (((40, 48), 5), ((40, 48), (3, 6)), ((16, 30, 30), (3, 5, 5))):
+        ndim = len(shape)
+        image = rng.randint(0, 255, shape).astype(np.uint8)
+        for variant in range(4):
+            n = variant + 1
+            centre = np.array([rng.uniform(r + 1, s - r - 1) for r, s in
+                               zip(np.broadcast_to(radius, ndim), shape)])
+            coords = centre + rng.uniform(-1, 1, (n, ndim)) * np.broadcast_to(radius, ndim) * 1.2
+            if variant == 1:
+                coords = np.round(coords)                  # boundary pixels with dist == 1 exactly
+            if variant == 3:
+                coords[0] = 0.4                            # close to the image corner
+            vals, mesh, masks = prepare_subimage(coords, image, radius)
+            save("pixels_%02d" % k, image=image, radius=np.array(radius), coords=coords, values=vals,
+                 mesh=mesh, masks=masks)
+            k += 1
+
+
+def golden_clusters(ct):
+    rng = np.random.RandomState(21)
+    for k, (ndim, sep) in enumerate(((2, 11), (2, (8, 12)), (3, (6, 10, 10)))):
+        rows = []
+        for frame in range(3):
+            n = 150
+            pos = rng.uniform(0, 200 if ndim == 2 else 60, (n, ndim))
+            df = pd.DataFrame(pos, columns=['z', 'y', 'x'][-ndim:])
+            df['frame'] = frame
+            rows.append(df)
+        f = pd.concat(rows, ignore_index=True)
+        f = f.sample(frac=1, random_state=3)               # shuffled index order
+        res = ct.find_clusters(f, sep)
+        save("clusters_%02d" % k, separation=np.array(sep), **frame_to_arrays("in_", f),
+             **frame_to_arrays("out_", res))
+
+
+# ------------------------------------------------------------------------------------------------
+def _draw(shape, pos, size, signal, feat_func, noise, rng, **feat_kwargs):
+    from clustertracking.artificial import draw_feature
+    image = np.zeros(shape, dtype=np.uint8)
+    for p, s in zip(pos, np.broadcast_to(signal, len(pos))):
+        draw_feature(image, p, size, float(s), feat_func, **feat_kwargs)
+    if noise > 0:
+        image = np.clip(image + rng.poisson(noise, shape), 0, 255).astype(np.uint8)
+    return image
+
+
+def _grow_clusters(rng, centres, sizes_k, bond, ndim):
+    """clusters of k members, each attached at distance `bond` to a random earlier member."""
+    pos, member_of = [], []
+    for c_id, (c, k) in enumerate(zip(centres, sizes_k)):
+        members = [np.array(c, dtype=float)]
+        while len(members) < k:
+            base = members[rng.randint(len(members))]
+            v = rng.normal(size=ndim)
+            v *= np.broadcast_to(bond, ndim) / np.linalg.norm(v)
+            cand = base + v
+            if all(np.sum(((cand - m) / np.broadcast_to(bond, ndim)) ** 2) >= 0.998 for m in members):
+                members.append(cand)
+        pos.extend(members)
+        member_of.extend([c_id] * k)
+    return np.array(pos), np.array(member_of)
+
+
+def _refine_case(ct, name, image, f0, diameter, call_kwargs, frames=None, constraint=None):
+    """Run the reference with default tol and tol=1e-12 and store everything.
+    ``constraint`` = (kind, dist) describes ``call_kwargs['constraints']`` for the fixture."""
+    reader = image if frames is None else frames
+    outs = {}
+    for tag, extra in (("ref_", {}), ("tight_", dict(tol=1e-12, options=dict(maxiter=1000)))):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = ct.refine_leastsq(f0.copy(), reader, diameter, **dict(call_kwargs, **extra))
+        outs.update(frame_to_arrays(tag, res))
+    meta = dict(diameter=diameter, constraint=constraint,
+                kwargs={k: v for k, v in call_kwargs.items() if k != 'constraints'})
+    save(name, image=np.asarray(image), meta=np.array(json.dumps(meta)),
+         **frame_to_arrays("in_", f0), **outs)
+
+
+class _Video(object):
+    """FramesSequence-like reader over a pre-rendered stack (refine.py:252-256 only needs
+    ``frame_shape`` and ``__getitem__``)."""
+
+    def __init__(self, stack):
+        self.stack = stack
+        self.frame_shape = stack.shape[1:]
+
+    def __getitem__(self, i):
+        return self.stack[i]
+
+    def __len__(self):
+        return len(self.stack)
+
+
+def golden_refine(ct):
+    from clustertracking.constraints import dimer, trimer
+    from clustertracking.artificial import feat_gauss, feat_ring, feat_disc, draw_cluster
+    rng = np.random.RandomState(1234)
+
+    def grid_positions(shape, pitch, margin, jitter):
+        axes = [np.arange(margin, s - margin + 1e-9, pitch) for s in shape]
+        pos = np.array([g.ravel() for g in np.meshgrid(*axes, indexing='ij')], float).T
+        return pos + rng.uniform(-jitter, jitter, pos.shape)
+
+    def start_frame(pos, err, cols, **const):
+        f0 = pd.DataFrame(pos + rng.uniform(-err, err, pos.shape), columns=cols)
+        for k, v in const.items():
+            f0[k] = v
+        return f0
+
+    # 1. config-1-like: isolated gaussians, Poisson(8) noise, default modes
+    pos = grid_positions((128, 128), 24, 14, 3)
+    signal = rng.uniform(80, 160, len(pos))
+    image = _draw((128, 128), pos, 2.75, signal, feat_gauss, 8, rng)
+    f0 = start_frame(pos, 0.5, ['y', 'x'], signal=120., size=2.75, background=4.)
+    _refine_case(ct, "refine_gauss2d_isolated", image, f0, 11, {})
+    _refine_case(ct, "refine_gauss2d_isolated_sizevar", image, f0, 11,
+                 dict(param_mode=dict(size='var')))
+
+    # 2. config-2-like: clusters of 2-6 at bond length 2*size
+    centres = grid_positions((176, 176), 44, 22, 3)
+    ks = rng.randint(2, 7, len(centres))
+    pos, _ = _grow_clusters(rng, centres, ks, 5.5, 2)
+    signal = rng.uniform(80, 160, len(pos))
+    image = _draw((176, 176), pos, 2.75, signal, feat_gauss, 8, rng)
+    f0 = start_frame(pos, 0.5, ['y', 'x'], signal=120., size=2.75, background=4.)
+    _refine_case(ct, "refine_gauss2d_clusters", image, f0, 11, {})
+    _refine_case(ct, "refine_gauss2d_clusters_sizevar", image, f0, 11,
+                 dict(param_mode=dict(size='var')))
+    _refine_case(ct, "refine_gauss2d_clusters_sigcluster", image, f0, 11,
+                 dict(param_mode=dict(signal='cluster', size='cluster')))
+    # no background column / signal constant / user bounds
+    f1 = f0.drop(columns=['background'])
+    _refine_case(ct, "refine_gauss2d_clusters_bounds", image, f1, 11,
+                 dict(param_mode=dict(size='var'),
+                      bounds=dict(signal=(20, 2000), size=(1.0, 9), pos_diff=2.0,
+                                  signal_rel_diff=0.5)))
+
+    # 3. noise free, integer start coordinates (mask-boundary pixels, active background bound)
+    pos = grid_positions((96, 96), 24, 14, 3)
+    image = _draw((96, 96), pos, 2.75, 150., feat_gauss, 0, rng)
+    f0 = pd.DataFrame(np.round(pos), columns=['y', 'x'])
+    f0['signal'] = 120.
+    f0['size'] = 2.75
+    _refine_case(ct, "refine_gauss2d_integer_start", image, f0, 11, {})
+
+    # 4. anisotropic 2D, size var per axis
+    pos = grid_positions((120, 100), 32, 18, 2)
+    image = _draw((120, 100), pos, (5., 3.), 160., feat_gauss, 4, rng)
+    f0 = start_frame(pos, 1.0, ['y', 'x'], signal=140., size_y=4.5, size_x=3.3, background=2.)
+    _refine_case(ct, "refine_gauss2d_aniso", image, f0, (20, 12), dict(param_mode=dict(size='var')))
+
+    # 5. 3D isotropic and anisotropic dimers
+    centres = grid_positions((24, 56, 56), 28, 12, 1)
+    pos, _ = _grow_clusters(rng, centres, [2] * len(centres), 5.0, 3)
+    image = _draw((24, 56, 56), pos, 2.5, 140., feat_gauss, 4, rng)
+    f0 = start_frame(pos, 0.5, ['z', 'y', 'x'], signal=120., size=2.5, background=2.)
+    _refine_case(ct, "refine_gauss3d_iso", image, f0, 10, {})
+    centres = grid_positions((28, 72, 72), 36, 14, 1)
+    ks = rng.randint(1, 4, len(centres))
+    pos, _ = _grow_clusters(rng, centres, ks, (4.5, 6.5, 6.5), 3)
+    image = _draw((28, 72, 72), pos, (2.25, 3.25, 3.25), 140., feat_gauss, 4, rng)
+    f0 = start_frame(pos, 0.5, ['z', 'y', 'x'], signal=120., size_z=2.4, size_y=3.1, size_x=3.4,
+                     background=2.)
+    _refine_case(ct, "refine_gauss3d_aniso", image, f0, (9, 13, 13),
+                 dict(param_mode=dict(size='var')))
+
+    # 6. ring and disc
+    pos = grid_positions((120, 120), 32, 18, 2)
+    image = _draw((120, 120), pos, 4., 160., feat_ring, 4, rng, thickness=0.2)
+    f0 = start_frame(pos, 0.8, ['y', 'x'], signal=150., size=4., background=2.)
+    _refine_case(ct, "refine_ring2d", image, f0, 16, dict(fit_function='ring',
+                                                         param_val=dict(thickness=0.2)))
+    _refine_case(ct, "refine_ring2d_sizevar", image, f0, 16,
+                 dict(fit_function='ring', param_val=dict(thickness=0.2),
+                      param_mode=dict(size='var')))
+    image = _draw((120, 120), pos, 4., 160., feat_disc, 4, rng, disc_size=0.5)
+    _refine_case(ct, "refine_disc2d", image, f0, 16, dict(fit_function='disc',
+                                                         param_val=dict(disc_size=0.5)))
+
+    # 7. constrained dimers / trimers (one constraint kind per call)
+    for k, cname, maker in ((2, "dimer", dimer), (3, "trimer", trimer)):
+        shape = (150, 150)
+        centres = grid_positions(shape, 40, 24, 2)
+        image = np.zeros(shape, dtype=np.uint8)
+        pos = []
+        for c in centres:
+            pos.extend(draw_cluster(image, c, (4., 4.), k, 1., rng.uniform(0, 2 * np.pi),
+                                    max_value=float(rng.uniform(128, 192)), feat_func=feat_gauss))
+        pos = np.array(pos)
+        image = np.clip(image + rng.poisson(6, shape), 0, 255).astype(np.uint8)
+        f0 = start_frame(pos, 1.0, ['y', 'x'], signal=160., size=4., background=3.)
+        cons = maker(8.0, 2)
+        _refine_case(ct, "refine_%s2d_constrained" % cname, image, f0, 16, dict(constraints=cons),
+                     constraint=(cname, 8.0))
+        _refine_case(ct, "refine_%s2d_free" % cname, image, f0, 16, {})
+    shape = (32, 64, 64)
+    centres = grid_positions(shape, 32, 16, 1)
+    image = np.zeros(shape, dtype=np.uint8)
+    pos = []
+    for c in centres:
+        pos.extend(draw_cluster(image, c, (3., 4., 4.), 2, 1., rng.uniform(0, 2 * np.pi, 3),
+                                max_value=160., feat_func=feat_gauss))
+    pos = np.array(pos)
+    f0 = start_frame(pos, 0.7, ['z', 'y', 'x'], signal=150., size_z=3., size_y=4., size_x=4.)
+    _refine_case(ct, "refine_dimer3d_constrained", image, f0, (12, 16, 16),
+                 dict(constraints=dimer((6., 8., 8.), 3)), constraint=("dimer", (6., 8., 8.)))
+
+    # 8. large initial error: the outer re-mask loop runs more than once (tests/test_refine.py:913)
+    from clustertracking.artificial import SimulatedImage
+    np.random.seed(7)
+    im = SimulatedImage((160, 160), 5.25, dtype=np.uint8, signal=200, feat_func=feat_gauss, noise=0)
+    im.draw_features(40, 15, 21)
+    f0 = im.f(noise=7)
+    _refine_case(ct, "refine_gauss2d_overlap_7px", np.asarray(im()), f0, 21, dict(separation=24))
+
+    # 9. failure path: rms_dev above max_rms_dev -> cost NaN, parameters unchanged
+    pos = grid_positions((96, 96), 24, 14, 3)
+    image = _draw((96, 96), pos, 2.75, 150., feat_gauss, 8, rng)
+    f0 = start_frame(pos, 0.5, ['y', 'x'], signal=120., size=2.75)
+    _refine_case(ct, "refine_failure_rms", image, f0, 11, dict(max_rms_dev=1e-4))
+
+    # 10. multi-frame reader, shuffled row order, frame numbers not starting at 0
+    stack, rows = [], []
+    for t in range(3):
+        centres = grid_positions((96, 96), 44, 24, 3)
+        ks = rng.randint(1, 5, len(centres))
+        pos, _ = _grow_clusters(rng, centres, ks, 5.5, 2)
+        stack.append(_draw((96, 96), pos, 2.75, rng.uniform(80, 160, len(pos)), feat_gauss, 8, rng))
+        df = start_frame(pos, 0.5, ['y', 'x'], signal=120., size=2.75, background=4.)
+        df['frame'] = t
+        rows.append(df)
+    f0 = pd.concat(rows, ignore_index=True).sample(frac=1, random_state=9)
+    video = _Video(np.array(stack))
+    _refine_case(ct, "refine_gauss2d_video", np.array(stack), f0, 11, {}, frames=video)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    ct = ref_loader.load()
+    only = sys.argv[1:] or ["fitfunc", "pixels", "clusters", "refine"]
+    for part in only:
+        globals()["golden_" + part](ct)
