@@ -1,0 +1,92 @@
+"""ctypes binding of ``libctk.so`` (include/ctk.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``python -m clustertracking_b200.build``.
+There is no fallback: if the shared object is missing or a symbol is absent, importing this module's
+users fails with an explicit error.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+CTK_MAX_PARAMS = 12
+CTK_MAX_CLUSTER_FEATURES = 32
+CTK_MAX_RADIUS = 30
+
+MODE_CONST, MODE_VAR, MODE_CLUSTER = 0, 1, 3
+PIXEL_CODES = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2,
+               np.dtype(np.float64): 3, np.dtype(np.int16): 4, np.dtype(np.int32): 5}
+COMPUTE_F32, COMPUTE_F64 = 0, 1
+CONSTRAINT_DIMER, CONSTRAINT_TRIMER = 1, 2
+
+STATUS_NAMES = {0: 'ok', 1: 'non-finite initial parameters', 2: 'cluster outside of the image',
+                3: 'solver did not converge', 4: 'rms deviation above max_rms_dev',
+                5: 'lower bound above upper bound', 6: 'cluster exceeds the kernel capacity',
+                7: 'non-finite value during the fit'}
+STATUS_TOO_LARGE = 6
+
+
+class Problem(ctypes.Structure):
+    """``ctk_problem_t`` of include/ctk.h."""
+    _fields_ = [
+        ("ndim", ctypes.c_int32), ("isotropic", ctypes.c_int32), ("family", ctypes.c_int32),
+        ("n_params", ctypes.c_int32), ("modes", ctypes.c_int32 * CTK_MAX_PARAMS),
+        ("radius", ctypes.c_int32 * 3), ("pixel_dtype", ctypes.c_int32),
+        ("compute_dtype", ctypes.c_int32), ("max_iter", ctypes.c_int32),
+        ("lm_max_iter", ctypes.c_int32), ("max_shift", ctypes.c_double),
+        ("max_rms_dev", ctypes.c_double), ("residual_factor", ctypes.c_double),
+        ("xtol", ctypes.c_double), ("constraint_mask", ctypes.c_int32),
+        ("reserved0", ctypes.c_int32), ("dimer_dist", ctypes.c_double * 3),
+        ("trimer_dist", ctypes.c_double * 3),
+    ]
+
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libctk.so")
+_lib = None
+
+_vp, _i32, _i64, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
+_PROTOTYPES = {
+    "ctk_version": (ctypes.c_int, []),
+    "ctk_last_error": (ctypes.c_char_p, []),
+    "ctk_frame_max": (ctypes.c_int, [_vp, _i32, _i64, _i32, _vp, _vp]),
+    "ctk_refine_workspace_bytes": (_sz, []),
+    "ctk_refine_shared_bytes": (_sz, [ctypes.POINTER(Problem), _i32]),
+    "ctk_refine_batch": (ctypes.c_int, [ctypes.POINTER(Problem), _vp, ctypes.POINTER(_i64), _vp,
+                                        _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                        _vp, _vp, _vp]),
+    "ctk_label_clusters": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
+}
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises if the CUDA library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "clustertracking_b200: %s not found. Build the CUDA library first "
+            "(python -m clustertracking_b200.build). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in _PROTOTYPES.items():
+        fn = getattr(lib, name)                 # AttributeError if the symbol is missing
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().ctk_last_error()
+        raise RuntimeError("%s failed (%d): %s" % (what, code, msg.decode() if msg else "?"))
+
+
+def label_clusters(pairs, n):
+    """Host helper ``ctk_label_clusters``: labels and sizes from close pairs in visiting order."""
+    pairs = np.ascontiguousarray(pairs, dtype=np.int64)
+    labels = np.empty(n, dtype=np.int64)
+    sizes = np.empty(n, dtype=np.int64)
+    check(load().ctk_label_clusters(pairs.ctypes.data, len(pairs), n, labels.ctypes.data,
+                                    sizes.ctypes.data), "ctk_label_clusters")
+    return labels, sizes

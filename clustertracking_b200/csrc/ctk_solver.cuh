@@ -1,0 +1,1107 @@
+// ctk_solver.cuh -- one warp refines one cluster.
+//
+// The reference loops over (frame, cluster) groups in Python (refine.py:343-430) and hands every
+// group to scipy's SLSQP.  Here one warp owns one cluster from the first pixel load to the final
+// rms check; nothing goes back to the host in between.  Per outer re-mask iteration (refine.py:365):
+//
+//   build_pixels()  pixel set of the cluster (refine.py:28-58, masks.py:30-68): float64 ellipse tests
+//                   in the reference's exact operation order (separable tables of ((idx-c)/r)^2),
+//                   warp-ballot compaction of the union into shared memory, per-feature pixel lists,
+//                   and lists of the pixels shared by two features;
+//   evaluate()      one pass over the per-feature lists: model values (cached) and residuals
+//                   (fitfunc.py:436-450);
+//   accumulate()    J^T J and J^T r from the cached model values: per-feature blocks in registers,
+//                   warp-shuffle reduction, scatter into the packed normal matrix (float64, shared);
+//                   cross blocks from the shared-pixel lists (the analytic Jacobian of
+//                   fitfunc.py:455-487; disc gets the analytic derivative the reference lacks);
+//   solve()         active-set treatment of the box bounds (fitfunc.py:535-558), Marquardt damping,
+//                   packed Cholesky in shared memory, augmented-Lagrangian rows for the dimer/trimer
+//                   distance constraints (constraints.py:59-99).
+//
+// The same source compiles for the device (nvcc, 32 lanes) and, with -DCTK_EMUL, as plain C++ with a
+// one-lane "warp".  The one-lane build exists ONLY so that tests/ can exercise the solver logic in
+// the GPU-less build container; the package never loads it.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#include "ctk.h"
+
+#ifdef CTK_EMUL
+#define CTK_DEV inline
+#define CTK_WARP 1
+#else
+#define CTK_DEV __device__ __forceinline__
+#define CTK_WARP 32
+#endif
+
+namespace ctk {
+
+// ------------------------------------------------------------------------------------------------
+// lane primitives
+// ------------------------------------------------------------------------------------------------
+#ifdef CTK_EMUL
+CTK_DEV int lane_id() { return 0; }
+CTK_DEV void warp_sync() {}
+CTK_DEV uint32_t ballot(bool p) { return p ? 1u : 0u; }
+CTK_DEV uint32_t lanemask_lt() { return 0u; }
+template <class T> CTK_DEV T shfl_xor(T v, int) { return v; }
+template <class T> CTK_DEV T shfl(T v, int) { return v; }
+CTK_DEV int popc(uint32_t v) { return __builtin_popcount(v); }
+CTK_DEV double dsub(double a, double b) { return a - b; }   // built with -ffp-contract=off
+CTK_DEV double ddiv(double a, double b) { return a / b; }
+CTK_DEV double dmul(double a, double b) { return a * b; }
+CTK_DEV double dadd(double a, double b) { return a + b; }
+CTK_DEV float fast_exp(float x) { return expf(x); }
+CTK_DEV int atomic_next(int32_t* c) { return (*c)++; }
+#else
+CTK_DEV int lane_id() { return threadIdx.x & 31; }
+CTK_DEV void warp_sync() { __syncwarp(); }
+CTK_DEV uint32_t ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+CTK_DEV uint32_t lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
+template <class T> CTK_DEV T shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <class T> CTK_DEV T shfl(T v, int s) { return __shfl_sync(0xffffffffu, v, s); }
+CTK_DEV int popc(uint32_t v) { return __popc(v); }
+// float64 without FMA contraction: the mask test must round exactly like numpy (refine.py:43)
+CTK_DEV double dsub(double a, double b) { return __dsub_rn(a, b); }
+CTK_DEV double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+CTK_DEV double dmul(double a, double b) { return __dmul_rn(a, b); }
+CTK_DEV double dadd(double a, double b) { return __dadd_rn(a, b); }
+CTK_DEV float fast_exp(float x) { return __expf(x); }
+CTK_DEV int atomic_next(int32_t* c) { return atomicAdd(c, 1); }
+#endif
+CTK_DEV double fast_exp(double x) { return exp(x); }
+
+template <class T> CTK_DEV T warp_sum(T v) {
+#pragma unroll
+  for (int m = CTK_WARP / 2; m > 0; m >>= 1) v += shfl_xor(v, m);
+  return v;
+}
+CTK_DEV int warp_min_i(int v) {
+#pragma unroll
+  for (int m = CTK_WARP / 2; m > 0; m >>= 1) { int o = shfl_xor(v, m); v = o < v ? o : v; }
+  return v;
+}
+CTK_DEV int warp_max_i(int v) {
+#pragma unroll
+  for (int m = CTK_WARP / 2; m > 0; m >>= 1) { int o = shfl_xor(v, m); v = o > v ? o : v; }
+  return v;
+}
+CTK_DEV double warp_max_d(double v) {
+#pragma unroll
+  for (int m = CTK_WARP / 2; m > 0; m >>= 1) { double o = shfl_xor(v, m); v = o > v ? o : v; }
+  return v;
+}
+CTK_DEV bool warp_any(bool p) { return ballot(p) != 0u; }
+CTK_DEV bool finite_d(double v) { return fabs(v) <= 1.79769313486231571e308; }  // false for NaN
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory layout of one cluster (computed on the host, identical for every warp of a launch)
+// ------------------------------------------------------------------------------------------------
+struct Layout {
+  int n_max;       // features per cluster this launch can hold
+  int v_max;       // free variables
+  int m_cap;       // union pixels
+  int f_cap;       // pixels of one feature's mask
+  int pair_cap;    // entries over all shared-pixel lists
+  int npair_cap;   // number of shared-pixel lists
+  int tab_len[3];  // 2 r_k + 3 entries per (feature, axis) table
+  int tab_stride;  // sum of tab_len
+  int real_bytes;  // 4 | 8
+  // byte offsets into the cluster's slice
+  int o_x, o_xt, o_x0, o_lo, o_hi, o_rhs, o_rhsf, o_d, o_dg, o_act;
+  int o_H, o_L;
+  int o_mc, o_fi, o_fr;
+  int o_tab;      // aliases o_fe (tables are dead once the lists are built)
+  int o_fe;
+  int o_pval, o_pr, o_pbits, o_pcrd;
+  int o_flist, o_pairs, o_phdr;
+  int total;
+};
+
+CTK_DEV int tri(int v) { return v * (v + 1) / 2; }
+
+// integer record of a feature (shared memory)
+enum { FI_CI = 0, FI_TS = 3, FI_CNT = 6, FI_INB = 7, FI_STRIDE = 8 };
+// real record of a feature: signal, frac[3], inverse size[3], extra
+enum { FR_S = 0, FR_FRAC = 1, FR_IS = 4, FR_EX = 7, FR_STRIDE = 8 };
+
+// flist entry: pixel index (14 bits) | three 6-bit offsets from the integer mask centre (biased +32)
+CTK_DEV uint32_t pack_entry(int p, int o0, int o1, int o2) {
+  return (uint32_t)p | ((uint32_t)(o0 + 32) << 14) | ((uint32_t)(o1 + 32) << 20) |
+         ((uint32_t)(o2 + 32) << 26);
+}
+CTK_DEV int entry_pixel(uint32_t e) { return (int)(e & 0x3fffu); }
+CTK_DEV int entry_off(uint32_t e, int k) { return (int)((e >> (14 + 6 * k)) & 0x3fu) - 32; }
+
+// ------------------------------------------------------------------------------------------------
+// kernel arguments
+// ------------------------------------------------------------------------------------------------
+struct BatchArgs {
+  ctk_problem_t prob;
+  const void* const* frames;
+  int64_t shape[3];
+  const double* frame_max;
+  int n_work;
+  const int32_t* work_ids;
+  const int32_t* cluster_frame;
+  const int32_t* cluster_offset;
+  const double* params_in;
+  const double* lo_in;
+  const double* hi_in;
+  double* params_out;
+  double* cost_out;
+  int32_t* status_out;
+  int32_t* iters_out;
+  int32_t* counter;
+  Layout lay;
+};
+
+// compile-time configuration of a kernel instance
+template <class Real_, int ND_, bool ISO_, int FAM_, bool SZ_, bool EX_>
+struct Config {
+  typedef Real_ Real;
+  static const int ND = ND_;
+  static const bool ISO = ISO_;
+  static const int FAM = FAM_;
+  static const bool SZ = SZ_;   // size column(s) carry derivatives
+  static const bool EX = EX_;   // extra column (thickness / disc_size) carries a derivative
+  static const int NS = ISO_ ? 1 : ND_;
+  static const int NE = (FAM_ == CTK_FAMILY_GAUSS) ? 0 : 1;
+  static const int P = 2 + ND_ + NS + NE;
+  static const int LD = 1 + ND_ + (SZ_ ? NS : 0) + ((EX_ && NE) ? 1 : 0);   // derivative slots
+  static const int LT = LD * (LD + 1) / 2;
+};
+
+template <class C>
+struct ClusterSolver {
+  typedef typename C::Real Real;
+  enum { ND = C::ND, P = C::P, LD = C::LD, LT = C::LT, NS = C::NS };
+
+  const BatchArgs& a;
+  const Layout& L;
+  char* sm;
+  int lane;
+
+  // cluster
+  int n, feat0, V, M, npairs;
+  int base[CTK_MAX_PARAMS];      // first variable of each column (or -1)
+  int blo[3], bdim[3];
+  const void* frame;
+  double fmax_;
+  int evals;
+  // residual statistics of the last evaluate()
+  double sum_r, n_valid;
+  // augmented Lagrangian
+  int n_con;
+  double mu[3], pen_w;
+  double cdist[3];
+
+  CTK_DEV ClusterSolver(const BatchArgs& args, char* smem)
+      : a(args), L(args.lay), sm(smem), lane(lane_id()) {}
+
+  // ---- typed views ------------------------------------------------------------------------------
+  CTK_DEV double* dvec(int off) const { return reinterpret_cast<double*>(sm + off); }
+  CTK_DEV double* X() const { return dvec(L.o_x); }
+  CTK_DEV double* XT() const { return dvec(L.o_xt); }
+  CTK_DEV double* X0() const { return dvec(L.o_x0); }
+  CTK_DEV double* LO() const { return dvec(L.o_lo); }
+  CTK_DEV double* HI() const { return dvec(L.o_hi); }
+  CTK_DEV double* RHS() const { return dvec(L.o_rhs); }
+  CTK_DEV double* D() const { return dvec(L.o_d); }
+  CTK_DEV double* DG() const { return dvec(L.o_dg); }
+  CTK_DEV int* ACT() const { return reinterpret_cast<int*>(sm + L.o_act); }
+  CTK_DEV double* Hm() const { return dvec(L.o_H); }
+  CTK_DEV double* Lm() const { return dvec(L.o_L); }
+  CTK_DEV double* MC() const { return dvec(L.o_mc); }
+  CTK_DEV int* FI() const { return reinterpret_cast<int*>(sm + L.o_fi); }
+  CTK_DEV Real* FR() const { return reinterpret_cast<Real*>(sm + L.o_fr); }
+  CTK_DEV double* TAB() const { return dvec(L.o_tab); }
+  CTK_DEV Real* FE() const { return reinterpret_cast<Real*>(sm + L.o_fe); }
+  CTK_DEV Real* PVAL() const { return reinterpret_cast<Real*>(sm + L.o_pval); }
+  CTK_DEV Real* PR() const { return reinterpret_cast<Real*>(sm + L.o_pr); }
+  CTK_DEV uint32_t* PBITS() const { return reinterpret_cast<uint32_t*>(sm + L.o_pbits); }
+  CTK_DEV uint32_t* PCRD() const { return reinterpret_cast<uint32_t*>(sm + L.o_pcrd); }
+  CTK_DEV uint32_t* FLIST() const { return reinterpret_cast<uint32_t*>(sm + L.o_flist); }
+  CTK_DEV uint32_t* PAIRS() const { return reinterpret_cast<uint32_t*>(sm + L.o_pairs); }
+  CTK_DEV int* PHDR() const { return reinterpret_cast<int*>(sm + L.o_phdr); }
+
+  CTK_DEV int mode(int col) const { return a.prob.modes[col]; }
+  // variable index of (column, feature), -1 when the column is constant
+  CTK_DEV int var_of(int col, int i) const {
+    int b = base[col];
+    return b < 0 ? -1 : (mode(col) == CTK_MODE_VAR ? b + i : b);
+  }
+  // column of derivative slot `s`
+  CTK_DEV static int slot_col(int s) {
+    if (s <= ND) return 1 + s;                       // signal, positions
+    if (C::SZ && s < 1 + ND + NS) return 2 + ND + (s - 1 - ND);
+    return 2 + ND + NS;                              // extra
+  }
+
+  CTK_DEV Real load_pixel(int64_t idx) const {
+    switch (a.prob.pixel_dtype) {
+      case CTK_PIXEL_U8: return (Real) reinterpret_cast<const uint8_t*>(frame)[idx];
+      case CTK_PIXEL_U16: return (Real) reinterpret_cast<const uint16_t*>(frame)[idx];
+      case CTK_PIXEL_F32: return (Real) reinterpret_cast<const float*>(frame)[idx];
+      case CTK_PIXEL_F64: return (Real) reinterpret_cast<const double*>(frame)[idx];
+      case CTK_PIXEL_I16: return (Real) reinterpret_cast<const int16_t*>(frame)[idx];
+      default: return (Real) reinterpret_cast<const int32_t*>(frame)[idx];
+    }
+  }
+
+  // ---- variables, start vector and bounds (refine.py:361-364, fitfunc.py:207-263, 552-558) ------
+  CTK_DEV int setup_variables() {
+    int v = 0;
+#pragma unroll
+    for (int c = 0; c < CTK_MAX_PARAMS; ++c) {
+      base[c] = -1;
+      if (c < P) {
+        if (mode(c) == CTK_MODE_VAR) { base[c] = v; v += n; }
+        else if (mode(c) == CTK_MODE_CLUSTER) { base[c] = v; v += 1; }
+      }
+    }
+    V = v;
+    if (V > L.v_max) return CTK_FAIL_TOO_LARGE;
+    const double* pin = a.params_in + (int64_t)feat0 * P;
+    const double* lin = a.lo_in + (int64_t)feat0 * P;
+    const double* hin = a.hi_in + (int64_t)feat0 * P;
+    bool bad = false;
+    for (int t = lane; t < n * P; t += CTK_WARP) bad |= !finite_d(pin[t]);
+    if (warp_any(bad)) return CTK_FAIL_NONFINITE;
+    double *x0 = X0(), *lo = LO(), *hi = HI();
+    for (int c = 0; c < P; ++c) {
+      if (base[c] < 0) continue;
+      if (mode(c) == CTK_MODE_VAR) {
+        for (int i = lane; i < n; i += CTK_WARP) {
+          x0[base[c] + i] = pin[i * P + c];
+          lo[base[c] + i] = lin[i * P + c];
+          hi[base[c] + i] = hin[i * P + c];
+        }
+      } else if (lane == 0) {          // shared entry: mean start, widest bound
+        double s = 0., l = INFINITY, h = -INFINITY;
+        for (int i = 0; i < n; ++i) {
+          s += pin[i * P + c];
+          l = fmin(l, lin[i * P + c]);
+          h = fmax(h, hin[i * P + c]);
+        }
+        x0[base[c]] = s / n; lo[base[c]] = l; hi[base[c]] = h;
+      }
+    }
+    warp_sync();
+    bad = false;
+    for (int v2 = lane; v2 < V; v2 += CTK_WARP) {
+      bad |= !(lo[v2] <= hi[v2]);
+      x0[v2] = fmin(fmax(x0[v2], lo[v2]), hi[v2]);     // scipy clips the start into the box
+    }
+    if (warp_any(bad)) return CTK_FAIL_BOUNDS;
+    warp_sync();
+    return CTK_OK;
+  }
+
+  // ---- pixel set (refine.py:28-58, masks.py:30-68) ----------------------------------------------
+  CTK_DEV int build_pixels() {
+    const double* mc = MC();
+    int* fi = FI();
+    // integer centres (round half to even) and the in-bounds test of masks.py:42-46
+    int mn[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, mx[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
+    for (int i = lane; i < n; i += CTK_WARP) {
+      bool inb = true;
+      int ci[3] = {0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < ND; ++k) {
+        double r = rint(mc[i * 3 + k]);
+        r = fmin(fmax(r, -1.0e9), 1.0e9);
+        ci[k] = (int) r;
+        fi[i * FI_STRIDE + FI_CI + k] = ci[k];
+        inb = inb && (ci[k] >= -a.prob.radius[k]) && (ci[k] < (int) a.shape[k] + a.prob.radius[k]);
+      }
+      fi[i * FI_STRIDE + FI_INB] = inb ? 1 : 0;
+      if (inb) {
+#pragma unroll
+        for (int k = 0; k < ND; ++k) { mn[k] = min(mn[k], ci[k]); mx[k] = max(mx[k], ci[k]); }
+      }
+    }
+    int64_t total = 1;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      int lo_k = warp_min_i(mn[k]), hi_k = warp_max_i(mx[k]);
+      if (lo_k == INT32_MAX) return CTK_FAIL_OUT_OF_IMAGE;
+      blo[k] = max(0, lo_k - a.prob.radius[k]);
+      int bhi = min((int) a.shape[k], hi_k + a.prob.radius[k] + 1);
+      bdim[k] = bhi - blo[k];
+      total *= bdim[k];
+    }
+    if (total <= 0 || total > (int64_t) 1 << 30) return CTK_FAIL_TOO_LARGE;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) if (bdim[k] > 1023) return CTK_FAIL_TOO_LARGE;
+    warp_sync();
+    // separable tables: tab[i][k][e] = (((ts + e) - (c - origin)) / r)^2, float64, numpy's order
+    double* tab = TAB();
+    for (int t = lane; t < n * ND; t += CTK_WARP) {
+      int i = t / ND, k = t - i * ND;
+      double crel = dsub(mc[i * 3 + k], (double) blo[k]);
+      double s = floor(crel - (double) a.prob.radius[k]);
+      s = fmin(fmax(s, -1.0e9), 1.0e9);
+      fi[i * FI_STRIDE + FI_TS + k] = (int) s;
+    }
+    warp_sync();
+    for (int t = lane; t < n * L.tab_stride; t += CTK_WARP) {
+      int i = t / L.tab_stride, e = t - i * L.tab_stride, k = 0;
+      while (k < ND - 1 && e >= L.tab_len[k]) { e -= L.tab_len[k]; ++k; }
+      double crel = dsub(mc[i * 3 + k], (double) blo[k]);
+      double idx = (double) (fi[i * FI_STRIDE + FI_TS + k] + e);
+      double q = ddiv(dsub(idx, crel), (double) a.prob.radius[k]);
+      tab[t] = dmul(q, q);
+    }
+    warp_sync();
+    // walk the box in C order, ballot-compact the union
+    Real* pval = PVAL();
+    uint32_t *pbits = PBITS(), *pcrd = PCRD();
+    int count = 0;
+    const int itotal = (int) total;
+    for (int q0 = 0; q0 < itotal; q0 += CTK_WARP) {
+      int q = q0 + lane;
+      uint32_t bits = 0u;
+      int c[3] = {0, 0, 0};
+      if (q < itotal) {
+        int rem = q;
+#pragma unroll
+        for (int k = ND - 1; k >= 0; --k) { c[k] = rem % bdim[k]; rem /= bdim[k]; }
+        for (int i = 0; i < n; ++i) {
+          const int* f = fi + i * FI_STRIDE;
+          const double* tb = tab + i * L.tab_stride;
+          double s = 0.;
+          bool in = true;
+#pragma unroll
+          for (int k = 0; k < ND; ++k) {
+            int e = c[k] - f[FI_TS + k];
+            in = in && (e >= 0) && (e < L.tab_len[k]);
+            if (in) s = (k == 0) ? tb[e] : dadd(s, tb[e]);
+            tb += L.tab_len[k];
+          }
+          if (in && s <= 1.0) bits |= (1u << i);
+        }
+      }
+      uint32_t ball = ballot(bits != 0u);
+      if (bits != 0u) {
+        int pos = count + popc(ball & lanemask_lt());
+        if (pos < L.m_cap) {
+          int64_t gi = 0;
+#pragma unroll
+          for (int k = 0; k < ND; ++k) gi = gi * a.shape[k] + (blo[k] + c[k]);
+          pval[pos] = load_pixel(gi);
+          pbits[pos] = bits;
+          pcrd[pos] = (uint32_t) c[0] | ((uint32_t) c[1] << 10) | ((uint32_t) c[2] << 20);
+        }
+      }
+      count += popc(ball);
+    }
+    M = count;
+    if (M > L.m_cap || M == 0) return M == 0 ? CTK_FAIL_OUT_OF_IMAGE : CTK_FAIL_TOO_LARGE;
+    warp_sync();
+    // per-feature pixel lists, in union order
+    uint32_t* flist = FLIST();
+    bool overflow = false;
+    for (int i = 0; i < n; ++i) {
+      const int* f = fi + i * FI_STRIDE;
+      int oc[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) oc[k] = (k < ND) ? f[FI_CI + k] - blo[k] : 0;
+      int cnt = 0;
+      for (int p0 = 0; p0 < M; p0 += CTK_WARP) {
+        int p = p0 + lane;
+        bool has = (p < M) && ((pbits[p] >> i) & 1u);
+        uint32_t ball = ballot(has);
+        if (has) {
+          int t = cnt + popc(ball & lanemask_lt());
+          if (t < L.f_cap) {
+            uint32_t crd = pcrd[p];
+            int o0 = (int) (crd & 1023u) - oc[0], o1 = (int) ((crd >> 10) & 1023u) - oc[1],
+                o2 = (int) ((crd >> 20) & 1023u) - oc[2];
+            flist[i * L.f_cap + t] = pack_entry(p, o0, ND > 1 ? o1 : 0, ND > 2 ? o2 : 0);
+          }
+        }
+        cnt += popc(ball);
+      }
+      if (lane == 0) fi[i * FI_STRIDE + FI_CNT] = cnt;
+      overflow |= cnt > L.f_cap;
+    }
+    if (overflow) return CTK_FAIL_TOO_LARGE;
+    warp_sync();
+    // pixels shared by two features: entries (t_i | t_j << 16) grouped per pair
+    uint32_t* pairs = PAIRS();
+    int* phdr = PHDR();
+    int np = 0, ptotal = 0;
+    for (int i = 0; i < n - 1; ++i) {
+      const int* f_i = fi + i * FI_STRIDE;
+      const int cnt_i = f_i[FI_CNT];
+      for (int j = i + 1; j < n; ++j) {
+        const int* f_j = fi + j * FI_STRIDE;
+        bool apart = false;
+#pragma unroll
+        for (int k = 0; k < ND; ++k)
+          apart |= abs(f_i[FI_CI + k] - f_j[FI_CI + k]) > 2 * a.prob.radius[k] + 2;
+        if (apart) continue;
+        const int cnt_j = f_j[FI_CNT];
+        const uint32_t* fl_j = flist + j * L.f_cap;
+        int cnt = 0;
+        for (int t0 = 0; t0 < cnt_i; t0 += CTK_WARP) {
+          int t = t0 + lane;
+          int p = -1;
+          bool has = false;
+          if (t < cnt_i) {
+            p = entry_pixel(flist[i * L.f_cap + t]);
+            has = (pbits[p] >> j) & 1u;
+          }
+          uint32_t ball = ballot(has);
+          if (has) {
+            int lo_ = 0, hi_ = cnt_j;            // lower bound of p in feature j's (sorted) list
+            while (lo_ < hi_) {
+              int mid = (lo_ + hi_) >> 1;
+              if (entry_pixel(fl_j[mid]) < p) lo_ = mid + 1; else hi_ = mid;
+            }
+            int pos = ptotal + cnt + popc(ball & lanemask_lt());
+            if (pos < L.pair_cap) pairs[pos] = (uint32_t) t | ((uint32_t) lo_ << 16);
+          }
+          cnt += popc(ball);
+        }
+        if (cnt > 0) {
+          if (np >= L.npair_cap || ptotal + cnt > L.pair_cap) return CTK_FAIL_TOO_LARGE;
+          if (lane == 0) {
+            phdr[np * 4 + 0] = i; phdr[np * 4 + 1] = j; phdr[np * 4 + 2] = ptotal;
+            phdr[np * 4 + 3] = cnt;
+          }
+          ++np;
+          ptotal += cnt;
+        }
+      }
+    }
+    npairs = np;
+    warp_sync();
+    return CTK_OK;
+  }
+
+  // ---- per-feature constants of the pixel pass from the variable vector ------------------------
+  CTK_DEV double value_of(const double* x, int col, int i) const {
+    int v = var_of(col, i);
+    return v < 0 ? a.params_in[(int64_t) (feat0 + i) * P + col] : x[v];
+  }
+
+  CTK_DEV void load_features(const double* x) {
+    Real* fr = FR();
+    const int* fi = FI();
+    for (int i = lane; i < n; i += CTK_WARP) {
+      Real* r = fr + i * FR_STRIDE;
+      r[FR_S] = (Real) value_of(x, 1, i);
+#pragma unroll
+      for (int k = 0; k < ND; ++k) {
+        r[FR_FRAC + k] = (Real) (value_of(x, 2 + k, i) - (double) fi[i * FI_STRIDE + FI_CI + k]);
+        double size = value_of(x, 2 + ND + (C::ISO ? 0 : k), i);
+        r[FR_IS + k] = (Real) (1.0 / size);
+      }
+      r[FR_EX] = (C::NE > 0) ? (Real) value_of(x, 2 + ND + NS, i) : (Real) 0;
+    }
+    warp_sync();
+  }
+
+  struct Feat { Real s, frac[3], is[3], ex; };
+  CTK_DEV Feat feat(int i) const {
+    const Real* r = FR() + i * FR_STRIDE;
+    Feat f;
+    f.s = r[FR_S];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { f.frac[k] = r[FR_FRAC + k]; f.is[k] = r[FR_IS + k]; }
+    f.ex = r[FR_EX];
+    return f;
+  }
+
+  // geometry of one (pixel, feature): q_k = (x_k - c_k)/size_k, r2 = sum q_k^2, d2 = pixel dist^2
+  struct Geo { Real q[3], r2, d2; };
+  CTK_DEV Geo geometry(uint32_t e, const Feat& f) const {
+    Geo g;
+    g.r2 = 0; g.d2 = 0;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      Real d = (Real) entry_off(e, k) - f.frac[k];
+      g.q[k] = d * f.is[k];
+      g.r2 += g.q[k] * g.q[k];
+      g.d2 += d * d;
+    }
+    return g;
+  }
+
+  // model value; `drop` = the reference produces NaN here (pixel leaves every sum, fitfunc.py:449)
+  CTK_DEV Real model_value(const Geo& g, const Feat& f, bool& drop) const {
+    drop = false;
+    const Real half_nd = (Real) (0.5 * ND);
+    if (C::FAM == CTK_FAMILY_GAUSS) return fast_exp(-half_nd * g.r2);
+    const bool safe_nan = g.d2 < (Real) 1;                 // the *_safe r2 variants, fitfunc.py:20-26
+    if (C::FAM == CTK_FAMILY_RING) {
+      drop = safe_nan;
+      Real u = (sqrt(g.r2) - (Real) 1 + f.ex) / f.ex;
+      return fast_exp(-half_nd * u * u);
+    }
+    // disc, fitfunc.py:121-131
+    Real d = f.ex;
+    if (d <= (Real) 0) { drop = safe_nan; return fast_exp(-half_nd * g.r2); }
+    if (d >= (Real) 1) d = (Real) 0.999;
+    if (safe_nan || !(g.r2 > d * d)) return (Real) 1;
+    Real u = (sqrt(g.r2) - d) / ((Real) 1 - d);
+    return fast_exp(-half_nd * u * u);
+  }
+
+  // derivatives of s*g wrt the LD slots, given the cached model value g
+  CTK_DEV void model_derivs(const Geo& g, const Feat& f, Real gv, Real* m) const {
+    const Real nd = (Real) ND;
+    Real W;              // -2 * s * dg/dr2
+    Real dex = 0;        // s * dg/dextra
+    if (C::FAM == CTK_FAMILY_GAUSS) {
+      W = f.s * nd * gv;
+    } else if (C::FAM == CTK_FAMILY_RING) {
+      Real rr = sqrt(g.r2), t = f.ex;
+      Real u = (rr - (Real) 1 + t) / t;
+      W = f.s * nd * gv * u / (rr * t);
+      dex = f.s * gv * nd * u * (u - (Real) 1) / t;
+    } else {
+      Real d = f.ex;
+      if (d <= (Real) 0) {
+        W = f.s * nd * gv;
+      } else {
+        bool clamp = d >= (Real) 1;
+        if (clamp) d = (Real) 0.999;
+        if (g.d2 < (Real) 1 || !(g.r2 > d * d)) {
+          W = 0;
+        } else {
+          Real rr = sqrt(g.r2), om = (Real) 1 - d;
+          Real u = (rr - d) / om;
+          W = f.s * nd * gv * u / (rr * om);
+          dex = clamp ? (Real) 0 : f.s * gv * nd * u * ((Real) 1 - rr) / (om * om);
+        }
+      }
+    }
+    m[0] = gv;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) m[1 + k] = W * g.q[k] * f.is[k];
+    if (C::SZ) {
+      if (C::ISO) m[1 + ND] = W * g.r2 * f.is[0];
+      else {
+#pragma unroll
+        for (int k = 0; k < ND; ++k) m[1 + ND + k] = W * g.q[k] * g.q[k] * f.is[k];
+      }
+    }
+    if (C::EX && C::NE) m[LD - 1] = dex;
+  }
+
+  // ---- objective: 0.5 * sum of squared residuals (fitfunc.py:436-450, without the 1/M/norm) ----
+  CTK_DEV double evaluate(const double* x) {
+    ++evals;
+    load_features(x);
+    Real* pr = PR();
+    for (int p = lane; p < M; p += CTK_WARP) pr[p] = 0;
+    warp_sync();
+    const uint32_t* flist = FLIST();
+    Real* fe = FE();
+    const int* fi = FI();
+    for (int i = 0; i < n; ++i) {
+      const Feat f = feat(i);
+      const int cnt = fi[i * FI_STRIDE + FI_CNT];
+      const uint32_t* fl = flist + i * L.f_cap;
+      Real* ge = fe + i * L.f_cap;
+      for (int t = lane; t < cnt; t += CTK_WARP) {
+        uint32_t e = fl[t];
+        Geo g = geometry(e, f);
+        bool drop;
+        Real gv = model_value(g, f, drop);
+        ge[t] = gv;
+        int p = entry_pixel(e);
+        pr[p] += drop ? (Real) NAN : f.s * gv;
+      }
+      warp_sync();
+    }
+    const Real bg = (Real) value_of(x, 0, 0);
+    const Real* pval = PVAL();
+    double acc = 0., sr = 0., nv = 0.;
+    for (int p = lane; p < M; p += CTK_WARP) {
+      Real r = pval[p] - bg - pr[p];
+      pr[p] = r;
+      if (r == r) { acc += (double) r * (double) r; sr += (double) r; nv += 1.; }
+    }
+    acc = warp_sum(acc);
+    sum_r = warp_sum(sr);
+    n_valid = warp_sum(nv);
+    warp_sync();
+    return 0.5 * acc;
+  }
+
+  CTK_DEV void h_add(int u, int v, double val) const {
+    double* H = Hm();
+    if (u == v) H[tri(u) + u] += 2. * val;
+    else if (u > v) H[tri(u) + v] += val;
+    else H[tri(v) + u] += val;
+  }
+
+  // ---- normal equations from the caches of the last evaluate() ---------------------------------
+  // H = sum m m^T (packed lower), RHS = sum m r  (= -gradient of 0.5 sum r^2)
+  CTK_DEV void accumulate() {
+    double* H = Hm();
+    double* rhs = RHS();
+    for (int t = lane; t < tri(V); t += CTK_WARP) H[t] = 0.;
+    for (int v = lane; v < V; v += CTK_WARP) rhs[v] = 0.;
+    warp_sync();
+    const int vb = base[0];
+    if (vb >= 0 && lane == 0) { H[tri(vb) + vb] = n_valid; rhs[vb] = sum_r; }
+    warp_sync();
+    const uint32_t* flist = FLIST();
+    const Real* fe = FE();
+    const Real* pr = PR();
+    const int* fi = FI();
+    for (int i = 0; i < n; ++i) {
+      const Feat f = feat(i);
+      const int cnt = fi[i * FI_STRIDE + FI_CNT];
+      const uint32_t* fl = flist + i * L.f_cap;
+      const Real* ge = fe + i * L.f_cap;
+      Real acc[LT], accr[LD], acc1[LD];
+#pragma unroll
+      for (int k = 0; k < LT; ++k) acc[k] = 0;
+#pragma unroll
+      for (int k = 0; k < LD; ++k) { accr[k] = 0; acc1[k] = 0; }
+      for (int t = lane; t < cnt; t += CTK_WARP) {
+        uint32_t e = fl[t];
+        Real r = pr[entry_pixel(e)];
+        if (!(r == r)) continue;
+        Geo g = geometry(e, f);
+        Real m[LD];
+        model_derivs(g, f, ge[t], m);
+        int k = 0;
+#pragma unroll
+        for (int u = 0; u < LD; ++u) {
+          accr[u] += m[u] * r;
+          acc1[u] += m[u];
+#pragma unroll
+          for (int v = 0; v <= u; ++v) acc[k++] += m[u] * m[v];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < LT; ++k) acc[k] = warp_sum(acc[k]);
+#pragma unroll
+      for (int k = 0; k < LD; ++k) { accr[k] = warp_sum(accr[k]); acc1[k] = warp_sum(acc1[k]); }
+      if (lane == 0) {
+        int k = 0;
+#pragma unroll
+        for (int u = 0; u < LD; ++u) {
+          int vu = var_of(slot_col(u), i);
+          if (vu >= 0) {
+            rhs[vu] += (double) accr[u];
+            if (vb >= 0) { if (vu > vb) H[tri(vu) + vb] += (double) acc1[u];
+                           else H[tri(vb) + vu] += (double) acc1[u]; }
+          }
+#pragma unroll
+          for (int v = 0; v <= u; ++v, ++k) {
+            if (vu < 0) continue;
+            int vv = var_of(slot_col(v), i);
+            if (vv < 0) continue;
+            if (u == v) H[tri(vu) + vu] += (double) acc[k];
+            else if (vu > vv) H[tri(vu) + vv] += (double) acc[k];
+            else H[tri(vv) + vu] += (double) acc[k];
+          }
+        }
+      }
+      warp_sync();
+    }
+    // cross blocks over the pixels two features share
+    const uint32_t* pairs = PAIRS();
+    const int* phdr = PHDR();
+    for (int q = 0; q < npairs; ++q) {
+      const int i = phdr[q * 4], j = phdr[q * 4 + 1], start = phdr[q * 4 + 2], cnt = phdr[q * 4 + 3];
+      const Feat f_i = feat(i), f_j = feat(j);
+      const uint32_t *fl_i = flist + i * L.f_cap, *fl_j = flist + j * L.f_cap;
+      const Real *ge_i = fe + i * L.f_cap, *ge_j = fe + j * L.f_cap;
+      Real B[LD * LD];
+#pragma unroll
+      for (int k = 0; k < LD * LD; ++k) B[k] = 0;
+      for (int t = lane; t < cnt; t += CTK_WARP) {
+        uint32_t pe = pairs[start + t];
+        int ti = (int) (pe & 0xffffu), tj = (int) (pe >> 16);
+        uint32_t ei = fl_i[ti], ej = fl_j[tj];
+        Real r = pr[entry_pixel(ei)];
+        if (!(r == r)) continue;
+        Real mi[LD], mj[LD];
+        model_derivs(geometry(ei, f_i), f_i, ge_i[ti], mi);
+        model_derivs(geometry(ej, f_j), f_j, ge_j[tj], mj);
+#pragma unroll
+        for (int u = 0; u < LD; ++u)
+#pragma unroll
+          for (int v = 0; v < LD; ++v) B[u * LD + v] += mi[u] * mj[v];
+      }
+#pragma unroll
+      for (int k = 0; k < LD * LD; ++k) B[k] = warp_sum(B[k]);
+      if (lane == 0) {
+#pragma unroll
+        for (int u = 0; u < LD; ++u) {
+          int vu = var_of(slot_col(u), i);
+          if (vu < 0) continue;
+#pragma unroll
+          for (int v = 0; v < LD; ++v) {
+            int vv = var_of(slot_col(v), j);
+            if (vv < 0) continue;
+            h_add(vu, vv, (double) B[u * LD + v]);
+          }
+        }
+      }
+      warp_sync();
+    }
+  }
+
+  // ---- distance constraints (constraints.py:59-99) as augmented-Lagrangian rows ----------------
+  CTK_DEV void con_pair(int j, int& p, int& q) const {
+    if (n == 2) { p = 0; q = 1; return; }
+    p = (j == 1) ? 1 : 0;                    // (0,1), (1,2), (0,2)
+    q = (j == 0) ? 1 : 2;
+  }
+  CTK_DEV double con_value(const double* x, int j) const {
+    int p, q;
+    con_pair(j, p, q);
+    double s = 0.;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      double d = (x[base[2 + k] + p] - x[base[2 + k] + q]) / cdist[k];
+      s += d * d;
+    }
+    return 1. - s;
+  }
+  CTK_DEV double penalty(const double* x) const {
+    double v = 0.;
+    for (int j = 0; j < n_con; ++j) {
+      double c = con_value(x, j);
+      v += mu[j] * c + 0.5 * pen_w * c * c;
+    }
+    return v;
+  }
+  CTK_DEV double con_violation(const double* x) const {
+    double v = 0.;
+    for (int j = 0; j < n_con; ++j) v = fmax(v, fabs(con_value(x, j)));
+    return v;
+  }
+  // add w A^T A to the packed matrix Kp and -(mu + w c) A^T to rhs (lane 0 only)
+  CTK_DEV void add_constraint_rows(const double* x, double* Kp, double* rhs) const {
+    for (int j = 0; j < n_con; ++j) {
+      int p, q;
+      con_pair(j, p, q);
+      int idx[6];
+      double g[6];
+#pragma unroll
+      for (int k = 0; k < ND; ++k) {
+        double d = (x[base[2 + k] + p] - x[base[2 + k] + q]) / (cdist[k] * cdist[k]);
+        idx[2 * k] = base[2 + k] + p; g[2 * k] = -2. * d;
+        idx[2 * k + 1] = base[2 + k] + q; g[2 * k + 1] = 2. * d;
+      }
+      double c = con_value(x, j);
+      double lam = mu[j] + pen_w * c;
+      for (int u = 0; u < 2 * ND; ++u) {
+        rhs[idx[u]] -= lam * g[u];
+        for (int v = 0; v < 2 * ND; ++v) {
+          if (idx[v] > idx[u]) continue;
+          Kp[tri(idx[u]) + idx[v]] += pen_w * g[u] * g[v];
+        }
+      }
+    }
+  }
+
+  // ---- damped, bound-aware step --------------------------------------------------------------------
+  // Builds K = H (+ constraint rows) in Lm, the full right-hand side in D, freezes the active set,
+  // adds lambda*diag, factorises and solves.  On return D holds the step, RHS the un-frozen
+  // right-hand side (with constraint terms) and Lm the Cholesky factor.  Returns false on breakdown.
+  CTK_DEV bool solve(double lambda, double* rhs_full) {
+    const double* H = Hm();
+    double* Kf = Lm();
+    double* d = D();
+    double* dg = DG();
+    int* act = ACT();
+    const double *x = X(), *lo = LO(), *hi = HI();
+    for (int t = lane; t < tri(V); t += CTK_WARP) Kf[t] = H[t];
+    for (int v = lane; v < V; v += CTK_WARP) rhs_full[v] = RHS()[v];
+    warp_sync();
+    if (n_con > 0 && lane == 0) add_constraint_rows(x, Kf, rhs_full);
+    warp_sync();
+    double dmax = 0.;
+    for (int v = lane; v < V; v += CTK_WARP) dmax = fmax(dmax, Kf[tri(v) + v]);
+    dmax = warp_max_d(dmax);
+    const double floor_ = fmax(dmax * 1e-14, 1e-300);
+    for (int v = lane; v < V; v += CTK_WARP) {
+      double g = rhs_full[v];
+      bool frozen = (x[v] <= lo[v] && g < 0.) || (x[v] >= hi[v] && g > 0.) || !(lo[v] < hi[v]);
+      act[v] = frozen ? 1 : 0;
+      dg[v] = fmax(Kf[tri(v) + v], floor_);
+      d[v] = frozen ? 0. : g;
+    }
+    warp_sync();
+    for (int u = 0; u < V; ++u) {
+      for (int v = lane; v <= u; v += CTK_WARP) {
+        int t = tri(u) + v;
+        if (act[u] || act[v]) Kf[t] = (u == v) ? 1. : 0.;
+        else if (u == v) Kf[t] += lambda * dg[u];
+      }
+    }
+    warp_sync();
+    // packed Cholesky, right-looking; lanes own rows
+    bool ok = true;
+    for (int j = 0; j < V; ++j) {
+      double piv = Kf[tri(j) + j];
+      if (!(piv > 0.) || !finite_d(piv)) { ok = false; break; }
+      double inv = 1. / sqrt(piv);
+      warp_sync();
+      for (int r = j + lane; r < V; r += CTK_WARP) Kf[tri(r) + j] *= inv;
+      warp_sync();
+      for (int r = j + 1 + lane; r < V; r += CTK_WARP) {
+        double lrj = Kf[tri(r) + j];
+        for (int c = j + 1; c <= r; ++c) Kf[tri(r) + c] -= lrj * Kf[tri(c) + j];
+      }
+      warp_sync();
+    }
+    if (!ok) return false;
+    // forward and back substitution
+    for (int j = 0; j < V; ++j) {
+      double yj = d[j] / Kf[tri(j) + j];
+      warp_sync();
+      if (lane == 0) d[j] = yj;
+      for (int r = j + 1 + lane; r < V; r += CTK_WARP) d[r] -= Kf[tri(r) + j] * yj;
+      warp_sync();
+    }
+    for (int j = V - 1; j >= 0; --j) {
+      double yj = d[j] / Kf[tri(j) + j];
+      warp_sync();
+      if (lane == 0) d[j] = yj;
+      for (int r = lane; r < j; r += CTK_WARP) d[r] -= Kf[tri(j) + r] * yj;
+      warp_sync();
+    }
+    return true;
+  }
+
+  // predicted decrease of the (augmented) objective for step s: rhs.s - 0.5 s^T K s
+  CTK_DEV double predicted(const double* s, const double* rhs_full) const {
+    const double* H = Hm();
+    double acc = 0.;
+    for (int u = lane; u < V; u += CTK_WARP) {
+      double hs = 0.;
+      for (int v = 0; v < V; ++v) hs += (u >= v ? H[tri(u) + v] : H[tri(v) + u]) * s[v];
+      acc += s[u] * (rhs_full[u] - 0.5 * hs);
+    }
+    acc = warp_sum(acc);
+    // constraint rows: gradient part is already in rhs_full; add -0.5 w (A s)^2
+    for (int j = 0; j < n_con; ++j) {
+      int p, q;
+      con_pair(j, p, q);
+      double as = 0.;
+#pragma unroll
+      for (int k = 0; k < ND; ++k) {
+        double dd = (X()[base[2 + k] + p] - X()[base[2 + k] + q]) / (cdist[k] * cdist[k]);
+        as += -2. * dd * (s[base[2 + k] + p] - s[base[2 + k] + q]);
+      }
+      acc -= 0.5 * pen_w * as * as;
+    }
+    return acc;
+  }
+
+  CTK_DEV bool is_pos_var(int v) const {
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      int b = base[2 + k];
+      if (b >= 0 && v >= b && v < b + (mode(2 + k) == CTK_MODE_VAR ? n : 1)) return true;
+    }
+    return false;
+  }
+
+  // ---- projected Levenberg-Marquardt with augmented-Lagrangian constraints ---------------------
+  // Minimises from X() (already holding the start vector).  Returns status; *f_data = 0.5 sum r^2.
+  CTK_DEV int minimise(double* f_data) {
+    const bool f32 = sizeof(Real) == 4;
+    const double xtol = a.prob.xtol > 0. ? a.prob.xtol : (f32 ? 2e-6 : 1e-9);
+    const double eps_f = f32 ? 4e-6 : 1e-13;      // resolution of the objective
+    const double ctol = f32 ? 1e-8 : 1e-10;
+    double *x = X(), *xt = XT(), *d = D();
+    double* rhs_full = dvec(L.o_rhsf);            // rhs incl. constraint terms, before freezing
+    double lambda = 1e-3, nu = 2.;
+    for (int j = 0; j < 3; ++j) mu[j] = 0.;
+    pen_w = 0.;
+    double fd = evaluate(x);
+    if (!finite_d(fd)) return CTK_FAIL_NUMERIC;
+    accumulate();
+    if (n_con > 0) {
+      // penalty weight relative to the curvature of the data term in the position variables
+      double hmax = 0.;
+      for (int v = lane; v < V; v += CTK_WARP)
+        if (is_pos_var(v)) hmax = fmax(hmax, Hm()[tri(v) + v]);
+      hmax = warp_max_d(hmax);
+      double a2 = 0.;
+#pragma unroll
+      for (int k = 0; k < ND; ++k) a2 = fmax(a2, 8. / (cdist[k] * cdist[k]));
+      pen_w = 100. * fmax(hmax, 1e-30) / a2;
+    }
+    double fa = fd + penalty(x);
+    double c_prev = n_con > 0 ? con_violation(x) : 0.;
+    int al_rounds = 0;
+    double prev_small_step = INFINITY;
+    int rejects = 0;
+    for (int it = 0; it < a.prob.lm_max_iter; ++it) {
+      if (!solve(lambda, rhs_full)) {
+        lambda = fmax(lambda * 10., 1e-8);
+        if (++rejects > 60) { *f_data = fd; return CTK_FAIL_NUMERIC; }
+        continue;
+      }
+      // trial point, projected on the box
+      double worst = 0.;
+      for (int v = lane; v < V; v += CTK_WARP) {
+        double t = fmin(fmax(x[v] + d[v], LO()[v]), HI()[v]);
+        xt[v] = t;
+        double s = t - x[v];
+        d[v] = s;
+        double scale = is_pos_var(v) ? 1. : fmax(1., fabs(x[v]));
+        worst = fmax(worst, fabs(s) / scale);
+      }
+      worst = warp_max_d(worst);
+      warp_sync();
+      if (!finite_d(worst)) { *f_data = fd; return CTK_FAIL_NUMERIC; }
+      if (worst <= xtol) {
+        // stationary for the current multipliers
+        if (n_con == 0) { *f_data = fd; return CTK_OK; }
+        double cv = con_violation(x);
+        if (cv <= ctol || al_rounds >= 40) { *f_data = fd; return CTK_OK; }
+        for (int j = 0; j < n_con; ++j) mu[j] += pen_w * con_value(x, j);
+        if (al_rounds > 0 && cv > 0.25 * c_prev) pen_w *= 10.;
+        c_prev = cv;
+        ++al_rounds;
+        fa = fd + penalty(x);
+        lambda = fmin(lambda, 1e-3);
+        continue;
+      }
+      double pred = predicted(d, rhs_full);
+      double fdt = evaluate(xt);
+      double fat = fdt + penalty(xt);
+      // below the resolution of the objective the comparison fat < fa is rounding noise: trust the
+      // quadratic model there (the gradient stays accurate long after the objective has gone flat)
+      bool noise = pred > 0. && pred <= eps_f * fabs(fa);
+      if (finite_d(fat) && pred > 0. && (fat < fa || noise)) {
+        if (!noise) {
+          double rho = (fa - fat) / pred;
+          double t = 2. * rho - 1.;
+          lambda *= fmax(1. / 3., 1. - t * t * t);
+          lambda = fmax(lambda, 1e-12);
+        } else {
+          if (worst > 0.9 * prev_small_step) lambda *= 4.;    // not contracting: damp harder
+          prev_small_step = worst;
+        }
+        nu = 2.;
+        rejects = 0;
+        for (int v = lane; v < V; v += CTK_WARP) x[v] = xt[v];
+        warp_sync();
+        fd = fdt;
+        fa = fat;
+        accumulate();
+      } else {
+        lambda *= nu;
+        nu *= 2.;
+        if (++rejects > 40 || lambda > 1e18) {
+          // no representable descent step is left: x is a numerical minimiser
+          *f_data = fd;
+          return (n_con == 0 || con_violation(x) <= 1e-6) ? CTK_OK : CTK_FAIL_NO_CONVERGENCE;
+        }
+      }
+    }
+    *f_data = fd;
+    return CTK_FAIL_NO_CONVERGENCE;
+  }
+
+  // ---- whole cluster (refine.py:343-430) -------------------------------------------------------
+  CTK_DEV void run(int cluster) {
+    feat0 = a.cluster_offset[cluster];
+    n = a.cluster_offset[cluster + 1] - feat0;
+    const int fidx = a.cluster_frame[cluster];
+    frame = a.frames[fidx];
+    fmax_ = a.frame_max[fidx];
+    evals = 0;
+    M = 0;
+    int status = CTK_OK;
+    double cost = NAN;
+    if (n <= 0 || n > L.n_max || n > CTK_MAX_CLUSTER_FEATURES) status = CTK_FAIL_TOO_LARGE;
+    if (status == CTK_OK) status = setup_variables();
+    // constraints apply to clusters of exactly their size, with free per-feature positions
+    n_con = 0;
+    if (status == CTK_OK) {
+      bool pos_var = true;
+#pragma unroll
+      for (int k = 0; k < ND; ++k) pos_var = pos_var && mode(2 + k) == CTK_MODE_VAR;
+      if (pos_var && n == 2 && (a.prob.constraint_mask & CTK_CONSTRAINT_DIMER)) {
+        n_con = 1;
+        for (int k = 0; k < ND; ++k) cdist[k] = a.prob.dimer_dist[k];
+      } else if (pos_var && n == 3 && (a.prob.constraint_mask & CTK_CONSTRAINT_TRIMER)) {
+        n_con = 3;
+        for (int k = 0; k < ND; ++k) cdist[k] = a.prob.trimer_dist[k];
+      }
+    }
+    double fd = 0.;
+    if (status == CTK_OK) {
+      double* mc = MC();
+      for (int t = lane; t < n * ND; t += CTK_WARP) {
+        int i = t / ND, k = t - i * ND;
+        mc[i * 3 + k] = a.params_in[(int64_t) (feat0 + i) * P + 2 + k];
+      }
+      warp_sync();
+      for (int outer = 0; outer < a.prob.max_iter; ++outer) {
+        status = build_pixels();
+        if (status != CTK_OK) break;
+        for (int v = lane; v < V; v += CTK_WARP) X()[v] = X0()[v];   // restart, refine.py:361-365
+        warp_sync();
+        status = minimise(&fd);
+        if (status != CTK_OK) break;
+        // accept when every feature stayed within max_shift of its mask centre, refine.py:383-385
+        bool moved = false;
+        for (int i = lane; i < n; i += CTK_WARP) {
+          double s = 0.;
+#pragma unroll
+          for (int k = 0; k < ND; ++k) {
+            double dlt = value_of(X(), 2 + k, i) - mc[i * 3 + k];
+            s += dlt * dlt;
+          }
+          moved |= !(s < a.prob.max_shift * a.prob.max_shift);
+        }
+        moved = warp_any(moved);
+        if (!moved) break;
+        warp_sync();
+        for (int t = lane; t < n * ND; t += CTK_WARP) {
+          int i = t / ND, k = t - i * ND;
+          mc[i * 3 + k] = value_of(X(), 2 + k, i);
+        }
+        warp_sync();
+      }
+    }
+    if (status == CTK_OK) {
+      // rms_dev = sqrt(fun / residual_factor), fun = sum diff^2 / M / norm   (refine.py:354, 379)
+      double norm = fmax_ * fmax_ / a.prob.residual_factor;
+      double fun = 2. * fd / (double) M / norm;
+      cost = sqrt(fun / a.prob.residual_factor);
+      if (!finite_d(cost)) status = CTK_FAIL_NUMERIC;
+      else if (cost > a.prob.max_rms_dev) status = CTK_FAIL_RMS_DEV;
+    }
+    // write back (refine.py:408-427): failure leaves the parameters untouched and cost = NaN
+    if (n > 0) {
+      const double* pin = a.params_in + (int64_t) feat0 * P;
+      double* pout = a.params_out + (int64_t) feat0 * P;
+      for (int t = lane; t < n * P; t += CTK_WARP) {
+        int i = t / P, c = t - i * P;
+        double v = pin[t];
+        if (status == CTK_OK) v = value_of(X(), c, i);
+        pout[t] = v;
+      }
+    }
+    if (lane == 0) {
+      a.cost_out[cluster] = status == CTK_OK ? cost : NAN;
+      a.status_out[cluster] = status;
+      a.iters_out[cluster] = evals;
+    }
+    warp_sync();
+  }
+};
+
+}  // namespace ctk

@@ -1,0 +1,152 @@
+/*
+ * ctk.h -- C ABI of libctk, the B200 (sm_100a) implementation of clustertracking's
+ * least-squares refinement hot path.
+ *
+ * The reference (caspervdw/clustertracking) is pure Python and has no FFI of its own; its boundary
+ * for this path is the public function `refine_leastsq` (clustertracking/refine.py:82-452).  The
+ * entry points below are what a ctypes binding inside that function would call in place of its
+ * per-cluster Python loop (refine.py:343-430): one call per batch of frames per device.  Each
+ * declaration cites the reference lines it replaces.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; all sizes explicit;
+ *   - every `d_` pointer is a DEVICE pointer owned by the caller; the library allocates nothing
+ *     that outlives a call and never synchronises the stream (except where stated);
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = default stream);
+ *   - return value 0 on success, a negative `CTK_E_*` code otherwise; `ctk_last_error()` returns a
+ *     thread-local message.  Per-cluster numerical failures are NOT errors: they are reported in
+ *     `status_out` (reference semantics: cost = NaN, parameters unchanged, refine.py:408-418).
+ */
+#ifndef CTK_H_
+#define CTK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTK_VERSION 100          /* major*10000 + minor*100 + patch */
+#define CTK_MAX_PARAMS 12        /* background, signal, <=3 pos, <=3 size, <=1 extra (+ spare) */
+#define CTK_MAX_CLUSTER_FEATURES 32   /* features per cluster handled by the warp-per-cluster kernel */
+#define CTK_MAX_RADIUS 30        /* mask radius per axis (pixel offsets are packed in 6 bits) */
+
+/* parameter modes, same codes as fitfunc.py:9-11 (2 = 'global' is out of scope) */
+enum { CTK_MODE_CONST = 0, CTK_MODE_VAR = 1, CTK_MODE_CLUSTER = 3 };
+/* radial model families, fitfunc.py:112-146, 195-204 */
+enum { CTK_FAMILY_GAUSS = 0, CTK_FAMILY_RING = 1, CTK_FAMILY_DISC = 2 };
+/* pixel types of the frames */
+enum { CTK_PIXEL_U8 = 0, CTK_PIXEL_U16 = 1, CTK_PIXEL_F32 = 2, CTK_PIXEL_F64 = 3,
+       CTK_PIXEL_I16 = 4, CTK_PIXEL_I32 = 5 };
+/* arithmetic of the pixel pass (normal equations, factorisation and parameters are always f64) */
+enum { CTK_COMPUTE_F32 = 0, CTK_COMPUTE_F64 = 1 };
+/* equality constraints, constraints.py:59-99; applied to clusters of exactly that size */
+enum { CTK_CONSTRAINT_DIMER = 1, CTK_CONSTRAINT_TRIMER = 2 };
+
+/* per-cluster status (status_out).  0 = success; anything else = the reference's RefineException
+ * path: cost NaN, parameters copied through unchanged. */
+enum {
+  CTK_OK = 0,
+  CTK_FAIL_NONFINITE = 1,     /* non-finite initial parameters          refine.py:356-357 */
+  CTK_FAIL_OUT_OF_IMAGE = 2,  /* no coordinate within the image + radius refine.py:33-34  */
+  CTK_FAIL_NO_CONVERGENCE = 3,/* inner solver iteration limit           refine.py:376-377 */
+  CTK_FAIL_RMS_DEV = 4,       /* rms_dev > max_rms_dev                  refine.py:391-394 */
+  CTK_FAIL_BOUNDS = 5,        /* lower bound above upper bound                            */
+  CTK_FAIL_TOO_LARGE = 6,     /* cluster exceeds the capacity of this launch (see ctk_refine_batch) */
+  CTK_FAIL_NUMERIC = 7        /* non-finite value met during the fit    fitfunc.py:437-438 */
+};
+
+/* library error codes (return values) */
+enum {
+  CTK_E_INVALID = -1,         /* bad argument */
+  CTK_E_UNSUPPORTED = -2,     /* combination not built into the library */
+  CTK_E_CUDA = -3,            /* a CUDA runtime call failed */
+  CTK_E_CAPACITY = -4         /* requested capacity does not fit the device's shared memory */
+};
+
+/* Problem description, host memory, plain old data.  Mirrors the keyword arguments of
+ * refine_leastsq (refine.py:82-87) after FitFunctions.__init__ (fitfunc.py:325-413) resolved them. */
+typedef struct {
+  int32_t ndim;               /* 2 | 3                                   refine.py:254-283 */
+  int32_t isotropic;          /* 1: one `size` column, 0: ndim columns   refine.py:287      */
+  int32_t family;             /* CTK_FAMILY_*                            fitfunc.py:195-204 */
+  int32_t n_params;           /* P = 2 + ndim + n_size + n_extra         fitfunc.py:353-354 */
+  int32_t modes[CTK_MAX_PARAMS]; /* per column, order background, signal, pos.., size.., extra */
+  int32_t radius[3];          /* mask radii diameter//2, axis order z,y,x (first ndim used) */
+  int32_t pixel_dtype;        /* CTK_PIXEL_*                                                */
+  int32_t compute_dtype;      /* CTK_COMPUTE_*                                              */
+  int32_t max_iter;           /* outer re-mask iterations                refine.py:365      */
+  int32_t lm_max_iter;        /* inner solver iteration cap (SLSQP maxiter, refine.py:243)  */
+  double  max_shift;          /* refine.py:383-385 */
+  double  max_rms_dev;        /* refine.py:391-394 */
+  double  residual_factor;    /* refine.py:354, 379 */
+  double  xtol;               /* inner solver step tolerance; <= 0 selects the default      */
+  int32_t constraint_mask;    /* OR of CTK_CONSTRAINT_*                                     */
+  int32_t reserved0;
+  double  dimer_dist[3];      /* constraints.py:70-76, per axis */
+  double  trimer_dist[3];     /* constraints.py:93-99, per axis */
+} ctk_problem_t;
+
+int ctk_version(void);
+const char* ctk_last_error(void);
+
+/* Maximum pixel value of each frame, as float64 (replaces `frame.max()` at refine.py:354, which the
+ * reference re-evaluates for every cluster).  HBM-bound streaming reduction.
+ *   d_frames   [n_frames] device array of device pointers to C-contiguous frames
+ *   n_pixels   pixels per frame
+ *   d_max_out  [n_frames] float64 */
+int ctk_frame_max(const void* const* d_frames, int32_t n_frames, int64_t n_pixels,
+                  int32_t pixel_dtype, double* d_max_out, void* stream);
+
+/* Bytes of scratch `ctk_refine_batch` needs in `d_workspace`. */
+size_t ctk_refine_workspace_bytes(void);
+
+/* Shared memory (bytes per cluster) a launch with this capacity would use, or 0 when it does not
+ * fit the device limit (227 KB on sm_100a).  Lets the caller bin clusters by size. */
+size_t ctk_refine_shared_bytes(const ctk_problem_t* prob, int32_t max_cluster_features);
+
+/* Refine a batch of clusters: the body of the reference's loop over (frame, cluster) groups
+ * (refine.py:343-430) including the pixel-set construction (refine.py:28-58, masks.py:30-68), the
+ * objective (fitfunc.py:421-489), the bounds (fitfunc.py:535-558), the dimer/trimer constraints
+ * (constraints.py:59-99), the outer re-mask loop (refine.py:365-388) and the rms check (391-394).
+ * The reference minimises with scipy's SLSQP (refine.py:373-375); this library reaches the same
+ * bound/equality-constrained minimum with a projected Levenberg-Marquardt iteration and an
+ * augmented-Lagrangian treatment of the distance constraints, entirely on the device.
+ *
+ *   d_frames        [n_frames] device array of device pointers to C-contiguous frames
+ *   frame_shape     [ndim] (host) frame shape, axis order z,y,x
+ *   d_frame_max     [n_frames] float64, from ctk_frame_max
+ *   n_work          number of clusters to process in this launch
+ *   d_work_ids      [n_work] cluster indices to process (NULL = 0..n_work-1); put expensive first
+ *   max_cluster_features  capacity of this launch; clusters with more features (or whose pixel
+ *                   lists overflow the derived capacity) get CTK_FAIL_TOO_LARGE
+ *   d_cluster_frame [n_clusters] index into d_frames
+ *   d_cluster_offset[n_clusters + 1] feature ranges; features of a cluster are consecutive rows
+ *   d_params_in     [n_features, P] float64 row-major, columns as in `modes`   (refine.py:345)
+ *   d_bounds_lo/hi  [n_features, P] float64 per-feature bounds, +-inf allowed  (fitfunc.py:538-551)
+ *   d_params_out    [n_features, P] float64                                   (refine.py:380, 426)
+ *   d_cost_out      [n_clusters] rms_dev, NaN on failure                      (refine.py:379, 427)
+ *   d_status_out    [n_clusters] CTK_OK or CTK_FAIL_*
+ *   d_iters_out     [n_clusters] pixel passes executed (objective evaluations), for accounting
+ *   d_workspace     ctk_refine_workspace_bytes() bytes of device scratch
+ */
+int ctk_refine_batch(const ctk_problem_t* prob,
+                     const void* const* d_frames, const int64_t* frame_shape,
+                     const double* d_frame_max,
+                     int32_t n_work, const int32_t* d_work_ids, int32_t max_cluster_features,
+                     const int32_t* d_cluster_frame, const int32_t* d_cluster_offset,
+                     const double* d_params_in, const double* d_bounds_lo, const double* d_bounds_hi,
+                     double* d_params_out, double* d_cost_out, int32_t* d_status_out,
+                     int32_t* d_iters_out, void* d_workspace, void* stream);
+
+/* Host helper (no GPU): cluster labels of one frame from the close pairs, visiting the pairs in the
+ * given order with the reference's "the label of a's cluster survives" rule (find.py:41-48, 84-93).
+ *   pairs [n_pairs, 2] int64; labels_out, sizes_out [n] int64 */
+int ctk_label_clusters(const int64_t* pairs, int64_t n_pairs, int64_t n,
+                       int64_t* labels_out, int64_t* sizes_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* CTK_H_ */
