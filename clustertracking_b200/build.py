@@ -65,7 +65,7 @@ def _compile(job):
 def build(force=False, verbose=True):
     """Compile and link ``libctk.so``; returns its path."""
     stamp = os.path.join(BUILD, "stamp")
-    want = _source_hash((ARCH, COMMON))
+    want = _source_hash((ARCH, [c for c in COMMON if ROOT not in c]))
     if not force and os.path.exists(OUT) and os.path.exists(stamp):
         with open(stamp) as fh:
             if fh.read().strip() == want:

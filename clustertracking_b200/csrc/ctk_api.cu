@@ -110,14 +110,14 @@ int ctk_refine_batch(const ctk_problem_t* prob, const void* const* d_frames,
                      const int32_t* d_cluster_frame, const int32_t* d_cluster_offset,
                      const double* d_params_in, const double* d_bounds_lo, const double* d_bounds_hi,
                      double* d_params_out, double* d_cost_out, int32_t* d_status_out,
-                     int32_t* d_iters_out, void* d_workspace, void* stream) {
+                     int32_t* d_stats_out, void* d_workspace, void* stream) {
   if (!prob) return fail(CTK_E_INVALID, "ctk_refine_batch: prob is NULL");
   if (const char* why = ctk::validate_problem(*prob)) return fail(CTK_E_INVALID, "ctk_refine_batch: %s", why);
   if (n_work < 0) return fail(CTK_E_INVALID, "ctk_refine_batch: n_work < 0");
   if (n_work == 0) return 0;
   if (!d_frames || !frame_shape || !d_frame_max || !d_cluster_frame || !d_cluster_offset ||
       !d_params_in || !d_bounds_lo || !d_bounds_hi || !d_params_out || !d_cost_out ||
-      !d_status_out || !d_iters_out || !d_workspace)
+      !d_status_out || !d_stats_out || !d_workspace)
     return fail(CTK_E_INVALID, "ctk_refine_batch: NULL pointer argument");
   ctk::BatchArgs a;
   memset(&a, 0, sizeof(a));
@@ -139,7 +139,7 @@ int ctk_refine_batch(const ctk_problem_t* prob, const void* const* d_frames,
   a.params_out = d_params_out;
   a.cost_out = d_cost_out;
   a.status_out = d_status_out;
-  a.iters_out = d_iters_out;
+  a.stats_out = d_stats_out;
   a.counter = static_cast<int32_t*>(d_workspace);
   if (!ctk::compute_layout(*prob, max_cluster_features, &a.lay))
     return fail(CTK_E_CAPACITY, "ctk_refine_batch: max_cluster_features %d out of range [1, %d]",

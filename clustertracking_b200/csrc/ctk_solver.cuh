@@ -153,7 +153,7 @@ struct BatchArgs {
   double* params_out;
   double* cost_out;
   int32_t* status_out;
-  int32_t* iters_out;
+  int32_t* stats_out;        // [n_clusters, CTK_STATS] counters, see ctk.h
   int32_t* counter;
   Layout lay;
 };
@@ -190,7 +190,7 @@ struct ClusterSolver {
   int blo[3], bdim[3];
   const void* frame;
   double fmax_;
-  int evals;
+  int evals, accums, outers, n_entries, n_pair_entries;
   // residual statistics of the last evaluate()
   double sum_r, n_valid;
   // augmented Lagrangian
@@ -479,6 +479,9 @@ struct ClusterSolver {
       }
     }
     npairs = np;
+    n_pair_entries = ptotal;
+    n_entries = 0;
+    for (int i = 0; i < n; ++i) n_entries += fi[i * FI_STRIDE + FI_CNT];
     warp_sync();
     return CTK_OK;
   }
@@ -645,6 +648,7 @@ struct ClusterSolver {
   // ---- normal equations from the caches of the last evaluate() ---------------------------------
   // H = sum m m^T (packed lower), RHS = sum m r  (= -gradient of 0.5 sum r^2)
   CTK_DEV void accumulate() {
+    ++accums;
     double* H = Hm();
     double* rhs = RHS();
     for (int t = lane; t < tri(V); t += CTK_WARP) H[t] = 0.;
@@ -1020,8 +1024,9 @@ struct ClusterSolver {
     const int fidx = a.cluster_frame[cluster];
     frame = a.frames[fidx];
     fmax_ = a.frame_max[fidx];
-    evals = 0;
+    evals = accums = outers = n_entries = n_pair_entries = 0;
     M = 0;
+    V = 0;
     int status = CTK_OK;
     double cost = NAN;
     if (n <= 0 || n > L.n_max || n > CTK_MAX_CLUSTER_FEATURES) status = CTK_FAIL_TOO_LARGE;
@@ -1049,6 +1054,7 @@ struct ClusterSolver {
       }
       warp_sync();
       for (int outer = 0; outer < a.prob.max_iter; ++outer) {
+        ++outers;
         status = build_pixels();
         if (status != CTK_OK) break;
         for (int v = lane; v < V; v += CTK_WARP) X()[v] = X0()[v];   // restart, refine.py:361-365
@@ -1098,7 +1104,10 @@ struct ClusterSolver {
     if (lane == 0) {
       a.cost_out[cluster] = status == CTK_OK ? cost : NAN;
       a.status_out[cluster] = status;
-      a.iters_out[cluster] = evals;
+      int32_t* st = a.stats_out + (int64_t) cluster * CTK_STATS;
+      st[CTK_STAT_EVALS] = evals; st[CTK_STAT_ACCUMS] = accums; st[CTK_STAT_OUTER] = outers;
+      st[CTK_STAT_PIXELS] = M; st[CTK_STAT_ENTRIES] = n_entries;
+      st[CTK_STAT_PAIR_ENTRIES] = n_pair_entries; st[CTK_STAT_VARS] = V; st[7] = 0;
     }
     warp_sync();
   }

@@ -60,7 +60,11 @@ class Result(object):
         self.params_out = plan.params_in.copy()
         self.cost = np.full(plan.n_clusters, np.nan)
         self.status = np.full(plan.n_clusters, -1, dtype=np.int32)
-        self.iters = np.zeros(plan.n_clusters, dtype=np.int32)
+        self.stats = np.zeros((plan.n_clusters, 8), dtype=np.int32)   # CTK_STAT_* counters
+
+    @property
+    def iters(self):
+        return self.stats[:, 0]
 
 
 # --------------------------------------------------------------------------------------------------
@@ -285,73 +289,156 @@ def finalize(plan, result):
 # --------------------------------------------------------------------------------------------------
 # device execution
 # --------------------------------------------------------------------------------------------------
+class DeviceSession(object):
+    """Device-side state of one plan: feature-level buffers stay resident for the whole call, frames
+    are uploaded in batches through pinned host memory.  torch is used for device memory and the
+    stream only; all arithmetic happens inside libctk (C ABI, include/ctk.h)."""
+
+    def __init__(self, plan, device=None):
+        import torch
+        self.torch = torch
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("clustertracking_b200 needs a CUDA device (B200, sm_100a); "
+                               "there is no CPU fallback")
+        self.dev = (torch.device('cuda', torch.cuda.current_device()) if device is None
+                    else torch.device(device))
+        self.plan = plan
+        self.sizes = plan.cluster_sizes()
+        self.n_frames = len(plan.frame_numbers)
+        self.n_pixels = int(np.prod(plan.frame_shape))
+        self.frame_bytes = self.n_pixels * np.dtype(plan.pixel_dtype).itemsize
+        self.shape_arr = (_lib.ctypes.c_int64 * 3)(
+            *(list(plan.frame_shape) + [1] * (3 - len(plan.frame_shape))))
+        self.torch_dtype = {
+            np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.uint16,
+            np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+            np.dtype(np.int16): torch.int16, np.dtype(np.int32): torch.int32,
+        }[np.dtype(plan.pixel_dtype)]
+        self.first_cluster_of_frame = np.searchsorted(plan.cluster_frame,
+                                                      np.arange(self.n_frames + 1))
+        self.launches = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self.host_status = np.full(plan.n_clusters, -1, dtype=np.int32)
+        with torch.cuda.device(self.dev):
+            dev = self.dev
+            self.workspace = torch.empty(int(self.lib.ctk_refine_workspace_bytes()),
+                                         dtype=torch.uint8, device=dev)
+            self.d_offset = self._up(plan.cluster_offset)
+            self.d_params = self._up(plan.params_in)
+            self.d_lo = self._up(plan.bounds_lo)
+            self.d_hi = self._up(plan.bounds_hi)
+            self.d_out = torch.empty_like(self.d_params)
+            self.d_cost = torch.empty(plan.n_clusters, dtype=torch.float64, device=dev)
+            self.d_status = torch.full((plan.n_clusters,), -1, dtype=torch.int32, device=dev)
+            self.d_stats = torch.zeros((plan.n_clusters, 8), dtype=torch.int32, device=dev)
+
+    def _up(self, array):
+        t = self.torch.from_numpy(np.ascontiguousarray(array))
+        self.h2d_bytes += t.numel() * t.element_size()
+        return t.to(self.dev, non_blocking=False)
+
+    def stream_ptr(self):
+        return _lib.ctypes.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def attach_frames(self, d_frames, f0):
+        """Describe a batch of frames already resident on the device: ``d_frames`` is a torch
+        tensor [n, *frame_shape] holding frames f0 .. f0 + n - 1 of the plan."""
+        torch = self.torch
+        n = int(d_frames.shape[0])
+        ptrs = d_frames.data_ptr() + self.frame_bytes * np.arange(n, dtype=np.int64)
+        batch = dict(frames=d_frames, f0=f0, n=n, d_ptrs=self._up(ptrs),
+                     d_fmax=torch.empty(n, dtype=torch.float64, device=self.dev),
+                     d_cframe=self._up(self.plan.cluster_frame - f0),
+                     c0=int(self.first_cluster_of_frame[f0]),
+                     c1=int(self.first_cluster_of_frame[f0 + n]))
+        ids = np.arange(batch['c0'], batch['c1'])
+        batch['bins'] = [(cap, sel, self._up(sel)) for cap, sel in bin_clusters(self.sizes, ids)]
+        return batch
+
+    def upload_frames(self, f0, f1, staging=None):
+        """Copy frames f0..f1-1 of the plan's source into pinned memory and on to the device."""
+        torch = self.torch
+        n = f1 - f0
+        if staging is None or staging.shape[0] < n:
+            staging = torch.empty((n,) + tuple(self.plan.frame_shape), dtype=self.torch_dtype,
+                                  pin_memory=True)
+        view = staging.numpy()
+        for k in range(f0, f1):
+            view[k - f0] = load_frame(self.plan, self.plan.frame_numbers[k])
+        d_frames = staging[:n].to(self.dev, non_blocking=True)
+        self.h2d_bytes += n * self.frame_bytes
+        return self.attach_frames(d_frames, f0), staging
+
+    def _launch(self, batch, cap, ids, d_ids):
+        prob = self.plan.problem
+        _lib.check(self.lib.ctk_refine_batch(
+            _lib.ctypes.byref(prob), batch['d_ptrs'].data_ptr(), self.shape_arr,
+            batch['d_fmax'].data_ptr(), len(ids), d_ids.data_ptr(), int(cap),
+            batch['d_cframe'].data_ptr(), self.d_offset.data_ptr(), self.d_params.data_ptr(),
+            self.d_lo.data_ptr(), self.d_hi.data_ptr(), self.d_out.data_ptr(),
+            self.d_cost.data_ptr(), self.d_status.data_ptr(), self.d_stats.data_ptr(),
+            self.workspace.data_ptr(), self.stream_ptr()), "ctk_refine_batch")
+        self.launches += 1
+
+    def run_batch(self, batch, retry=True):
+        """Frame maxima, then one refine launch per size bin; clusters whose pixel lists overflowed
+        their bin (status TOO_LARGE) are relaunched once with a larger capacity."""
+        prob = self.plan.problem
+        _lib.check(self.lib.ctk_frame_max(batch['d_ptrs'].data_ptr(), batch['n'], self.n_pixels,
+                                          prob.pixel_dtype, batch['d_fmax'].data_ptr(),
+                                          self.stream_ptr()), "ctk_frame_max")
+        self.launches += 1
+        for cap, ids, d_ids in batch['bins']:
+            self._launch(batch, cap, ids, d_ids)
+        ids = np.arange(batch['c0'], batch['c1'])
+        self.host_status[ids[self.sizes[ids] > _BINS[-1]]] = _lib.STATUS_TOO_LARGE
+        if not retry:
+            return
+        # one small device->host read decides whether anything has to be relaunched
+        status = self.d_status[batch['c0']:batch['c1']].cpu().numpy()
+        self.d2h_bytes += status.nbytes
+        over = ids[(status == _lib.STATUS_TOO_LARGE) & (self.sizes[ids] <= _BINS[-1])]
+        for cap in _BINS:
+            sel = over[(self.sizes[over] <= cap)]
+            over = over[self.sizes[over] > cap]
+            bigger = [c for c in _BINS if c > cap]
+            if len(sel) and bigger:
+                sel = np.ascontiguousarray(sel, dtype=np.int32)
+                self._launch(batch, bigger[min(1, len(bigger) - 1)], sel, self._up(sel))
+
+    def download(self):
+        result = Result(self.plan)
+        self.torch.cuda.current_stream(self.dev).synchronize()
+        result.params_out = self.d_out.cpu().numpy()
+        result.cost = self.d_cost.cpu().numpy()
+        status = self.d_status.cpu().numpy()
+        result.status = np.where(self.host_status == _lib.STATUS_TOO_LARGE, self.host_status, status)
+        result.stats = self.d_stats.cpu().numpy()
+        self.d2h_bytes += (result.params_out.nbytes + result.cost.nbytes + status.nbytes
+                           + result.stats.nbytes)
+        # clusters that never ran (too many features) keep their input parameters
+        never = np.repeat(result.status == _lib.STATUS_TOO_LARGE, self.sizes)
+        result.params_out[never] = self.plan.params_in[never]
+        return result
+
+
 def execute_cuda(plan, device=None):
     """Run the plan on the current (or given) CUDA device through the C ABI.  Frames are staged
     through pinned host memory in batches of about 1 GiB."""
-    import torch
-    lib = _lib.load()
-    if not torch.cuda.is_available():
-        raise RuntimeError("clustertracking_b200 needs a CUDA device (B200, sm_100a); "
-                           "there is no CPU fallback")
-    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
-    result = Result(plan)
-    sizes = plan.cluster_sizes()
-    prob = plan.problem
-    n_frames = len(plan.frame_numbers)
-    frame_bytes = int(np.prod(plan.frame_shape)) * np.dtype(plan.pixel_dtype).itemsize
-    per_batch = max(1, min(n_frames, _FRAME_BATCH_BYTES // max(frame_bytes, 1)))
-    shape_arr = (_lib.ctypes.c_int64 * 3)(*(list(plan.frame_shape) + [1] * (3 - len(plan.frame_shape))))
-    torch_dtype = {np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.uint16,
-                   np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
-                   np.dtype(np.int16): torch.int16, np.dtype(np.int32): torch.int32}[np.dtype(plan.pixel_dtype)]
-
-    with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream()
-        sptr = _lib.ctypes.c_void_p(stream.cuda_stream)
-        workspace = torch.empty(int(lib.ctk_refine_workspace_bytes()), dtype=torch.uint8, device=dev)
-        # feature-level buffers live on the device for the whole call
-        d_offset = torch.from_numpy(plan.cluster_offset).to(dev)
-        d_params = torch.from_numpy(plan.params_in).to(dev)
-        d_lo = torch.from_numpy(plan.bounds_lo).to(dev)
-        d_hi = torch.from_numpy(plan.bounds_hi).to(dev)
-        d_out = d_params.clone()
-        d_cost = torch.full((plan.n_clusters,), float('nan'), dtype=torch.float64, device=dev)
-        d_status = torch.full((plan.n_clusters,), -1, dtype=torch.int32, device=dev)
-        d_iters = torch.zeros(plan.n_clusters, dtype=torch.int32, device=dev)
-        first_cluster_of_frame = np.searchsorted(plan.cluster_frame, np.arange(n_frames + 1))
-        staging = torch.empty((per_batch,) + plan.frame_shape, dtype=torch_dtype, pin_memory=True)
-        staging_np = staging.numpy()
-        for f0 in range(0, n_frames, per_batch):
-            f1 = min(n_frames, f0 + per_batch)
-            for k in range(f0, f1):
-                staging_np[k - f0] = load_frame(plan, plan.frame_numbers[k])
-            d_frames = staging[:f1 - f0].to(dev, non_blocking=True)
-            ptrs = d_frames.data_ptr() + frame_bytes * np.arange(f1 - f0, dtype=np.int64)
-            d_ptrs = torch.from_numpy(ptrs).to(dev)
-            d_fmax = torch.empty(f1 - f0, dtype=torch.float64, device=dev)
-            _lib.check(lib.ctk_frame_max(d_ptrs.data_ptr(), f1 - f0, int(np.prod(plan.frame_shape)),
-                                         prob.pixel_dtype, d_fmax.data_ptr(), sptr), "ctk_frame_max")
-            c0, c1 = int(first_cluster_of_frame[f0]), int(first_cluster_of_frame[f1])
-            d_cframe = torch.from_numpy(plan.cluster_frame - f0).to(dev)   # batch-relative index
-            host_status = result.status
-
-            def launch(cap, ids):
-                d_ids = torch.from_numpy(np.ascontiguousarray(ids)).to(dev)
-                _lib.check(lib.ctk_refine_batch(
-                    _lib.ctypes.byref(prob), d_ptrs.data_ptr(), shape_arr, d_fmax.data_ptr(),
-                    len(ids), d_ids.data_ptr(), int(cap), d_cframe.data_ptr(), d_offset.data_ptr(),
-                    d_params.data_ptr(), d_lo.data_ptr(), d_hi.data_ptr(), d_out.data_ptr(),
-                    d_cost.data_ptr(), d_status.data_ptr(), d_iters.data_ptr(),
-                    workspace.data_ptr(), sptr), "ctk_refine_batch")
-                host_status[ids] = d_status[torch.from_numpy(ids.astype(np.int64)).to(dev)].cpu().numpy()
-
-            run_bins(sizes, np.arange(c0, c1), host_status, launch)
-            stream.synchronize()        # staging buffer is reused by the next batch
-        result.params_out = d_out.cpu().numpy()
-        result.cost = d_cost.cpu().numpy()
-        result.status = np.where(result.status == _lib.STATUS_TOO_LARGE, result.status,
-                                 d_status.cpu().numpy())
-        result.iters = d_iters.cpu().numpy()
+    session = DeviceSession(plan, device)
+    torch = session.torch
+    per_batch = max(1, min(session.n_frames, _FRAME_BATCH_BYTES // max(session.frame_bytes, 1)))
+    staging = None
+    with torch.cuda.device(session.dev):
+        for f0 in range(0, session.n_frames, per_batch):
+            f1 = min(session.n_frames, f0 + per_batch)
+            batch, staging = session.upload_frames(f0, f1, staging)
+            session.run_batch(batch)
+            torch.cuda.current_stream(session.dev).synchronize()   # staging is reused next batch
+        result = session.download()
+    result.session = session
     return result
 
 

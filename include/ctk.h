@@ -57,6 +57,18 @@ enum {
   CTK_FAIL_NUMERIC = 7        /* non-finite value met during the fit    fitfunc.py:437-438 */
 };
 
+/* per-cluster counters written to stats_out[cluster * CTK_STATS + k] (accounting / roofline) */
+#define CTK_STATS 8
+enum {
+  CTK_STAT_EVALS = 0,         /* objective evaluations = passes over the per-feature pixel lists */
+  CTK_STAT_ACCUMS = 1,        /* normal-equation accumulations (accepted steps + 1 per restart)  */
+  CTK_STAT_OUTER = 2,         /* outer re-mask iterations executed            refine.py:365      */
+  CTK_STAT_PIXELS = 3,        /* union-mask pixels M of the last pixel set    refine.py:47       */
+  CTK_STAT_ENTRIES = 4,       /* sum over features of mask pixels (last pixel set)               */
+  CTK_STAT_PAIR_ENTRIES = 5,  /* pixels shared by two features, summed over pairs                */
+  CTK_STAT_VARS = 6           /* free variables V                                                */
+};
+
 /* library error codes (return values) */
 enum {
   CTK_E_INVALID = -1,         /* bad argument */
@@ -128,7 +140,7 @@ size_t ctk_refine_shared_bytes(const ctk_problem_t* prob, int32_t max_cluster_fe
  *   d_params_out    [n_features, P] float64                                   (refine.py:380, 426)
  *   d_cost_out      [n_clusters] rms_dev, NaN on failure                      (refine.py:379, 427)
  *   d_status_out    [n_clusters] CTK_OK or CTK_FAIL_*
- *   d_iters_out     [n_clusters] pixel passes executed (objective evaluations), for accounting
+ *   d_stats_out     [n_clusters, CTK_STATS] int32 counters (CTK_STAT_*), for accounting
  *   d_workspace     ctk_refine_workspace_bytes() bytes of device scratch
  */
 int ctk_refine_batch(const ctk_problem_t* prob,
@@ -138,7 +150,7 @@ int ctk_refine_batch(const ctk_problem_t* prob,
                      const int32_t* d_cluster_frame, const int32_t* d_cluster_offset,
                      const double* d_params_in, const double* d_bounds_lo, const double* d_bounds_hi,
                      double* d_params_out, double* d_cost_out, int32_t* d_status_out,
-                     int32_t* d_iters_out, void* d_workspace, void* stream);
+                     int32_t* d_stats_out, void* d_workspace, void* stream);
 
 /* Host helper (no GPU): cluster labels of one frame from the close pairs, visiting the pairs in the
  * given order with the reference's "the label of a's cluster survives" rule (find.py:41-48, 84-93).

@@ -55,7 +55,7 @@ extern "C" int ctk_emul_refine_batch(const ctk_problem_t* prob, const void* cons
   a.params_out = params_out;
   a.cost_out = cost_out;
   a.status_out = status_out;
-  a.iters_out = iters_out;
+  a.stats_out = iters_out;
   if (!ctk::compute_layout(*prob, max_cluster_features, &a.lay)) return CTK_E_CAPACITY;
   RunAll run{&a};
   bool ok = prob->compute_dtype == CTK_COMPUTE_F64 ? ctk::dispatch_config<double>(*prob, run)

@@ -64,7 +64,7 @@ def execute(plan):
             ids.ctypes.data, int(cap), plan.cluster_frame.ctypes.data,
             plan.cluster_offset.ctypes.data, plan.params_in.ctypes.data, plan.bounds_lo.ctypes.data,
             plan.bounds_hi.ctypes.data, result.params_out.ctypes.data, result.cost.ctypes.data,
-            result.status.ctypes.data, result.iters.ctypes.data)
+            result.status.ctypes.data, result.stats.ctypes.data)
         assert code == 0, "emulated launch failed: %d" % code
 
     _refine.run_bins(sizes, np.arange(plan.n_clusters), result.status, launch)
