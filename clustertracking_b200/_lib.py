@@ -38,6 +38,9 @@ class Problem(ctypes.Structure):
         ("xtol", ctypes.c_double), ("constraint_mask", ctypes.c_int32),
         ("reserved0", ctypes.c_int32), ("dimer_dist", ctypes.c_double * 3),
         ("trimer_dist", ctypes.c_double * 3),
+        ("bounds_abs", (ctypes.c_double * CTK_MAX_PARAMS) * 2),
+        ("bounds_diff", (ctypes.c_double * CTK_MAX_PARAMS) * 2),
+        ("bounds_rel", (ctypes.c_double * CTK_MAX_PARAMS) * 2),
     ]
 
 
@@ -55,6 +58,7 @@ _PROTOTYPES = {
                                         _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp]),
     "ctk_label_clusters": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
+    "ctk_pairs_set_order": (ctypes.c_int, [_vp, _i64, _vp]),
 }
 
 
@@ -90,3 +94,13 @@ def label_clusters(pairs, n):
     check(load().ctk_label_clusters(pairs.ctypes.data, len(pairs), n, labels.ctypes.data,
                                     sizes.ctypes.data), "ctk_label_clusters")
     return labels, sizes
+
+
+def pairs_set_order(pairs):
+    """Host helper ``ctk_pairs_set_order``: ``pairs`` (in ``query_pairs(output_type='ndarray')``
+    order) reordered into the iteration order of the python set scipy would have built."""
+    pairs = np.ascontiguousarray(pairs, dtype=np.int64)
+    order = np.empty(len(pairs), dtype=np.int64)
+    check(load().ctk_pairs_set_order(pairs.ctypes.data, len(pairs), order.ctypes.data),
+          "ctk_pairs_set_order")
+    return pairs[order]

@@ -116,7 +116,7 @@ int ctk_refine_batch(const ctk_problem_t* prob, const void* const* d_frames,
   if (n_work < 0) return fail(CTK_E_INVALID, "ctk_refine_batch: n_work < 0");
   if (n_work == 0) return 0;
   if (!d_frames || !frame_shape || !d_frame_max || !d_cluster_frame || !d_cluster_offset ||
-      !d_params_in || !d_bounds_lo || !d_bounds_hi || !d_params_out || !d_cost_out ||
+      !d_params_in || (!d_bounds_lo != !d_bounds_hi) || !d_params_out || !d_cost_out ||
       !d_status_out || !d_stats_out || !d_workspace)
     return fail(CTK_E_INVALID, "ctk_refine_batch: NULL pointer argument");
   ctk::BatchArgs a;

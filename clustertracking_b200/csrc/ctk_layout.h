@@ -44,6 +44,7 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
     else if (p.modes[c] == CTK_MODE_CLUSTER) v_max += 1;
   }
   if (v_max < 1) v_max = 1;
+  if (v_max > 255) return false;                        // packed (row, column) bytes
   const int rb = p.compute_dtype == CTK_COMPUTE_F64 ? 8 : 4;
   lay->n_max = n_max;
   lay->v_max = v_max;
@@ -72,8 +73,16 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
   lay->o_d = take(v_max * 8);
   lay->o_dg = take(v_max * 8);
   lay->o_act = take(v_max * 4);
-  lay->o_H = take(v_max * (v_max + 1) / 2 * 8);
-  lay->o_L = take(v_max * (v_max + 1) / 2 * 8);
+  lay->o_H = take(v_max * (v_max + 1) / 2 * rb);
+  lay->o_L = take(v_max * (v_max + 1) / 2 * rb);
+  lay->o_idg = take(v_max * rb);
+  lay->o_cs = take((v_max + 1) * 4);
+  lay->o_rc = take(v_max * (v_max + 1) / 2 * 2);
+  lay->o_cv = take(n_max * p.n_params * 4);
+  const int ld_max = p.n_params - 1;
+  lay->sidx_stride = ld_max * (ld_max + 1) / 2 + 2 * ld_max;
+  lay->o_sidx = take(n_max * lay->sidx_stride * 4);
+  lay->o_con = take(8 * 8);
   lay->o_mc = take(n_max * 3 * 8);
   lay->o_fi = take(n_max * FI_STRIDE * 4);
   lay->o_fr = take(n_max * FR_STRIDE * rb);

@@ -28,6 +28,13 @@
 
 #include "ctk.h"
 
+#if defined(CTK_EMUL) && defined(CTK_TRACE)
+#include <stdio.h>
+#define CTK_TRACEF(...) printf(__VA_ARGS__)
+#else
+#define CTK_TRACEF(...)
+#endif
+
 #ifdef CTK_EMUL
 #define CTK_DEV inline
 #define CTK_WARP 1
@@ -72,6 +79,13 @@ CTK_DEV float fast_exp(float x) { return __expf(x); }
 CTK_DEV int atomic_next(int32_t* c) { return atomicAdd(c, 1); }
 #endif
 CTK_DEV double fast_exp(double x) { return exp(x); }
+#ifdef CTK_EMUL
+CTK_DEV float fast_rsqrt(float x) { return 1.0f / sqrtf(x); }
+CTK_DEV double fast_rsqrt(double x) { return 1.0 / sqrt(x); }
+#else
+CTK_DEV float fast_rsqrt(float x) { return rsqrtf(x); }
+CTK_DEV double fast_rsqrt(double x) { return rsqrt(x); }
+#endif
 
 template <class T> CTK_DEV T warp_sum(T v) {
 #pragma unroll
@@ -111,7 +125,14 @@ struct Layout {
   int real_bytes;  // 4 | 8
   // byte offsets into the cluster's slice
   int o_x, o_xt, o_x0, o_lo, o_hi, o_rhs, o_rhsf, o_d, o_dg, o_act;
-  int o_H, o_L;
+  int o_H, o_L;            // normal matrix / its damped factor, packed lower, COLUMN-major
+  int o_idg;               // inverse diagonal of the factor
+  int o_cs;                // [v_max + 1] start of each packed column
+  int o_rc;                // [tri(v_max)] (row | col << 8) of each packed entry
+  int o_cv;                // [n_max, P] variable index of (feature, column), -1 = constant
+  int o_sidx;              // [n_max, sidx_stride] scatter targets of a feature's local block
+  int sidx_stride;
+  int o_con;               // multipliers mu[3], distances[3], penalty weight
   int o_mc, o_fi, o_fr;
   int o_tab;      // aliases o_fe (tables are dead once the lists are built)
   int o_fe;
@@ -186,20 +207,20 @@ struct ClusterSolver {
 
   // cluster
   int n, feat0, V, M, npairs;
-  int base[CTK_MAX_PARAMS];      // first variable of each column (or -1)
   int blo[3], bdim[3];
+  int cached_V;                  // V the packed-index tables were built for (-1 = none)
+  int shared_columns;            // parameter columns (besides background) shared within the cluster
   const void* frame;
   double fmax_;
   int evals, accums, outers, n_entries, n_pair_entries;
   // residual statistics of the last evaluate()
   double sum_r, n_valid;
-  // augmented Lagrangian
+  // augmented Lagrangian (multipliers and distances live in shared memory, see CON())
   int n_con;
-  double mu[3], pen_w;
-  double cdist[3];
+  double pen_w;
 
   CTK_DEV ClusterSolver(const BatchArgs& args, char* smem)
-      : a(args), L(args.lay), sm(smem), lane(lane_id()) {}
+      : a(args), L(args.lay), sm(smem), lane(lane_id()), cached_V(-1) {}
 
   // ---- typed views ------------------------------------------------------------------------------
   CTK_DEV double* dvec(int off) const { return reinterpret_cast<double*>(sm + off); }
@@ -212,8 +233,16 @@ struct ClusterSolver {
   CTK_DEV double* D() const { return dvec(L.o_d); }
   CTK_DEV double* DG() const { return dvec(L.o_dg); }
   CTK_DEV int* ACT() const { return reinterpret_cast<int*>(sm + L.o_act); }
-  CTK_DEV double* Hm() const { return dvec(L.o_H); }
-  CTK_DEV double* Lm() const { return dvec(L.o_L); }
+  // normal matrix, its factor and the factor's inverse diagonal are kept in the pixel arithmetic
+  // type: a step of limited accuracy still converges to the same point (the gradient decides)
+  CTK_DEV Real* Hm() const { return reinterpret_cast<Real*>(sm + L.o_H); }
+  CTK_DEV Real* Lm() const { return reinterpret_cast<Real*>(sm + L.o_L); }
+  CTK_DEV Real* IDG() const { return reinterpret_cast<Real*>(sm + L.o_idg); }
+  CTK_DEV int* CS() const { return reinterpret_cast<int*>(sm + L.o_cs); }
+  CTK_DEV uint16_t* RC() const { return reinterpret_cast<uint16_t*>(sm + L.o_rc); }
+  CTK_DEV int* CV() const { return reinterpret_cast<int*>(sm + L.o_cv); }
+  CTK_DEV int* SIDX() const { return reinterpret_cast<int*>(sm + L.o_sidx); }
+  CTK_DEV double* CON() const { return dvec(L.o_con); }        // mu[0..2], dist[3..5]
   CTK_DEV double* MC() const { return dvec(L.o_mc); }
   CTK_DEV int* FI() const { return reinterpret_cast<int*>(sm + L.o_fi); }
   CTK_DEV Real* FR() const { return reinterpret_cast<Real*>(sm + L.o_fr); }
@@ -229,10 +258,10 @@ struct ClusterSolver {
 
   CTK_DEV int mode(int col) const { return a.prob.modes[col]; }
   // variable index of (column, feature), -1 when the column is constant
-  CTK_DEV int var_of(int col, int i) const {
-    int b = base[col];
-    return b < 0 ? -1 : (mode(col) == CTK_MODE_VAR ? b + i : b);
-  }
+  CTK_DEV int var_of(int col, int i) const { return CV()[i * P + col]; }
+  // packed index of entry (r, c), r >= c, of a lower triangle stored column by column
+  CTK_DEV int pk(int r, int c) const { return CS()[c] + r - c; }
+  CTK_DEV int pk_sym(int u, int v) const { return u >= v ? pk(u, v) : pk(v, u); }
   // column of derivative slot `s`
   CTK_DEV static int slot_col(int s) {
     if (s <= ND) return 1 + s;                       // signal, positions
@@ -251,42 +280,63 @@ struct ClusterSolver {
     }
   }
 
+  // per-feature bounds from the tables (fitfunc.py:538-551); fmax/fmin skip NaN like np.fmax/fmin
+  CTK_DEV double bound_low(double p, int c) const {
+    double v = fmax(fmax(p - a.prob.bounds_diff[0][c], p * (1. - a.prob.bounds_rel[0][c])),
+                    a.prob.bounds_abs[0][c]);
+    return v == v ? v : -INFINITY;
+  }
+  CTK_DEV double bound_high(double p, int c) const {
+    double v = fmin(fmin(p + a.prob.bounds_diff[1][c], p * (1. + a.prob.bounds_rel[1][c])),
+                    a.prob.bounds_abs[1][c]);
+    return v == v ? v : INFINITY;
+  }
+
   // ---- variables, start vector and bounds (refine.py:361-364, fitfunc.py:207-263, 552-558) ------
   CTK_DEV int setup_variables() {
+    // variable numbering: columns in order; a 'var' column takes n entries, a 'cluster' column one
     int v = 0;
+    int* cv = CV();
 #pragma unroll
-    for (int c = 0; c < CTK_MAX_PARAMS; ++c) {
-      base[c] = -1;
-      if (c < P) {
-        if (mode(c) == CTK_MODE_VAR) { base[c] = v; v += n; }
-        else if (mode(c) == CTK_MODE_CLUSTER) { base[c] = v; v += 1; }
-      }
+    for (int c = 0; c < P; ++c) {
+      const int m = mode(c);
+      for (int i = lane; i < n; i += CTK_WARP)
+        cv[i * P + c] = m == CTK_MODE_VAR ? v + i : (m == CTK_MODE_CLUSTER ? v : -1);
+      v += m == CTK_MODE_VAR ? n : (m == CTK_MODE_CLUSTER ? 1 : 0);
     }
     V = v;
-    if (V > L.v_max) return CTK_FAIL_TOO_LARGE;
+    shared_columns = 0;
+#pragma unroll
+    for (int c = 1; c < P; ++c) shared_columns += mode(c) == CTK_MODE_CLUSTER ? 1 : 0;
+    if (V > L.v_max || V > 255) return CTK_FAIL_TOO_LARGE;
     const double* pin = a.params_in + (int64_t)feat0 * P;
-    const double* lin = a.lo_in + (int64_t)feat0 * P;
-    const double* hin = a.hi_in + (int64_t)feat0 * P;
+    const bool tables = a.lo_in == nullptr;            // bounds from the problem's tables
+    const double* lin = tables ? nullptr : a.lo_in + (int64_t)feat0 * P;
+    const double* hin = tables ? nullptr : a.hi_in + (int64_t)feat0 * P;
     bool bad = false;
     for (int t = lane; t < n * P; t += CTK_WARP) bad |= !finite_d(pin[t]);
     if (warp_any(bad)) return CTK_FAIL_NONFINITE;
+    warp_sync();
     double *x0 = X0(), *lo = LO(), *hi = HI();
+#pragma unroll
     for (int c = 0; c < P; ++c) {
-      if (base[c] < 0) continue;
-      if (mode(c) == CTK_MODE_VAR) {
+      const int m = mode(c);
+      if (m == CTK_MODE_VAR) {
         for (int i = lane; i < n; i += CTK_WARP) {
-          x0[base[c] + i] = pin[i * P + c];
-          lo[base[c] + i] = lin[i * P + c];
-          hi[base[c] + i] = hin[i * P + c];
+          const int vi = cv[i * P + c];
+          x0[vi] = pin[i * P + c];
+          lo[vi] = tables ? bound_low(pin[i * P + c], c) : lin[i * P + c];
+          hi[vi] = tables ? bound_high(pin[i * P + c], c) : hin[i * P + c];
         }
-      } else if (lane == 0) {          // shared entry: mean start, widest bound
+      } else if (m == CTK_MODE_CLUSTER && lane == 0) {   // shared entry: mean start, widest bound
         double s = 0., l = INFINITY, h = -INFINITY;
         for (int i = 0; i < n; ++i) {
           s += pin[i * P + c];
-          l = fmin(l, lin[i * P + c]);
-          h = fmax(h, hin[i * P + c]);
+          l = fmin(l, tables ? bound_low(pin[i * P + c], c) : lin[i * P + c]);
+          h = fmax(h, tables ? bound_high(pin[i * P + c], c) : hin[i * P + c]);
         }
-        x0[base[c]] = s / n; lo[base[c]] = l; hi[base[c]] = h;
+        const int vi = cv[c];
+        x0[vi] = s / n; lo[vi] = l; hi[vi] = h;
       }
     }
     warp_sync();
@@ -296,6 +346,39 @@ struct ClusterSolver {
       x0[v2] = fmin(fmax(x0[v2], lo[v2]), hi[v2]);     // scipy clips the start into the box
     }
     if (warp_any(bad)) return CTK_FAIL_BOUNDS;
+    // packed-index tables (depend on V only; consecutive clusters of a launch mostly share V)
+    if (V != cached_V) {
+      int* cs = CS();
+      uint16_t* rc = RC();
+      for (int c = lane; c <= V; c += CTK_WARP) cs[c] = c * V - c * (c - 1) / 2;
+      warp_sync();
+      for (int t = lane; t < V * V; t += CTK_WARP) {
+        int r = t / V, c = t - r * V;
+        if (r >= c) rc[cs[c] + r - c] = (uint16_t) (r | (c << 8));
+      }
+      cached_V = V;
+    }
+    warp_sync();
+    // scatter targets of every feature's local block: [LT] block entries, [LD] products with the
+    // background column, [LD] right-hand side entries
+    int* sidx = SIDX();
+    const int vb = cv[0];
+    for (int t = lane; t < n * (LT + 2 * LD); t += CTK_WARP) {
+      const int i = t / (LT + 2 * LD), k = t - i * (LT + 2 * LD);
+      int target = -1;
+      if (k < LT) {
+        int u = 0, rem = k;                       // k = u (u + 1) / 2 + w, w <= u
+        while (rem > u) { rem -= u + 1; ++u; }
+        const int vu = cv[i * P + slot_col(u)], vw = cv[i * P + slot_col(rem)];
+        if (vu >= 0 && vw >= 0) target = pk_sym(vu, vw);
+      } else if (k < LT + LD) {
+        const int vu = cv[i * P + slot_col(k - LT)];
+        if (vu >= 0 && vb >= 0) target = pk_sym(vu, vb);
+      } else {
+        target = cv[i * P + slot_col(k - LT - LD)];
+      }
+      sidx[i * L.sidx_stride + k] = target;
+    }
     warp_sync();
     return CTK_OK;
   }
@@ -638,39 +721,41 @@ struct ClusterSolver {
     return 0.5 * acc;
   }
 
-  CTK_DEV void h_add(int u, int v, double val) const {
-    double* H = Hm();
-    if (u == v) H[tri(u) + u] += 2. * val;
-    else if (u > v) H[tri(u) + v] += val;
-    else H[tri(v) + u] += val;
+  // value of a compile-time sized register array at a run-time position (no local memory)
+  template <int N> CTK_DEV static Real pick(const Real (&arr)[N], int k) {
+    Real v = 0;
+#pragma unroll
+    for (int q = 0; q < N; ++q) v = (q == k) ? arr[q] : v;
+    return v;
   }
 
   // ---- normal equations from the caches of the last evaluate() ---------------------------------
-  // H = sum m m^T (packed lower), RHS = sum m r  (= -gradient of 0.5 sum r^2)
+  // H = sum m m^T (packed lower, column-major), RHS = sum m r  (= -gradient of 0.5 sum r^2)
   CTK_DEV void accumulate() {
     ++accums;
-    double* H = Hm();
+    Real* H = Hm();
     double* rhs = RHS();
-    for (int t = lane; t < tri(V); t += CTK_WARP) H[t] = 0.;
+    const int nt = CS()[V];
+    for (int t = lane; t < nt; t += CTK_WARP) H[t] = 0;
     for (int v = lane; v < V; v += CTK_WARP) rhs[v] = 0.;
     warp_sync();
-    const int vb = base[0];
-    if (vb >= 0 && lane == 0) { H[tri(vb) + vb] = n_valid; rhs[vb] = sum_r; }
+    const int* cv = CV();
+    const int vb = cv[0];
+    if (vb >= 0 && lane == 0) { H[pk(vb, vb)] = (Real) n_valid; rhs[vb] = sum_r; }
     warp_sync();
     const uint32_t* flist = FLIST();
     const Real* fe = FE();
     const Real* pr = PR();
     const int* fi = FI();
+    const int* sidx = SIDX();
     for (int i = 0; i < n; ++i) {
       const Feat f = feat(i);
       const int cnt = fi[i * FI_STRIDE + FI_CNT];
       const uint32_t* fl = flist + i * L.f_cap;
       const Real* ge = fe + i * L.f_cap;
-      Real acc[LT], accr[LD], acc1[LD];
+      Real acc[LT + 2 * LD];       // [LT] m_u m_w, [LD] m_u, [LD] m_u r
 #pragma unroll
-      for (int k = 0; k < LT; ++k) acc[k] = 0;
-#pragma unroll
-      for (int k = 0; k < LD; ++k) { accr[k] = 0; acc1[k] = 0; }
+      for (int k = 0; k < LT + 2 * LD; ++k) acc[k] = 0;
       for (int t = lane; t < cnt; t += CTK_WARP) {
         uint32_t e = fl[t];
         Real r = pr[entry_pixel(e)];
@@ -681,35 +766,20 @@ struct ClusterSolver {
         int k = 0;
 #pragma unroll
         for (int u = 0; u < LD; ++u) {
-          accr[u] += m[u] * r;
-          acc1[u] += m[u];
+          acc[LT + u] += m[u];
+          acc[LT + LD + u] += m[u] * r;
 #pragma unroll
-          for (int v = 0; v <= u; ++v) acc[k++] += m[u] * m[v];
+          for (int w = 0; w <= u; ++w) acc[k++] += m[u] * m[w];
         }
       }
 #pragma unroll
-      for (int k = 0; k < LT; ++k) acc[k] = warp_sum(acc[k]);
-#pragma unroll
-      for (int k = 0; k < LD; ++k) { accr[k] = warp_sum(accr[k]); acc1[k] = warp_sum(acc1[k]); }
-      if (lane == 0) {
-        int k = 0;
-#pragma unroll
-        for (int u = 0; u < LD; ++u) {
-          int vu = var_of(slot_col(u), i);
-          if (vu >= 0) {
-            rhs[vu] += (double) accr[u];
-            if (vb >= 0) { if (vu > vb) H[tri(vu) + vb] += (double) acc1[u];
-                           else H[tri(vb) + vu] += (double) acc1[u]; }
-          }
-#pragma unroll
-          for (int v = 0; v <= u; ++v, ++k) {
-            if (vu < 0) continue;
-            int vv = var_of(slot_col(v), i);
-            if (vv < 0) continue;
-            if (u == v) H[tri(vu) + vu] += (double) acc[k];
-            else if (vu > vv) H[tri(vu) + vv] += (double) acc[k];
-            else H[tri(vv) + vu] += (double) acc[k];
-          }
+      for (int k = 0; k < LT + 2 * LD; ++k) acc[k] = warp_sum(acc[k]);
+      // every lane now holds every sum; lane k adds entry k to its target
+      for (int k = lane; k < LT + 2 * LD; k += CTK_WARP) {
+        const int target = sidx[i * L.sidx_stride + k];
+        if (target >= 0) {
+          const Real val = pick(acc, k);
+          if (k < LT + LD) H[target] += val; else rhs[target] += (double) val;
         }
       }
       warp_sync();
@@ -737,21 +807,31 @@ struct ClusterSolver {
 #pragma unroll
         for (int u = 0; u < LD; ++u)
 #pragma unroll
-          for (int v = 0; v < LD; ++v) B[u * LD + v] += mi[u] * mj[v];
+          for (int w = 0; w < LD; ++w) B[u * LD + w] += mi[u] * mj[w];
       }
 #pragma unroll
       for (int k = 0; k < LD * LD; ++k) B[k] = warp_sum(B[k]);
-      if (lane == 0) {
-#pragma unroll
-        for (int u = 0; u < LD; ++u) {
-          int vu = var_of(slot_col(u), i);
-          if (vu < 0) continue;
-#pragma unroll
-          for (int v = 0; v < LD; ++v) {
-            int vv = var_of(slot_col(v), j);
-            if (vv < 0) continue;
-            h_add(vu, vv, (double) B[u * LD + v]);
+      // entry (u, w) goes to (var(i,u), var(j,w)); two entries can share a target only when both
+      // columns are shared within the cluster, so the adds go one lane at a time in that case
+      for (int k0 = 0; k0 < LD * LD; k0 += CTK_WARP) {
+        const int k = k0 + lane;
+        int target = -1;
+        Real val = 0;
+        if (k < LD * LD) {
+          const int u = k / LD, w = k - u * LD;
+          const int vu = cv[i * P + slot_col(u)], vw = cv[j * P + slot_col(w)];
+          if (vu >= 0 && vw >= 0) {
+            target = pk_sym(vu, vw);
+            val = pick(B, k) * (vu == vw ? (Real) 2 : (Real) 1);
           }
+        }
+        if (shared_columns > 1) {
+          for (int turn = 0; turn < (LD * LD < CTK_WARP ? LD * LD : CTK_WARP); ++turn) {
+            if (turn == (k - k0) && target >= 0) H[target] += val;
+            warp_sync();
+          }
+        } else if (target >= 0) {
+          H[target] += val;
         }
       }
       warp_sync();
@@ -759,18 +839,20 @@ struct ClusterSolver {
   }
 
   // ---- distance constraints (constraints.py:59-99) as augmented-Lagrangian rows ----------------
+  // constraint j couples features (p, q): dimer (0,1); trimer (0,1), (1,2), (0,2)
   CTK_DEV void con_pair(int j, int& p, int& q) const {
-    if (n == 2) { p = 0; q = 1; return; }
-    p = (j == 1) ? 1 : 0;                    // (0,1), (1,2), (0,2)
-    q = (j == 0) ? 1 : 2;
+    p = (j == 1) ? 1 : 0;
+    q = (n == 2 || j == 0) ? 1 : 2;
   }
+  CTK_DEV int pos_var(int k, int i) const { return CV()[i * P + 2 + k]; }
   CTK_DEV double con_value(const double* x, int j) const {
     int p, q;
     con_pair(j, p, q);
+    const double* dist = CON() + 3;
     double s = 0.;
 #pragma unroll
     for (int k = 0; k < ND; ++k) {
-      double d = (x[base[2 + k] + p] - x[base[2 + k] + q]) / cdist[k];
+      double d = (x[pos_var(k, p)] - x[pos_var(k, q)]) / dist[k];
       s += d * d;
     }
     return 1. - s;
@@ -779,7 +861,7 @@ struct ClusterSolver {
     double v = 0.;
     for (int j = 0; j < n_con; ++j) {
       double c = con_value(x, j);
-      v += mu[j] * c + 0.5 * pen_w * c * c;
+      v += CON()[j] * c + 0.5 * pen_w * c * c;
     }
     return v;
   }
@@ -788,120 +870,128 @@ struct ClusterSolver {
     for (int j = 0; j < n_con; ++j) v = fmax(v, fabs(con_value(x, j)));
     return v;
   }
-  // add w A^T A to the packed matrix Kp and -(mu + w c) A^T to rhs (lane 0 only)
-  CTK_DEV void add_constraint_rows(const double* x, double* Kp, double* rhs) const {
+  // gradient of constraint j: entry u (< 2 ND) belongs to variable idx, value g
+  CTK_DEV void con_grad(const double* x, int j, int u, int& idx, double& g) const {
+    int p, q;
+    con_pair(j, p, q);
+    const int k = u >> 1;
+    const double dist = CON()[3 + k];
+    const double d = (x[pos_var(k, p)] - x[pos_var(k, q)]) / (dist * dist);
+    idx = pos_var(k, (u & 1) ? q : p);
+    g = (u & 1) ? 2. * d : -2. * d;
+  }
+  // add w A^T A to the packed matrix Kp and -(mu + w c) A^T to rhs (one lane)
+  CTK_DEV void add_constraint_rows(const double* x, Real* Kp, double* rhs) const {
     for (int j = 0; j < n_con; ++j) {
-      int p, q;
-      con_pair(j, p, q);
-      int idx[6];
-      double g[6];
-#pragma unroll
-      for (int k = 0; k < ND; ++k) {
-        double d = (x[base[2 + k] + p] - x[base[2 + k] + q]) / (cdist[k] * cdist[k]);
-        idx[2 * k] = base[2 + k] + p; g[2 * k] = -2. * d;
-        idx[2 * k + 1] = base[2 + k] + q; g[2 * k + 1] = 2. * d;
-      }
-      double c = con_value(x, j);
-      double lam = mu[j] + pen_w * c;
+      const double lam = CON()[j] + pen_w * con_value(x, j);
       for (int u = 0; u < 2 * ND; ++u) {
-        rhs[idx[u]] -= lam * g[u];
+        int iu; double gu;
+        con_grad(x, j, u, iu, gu);
+        rhs[iu] -= lam * gu;
         for (int v = 0; v < 2 * ND; ++v) {
-          if (idx[v] > idx[u]) continue;
-          Kp[tri(idx[u]) + idx[v]] += pen_w * g[u] * g[v];
+          int iv; double gv;
+          con_grad(x, j, v, iv, gv);
+          if (iv <= iu) Kp[pk(iu, iv)] += (Real) (pen_w * gu * gv);
         }
       }
     }
   }
 
   // ---- damped, bound-aware step --------------------------------------------------------------------
-  // Builds K = H (+ constraint rows) in Lm, the full right-hand side in D, freezes the active set,
-  // adds lambda*diag, factorises and solves.  On return D holds the step, RHS the un-frozen
-  // right-hand side (with constraint terms) and Lm the Cholesky factor.  Returns false on breakdown.
+  // Builds K = H (+ constraint rows) in Lm and the full right-hand side in rhs_full, freezes the
+  // active set, adds lambda*diag, factorises (Cholesky, column-major packed, every lane works on the
+  // trailing block) with the forward substitution folded in, then back-substitutes.  On return D()
+  // holds the step.  Returns false on breakdown.
   CTK_DEV bool solve(double lambda, double* rhs_full) {
-    const double* H = Hm();
-    double* Kf = Lm();
+    const Real* H = Hm();
+    Real* Kf = Lm();
     double* d = D();
-    double* dg = DG();
+    double* sc = DG();                 // Jacobi scaling 1/sqrt(K_vv)
+    Real* idg = IDG();
     int* act = ACT();
+    const int* cs = CS();
+    const uint16_t* rc = RC();
     const double *x = X(), *lo = LO(), *hi = HI();
-    for (int t = lane; t < tri(V); t += CTK_WARP) Kf[t] = H[t];
+    const int nt = cs[V];
+    for (int t = lane; t < nt; t += CTK_WARP) Kf[t] = H[t];
     for (int v = lane; v < V; v += CTK_WARP) rhs_full[v] = RHS()[v];
     warp_sync();
-    if (n_con > 0 && lane == 0) add_constraint_rows(x, Kf, rhs_full);
-    warp_sync();
+    if (n_con > 0) {
+      if (lane == 0) add_constraint_rows(x, Kf, rhs_full);
+      warp_sync();
+    }
     double dmax = 0.;
-    for (int v = lane; v < V; v += CTK_WARP) dmax = fmax(dmax, Kf[tri(v) + v]);
+    for (int v = lane; v < V; v += CTK_WARP) dmax = fmax(dmax, (double) Kf[cs[v]]);
     dmax = warp_max_d(dmax);
     const double floor_ = fmax(dmax * 1e-14, 1e-300);
     for (int v = lane; v < V; v += CTK_WARP) {
-      double g = rhs_full[v];
-      bool frozen = (x[v] <= lo[v] && g < 0.) || (x[v] >= hi[v] && g > 0.) || !(lo[v] < hi[v]);
+      const double g = rhs_full[v];
+      const bool frozen = (x[v] <= lo[v] && g < 0.) || (x[v] >= hi[v] && g > 0.) || !(lo[v] < hi[v]);
       act[v] = frozen ? 1 : 0;
-      dg[v] = fmax(Kf[tri(v) + v], floor_);
-      d[v] = frozen ? 0. : g;
+      const double s = 1. / sqrt(fmax((double) Kf[cs[v]], floor_));
+      sc[v] = s;
+      d[v] = frozen ? 0. : g * s;
     }
     warp_sync();
-    for (int u = 0; u < V; ++u) {
-      for (int v = lane; v <= u; v += CTK_WARP) {
-        int t = tri(u) + v;
-        if (act[u] || act[v]) Kf[t] = (u == v) ? 1. : 0.;
-        else if (u == v) Kf[t] += lambda * dg[u];
-      }
+    // scaled, damped system: (S K S + lambda I)(S^-1 step) = S rhs; frozen rows become identity
+    const Real lam1 = (Real) (1. + lambda);
+    for (int t = lane; t < nt; t += CTK_WARP) {
+      const int r = rc[t] & 0xff, c = rc[t] >> 8;
+      Real v;
+      if (act[r] || act[c]) v = (r == c) ? (Real) 1 : (Real) 0;
+      else if (r == c) v = lam1;
+      else v = Kf[t] * (Real) (sc[r] * sc[c]);
+      Kf[t] = v;
     }
     warp_sync();
-    // packed Cholesky, right-looking; lanes own rows
-    bool ok = true;
     for (int j = 0; j < V; ++j) {
-      double piv = Kf[tri(j) + j];
-      if (!(piv > 0.) || !finite_d(piv)) { ok = false; break; }
-      double inv = 1. / sqrt(piv);
+      const int cj = cs[j];
+      const Real piv = Kf[cj];
+      if (!(piv > (Real) 1e-7)) return false;              // also catches NaN
+      const Real inv = fast_rsqrt(piv);
+      const double yj = d[j] * (double) inv;               // forward substitution, row j
       warp_sync();
-      for (int r = j + lane; r < V; r += CTK_WARP) Kf[tri(r) + j] *= inv;
+      for (int r = j + lane; r < V; r += CTK_WARP) Kf[cj + r - j] *= inv;
+      if (lane == 0) { idg[j] = inv; d[j] = yj; }
       warp_sync();
-      for (int r = j + 1 + lane; r < V; r += CTK_WARP) {
-        double lrj = Kf[tri(r) + j];
-        for (int c = j + 1; c <= r; ++c) Kf[tri(r) + c] -= lrj * Kf[tri(c) + j];
+      for (int t = cs[j + 1] + lane; t < nt; t += CTK_WARP) {
+        const int r = rc[t] & 0xff, c = rc[t] >> 8;
+        Kf[t] -= Kf[cj + r - j] * Kf[cj + c - j];
       }
+      for (int r = j + 1 + lane; r < V; r += CTK_WARP) d[r] -= (double) Kf[cj + r - j] * yj;
       warp_sync();
     }
-    if (!ok) return false;
-    // forward and back substitution
-    for (int j = 0; j < V; ++j) {
-      double yj = d[j] / Kf[tri(j) + j];
+    for (int j = V - 1; j >= 0; --j) {                     // back substitution with L^T
+      const double zj = d[j] * (double) idg[j];
       warp_sync();
-      if (lane == 0) d[j] = yj;
-      for (int r = j + 1 + lane; r < V; r += CTK_WARP) d[r] -= Kf[tri(r) + j] * yj;
+      if (lane == 0) d[j] = zj;
+      for (int r = lane; r < j; r += CTK_WARP) d[r] -= (double) Kf[cs[r] + j - r] * zj;
       warp_sync();
     }
-    for (int j = V - 1; j >= 0; --j) {
-      double yj = d[j] / Kf[tri(j) + j];
-      warp_sync();
-      if (lane == 0) d[j] = yj;
-      for (int r = lane; r < j; r += CTK_WARP) d[r] -= Kf[tri(j) + r] * yj;
-      warp_sync();
-    }
+    for (int v = lane; v < V; v += CTK_WARP) d[v] *= sc[v];
+    warp_sync();
     return true;
   }
 
   // predicted decrease of the (augmented) objective for step s: rhs.s - 0.5 s^T K s
   CTK_DEV double predicted(const double* s, const double* rhs_full) const {
-    const double* H = Hm();
+    const Real* H = Hm();
+    const uint16_t* rc = RC();
+    const int nt = CS()[V];
     double acc = 0.;
-    for (int u = lane; u < V; u += CTK_WARP) {
-      double hs = 0.;
-      for (int v = 0; v < V; ++v) hs += (u >= v ? H[tri(u) + v] : H[tri(v) + u]) * s[v];
-      acc += s[u] * (rhs_full[u] - 0.5 * hs);
+    for (int t = lane; t < nt; t += CTK_WARP) {
+      const int r = rc[t] & 0xff, c = rc[t] >> 8;
+      acc -= (r == c ? 0.5 : 1.) * (double) H[t] * s[r] * s[c];
     }
+    for (int u = lane; u < V; u += CTK_WARP) acc += s[u] * rhs_full[u];
     acc = warp_sum(acc);
-    // constraint rows: gradient part is already in rhs_full; add -0.5 w (A s)^2
+    // constraint rows: the gradient part is already in rhs_full; add -0.5 w (A s)^2
     for (int j = 0; j < n_con; ++j) {
-      int p, q;
-      con_pair(j, p, q);
       double as = 0.;
-#pragma unroll
-      for (int k = 0; k < ND; ++k) {
-        double dd = (X()[base[2 + k] + p] - X()[base[2 + k] + q]) / (cdist[k] * cdist[k]);
-        as += -2. * dd * (s[base[2 + k] + p] - s[base[2 + k] + q]);
+      for (int u = 0; u < 2 * ND; ++u) {
+        int iu; double gu;
+        con_grad(X(), j, u, iu, gu);
+        as += gu * s[iu];
       }
       acc -= 0.5 * pen_w * as * as;
     }
@@ -909,12 +999,14 @@ struct ClusterSolver {
   }
 
   CTK_DEV bool is_pos_var(int v) const {
+    bool hit = false;
 #pragma unroll
     for (int k = 0; k < ND; ++k) {
-      int b = base[2 + k];
-      if (b >= 0 && v >= b && v < b + (mode(2 + k) == CTK_MODE_VAR ? n : 1)) return true;
+      const int m = mode(2 + k);
+      const int b = CV()[2 + k];                     // feature 0 holds the first index of the column
+      hit = hit || (m != CTK_MODE_CONST && v >= b && v < b + (m == CTK_MODE_VAR ? n : 1));
     }
-    return false;
+    return hit;
   }
 
   // ---- projected Levenberg-Marquardt with augmented-Lagrangian constraints ---------------------
@@ -927,7 +1019,8 @@ struct ClusterSolver {
     double *x = X(), *xt = XT(), *d = D();
     double* rhs_full = dvec(L.o_rhsf);            // rhs incl. constraint terms, before freezing
     double lambda = 1e-3, nu = 2.;
-    for (int j = 0; j < 3; ++j) mu[j] = 0.;
+    if (lane == 0) for (int j = 0; j < 3; ++j) CON()[j] = 0.;
+    warp_sync();
     pen_w = 0.;
     double fd = evaluate(x);
     if (!finite_d(fd)) return CTK_FAIL_NUMERIC;
@@ -936,13 +1029,14 @@ struct ClusterSolver {
       // penalty weight relative to the curvature of the data term in the position variables
       double hmax = 0.;
       for (int v = lane; v < V; v += CTK_WARP)
-        if (is_pos_var(v)) hmax = fmax(hmax, Hm()[tri(v) + v]);
+        if (is_pos_var(v)) hmax = fmax(hmax, (double) Hm()[CS()[v]]);
       hmax = warp_max_d(hmax);
       double a2 = 0.;
 #pragma unroll
-      for (int k = 0; k < ND; ++k) a2 = fmax(a2, 8. / (cdist[k] * cdist[k]));
+      for (int k = 0; k < ND; ++k) a2 = fmax(a2, 8. / (CON()[3 + k] * CON()[3 + k]));
       pen_w = 100. * fmax(hmax, 1e-30) / a2;
     }
+    const double pen_w0 = pen_w;
     double fa = fd + penalty(x);
     double c_prev = n_con > 0 ? con_violation(x) : 0.;
     int al_rounds = 0;
@@ -967,13 +1061,23 @@ struct ClusterSolver {
       worst = warp_max_d(worst);
       warp_sync();
       if (!finite_d(worst)) { *f_data = fd; return CTK_FAIL_NUMERIC; }
+      CTK_TRACEF("it %d lambda %.3g worst %.3g fa %.10g cv %.3g w %.3g al %d\n", it, lambda, worst, fa,
+                 n_con ? con_violation(x) : 0., pen_w, al_rounds);
       if (worst <= xtol) {
         // stationary for the current multipliers
         if (n_con == 0) { *f_data = fd; return CTK_OK; }
+        // take the (sub-tolerance) step: it carries the Newton correction towards c(x) = 0; the
+        // data term is flat at this scale, so its caches stay valid
+        for (int v = lane; v < V; v += CTK_WARP) x[v] = xt[v];
+        warp_sync();
         double cv = con_violation(x);
-        if (cv <= ctol || al_rounds >= 40) { *f_data = fd; return CTK_OK; }
-        for (int j = 0; j < n_con; ++j) mu[j] += pen_w * con_value(x, j);
-        if (al_rounds > 0 && cv > 0.25 * c_prev) pen_w *= 10.;
+        if (cv <= ctol || al_rounds >= 40 || (al_rounds > 2 && cv >= 0.5 * c_prev && cv <= 1e-6)) {
+          *f_data = fd;
+          return CTK_OK;
+        }
+        if (lane == 0) for (int j = 0; j < n_con; ++j) CON()[j] += pen_w * con_value(x, j);
+        warp_sync();
+        if (al_rounds > 0 && cv > 0.25 * c_prev && pen_w < 1e6 * pen_w0) pen_w *= 10.;
         c_prev = cv;
         ++al_rounds;
         fa = fd + penalty(x);
@@ -986,6 +1090,7 @@ struct ClusterSolver {
       // below the resolution of the objective the comparison fat < fa is rounding noise: trust the
       // quadratic model there (the gradient stays accurate long after the objective has gone flat)
       bool noise = pred > 0. && pred <= eps_f * fabs(fa);
+      CTK_TRACEF("   pred %.3g fat-fa %.3g noise %d\n", pred, fat - fa, (int) noise);
       if (finite_d(fat) && pred > 0. && (fat < fa || noise)) {
         if (!noise) {
           double rho = (fa - fat) / pred;
@@ -1039,10 +1144,10 @@ struct ClusterSolver {
       for (int k = 0; k < ND; ++k) pos_var = pos_var && mode(2 + k) == CTK_MODE_VAR;
       if (pos_var && n == 2 && (a.prob.constraint_mask & CTK_CONSTRAINT_DIMER)) {
         n_con = 1;
-        for (int k = 0; k < ND; ++k) cdist[k] = a.prob.dimer_dist[k];
+        if (lane == 0) for (int k = 0; k < ND; ++k) CON()[3 + k] = a.prob.dimer_dist[k];
       } else if (pos_var && n == 3 && (a.prob.constraint_mask & CTK_CONSTRAINT_TRIMER)) {
         n_con = 3;
-        for (int k = 0; k < ND; ++k) cdist[k] = a.prob.trimer_dist[k];
+        if (lane == 0) for (int k = 0; k < ND; ++k) CON()[3 + k] = a.prob.trimer_dist[k];
       }
     }
     double fd = 0.;

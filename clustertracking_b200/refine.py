@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 from . import constraints as _constraints
-from .find import find_clusters
+from .find import cluster_table, find_clusters
 from .fitfunc import FitFunctions
 from .utils import guess_pos_columns, is_isotropic, validate_tuple
 
@@ -44,8 +44,8 @@ class Plan(object):
         self.cluster_offset = None    # int32 [n_clusters + 1]
         self.cluster_frame = None     # int32 [n_clusters] index into frame_numbers
         self.params_in = None         # float64 [N, P]
-        self.bounds_lo = None
-        self.bounds_hi = None
+        self.bounds_lo = None         # optional float64 [N, P]; None = device derives them from
+        self.bounds_hi = None         # the tables in ``problem`` (fitfunc.py:538-551)
 
     @property
     def n_clusters(self):
@@ -157,7 +157,7 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
                                   % _lib.CTK_MAX_RADIUS)
     cons = _constraints.parse(constraints, ndim)
 
-    f = find_clusters(f, separation, pos_columns, t_column)            # refine.py:297 (a copy)
+    f, order = cluster_table(f, separation, pos_columns, t_column)     # refine.py:297 (a copy)
     if param_val is not None:                                          # refine.py:300-302
         for col in param_val:
             f[col] = param_val[col]
@@ -171,13 +171,10 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
     # column order of the parameter table follows ff.params, but positions are read from the
     # user's pos_columns (refine.py:345 reads ff.params; they coincide for the default names)
     params = np.ascontiguousarray(f[ff.params].values, dtype=np.float64)
-    lo, hi = ff.feature_bounds(tables, params)
 
     # (frame, cluster) groups in the order of f.groupby(['frame', 'cluster'])     refine.py:336
-    frames = f[t_column].values
-    cluster = f['cluster'].values
-    order = np.lexsort((cluster, frames))                              # stable: keeps row order
-    frames_s, cluster_s = frames[order], cluster[order]
+    # ``order`` lists the rows by (frame, cluster), row order kept inside a cluster
+    frames_s, cluster_s = f[t_column].values[order], f['cluster'].values[order]
     n = len(order)
     if n == 0:
         raise ValueError("no features to refine")
@@ -191,8 +188,6 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
     plan.frame_numbers = [int(x) if float(x).is_integer() else x for x in frame_numbers]
     plan.cluster_frame = frame_index.astype(np.int32)
     plan.params_in = np.ascontiguousarray(params[order])
-    plan.bounds_lo = np.ascontiguousarray(lo[order])
-    plan.bounds_hi = np.ascontiguousarray(hi[order])
     plan.frame_source = source
 
     first = np.asarray(source[plan.frame_numbers[0]])
@@ -223,6 +218,11 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
         for k in range(ndim):
             prob.trimer_dist[k] = cons['trimer'][k]
     prob.constraint_mask = mask
+    for which, table in zip(("bounds_abs", "bounds_diff", "bounds_rel"), tables):
+        dst = getattr(prob, which)
+        for side in range(2):
+            for j in range(_lib.CTK_MAX_PARAMS):
+                dst[side][j] = table[side, j] if j < len(ff.params) else np.nan
     plan.problem = prob
     return plan
 
@@ -327,8 +327,8 @@ class DeviceSession(object):
                                          dtype=torch.uint8, device=dev)
             self.d_offset = self._up(plan.cluster_offset)
             self.d_params = self._up(plan.params_in)
-            self.d_lo = self._up(plan.bounds_lo)
-            self.d_hi = self._up(plan.bounds_hi)
+            self.d_lo = self._up(plan.bounds_lo) if plan.bounds_lo is not None else None
+            self.d_hi = self._up(plan.bounds_hi) if plan.bounds_hi is not None else None
             self.d_out = torch.empty_like(self.d_params)
             self.d_cost = torch.empty(plan.n_clusters, dtype=torch.float64, device=dev)
             self.d_status = torch.full((plan.n_clusters,), -1, dtype=torch.int32, device=dev)
@@ -357,10 +357,32 @@ class DeviceSession(object):
         batch['bins'] = [(cap, sel, self._up(sel)) for cap, sel in bin_clusters(self.sizes, ids)]
         return batch
 
+    def _direct_view(self, f0, f1):
+        """Zero-copy host view of frames f0..f1-1 when the reader is backed by one contiguous array
+        of the right type (``reader.stack``); pinned memory then goes to the device by DMA."""
+        src = self.plan.frame_source
+        stack = getattr(src, 'stack', None)
+        first = getattr(src, 'first_frame', 0)
+        numbers = self.plan.frame_numbers[f0:f1]
+        if not isinstance(stack, np.ndarray) or stack.dtype != self.plan.pixel_dtype:
+            return None
+        if stack.shape[1:] != tuple(self.plan.frame_shape) or not stack.flags.c_contiguous:
+            return None
+        idx = np.asarray(numbers, dtype=np.int64) - first
+        if idx[0] < 0 or idx[-1] >= len(stack) or np.any(np.diff(idx) != 1):
+            return None
+        return stack[idx[0]:idx[-1] + 1]
+
     def upload_frames(self, f0, f1, staging=None):
-        """Copy frames f0..f1-1 of the plan's source into pinned memory and on to the device."""
+        """Copy frames f0..f1-1 of the plan's source to the device: straight from the reader's
+        array when it has one, else frame by frame through a pinned staging buffer."""
         torch = self.torch
         n = f1 - f0
+        view = self._direct_view(f0, f1)
+        if view is not None:
+            d_frames = torch.from_numpy(view).to(self.dev, non_blocking=True)
+            self.h2d_bytes += n * self.frame_bytes
+            return self.attach_frames(d_frames, f0), staging
         if staging is None or staging.shape[0] < n:
             staging = torch.empty((n,) + tuple(self.plan.frame_shape), dtype=self.torch_dtype,
                                   pin_memory=True)
@@ -371,27 +393,41 @@ class DeviceSession(object):
         self.h2d_bytes += n * self.frame_bytes
         return self.attach_frames(d_frames, f0), staging
 
-    def _launch(self, batch, cap, ids, d_ids):
+    def _launch(self, batch, cap, ids, d_ids, events=None):
         prob = self.plan.problem
+        if events is not None:
+            start, stop = (self.torch.cuda.Event(enable_timing=True) for _ in range(2))
+            start.record()
         _lib.check(self.lib.ctk_refine_batch(
             _lib.ctypes.byref(prob), batch['d_ptrs'].data_ptr(), self.shape_arr,
             batch['d_fmax'].data_ptr(), len(ids), d_ids.data_ptr(), int(cap),
             batch['d_cframe'].data_ptr(), self.d_offset.data_ptr(), self.d_params.data_ptr(),
-            self.d_lo.data_ptr(), self.d_hi.data_ptr(), self.d_out.data_ptr(),
+            self.d_lo.data_ptr() if self.d_lo is not None else None,
+            self.d_hi.data_ptr() if self.d_hi is not None else None, self.d_out.data_ptr(),
             self.d_cost.data_ptr(), self.d_status.data_ptr(), self.d_stats.data_ptr(),
             self.workspace.data_ptr(), self.stream_ptr()), "ctk_refine_batch")
         self.launches += 1
+        if events is not None:
+            stop.record()
+            events.append(("refine", start, stop))
 
-    def run_batch(self, batch, retry=True):
+    def run_batch(self, batch, retry=True, events=None):
         """Frame maxima, then one refine launch per size bin; clusters whose pixel lists overflowed
-        their bin (status TOO_LARGE) are relaunched once with a larger capacity."""
+        their bin (status TOO_LARGE) are relaunched once with a larger capacity.  ``events``: list
+        that receives (kind, start, stop) CUDA-event triples of every launch (bench.py)."""
         prob = self.plan.problem
+        if events is not None:
+            start, stop = (self.torch.cuda.Event(enable_timing=True) for _ in range(2))
+            start.record()
         _lib.check(self.lib.ctk_frame_max(batch['d_ptrs'].data_ptr(), batch['n'], self.n_pixels,
                                           prob.pixel_dtype, batch['d_fmax'].data_ptr(),
                                           self.stream_ptr()), "ctk_frame_max")
         self.launches += 1
+        if events is not None:
+            stop.record()
+            events.append(("frame_max", start, stop))
         for cap, ids, d_ids in batch['bins']:
-            self._launch(batch, cap, ids, d_ids)
+            self._launch(batch, cap, ids, d_ids, events)
         ids = np.arange(batch['c0'], batch['c1'])
         self.host_status[ids[self.sizes[ids] > _BINS[-1]]] = _lib.STATUS_TOO_LARGE
         if not retry:
@@ -463,8 +499,23 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
     * ``**kwargs``: ``options=dict(maxiter=...)`` caps the inner iterations; ``tol`` is accepted and
       ignored; ``precision='float64'`` switches the pixel arithmetic from float32 to float64.
     """
+    import time
+    t0 = time.perf_counter()
     plan = prepare(f, reader, diameter, separation, fit_function, param_mode, param_val,
                    constraints, bounds, pos_columns, t_column, noise_size, threshold, max_iter,
                    max_shift, max_rms_dev, residual_factor, compute_error, **kwargs)
+    t1 = time.perf_counter()
     result = execute_cuda(plan)
-    return finalize(plan, result)
+    t2 = time.perf_counter()
+    out = finalize(plan, result)
+    t3 = time.perf_counter()
+    LAST_CALL.clear()
+    LAST_CALL.update(h2d_bytes=result.session.h2d_bytes, d2h_bytes=result.session.d2h_bytes,
+                     launches=result.session.launches,
+                     phases_ms=dict(prepare=1e3 * (t1 - t0), device=1e3 * (t2 - t1),
+                                    finalize=1e3 * (t3 - t2)))
+    return out
+
+
+# diagnostics of the most recent refine_leastsq call (bytes copied, kernel launches, host phases)
+LAST_CALL = {}

@@ -98,6 +98,13 @@ typedef struct {
   int32_t reserved0;
   double  dimer_dist[3];      /* constraints.py:70-76, per axis */
   double  trimer_dist[3];     /* constraints.py:93-99, per axis */
+  /* Bounds tables of FitFunctions.validate_bounds (fitfunc.py:492-533), [0] = lower, [1] = upper,
+   * NaN = no bound.  Used when d_bounds_lo / d_bounds_hi are NULL: per feature and column
+   *   low  = fmax(fmax(p - diff[0], p * (1 - rel[0])), abs[0]), NaN -> -inf
+   *   high = fmin(fmin(p + diff[1], p * (1 + rel[1])), abs[1]), NaN -> +inf   (fitfunc.py:538-551) */
+  double  bounds_abs[2][CTK_MAX_PARAMS];
+  double  bounds_diff[2][CTK_MAX_PARAMS];
+  double  bounds_rel[2][CTK_MAX_PARAMS];
 } ctk_problem_t;
 
 int ctk_version(void);
@@ -136,7 +143,8 @@ size_t ctk_refine_shared_bytes(const ctk_problem_t* prob, int32_t max_cluster_fe
  *   d_cluster_frame [n_clusters] index into d_frames
  *   d_cluster_offset[n_clusters + 1] feature ranges; features of a cluster are consecutive rows
  *   d_params_in     [n_features, P] float64 row-major, columns as in `modes`   (refine.py:345)
- *   d_bounds_lo/hi  [n_features, P] float64 per-feature bounds, +-inf allowed  (fitfunc.py:538-551)
+ *   d_bounds_lo/hi  [n_features, P] float64 per-feature bounds, +-inf allowed  (fitfunc.py:538-551);
+ *                   both NULL = derive them on the device from prob->bounds_* and d_params_in
  *   d_params_out    [n_features, P] float64                                   (refine.py:380, 426)
  *   d_cost_out      [n_clusters] rms_dev, NaN on failure                      (refine.py:379, 427)
  *   d_status_out    [n_clusters] CTK_OK or CTK_FAIL_*
@@ -157,6 +165,12 @@ int ctk_refine_batch(const ctk_problem_t* prob,
  *   pairs [n_pairs, 2] int64; labels_out, sizes_out [n] int64 */
 int ctk_label_clusters(const int64_t* pairs, int64_t n_pairs, int64_t n,
                        int64_t* labels_out, int64_t* sizes_out);
+
+/* Host helper (no GPU): the order in which CPython iterates the set that
+ * scipy.spatial.cKDTree.query_pairs(output_type='set') builds from `pairs` given in the order of
+ * query_pairs(output_type='ndarray').  The reference visits the pairs in that order (find.py:87-91),
+ * which fixes its cluster label values.  order_out [n_pairs] = insertion indices in iteration order. */
+int ctk_pairs_set_order(const int64_t* pairs, int64_t n_pairs, int64_t* order_out);
 
 #ifdef __cplusplus
 }

@@ -62,8 +62,10 @@ def execute(plan):
         code = handle.ctk_emul_refine_batch(
             ctypes.byref(plan.problem), ptrs.ctypes.data, shape, fmax.ctypes.data, len(ids),
             ids.ctypes.data, int(cap), plan.cluster_frame.ctypes.data,
-            plan.cluster_offset.ctypes.data, plan.params_in.ctypes.data, plan.bounds_lo.ctypes.data,
-            plan.bounds_hi.ctypes.data, result.params_out.ctypes.data, result.cost.ctypes.data,
+            plan.cluster_offset.ctypes.data, plan.params_in.ctypes.data,
+            plan.bounds_lo.ctypes.data if plan.bounds_lo is not None else None,
+            plan.bounds_hi.ctypes.data if plan.bounds_hi is not None else None,
+            result.params_out.ctypes.data, result.cost.ctypes.data,
             result.status.ctypes.data, result.stats.ctypes.data)
         assert code == 0, "emulated launch failed: %d" % code
 

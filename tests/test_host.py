@@ -1,0 +1,199 @@
+"""CPU tests of the host side: clustering, parameter bookkeeping, bounds, constraint descriptors,
+packing, argument errors, and that the C-ABI library loads and exports every declared symbol
+(no compute calls -- there is no GPU here)."""
+import ctypes
+import os
+import re
+import warnings
+
+import numpy as np
+import pandas as pd
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+import golden_io
+import clustertracking_b200 as ctb
+from clustertracking_b200 import _lib, refine
+from oracle import cluster_oracle as oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- library --------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ctk.h")).read()
+    declared = set(re.findall(r"\b(ctk_[a-z_]+)\s*\(", header))
+    assert {"ctk_refine_batch", "ctk_frame_max", "ctk_label_clusters", "ctk_version"} <= declared
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().ctk_version() >= 100
+
+
+def test_problem_struct_matches_header_size():
+    # ctk_problem_t: 4 + 12 + 3 + 4 int32, 4 doubles, 2 int32, 6 doubles, 3 x 2 x 12 doubles
+    assert ctypes.sizeof(_lib.Problem) == (4 + 12 + 3 + 4) * 4 + 4 + 4 * 8 + 2 * 4 + 6 * 8 + 72 * 8
+
+
+def test_shared_bytes_query_needs_no_gpu():
+    plan = _tiny_plan()
+    lib = _lib.load()
+    small = lib.ctk_refine_shared_bytes(ctypes.byref(plan.problem), 2)
+    big = lib.ctk_refine_shared_bytes(ctypes.byref(plan.problem), 32)
+    assert 0 < small < big
+    assert lib.ctk_refine_shared_bytes(ctypes.byref(plan.problem), 33) == 0
+
+
+def test_label_clusters_rule():
+    # (0,1) then (2,1): label of the first argument's cluster survives (find.py:41-48)
+    labels, sizes = _lib.label_clusters(np.array([[0, 1], [2, 1], [4, 5]]), 6)
+    assert_array_equal(labels, [2, 2, 2, 3, 4, 4])
+    assert_array_equal(sizes, [3, 3, 3, 1, 2, 2])
+    labels, sizes = _lib.label_clusters(np.zeros((0, 2), np.int64), 3)
+    assert_array_equal(labels, [0, 1, 2])
+
+
+# ---- clustering ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_io.names("clusters_"))
+def test_find_clusters_matches_reference(name):
+    d = golden_io.load(name)
+    f = golden_io.frame(d, "in_")
+    want = golden_io.frame(d, "out_")
+    sep = d["separation"]
+    got = ctb.find_clusters(f, tuple(sep) if sep.ndim else float(sep))
+    assert list(got.columns) == list(want.columns)
+    assert_array_equal(got.index.values, want.index.values)
+    for col in want.columns:
+        assert_array_equal(got[col].values, want[col].values)
+        assert got[col].dtype == want[col].dtype
+
+
+def test_find_clusters_without_frame_column():
+    f = pd.DataFrame(dict(y=np.zeros(10), x=np.arange(10) * 0.9))
+    out = ctb.find_clusters(f, 1.0)
+    assert out['cluster'].nunique() == 1 and (out['cluster_size'] == 10).all()
+    assert 'frame' in out and 'frame' not in f
+    far = pd.DataFrame(dict(y=np.zeros(10), x=np.arange(10) * 1.1))
+    assert ctb.find_clusters(far, 1.0)['cluster'].nunique() == 10
+
+
+# ---- FitFunctions ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("family,ndim,iso,mode", [
+    ('gauss', 2, True, None), ('gauss', 2, False, dict(size='var')),
+    ('gauss', 3, False, dict(size='cluster', signal='const')), ('ring', 2, True, dict(thickness='var')),
+    ('disc', 3, True, dict(pos='const', size='var')), ('gauss', 3, True, dict(background='var'))])
+def test_fitfunctions_bookkeeping_matches_oracle(family, ndim, iso, mode):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ours = ctb.FitFunctions(family, ndim, iso, mode)
+        ref = oracle.ModelSpec(family, ndim, iso, mode)
+    assert ours.params == ref.params
+    assert ours.modes == ref.modes
+    assert ours.default == ref.default
+
+
+@pytest.mark.parametrize("bounds", [
+    None, dict(signal=(20, 2000), size=(.9, 9)), dict(pos_diff=2.0, signal_rel_diff=0.5),
+    dict(x=(2, 60), x_diff=(5, 3), size_rel_diff=(0.2, 0.4), background=(1, 5))])
+def test_feature_bounds_match_oracle(bounds):
+    rng = np.random.RandomState(3)
+    for ndim, iso in ((2, True), (3, False)):
+        ours = ctb.FitFunctions('gauss', ndim, iso)
+        ref = oracle.ModelSpec('gauss', ndim, iso)
+        radius = (5,) * ndim
+        if bounds and 'size' in bounds and not iso:
+            pass
+        params = rng.uniform(0.5, 50, (7, len(ours.params)))
+        lo, hi = ours.feature_bounds(ours.validate_bounds(bounds, radius), params)
+        lo_r, hi_r = ref.feature_bounds(ref.bounds_tables(bounds, radius), params)
+        assert_array_equal(lo, lo_r)
+        assert_array_equal(hi, hi_r)
+
+
+def test_unsupported_options_raise():
+    f = pd.DataFrame(dict(y=[10.], x=[10.], signal=[100.], size=[2.]))
+    img = np.zeros((32, 32), np.uint8)
+    with pytest.raises(NotImplementedError):
+        refine.prepare(f.copy(), img, 9, param_mode=dict(signal='global'))
+    with pytest.raises(NotImplementedError):
+        refine.prepare(f.copy(), img, 9, fit_function=dict(params=[], func=None))
+    with pytest.raises(NotImplementedError):
+        refine.prepare(f.copy(), img, 9, fit_function='inv_series_3')
+    with pytest.raises(NotImplementedError):
+        refine.prepare(f.copy(), img, 9, noise_size=1)
+    with pytest.raises(NotImplementedError):
+        refine.prepare(f.copy(), img, 9, compute_error=True)
+    with pytest.raises(NotImplementedError):
+        refine.prepare(f.copy(), img, 9, constraints=ctb.constraints.tetramer(4.))
+    with pytest.raises(NotImplementedError):
+        refine.prepare(f.copy(), img, 9, constraints=[dict(type='eq', fun=lambda x: x)])
+    with pytest.raises(ValueError):
+        refine.prepare(f.copy(), [img], 9)                  # refine.py:260-262
+    with pytest.raises(AssertionError):
+        refine.prepare(f.copy(), np.zeros((4, 32, 32), np.uint8), 9)   # refine.py:283
+
+
+def test_constraint_descriptors():
+    (d,) = ctb.constraints.dimer(8.0, 2)
+    assert d['type'] == 'eq' and d['cluster_size'] == 2
+    x = np.zeros((1, 2, 5))
+    x[0, 1, 2:4] = (8.0, 0.)
+    assert_allclose(d['fun'](x, *d['args']), 0.)
+    (o,) = oracle.dimer(8.0, 2)
+    assert_allclose(o['fun'](x, *o['args']), d['fun'](x, *d['args']))
+    (t,) = ctb.constraints.trimer((6., 8.), 2)
+    x = np.random.RandomState(0).uniform(0, 10, (1, 3, 6))
+    (ot,) = oracle.trimer((6., 8.), 2)
+    assert_allclose(t['fun'](x, *t['args']), ot['fun'](x, *ot['args']))
+    parsed = ctb.constraints.parse(ctb.constraints.dimer(8.) + ctb.constraints.trimer(7.), 2)
+    assert_array_equal(parsed['dimer'], [8., 8.])
+    assert_array_equal(parsed['trimer'], [7., 7.])
+
+
+# ---- packing ---------------------------------------------------------------------------------------
+def _tiny_plan():
+    d = golden_io.load("refine_gauss2d_video")
+    f0, reader, diameter, kwargs = golden_io.refine_inputs(d, ctb.constraints)
+    return refine.prepare(f0, reader, diameter, **kwargs)
+
+
+def test_plan_groups_follow_reference_order():
+    d = golden_io.load("refine_gauss2d_video")
+    f0, reader, diameter, kwargs = golden_io.refine_inputs(d, ctb.constraints)
+    plan = refine.prepare(f0, reader, diameter, **kwargs)
+    f = plan.f
+    want_groups = [list(g.index) for _, g in f.groupby(['frame', 'cluster'])]
+    got_groups = [list(f.index[plan.order[a:b]])
+                  for a, b in zip(plan.cluster_offset[:-1], plan.cluster_offset[1:])]
+    assert got_groups == want_groups
+    assert_array_equal(plan.params_in, f[plan.ff.params].values[plan.order])
+    assert plan.frame_numbers == [0, 1, 2]
+    assert plan.cluster_frame.dtype == np.int32 and (np.diff(plan.cluster_frame) >= 0).all()
+    assert plan.problem.n_params == 5 and list(plan.problem.modes)[:5] == [3, 1, 1, 1, 0]
+
+
+def test_finalize_failure_semantics():
+    plan = _tiny_plan()
+    res = refine.Result(plan)
+    res.params_out = plan.params_in + 1.0
+    res.status[:] = 0
+    res.cost[:] = 0.01
+    res.status[1] = 3                      # one failed cluster: unchanged parameters, NaN cost
+    before = plan.f[plan.ff.params].values.copy()
+    out = refine.finalize(plan, res)
+    a, b = plan.cluster_offset[1], plan.cluster_offset[2]
+    failed_rows = plan.order[a:b]
+    assert np.isnan(out['cost'].values[failed_rows]).all()
+    assert_array_equal(out[plan.ff.params].values[failed_rows], before[failed_rows])
+    ok = np.setdiff1d(np.arange(len(out)), failed_rows)
+    assert_allclose(out[plan.ff.params].values[ok], before[ok] + 1.0)
+    assert (out['cost'].values[ok] == 0.01).all()
+    assert list(out.columns)[-1] == 'cost'
+
+
+def test_frame_column_is_added_in_place_like_the_reference():
+    f = pd.DataFrame(dict(y=[10., 20.], x=[10., 20.], signal=[100., 100.], size=[2., 2.]))
+    img = np.zeros((32, 32), np.uint8)
+    plan = refine.prepare(f, img, 9)
+    assert 'frame' in f and (f['frame'] == 0).all()          # refine.py:279
+    assert list(plan.f.columns[:7]) == ['y', 'x', 'signal', 'size', 'frame', 'cluster', 'cluster_size']

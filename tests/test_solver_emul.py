@@ -1,0 +1,97 @@
+"""CPU tests of the solver LOGIC through the one-lane host build of the device source
+(tests/emul): the same ctk_solver.cuh that nvcc compiles for sm_100a, with a 1-lane "warp".
+This is a logic check for the GPU-less container, not a product path; the parity tests proper are
+tests/test_gpu_parity.py (``-m gpu``).  Tolerances as there: 1e-3 px / 1e-3 relative against the
+reference's default run, 2e-5 against its tol=1e-12 run."""
+import warnings
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+import golden_io
+import emul_backend
+import clustertracking_b200 as ctb
+from test_gpu_parity import _compare, POS_TOL, REL_TOL, POS_TOL_TIGHT, REL_TOL_TIGHT
+
+CASES = golden_io.names("refine_")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_emulated_solver_matches_reference_golden(name):
+    d = golden_io.load(name)
+    f0, reader, diameter, kwargs = golden_io.refine_inputs(d, ctb.constraints)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got, plan = emul_backend.refine_leastsq(f0, reader, diameter, **kwargs)
+    _compare(got, golden_io.frame(d, "ref_"), POS_TOL, REL_TOL)
+    _compare(got, golden_io.frame(d, "tight_"), POS_TOL_TIGHT, REL_TOL_TIGHT)
+
+
+@pytest.mark.parametrize("name", ["refine_gauss2d_clusters", "refine_trimer2d_constrained",
+                                  "refine_gauss3d_aniso", "refine_ring2d"])
+def test_emulated_solver_float64(name):
+    d = golden_io.load(name)
+    f0, reader, diameter, kwargs = golden_io.refine_inputs(d, ctb.constraints)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got, _ = emul_backend.refine_leastsq(f0, reader, diameter, precision='float64', **kwargs)
+    _compare(got, golden_io.frame(d, "tight_"), 1e-6, 1e-6)
+
+
+def test_constraints_are_satisfied():
+    d = golden_io.load("refine_trimer2d_constrained")
+    f0, reader, diameter, kwargs = golden_io.refine_inputs(d, ctb.constraints)
+    got, _ = emul_backend.refine_leastsq(f0, reader, diameter, **kwargs)
+    for _, g in got.groupby('cluster'):
+        p = g[['y', 'x']].values
+        if len(p) == 3:
+            for a, b in ((0, 1), (1, 2), (0, 2)):
+                assert abs(np.linalg.norm(p[a] - p[b]) - 8.0) < 1e-6
+
+
+def test_failure_statuses():
+    import pandas as pd
+    img = np.zeros((40, 40), np.uint8)
+    img[18:23, 18:23] = 100
+    f = pd.DataFrame(dict(y=[20., 500., 20.], x=[20., 500., 32.], signal=[100., 100., np.nan],
+                          size=2.))
+    got, plan = emul_backend.refine_leastsq(f, img, 9, separation=4)
+    res = emul_backend.execute(plan)
+    by_row = dict(zip(plan.order[plan.cluster_offset[:-1]], res.status))
+    assert by_row[0] == 0                        # fine
+    assert by_row[1] == 2                        # outside of the image  (refine.py:33-34)
+    assert by_row[2] == 1                        # non-finite parameters (refine.py:356-357)
+    assert np.isnan(got['cost'].values[1:]).all() and np.isfinite(got['cost'].values[0])
+    assert got['y'].values[1] == 500.            # failed fits keep their parameters
+
+
+def test_cluster_larger_than_capacity_fails_loudly():
+    import pandas as pd
+    rng = np.random.RandomState(0)
+    n = 40
+    f = pd.DataFrame(dict(y=30 + rng.uniform(-4, 4, n), x=30 + rng.uniform(-4, 4, n),
+                          signal=50., size=2.))
+    img = rng.randint(0, 50, (64, 64)).astype(np.uint8)
+    got, plan = emul_backend.refine_leastsq(f, img, 9)
+    assert plan.n_clusters == 1 and np.isnan(got['cost'].values).all()
+
+
+def test_edge_clipped_and_overlapping_masks():
+    """Features at the image border and coincident features still give the oracle's answer."""
+    from clustertracking_b200 import artificial
+    from oracle import cluster_oracle
+    import pandas as pd
+    rng = np.random.default_rng(5)
+    pos = np.array([[2.3, 3.1], [2.9, 37.2], [36.8, 20.4], [20.2, 20.9], [23.1, 24.8]])
+    img = artificial.draw_features((40, 40), pos, 2.0, 150., noise=4, rng=rng)
+    f0 = pd.DataFrame(pos + rng.uniform(-0.4, 0.4, pos.shape), columns=['y', 'x'])
+    f0['signal'] = 120.
+    f0['size'] = 2.0
+    got, _ = emul_backend.refine_leastsq(f0.copy(), img, 9, precision='float64')
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = cluster_oracle.refine_leastsq(f0.copy(), img, 9, tol=1e-12)
+    assert_array_equal(got['cluster'].values, want['cluster'].values)
+    assert_allclose(got[['y', 'x']].values, want[['y', 'x']].values, atol=1e-5)
+    assert_allclose(got['cost'].values, want['cost'].values, rtol=1e-6)
