@@ -10,10 +10,8 @@ namespace ctk {
 // Persistent warps, one cluster per warp at a time; clusters are handed out by an atomic counter so
 // that clusters of different cost do not leave the other warps of a block idle.
 template <class C>
-__global__ void __launch_bounds__(128, 4) refine_kernel(const __grid_constant__ BatchArgs a) {
-  extern __shared__ __align__(128) char smem[];
-  char* sm = smem + (size_t) (threadIdx.x >> 5) * a.lay.total;
-  ClusterSolver<C> solver(a, sm);
+__global__ void __launch_bounds__(128, 4) refine_kernel(const BatchArgs a) {
+  ClusterSolver<C> solver(a, (uint32_t) (threadIdx.x >> 5) * (uint32_t) a.lay.total);
   for (;;) {
     int w = 0;
     if ((threadIdx.x & 31) == 0) w = atomicAdd(a.counter, 1);

@@ -31,6 +31,38 @@ inline int mask_capacity(const int32_t* radius, int ndim) {
   return count;
 }
 
+// Largest pixel count of one mask over a 16^ndim grid of sub-pixel centre offsets, plus a margin.
+// Used for the optimistic capacities: a cluster that overflows them gets CTK_FAIL_TOO_LARGE and
+// is relaunched by the caller with a larger capacity (see ctk_refine_batch).
+inline int mask_typical(const int32_t* radius, int ndim) {
+  int r[3] = {0, 0, 0};
+  for (int k = 0; k < ndim; ++k) r[3 - ndim + k] = radius[k];
+  const int steps = 16;
+  int best = 0;
+  for (int a = 0; a < (r[0] ? steps : 1); ++a)
+    for (int b = 0; b < (r[1] ? steps : 1); ++b)
+      for (int c = 0; c < (r[2] ? steps : 1); ++c) {
+        const double off[3] = {a / (double) steps - 0.5, b / (double) steps - 0.5,
+                               c / (double) steps - 0.5};
+        int count = 0;
+        for (int z = -r[0] - 1; z <= r[0] + 1; ++z)
+          for (int y = -r[1] - 1; y <= r[1] + 1; ++y)
+            for (int x = -r[2] - 1; x <= r[2] + 1; ++x) {
+              const int o[3] = {z, y, x};
+              double s = 0.;
+              bool out = false;
+              for (int k = 0; k < 3; ++k) {
+                if (r[k] == 0) { out = out || o[k] != 0; continue; }
+                const double q = (o[k] - off[k]) / r[k];
+                s += q * q;
+              }
+              if (!out && s <= 1.0) ++count;
+            }
+        if (count > best) best = count;
+      }
+  return best;
+}
+
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // Fills `lay` for clusters of up to n_max features.  Returns false on an invalid request.
@@ -48,11 +80,20 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
   const int rb = p.compute_dtype == CTK_COMPUTE_F64 ? 8 : 4;
   lay->n_max = n_max;
   lay->v_max = v_max;
-  lay->f_cap = mask_capacity(p.radius, nd);
-  lay->m_cap = n_max * lay->f_cap;
-  if (lay->m_cap > 16384) lay->m_cap = 16384;          // pixel index is packed in 14 bits
+  // Capacities.  The largest launch class provisions for the rigorous worst case; smaller classes
+  // provision for what clusters of that size typically need and rely on the relaunch of overflowing
+  // clusters (status CTK_FAIL_TOO_LARGE) with a larger class.
+  const bool rigorous = n_max >= CTK_MAX_CLUSTER_FEATURES;
+  const int f_bound = mask_capacity(p.radius, nd);
+  int f_typ = mask_typical(p.radius, nd) + 2;
+  if (f_typ > f_bound) f_typ = f_bound;
+  lay->f_cap = rigorous ? f_bound : f_typ;
   if (lay->f_cap > 16384) return false;
+  lay->m_cap = n_max * lay->f_cap;
+  if (!rigorous && n_max >= 3) lay->m_cap = (3 * n_max * lay->f_cap + 3) / 4 + 8;
+  if (lay->m_cap > 16384) lay->m_cap = 16384;          // pixel index is packed in 14 bits
   lay->pair_cap = n_max > 1 ? n_max * lay->f_cap : 1;
+  if (!rigorous && n_max >= 3) lay->pair_cap = (3 * n_max * lay->f_cap + 4) / 5;
   int np = n_max * (n_max - 1) / 2;
   lay->npair_cap = np < 1 ? 1 : (np < 4 * n_max ? np : 4 * n_max);
   lay->tab_stride = 0;
@@ -61,21 +102,15 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
     lay->tab_stride += lay->tab_len[k];
   }
   lay->real_bytes = rb;
+  const int px_bytes = p.pixel_dtype == CTK_PIXEL_U8 ? 1
+                       : (p.pixel_dtype == CTK_PIXEL_U16 || p.pixel_dtype == CTK_PIXEL_I16) ? 2
+                       : p.pixel_dtype == CTK_PIXEL_F64 ? 8 : 4;
   int o = 0;
   auto take = [&o](int bytes) { int at = o; o = align_up(o + bytes, 16); return at; };
-  lay->o_x = take(v_max * 8);
-  lay->o_xt = take(v_max * 8);
+  // persistent over the whole cluster
   lay->o_x0 = take(v_max * 8);
   lay->o_lo = take(v_max * 8);
   lay->o_hi = take(v_max * 8);
-  lay->o_rhs = take(v_max * 8);
-  lay->o_rhsf = take(v_max * 8);
-  lay->o_d = take(v_max * 8);
-  lay->o_dg = take(v_max * 8);
-  lay->o_act = take(v_max * 4);
-  lay->o_H = take(v_max * (v_max + 1) / 2 * rb);
-  lay->o_L = take(v_max * (v_max + 1) / 2 * rb);
-  lay->o_idg = take(v_max * rb);
   lay->o_cs = take((v_max + 1) * 4);
   lay->o_rc = take(v_max * (v_max + 1) / 2 * 2);
   lay->o_cv = take(n_max * p.n_params * 4);
@@ -86,14 +121,28 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
   lay->o_mc = take(n_max * 3 * 8);
   lay->o_fi = take(n_max * FI_STRIDE * 4);
   lay->o_fr = take(n_max * FR_STRIDE * rb);
+  // solver scratch; the per-pixel feature bitmasks (needed only while the lists are built) share it
+  const int scratch = o;
+  lay->o_x = take(v_max * 8);
+  lay->o_xt = take(v_max * 8);
+  lay->o_rhs = take(v_max * 8);
+  lay->o_rhsf = take(v_max * 8);
+  lay->o_d = take(v_max * 8);
+  lay->o_dg = take(v_max * 8);
+  lay->o_act = take(v_max * 4);
+  lay->o_H = take(v_max * (v_max + 1) / 2 * rb);
+  lay->o_L = take(v_max * (v_max + 1) / 2 * rb);
+  lay->o_idg = take(v_max * rb);
+  lay->o_pbits = scratch;
+  if (o - scratch < lay->m_cap * 4) o = align_up(scratch + lay->m_cap * 4, 16);
+  // pixel lists
   const int tab_bytes = n_max * lay->tab_stride * 8;
   const int fe_bytes = n_max * lay->f_cap * rb;
   lay->o_fe = take(tab_bytes > fe_bytes ? tab_bytes : fe_bytes);
   lay->o_tab = lay->o_fe;
-  lay->o_pval = take(lay->m_cap * rb);
-  lay->o_pr = take(lay->m_cap * rb);
-  lay->o_pbits = take(lay->m_cap * 4);
-  lay->o_pcrd = take(lay->m_cap * 4);
+  lay->o_pval = take(lay->m_cap * px_bytes);
+  lay->o_pr = take(lay->m_cap * (rb > 4 ? rb : 4));
+  lay->o_pcrd = lay->o_pr;                 // box coordinates are dead once the lists exist
   lay->o_flist = take(n_max * lay->f_cap * 4);
   lay->o_pairs = take(lay->pair_cap * 4);
   lay->o_phdr = take(lay->npair_cap * 16);

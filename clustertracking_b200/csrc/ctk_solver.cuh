@@ -37,9 +37,11 @@
 
 #ifdef CTK_EMUL
 #define CTK_DEV inline
+#define CTK_DEV_BIG inline
 #define CTK_WARP 1
 #else
 #define CTK_DEV __device__ __forceinline__
+#define CTK_DEV_BIG __device__ __forceinline__  // large phases: each has exactly ONE call site
 #define CTK_WARP 32
 #endif
 
@@ -200,10 +202,23 @@ struct ClusterSolver {
   typedef typename C::Real Real;
   enum { ND = C::ND, P = C::P, LD = C::LD, LT = C::LT, NS = C::NS };
 
-  const BatchArgs& a;
-  const Layout& L;
-  char* sm;
+  // Kernel arguments BY VALUE: with every access at a compile-time index the compiler keeps them
+  // in the constant bank (a reference would turn each read into a generic load).
+  const BatchArgs a;
   int lane;
+  // The cluster's slice of shared memory.  On the device it is always addressed as an offset from
+  // the kernel's extern __shared__ array, so that the compiler emits shared-space loads/stores
+  // (LDS/STS with 32-bit addresses) instead of generic ones.
+#ifdef CTK_EMUL
+  char* sm_;
+  CTK_DEV char* slice() const { return sm_; }
+#else
+  uint32_t sm_off;
+  CTK_DEV char* slice() const {
+    extern __shared__ __align__(128) char ctk_smem[];
+    return ctk_smem + sm_off;
+  }
+#endif
 
   // cluster
   int n, feat0, V, M, npairs;
@@ -219,42 +234,46 @@ struct ClusterSolver {
   int n_con;
   double pen_w;
 
+#ifdef CTK_EMUL
   CTK_DEV ClusterSolver(const BatchArgs& args, char* smem)
-      : a(args), L(args.lay), sm(smem), lane(lane_id()), cached_V(-1) {}
+      : a(args), lane(lane_id()), sm_(smem), cached_V(-1) {}
+#else
+  CTK_DEV ClusterSolver(const BatchArgs& args, uint32_t smem_offset)
+      : a(args), lane(lane_id()), sm_off(smem_offset), cached_V(-1) {}
+#endif
 
   // ---- typed views ------------------------------------------------------------------------------
-  CTK_DEV double* dvec(int off) const { return reinterpret_cast<double*>(sm + off); }
-  CTK_DEV double* X() const { return dvec(L.o_x); }
-  CTK_DEV double* XT() const { return dvec(L.o_xt); }
-  CTK_DEV double* X0() const { return dvec(L.o_x0); }
-  CTK_DEV double* LO() const { return dvec(L.o_lo); }
-  CTK_DEV double* HI() const { return dvec(L.o_hi); }
-  CTK_DEV double* RHS() const { return dvec(L.o_rhs); }
-  CTK_DEV double* D() const { return dvec(L.o_d); }
-  CTK_DEV double* DG() const { return dvec(L.o_dg); }
-  CTK_DEV int* ACT() const { return reinterpret_cast<int*>(sm + L.o_act); }
+  CTK_DEV double* dvec(int off) const { return reinterpret_cast<double*>(slice() + off); }
+  CTK_DEV double* X() const { return dvec(a.lay.o_x); }
+  CTK_DEV double* XT() const { return dvec(a.lay.o_xt); }
+  CTK_DEV double* X0() const { return dvec(a.lay.o_x0); }
+  CTK_DEV double* LO() const { return dvec(a.lay.o_lo); }
+  CTK_DEV double* HI() const { return dvec(a.lay.o_hi); }
+  CTK_DEV double* RHS() const { return dvec(a.lay.o_rhs); }
+  CTK_DEV double* D() const { return dvec(a.lay.o_d); }
+  CTK_DEV double* DG() const { return dvec(a.lay.o_dg); }
+  CTK_DEV int* ACT() const { return reinterpret_cast<int*>(slice() + a.lay.o_act); }
   // normal matrix, its factor and the factor's inverse diagonal are kept in the pixel arithmetic
   // type: a step of limited accuracy still converges to the same point (the gradient decides)
-  CTK_DEV Real* Hm() const { return reinterpret_cast<Real*>(sm + L.o_H); }
-  CTK_DEV Real* Lm() const { return reinterpret_cast<Real*>(sm + L.o_L); }
-  CTK_DEV Real* IDG() const { return reinterpret_cast<Real*>(sm + L.o_idg); }
-  CTK_DEV int* CS() const { return reinterpret_cast<int*>(sm + L.o_cs); }
-  CTK_DEV uint16_t* RC() const { return reinterpret_cast<uint16_t*>(sm + L.o_rc); }
-  CTK_DEV int* CV() const { return reinterpret_cast<int*>(sm + L.o_cv); }
-  CTK_DEV int* SIDX() const { return reinterpret_cast<int*>(sm + L.o_sidx); }
-  CTK_DEV double* CON() const { return dvec(L.o_con); }        // mu[0..2], dist[3..5]
-  CTK_DEV double* MC() const { return dvec(L.o_mc); }
-  CTK_DEV int* FI() const { return reinterpret_cast<int*>(sm + L.o_fi); }
-  CTK_DEV Real* FR() const { return reinterpret_cast<Real*>(sm + L.o_fr); }
-  CTK_DEV double* TAB() const { return dvec(L.o_tab); }
-  CTK_DEV Real* FE() const { return reinterpret_cast<Real*>(sm + L.o_fe); }
-  CTK_DEV Real* PVAL() const { return reinterpret_cast<Real*>(sm + L.o_pval); }
-  CTK_DEV Real* PR() const { return reinterpret_cast<Real*>(sm + L.o_pr); }
-  CTK_DEV uint32_t* PBITS() const { return reinterpret_cast<uint32_t*>(sm + L.o_pbits); }
-  CTK_DEV uint32_t* PCRD() const { return reinterpret_cast<uint32_t*>(sm + L.o_pcrd); }
-  CTK_DEV uint32_t* FLIST() const { return reinterpret_cast<uint32_t*>(sm + L.o_flist); }
-  CTK_DEV uint32_t* PAIRS() const { return reinterpret_cast<uint32_t*>(sm + L.o_pairs); }
-  CTK_DEV int* PHDR() const { return reinterpret_cast<int*>(sm + L.o_phdr); }
+  CTK_DEV Real* Hm() const { return reinterpret_cast<Real*>(slice() + a.lay.o_H); }
+  CTK_DEV Real* Lm() const { return reinterpret_cast<Real*>(slice() + a.lay.o_L); }
+  CTK_DEV Real* IDG() const { return reinterpret_cast<Real*>(slice() + a.lay.o_idg); }
+  CTK_DEV int* CS() const { return reinterpret_cast<int*>(slice() + a.lay.o_cs); }
+  CTK_DEV uint16_t* RC() const { return reinterpret_cast<uint16_t*>(slice() + a.lay.o_rc); }
+  CTK_DEV int* CV() const { return reinterpret_cast<int*>(slice() + a.lay.o_cv); }
+  CTK_DEV int* SIDX() const { return reinterpret_cast<int*>(slice() + a.lay.o_sidx); }
+  CTK_DEV double* CON() const { return dvec(a.lay.o_con); }        // mu[0..2], dist[3..5]
+  CTK_DEV double* MC() const { return dvec(a.lay.o_mc); }
+  CTK_DEV int* FI() const { return reinterpret_cast<int*>(slice() + a.lay.o_fi); }
+  CTK_DEV Real* FR() const { return reinterpret_cast<Real*>(slice() + a.lay.o_fr); }
+  CTK_DEV double* TAB() const { return dvec(a.lay.o_tab); }
+  CTK_DEV Real* FE() const { return reinterpret_cast<Real*>(slice() + a.lay.o_fe); }
+  CTK_DEV Real* PR() const { return reinterpret_cast<Real*>(slice() + a.lay.o_pr); }
+  CTK_DEV uint32_t* PBITS() const { return reinterpret_cast<uint32_t*>(slice() + a.lay.o_pbits); }
+  CTK_DEV uint32_t* PCRD() const { return reinterpret_cast<uint32_t*>(slice() + a.lay.o_pcrd); }
+  CTK_DEV uint32_t* FLIST() const { return reinterpret_cast<uint32_t*>(slice() + a.lay.o_flist); }
+  CTK_DEV uint32_t* PAIRS() const { return reinterpret_cast<uint32_t*>(slice() + a.lay.o_pairs); }
+  CTK_DEV int* PHDR() const { return reinterpret_cast<int*>(slice() + a.lay.o_phdr); }
 
   CTK_DEV int mode(int col) const { return a.prob.modes[col]; }
   // variable index of (column, feature), -1 when the column is constant
@@ -269,14 +288,28 @@ struct ClusterSolver {
     return 2 + ND + NS;                              // extra
   }
 
-  CTK_DEV Real load_pixel(int64_t idx) const {
+  // pixel values are staged in shared memory in their native width
+  template <class T> CTK_DEV static void copy_px(const void* src, int64_t i, void* dst, int p) {
+    reinterpret_cast<T*>(dst)[p] = reinterpret_cast<const T*>(src)[i];
+  }
+  CTK_DEV void stage_pixel(int64_t idx, int p) const {
+    void* dst = slice() + a.lay.o_pval;
     switch (a.prob.pixel_dtype) {
-      case CTK_PIXEL_U8: return (Real) reinterpret_cast<const uint8_t*>(frame)[idx];
-      case CTK_PIXEL_U16: return (Real) reinterpret_cast<const uint16_t*>(frame)[idx];
-      case CTK_PIXEL_F32: return (Real) reinterpret_cast<const float*>(frame)[idx];
-      case CTK_PIXEL_F64: return (Real) reinterpret_cast<const double*>(frame)[idx];
-      case CTK_PIXEL_I16: return (Real) reinterpret_cast<const int16_t*>(frame)[idx];
-      default: return (Real) reinterpret_cast<const int32_t*>(frame)[idx];
+      case CTK_PIXEL_U8: copy_px<uint8_t>(frame, idx, dst, p); break;
+      case CTK_PIXEL_U16: case CTK_PIXEL_I16: copy_px<uint16_t>(frame, idx, dst, p); break;
+      case CTK_PIXEL_F64: copy_px<double>(frame, idx, dst, p); break;
+      default: copy_px<uint32_t>(frame, idx, dst, p); break;
+    }
+  }
+  CTK_DEV Real pixel_value(int p) const {
+    const void* src = slice() + a.lay.o_pval;
+    switch (a.prob.pixel_dtype) {
+      case CTK_PIXEL_U8: return (Real) reinterpret_cast<const uint8_t*>(src)[p];
+      case CTK_PIXEL_U16: return (Real) reinterpret_cast<const uint16_t*>(src)[p];
+      case CTK_PIXEL_F32: return (Real) reinterpret_cast<const float*>(src)[p];
+      case CTK_PIXEL_F64: return (Real) reinterpret_cast<const double*>(src)[p];
+      case CTK_PIXEL_I16: return (Real) reinterpret_cast<const int16_t*>(src)[p];
+      default: return (Real) reinterpret_cast<const int32_t*>(src)[p];
     }
   }
 
@@ -293,7 +326,7 @@ struct ClusterSolver {
   }
 
   // ---- variables, start vector and bounds (refine.py:361-364, fitfunc.py:207-263, 552-558) ------
-  CTK_DEV int setup_variables() {
+  CTK_DEV_BIG int setup_variables() {
     // variable numbering: columns in order; a 'var' column takes n entries, a 'cluster' column one
     int v = 0;
     int* cv = CV();
@@ -308,7 +341,7 @@ struct ClusterSolver {
     shared_columns = 0;
 #pragma unroll
     for (int c = 1; c < P; ++c) shared_columns += mode(c) == CTK_MODE_CLUSTER ? 1 : 0;
-    if (V > L.v_max || V > 255) return CTK_FAIL_TOO_LARGE;
+    if (V > a.lay.v_max || V > 255) return CTK_FAIL_TOO_LARGE;
     const double* pin = a.params_in + (int64_t)feat0 * P;
     const bool tables = a.lo_in == nullptr;            // bounds from the problem's tables
     const double* lin = tables ? nullptr : a.lo_in + (int64_t)feat0 * P;
@@ -377,14 +410,14 @@ struct ClusterSolver {
       } else {
         target = cv[i * P + slot_col(k - LT - LD)];
       }
-      sidx[i * L.sidx_stride + k] = target;
+      sidx[i * a.lay.sidx_stride + k] = target;
     }
     warp_sync();
     return CTK_OK;
   }
 
   // ---- pixel set (refine.py:28-58, masks.py:30-68) ----------------------------------------------
-  CTK_DEV int build_pixels() {
+  CTK_DEV_BIG int build_pixels() {
     const double* mc = MC();
     int* fi = FI();
     // integer centres (round half to even) and the in-bounds test of masks.py:42-46
@@ -422,25 +455,33 @@ struct ClusterSolver {
     warp_sync();
     // separable tables: tab[i][k][e] = (((ts + e) - (c - origin)) / r)^2, float64, numpy's order
     double* tab = TAB();
-    for (int t = lane; t < n * ND; t += CTK_WARP) {
-      int i = t / ND, k = t - i * ND;
-      double crel = dsub(mc[i * 3 + k], (double) blo[k]);
-      double s = floor(crel - (double) a.prob.radius[k]);
-      s = fmin(fmax(s, -1.0e9), 1.0e9);
-      fi[i * FI_STRIDE + FI_TS + k] = (int) s;
+    for (int i = lane; i < n; i += CTK_WARP) {
+#pragma unroll
+      for (int k = 0; k < ND; ++k) {
+        double crel = dsub(mc[i * 3 + k], (double) blo[k]);
+        double s = floor(crel - (double) a.prob.radius[k]);
+        s = fmin(fmax(s, -1.0e9), 1.0e9);
+        fi[i * FI_STRIDE + FI_TS + k] = (int) s;
+      }
     }
     warp_sync();
-    for (int t = lane; t < n * L.tab_stride; t += CTK_WARP) {
-      int i = t / L.tab_stride, e = t - i * L.tab_stride, k = 0;
-      while (k < ND - 1 && e >= L.tab_len[k]) { e -= L.tab_len[k]; ++k; }
-      double crel = dsub(mc[i * 3 + k], (double) blo[k]);
-      double idx = (double) (fi[i * FI_STRIDE + FI_TS + k] + e);
-      double q = ddiv(dsub(idx, crel), (double) a.prob.radius[k]);
-      tab[t] = dmul(q, q);
+    {
+      int tab_off = 0;
+#pragma unroll
+      for (int k = 0; k < ND; ++k) {
+        const int len = a.lay.tab_len[k];
+        for (int t = lane; t < n * len; t += CTK_WARP) {
+          const int i = t / len, e = t - i * len;
+          const double crel = dsub(mc[i * 3 + k], (double) blo[k]);
+          const double idx = (double) (fi[i * FI_STRIDE + FI_TS + k] + e);
+          const double q = ddiv(dsub(idx, crel), (double) a.prob.radius[k]);
+          tab[i * a.lay.tab_stride + tab_off + e] = dmul(q, q);
+        }
+        tab_off += len;
+      }
     }
     warp_sync();
     // walk the box in C order, ballot-compact the union
-    Real* pval = PVAL();
     uint32_t *pbits = PBITS(), *pcrd = PCRD();
     int count = 0;
     const int itotal = (int) total;
@@ -454,15 +495,15 @@ struct ClusterSolver {
         for (int k = ND - 1; k >= 0; --k) { c[k] = rem % bdim[k]; rem /= bdim[k]; }
         for (int i = 0; i < n; ++i) {
           const int* f = fi + i * FI_STRIDE;
-          const double* tb = tab + i * L.tab_stride;
+          const double* tb = tab + i * a.lay.tab_stride;
           double s = 0.;
           bool in = true;
 #pragma unroll
           for (int k = 0; k < ND; ++k) {
             int e = c[k] - f[FI_TS + k];
-            in = in && (e >= 0) && (e < L.tab_len[k]);
+            in = in && (e >= 0) && (e < a.lay.tab_len[k]);
             if (in) s = (k == 0) ? tb[e] : dadd(s, tb[e]);
-            tb += L.tab_len[k];
+            tb += a.lay.tab_len[k];
           }
           if (in && s <= 1.0) bits |= (1u << i);
         }
@@ -470,11 +511,11 @@ struct ClusterSolver {
       uint32_t ball = ballot(bits != 0u);
       if (bits != 0u) {
         int pos = count + popc(ball & lanemask_lt());
-        if (pos < L.m_cap) {
+        if (pos < a.lay.m_cap) {
           int64_t gi = 0;
 #pragma unroll
           for (int k = 0; k < ND; ++k) gi = gi * a.shape[k] + (blo[k] + c[k]);
-          pval[pos] = load_pixel(gi);
+          stage_pixel(gi, pos);
           pbits[pos] = bits;
           pcrd[pos] = (uint32_t) c[0] | ((uint32_t) c[1] << 10) | ((uint32_t) c[2] << 20);
         }
@@ -482,7 +523,7 @@ struct ClusterSolver {
       count += popc(ball);
     }
     M = count;
-    if (M > L.m_cap || M == 0) return M == 0 ? CTK_FAIL_OUT_OF_IMAGE : CTK_FAIL_TOO_LARGE;
+    if (M > a.lay.m_cap || M == 0) return M == 0 ? CTK_FAIL_OUT_OF_IMAGE : CTK_FAIL_TOO_LARGE;
     warp_sync();
     // per-feature pixel lists, in union order
     uint32_t* flist = FLIST();
@@ -499,17 +540,17 @@ struct ClusterSolver {
         uint32_t ball = ballot(has);
         if (has) {
           int t = cnt + popc(ball & lanemask_lt());
-          if (t < L.f_cap) {
+          if (t < a.lay.f_cap) {
             uint32_t crd = pcrd[p];
             int o0 = (int) (crd & 1023u) - oc[0], o1 = (int) ((crd >> 10) & 1023u) - oc[1],
                 o2 = (int) ((crd >> 20) & 1023u) - oc[2];
-            flist[i * L.f_cap + t] = pack_entry(p, o0, ND > 1 ? o1 : 0, ND > 2 ? o2 : 0);
+            flist[i * a.lay.f_cap + t] = pack_entry(p, o0, ND > 1 ? o1 : 0, ND > 2 ? o2 : 0);
           }
         }
         cnt += popc(ball);
       }
       if (lane == 0) fi[i * FI_STRIDE + FI_CNT] = cnt;
-      overflow |= cnt > L.f_cap;
+      overflow |= cnt > a.lay.f_cap;
     }
     if (overflow) return CTK_FAIL_TOO_LARGE;
     warp_sync();
@@ -528,14 +569,14 @@ struct ClusterSolver {
           apart |= abs(f_i[FI_CI + k] - f_j[FI_CI + k]) > 2 * a.prob.radius[k] + 2;
         if (apart) continue;
         const int cnt_j = f_j[FI_CNT];
-        const uint32_t* fl_j = flist + j * L.f_cap;
+        const uint32_t* fl_j = flist + j * a.lay.f_cap;
         int cnt = 0;
         for (int t0 = 0; t0 < cnt_i; t0 += CTK_WARP) {
           int t = t0 + lane;
           int p = -1;
           bool has = false;
           if (t < cnt_i) {
-            p = entry_pixel(flist[i * L.f_cap + t]);
+            p = entry_pixel(flist[i * a.lay.f_cap + t]);
             has = (pbits[p] >> j) & 1u;
           }
           uint32_t ball = ballot(has);
@@ -546,12 +587,12 @@ struct ClusterSolver {
               if (entry_pixel(fl_j[mid]) < p) lo_ = mid + 1; else hi_ = mid;
             }
             int pos = ptotal + cnt + popc(ball & lanemask_lt());
-            if (pos < L.pair_cap) pairs[pos] = (uint32_t) t | ((uint32_t) lo_ << 16);
+            if (pos < a.lay.pair_cap) pairs[pos] = (uint32_t) t | ((uint32_t) lo_ << 16);
           }
           cnt += popc(ball);
         }
         if (cnt > 0) {
-          if (np >= L.npair_cap || ptotal + cnt > L.pair_cap) return CTK_FAIL_TOO_LARGE;
+          if (np >= a.lay.npair_cap || ptotal + cnt > a.lay.pair_cap) return CTK_FAIL_TOO_LARGE;
           if (lane == 0) {
             phdr[np * 4 + 0] = i; phdr[np * 4 + 1] = j; phdr[np * 4 + 2] = ptotal;
             phdr[np * 4 + 3] = cnt;
@@ -681,7 +722,7 @@ struct ClusterSolver {
   }
 
   // ---- objective: 0.5 * sum of squared residuals (fitfunc.py:436-450, without the 1/M/norm) ----
-  CTK_DEV double evaluate(const double* x) {
+  CTK_DEV_BIG double evaluate(const double* x) {
     ++evals;
     load_features(x);
     Real* pr = PR();
@@ -693,8 +734,8 @@ struct ClusterSolver {
     for (int i = 0; i < n; ++i) {
       const Feat f = feat(i);
       const int cnt = fi[i * FI_STRIDE + FI_CNT];
-      const uint32_t* fl = flist + i * L.f_cap;
-      Real* ge = fe + i * L.f_cap;
+      const uint32_t* fl = flist + i * a.lay.f_cap;
+      Real* ge = fe + i * a.lay.f_cap;
       for (int t = lane; t < cnt; t += CTK_WARP) {
         uint32_t e = fl[t];
         Geo g = geometry(e, f);
@@ -707,10 +748,9 @@ struct ClusterSolver {
       warp_sync();
     }
     const Real bg = (Real) value_of(x, 0, 0);
-    const Real* pval = PVAL();
     double acc = 0., sr = 0., nv = 0.;
     for (int p = lane; p < M; p += CTK_WARP) {
-      Real r = pval[p] - bg - pr[p];
+      Real r = pixel_value(p) - bg - pr[p];
       pr[p] = r;
       if (r == r) { acc += (double) r * (double) r; sr += (double) r; nv += 1.; }
     }
@@ -731,7 +771,7 @@ struct ClusterSolver {
 
   // ---- normal equations from the caches of the last evaluate() ---------------------------------
   // H = sum m m^T (packed lower, column-major), RHS = sum m r  (= -gradient of 0.5 sum r^2)
-  CTK_DEV void accumulate() {
+  CTK_DEV_BIG void accumulate() {
     ++accums;
     Real* H = Hm();
     double* rhs = RHS();
@@ -751,8 +791,8 @@ struct ClusterSolver {
     for (int i = 0; i < n; ++i) {
       const Feat f = feat(i);
       const int cnt = fi[i * FI_STRIDE + FI_CNT];
-      const uint32_t* fl = flist + i * L.f_cap;
-      const Real* ge = fe + i * L.f_cap;
+      const uint32_t* fl = flist + i * a.lay.f_cap;
+      const Real* ge = fe + i * a.lay.f_cap;
       Real acc[LT + 2 * LD];       // [LT] m_u m_w, [LD] m_u, [LD] m_u r
 #pragma unroll
       for (int k = 0; k < LT + 2 * LD; ++k) acc[k] = 0;
@@ -776,7 +816,7 @@ struct ClusterSolver {
       for (int k = 0; k < LT + 2 * LD; ++k) acc[k] = warp_sum(acc[k]);
       // every lane now holds every sum; lane k adds entry k to its target
       for (int k = lane; k < LT + 2 * LD; k += CTK_WARP) {
-        const int target = sidx[i * L.sidx_stride + k];
+        const int target = sidx[i * a.lay.sidx_stride + k];
         if (target >= 0) {
           const Real val = pick(acc, k);
           if (k < LT + LD) H[target] += val; else rhs[target] += (double) val;
@@ -790,8 +830,8 @@ struct ClusterSolver {
     for (int q = 0; q < npairs; ++q) {
       const int i = phdr[q * 4], j = phdr[q * 4 + 1], start = phdr[q * 4 + 2], cnt = phdr[q * 4 + 3];
       const Feat f_i = feat(i), f_j = feat(j);
-      const uint32_t *fl_i = flist + i * L.f_cap, *fl_j = flist + j * L.f_cap;
-      const Real *ge_i = fe + i * L.f_cap, *ge_j = fe + j * L.f_cap;
+      const uint32_t *fl_i = flist + i * a.lay.f_cap, *fl_j = flist + j * a.lay.f_cap;
+      const Real *ge_i = fe + i * a.lay.f_cap, *ge_j = fe + j * a.lay.f_cap;
       Real B[LD * LD];
 #pragma unroll
       for (int k = 0; k < LD * LD; ++k) B[k] = 0;
@@ -902,7 +942,7 @@ struct ClusterSolver {
   // active set, adds lambda*diag, factorises (Cholesky, column-major packed, every lane works on the
   // trailing block) with the forward substitution folded in, then back-substitutes.  On return D()
   // holds the step.  Returns false on breakdown.
-  CTK_DEV bool solve(double lambda, double* rhs_full) {
+  CTK_DEV_BIG bool solve(double lambda, double* rhs_full) {
     const Real* H = Hm();
     Real* Kf = Lm();
     double* d = D();
@@ -974,7 +1014,7 @@ struct ClusterSolver {
   }
 
   // predicted decrease of the (augmented) objective for step s: rhs.s - 0.5 s^T K s
-  CTK_DEV double predicted(const double* s, const double* rhs_full) const {
+  CTK_DEV_BIG double predicted(const double* s, const double* rhs_full) const {
     const Real* H = Hm();
     const uint16_t* rc = RC();
     const int nt = CS()[V];
@@ -1011,51 +1051,98 @@ struct ClusterSolver {
 
   // ---- projected Levenberg-Marquardt with augmented-Lagrangian constraints ---------------------
   // Minimises from X() (already holding the start vector).  Returns status; *f_data = 0.5 sum r^2.
-  CTK_DEV int minimise(double* f_data) {
+  // Written as one loop in which evaluate(), accumulate(), solve() and predicted() each appear
+  // once, so that the (fully inlined) kernel holds a single copy of every phase.
+  CTK_DEV_BIG int minimise(double* f_data) {
     const bool f32 = sizeof(Real) == 4;
     const double xtol = a.prob.xtol > 0. ? a.prob.xtol : (f32 ? 2e-6 : 1e-9);
     const double eps_f = f32 ? 4e-6 : 1e-13;      // resolution of the objective
     const double ctol = f32 ? 1e-8 : 1e-10;
     double *x = X(), *xt = XT(), *d = D();
-    double* rhs_full = dvec(L.o_rhsf);            // rhs incl. constraint terms, before freezing
+    double* rhs_full = dvec(a.lay.o_rhsf);            // rhs incl. constraint terms, before freezing
     double lambda = 1e-3, nu = 2.;
     if (lane == 0) for (int j = 0; j < 3; ++j) CON()[j] = 0.;
+    for (int v = lane; v < V; v += CTK_WARP) xt[v] = x[v];
     warp_sync();
     pen_w = 0.;
-    double fd = evaluate(x);
-    if (!finite_d(fd)) return CTK_FAIL_NUMERIC;
-    accumulate();
-    if (n_con > 0) {
-      // penalty weight relative to the curvature of the data term in the position variables
-      double hmax = 0.;
-      for (int v = lane; v < V; v += CTK_WARP)
-        if (is_pos_var(v)) hmax = fmax(hmax, (double) Hm()[CS()[v]]);
-      hmax = warp_max_d(hmax);
-      double a2 = 0.;
-#pragma unroll
-      for (int k = 0; k < ND; ++k) a2 = fmax(a2, 8. / (CON()[3 + k] * CON()[3 + k]));
-      pen_w = 100. * fmax(hmax, 1e-30) / a2;
-    }
-    const double pen_w0 = pen_w;
-    double fa = fd + penalty(x);
-    double c_prev = n_con > 0 ? con_violation(x) : 0.;
-    int al_rounds = 0;
+    double pen_w0 = 0.;
+    double fd = 0., fa = 0., pred = 0., worst = 0.;
+    double c_prev = 0.;
+    int al_rounds = 0, rejects = 0;
     double prev_small_step = INFINITY;
-    int rejects = 0;
-    for (int it = 0; it < a.prob.lm_max_iter; ++it) {
+    bool first = true, need_eval = true;
+    for (int it = 0; it <= a.prob.lm_max_iter; ++it) {
+      if (need_eval) {
+        const double fdt = evaluate(xt);
+        const double fat = fdt + (first ? 0. : penalty(xt));
+        bool accept;
+        if (first) {
+          if (!finite_d(fdt)) return CTK_FAIL_NUMERIC;
+          accept = true;
+        } else {
+          // below the resolution of the objective the comparison fat < fa is rounding noise: trust
+          // the quadratic model there (the gradient stays accurate long after the objective is flat)
+          const bool noise = pred > 0. && pred <= eps_f * fabs(fa);
+          CTK_TRACEF("   pred %.3g fat-fa %.3g noise %d\n", pred, fat - fa, (int) noise);
+          accept = finite_d(fat) && pred > 0. && (fat < fa || noise);
+          if (accept) {
+            if (!noise) {
+              const double rho = (fa - fat) / pred;
+              const double t = 2. * rho - 1.;
+              lambda = fmax(lambda * fmax(1. / 3., 1. - t * t * t), 1e-12);
+            } else {
+              if (worst > 0.9 * prev_small_step) lambda *= 4.;    // not contracting: damp harder
+              prev_small_step = worst;
+            }
+            nu = 2.;
+            rejects = 0;
+          } else {
+            lambda *= nu;
+            nu *= 2.;
+            if (++rejects > 40 || lambda > 1e18) {
+              // no representable descent step is left: x is a numerical minimiser
+              *f_data = fd;
+              return (n_con == 0 || con_violation(x) <= 1e-6) ? CTK_OK : CTK_FAIL_NO_CONVERGENCE;
+            }
+          }
+        }
+        if (accept) {
+          for (int v = lane; v < V; v += CTK_WARP) x[v] = xt[v];
+          warp_sync();
+          fd = fdt;
+          fa = fat;
+          accumulate();
+          if (first && n_con > 0) {
+            // penalty weight relative to the curvature of the data term in the position variables
+            double hmax = 0.;
+            for (int v = lane; v < V; v += CTK_WARP)
+              if (is_pos_var(v)) hmax = fmax(hmax, (double) Hm()[CS()[v]]);
+            hmax = warp_max_d(hmax);
+            double a2 = 0.;
+#pragma unroll
+            for (int k = 0; k < ND; ++k) a2 = fmax(a2, 8. / (CON()[3 + k] * CON()[3 + k]));
+            pen_w = pen_w0 = 100. * fmax(hmax, 1e-30) / a2;
+            fa = fd + penalty(x);
+            c_prev = con_violation(x);
+          }
+          first = false;
+        }
+      }
+      need_eval = true;
       if (!solve(lambda, rhs_full)) {
         lambda = fmax(lambda * 10., 1e-8);
         if (++rejects > 60) { *f_data = fd; return CTK_FAIL_NUMERIC; }
+        need_eval = false;
         continue;
       }
       // trial point, projected on the box
-      double worst = 0.;
+      worst = 0.;
       for (int v = lane; v < V; v += CTK_WARP) {
-        double t = fmin(fmax(x[v] + d[v], LO()[v]), HI()[v]);
+        const double t = fmin(fmax(x[v] + d[v], LO()[v]), HI()[v]);
         xt[v] = t;
-        double s = t - x[v];
+        const double s = t - x[v];
         d[v] = s;
-        double scale = is_pos_var(v) ? 1. : fmax(1., fabs(x[v]));
+        const double scale = is_pos_var(v) ? 1. : fmax(1., fabs(x[v]));
         worst = fmax(worst, fabs(s) / scale);
       }
       worst = warp_max_d(worst);
@@ -1070,7 +1157,7 @@ struct ClusterSolver {
         // data term is flat at this scale, so its caches stay valid
         for (int v = lane; v < V; v += CTK_WARP) x[v] = xt[v];
         warp_sync();
-        double cv = con_violation(x);
+        const double cv = con_violation(x);
         if (cv <= ctol || al_rounds >= 40 || (al_rounds > 2 && cv >= 0.5 * c_prev && cv <= 1e-6)) {
           *f_data = fd;
           return CTK_OK;
@@ -1082,41 +1169,10 @@ struct ClusterSolver {
         ++al_rounds;
         fa = fd + penalty(x);
         lambda = fmin(lambda, 1e-3);
+        need_eval = false;
         continue;
       }
-      double pred = predicted(d, rhs_full);
-      double fdt = evaluate(xt);
-      double fat = fdt + penalty(xt);
-      // below the resolution of the objective the comparison fat < fa is rounding noise: trust the
-      // quadratic model there (the gradient stays accurate long after the objective has gone flat)
-      bool noise = pred > 0. && pred <= eps_f * fabs(fa);
-      CTK_TRACEF("   pred %.3g fat-fa %.3g noise %d\n", pred, fat - fa, (int) noise);
-      if (finite_d(fat) && pred > 0. && (fat < fa || noise)) {
-        if (!noise) {
-          double rho = (fa - fat) / pred;
-          double t = 2. * rho - 1.;
-          lambda *= fmax(1. / 3., 1. - t * t * t);
-          lambda = fmax(lambda, 1e-12);
-        } else {
-          if (worst > 0.9 * prev_small_step) lambda *= 4.;    // not contracting: damp harder
-          prev_small_step = worst;
-        }
-        nu = 2.;
-        rejects = 0;
-        for (int v = lane; v < V; v += CTK_WARP) x[v] = xt[v];
-        warp_sync();
-        fd = fdt;
-        fa = fat;
-        accumulate();
-      } else {
-        lambda *= nu;
-        nu *= 2.;
-        if (++rejects > 40 || lambda > 1e18) {
-          // no representable descent step is left: x is a numerical minimiser
-          *f_data = fd;
-          return (n_con == 0 || con_violation(x) <= 1e-6) ? CTK_OK : CTK_FAIL_NO_CONVERGENCE;
-        }
-      }
+      pred = predicted(d, rhs_full);
     }
     *f_data = fd;
     return CTK_FAIL_NO_CONVERGENCE;
@@ -1134,7 +1190,7 @@ struct ClusterSolver {
     V = 0;
     int status = CTK_OK;
     double cost = NAN;
-    if (n <= 0 || n > L.n_max || n > CTK_MAX_CLUSTER_FEATURES) status = CTK_FAIL_TOO_LARGE;
+    if (n <= 0 || n > a.lay.n_max || n > CTK_MAX_CLUSTER_FEATURES) status = CTK_FAIL_TOO_LARGE;
     if (status == CTK_OK) status = setup_variables();
     // constraints apply to clusters of exactly their size, with free per-feature positions
     n_con = 0;
@@ -1144,18 +1200,24 @@ struct ClusterSolver {
       for (int k = 0; k < ND; ++k) pos_var = pos_var && mode(2 + k) == CTK_MODE_VAR;
       if (pos_var && n == 2 && (a.prob.constraint_mask & CTK_CONSTRAINT_DIMER)) {
         n_con = 1;
-        if (lane == 0) for (int k = 0; k < ND; ++k) CON()[3 + k] = a.prob.dimer_dist[k];
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < ND; ++k) CON()[3 + k] = a.prob.dimer_dist[k];
+        }
       } else if (pos_var && n == 3 && (a.prob.constraint_mask & CTK_CONSTRAINT_TRIMER)) {
         n_con = 3;
-        if (lane == 0) for (int k = 0; k < ND; ++k) CON()[3 + k] = a.prob.trimer_dist[k];
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < ND; ++k) CON()[3 + k] = a.prob.trimer_dist[k];
+        }
       }
     }
     double fd = 0.;
     if (status == CTK_OK) {
       double* mc = MC();
-      for (int t = lane; t < n * ND; t += CTK_WARP) {
-        int i = t / ND, k = t - i * ND;
-        mc[i * 3 + k] = a.params_in[(int64_t) (feat0 + i) * P + 2 + k];
+      for (int i = lane; i < n; i += CTK_WARP) {
+#pragma unroll
+        for (int k = 0; k < ND; ++k) mc[i * 3 + k] = a.params_in[(int64_t) (feat0 + i) * P + 2 + k];
       }
       warp_sync();
       for (int outer = 0; outer < a.prob.max_iter; ++outer) {
@@ -1180,9 +1242,9 @@ struct ClusterSolver {
         moved = warp_any(moved);
         if (!moved) break;
         warp_sync();
-        for (int t = lane; t < n * ND; t += CTK_WARP) {
-          int i = t / ND, k = t - i * ND;
-          mc[i * 3 + k] = value_of(X(), 2 + k, i);
+        for (int i = lane; i < n; i += CTK_WARP) {
+#pragma unroll
+          for (int k = 0; k < ND; ++k) mc[i * 3 + k] = value_of(X(), 2 + k, i);
         }
         warp_sync();
       }

@@ -1,0 +1,83 @@
+"""World-size-2 test of the frame sharding (gloo backend, CPU).  The per-shard refinement is done by
+the one-lane host build of the device solver (test infrastructure, see tests/emul): the subject of
+this test is the host-side sharding, the no-collective data path and the final gather, which must
+reproduce the single-process result exactly, cluster ids included."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _video(n_frames=4):
+    sys.path.insert(0, ROOT)
+    from clustertracking_b200 import artificial
+    stack, rows = [], []
+    for t in range(n_frames):
+        frame, f0, _ = artificial.clustered_frame((96, 96), pitch=44, seed=50 + t)
+        f0['frame'] = t + 3                      # frame numbers need not start at 0
+        stack.append(frame)
+        rows.append(f0)
+    return artificial.FrameStack(np.array(stack), first_frame=3), pd.concat(rows, ignore_index=True)
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import emul_backend
+    from clustertracking_b200 import parallel, refine
+    refine.execute_cuda = lambda plan, device=None: _with_session(emul_backend.execute(plan))
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank,
+                            world_size=world)
+    reader, f0 = _video()
+    out = parallel.refine_leastsq_sharded(f0, reader, 11)
+    out.to_pickle(os.path.join(out_dir, "rank%d.pkl" % rank))
+    dist.destroy_process_group()
+
+
+class _Session(object):
+    h2d_bytes = d2h_bytes = launches = 0
+
+
+def _with_session(result):
+    result.session = _Session()
+    return result
+
+
+def test_two_rank_sharding_matches_single_process(tmp_path):
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emul_backend
+    emul_backend.lib()                           # build once, before the workers start
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    parts = [pd.read_pickle(os.path.join(str(tmp_path), "rank%d.pkl" % r)) for r in range(2)]
+    reader, f0 = _video()
+    single, _ = emul_backend.refine_leastsq(f0, reader, 11)
+    for part in parts:                           # every rank holds the full, identical result
+        assert list(part.columns) == list(single.columns)
+        assert np.array_equal(part.index.values, single.index.values)
+        for col in single.columns:
+            assert np.array_equal(part[col].values, single[col].values, equal_nan=True), col
+
+
+def test_shard_bounds_and_frame_shard():
+    sys.path.insert(0, ROOT)
+    from clustertracking_b200 import parallel
+    assert list(parallel.shard_bounds(10, 4)) == [0, 3, 6, 8, 10]
+    assert list(parallel.shard_bounds(2, 4)) == [0, 1, 2, 2, 2]
+    f = pd.DataFrame(dict(frame=[5, 5, 7, 9, 9, 9, 12], x=np.arange(7.)))
+    got = [list(parallel.frame_shard(f, r, 3)['frame'].unique()) for r in range(3)]
+    assert got == [[5, 7], [9], [12]]
+    assert len(parallel.frame_shard(f.iloc[:1], 1, 2)) == 0
