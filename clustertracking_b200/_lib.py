@@ -35,7 +35,8 @@ class Problem(ctypes.Structure):
         ("compute_dtype", ctypes.c_int32), ("max_iter", ctypes.c_int32),
         ("lm_max_iter", ctypes.c_int32), ("max_shift", ctypes.c_double),
         ("max_rms_dev", ctypes.c_double), ("residual_factor", ctypes.c_double),
-        ("xtol", ctypes.c_double), ("constraint_mask", ctypes.c_int32),
+        ("xtol", ctypes.c_double), ("chord_tol", ctypes.c_double),
+        ("constraint_mask", ctypes.c_int32),
         ("reserved0", ctypes.c_int32), ("dimer_dist", ctypes.c_double * 3),
         ("trimer_dist", ctypes.c_double * 3),
         ("bounds_abs", (ctypes.c_double * CTK_MAX_PARAMS) * 2),
@@ -44,7 +45,8 @@ class Problem(ctypes.Structure):
     ]
 
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libctk.so")
+LIB_PATH = os.environ.get("CTK_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                          "libctk.so")
 _lib = None
 
 _vp, _i32, _i64, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t

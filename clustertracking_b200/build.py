@@ -62,6 +62,27 @@ def _compile(job):
     return obj
 
 
+def build_variant(out, defines, only=None):
+    """Experiment helper: build a library variant with extra -D flags into ``out`` (objects in a
+    scratch directory).  ``only`` = iterable of job names to compile with the flags (all if None)."""
+    import tempfile
+    scratch = tempfile.mkdtemp(prefix="ctk_variant_")
+    objs = []
+
+    def one(job):
+        name, src, defs = job
+        obj = os.path.join(scratch, name + ".o")
+        cmd = [_nvcc()] + ARCH + COMMON + defs + list(defines) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        subprocess.run(cmd, check=True, capture_output=True)
+        return obj
+
+    with concurrent.futures.ThreadPoolExecutor(os.cpu_count() or 1) as pool:
+        objs = list(pool.map(one, _jobs()))
+    subprocess.run([_nvcc()] + ARCH + ["-shared", "-cudart", "static", "-o", out] + objs, check=True)
+    shutil.rmtree(scratch, ignore_errors=True)
+    return out
+
+
 def build(force=False, verbose=True):
     """Compile and link ``libctk.so``; returns its path."""
     stamp = os.path.join(BUILD, "stamp")

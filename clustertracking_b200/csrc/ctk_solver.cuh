@@ -38,10 +38,16 @@
 #ifdef CTK_EMUL
 #define CTK_DEV inline
 #define CTK_DEV_BIG inline
+#define CTK_COLD inline
 #define CTK_WARP 1
 #else
 #define CTK_DEV __device__ __forceinline__
 #define CTK_DEV_BIG __device__ __forceinline__  // large phases: each has exactly ONE call site
+#ifdef CTK_COLD_INLINE
+#define CTK_COLD static __device__ __forceinline__
+#else
+#define CTK_COLD static __device__ __noinline__ // rarely executed: keep it out of the hot loop's footprint
+#endif
 #define CTK_WARP 32
 #endif
 
@@ -181,6 +187,99 @@ struct BatchArgs {
   Layout lay;
 };
 
+// ------------------------------------------------------------------------------------------------
+// cold helpers (not inlined): bounds from the tables, distance constraints
+// ------------------------------------------------------------------------------------------------
+// fitfunc.py:538-551; fmax/fmin skip NaN exactly like np.fmax/np.fmin, all-NaN -> unbounded
+CTK_COLD double bound_from_tables(double p, double diff, double rel, double ab, int upper) {
+  if (upper) {
+    double v = fmin(fmin(p + diff, p * (1. + rel)), ab);
+    return v == v ? v : INFINITY;
+  }
+  double v = fmax(fmax(p - diff, p * (1. - rel)), ab);
+  return v == v ? v : -INFINITY;
+}
+
+// Distance constraints (constraints.py:59-99).  Constraint j couples features (p, q): dimer (0,1);
+// trimer (0,1), (1,2), (0,2).  con[0..2] multipliers, con[3..5] distances per axis.
+struct ConView {
+  const double* x;
+  const int* cv;        // [n, P] variable index of (feature, column)
+  const double* con;
+  int n, P, nd, n_con;
+  double w;             // penalty weight
+};
+CTK_COLD int con_pos_var(const ConView v, int k, int i) { return v.cv[i * v.P + 2 + k]; }
+CTK_COLD void con_pair(const ConView v, int j, int* p, int* q) {
+  *p = (j == 1) ? 1 : 0;
+  *q = (v.n == 2 || j == 0) ? 1 : 2;
+}
+CTK_COLD double con_value(const ConView v, int j) {
+  int p, q;
+  con_pair(v, j, &p, &q);
+  double s = 0.;
+  for (int k = 0; k < v.nd; ++k) {
+    double d = (v.x[con_pos_var(v, k, p)] - v.x[con_pos_var(v, k, q)]) / v.con[3 + k];
+    s += d * d;
+  }
+  return 1. - s;
+}
+CTK_COLD double con_penalty(const ConView v) {
+  double out = 0.;
+  for (int j = 0; j < v.n_con; ++j) {
+    double c = con_value(v, j);
+    out += v.con[j] * c + 0.5 * v.w * c * c;
+  }
+  return out;
+}
+CTK_COLD double con_violation(const ConView v) {
+  double out = 0.;
+  for (int j = 0; j < v.n_con; ++j) out = fmax(out, fabs(con_value(v, j)));
+  return out;
+}
+// gradient of constraint j: entry u (< 2 nd) belongs to variable *idx, value *g
+CTK_COLD void con_grad(const ConView v, int j, int u, int* idx, double* g) {
+  int p, q;
+  con_pair(v, j, &p, &q);
+  const int k = u >> 1;
+  const double dist = v.con[3 + k];
+  const double d = (v.x[con_pos_var(v, k, p)] - v.x[con_pos_var(v, k, q)]) / (dist * dist);
+  *idx = con_pos_var(v, k, (u & 1) ? q : p);
+  *g = (u & 1) ? 2. * d : -2. * d;
+}
+// add w A^T A to the packed (column-major lower, column starts cs) matrix Kp and
+// -(mu + w c) A^T to rhs; one lane calls this
+template <class Real>
+CTK_COLD void con_add_rows(const ConView v, Real* Kp, const int* cs, double* rhs) {
+  for (int j = 0; j < v.n_con; ++j) {
+    const double lam = v.con[j] + v.w * con_value(v, j);
+    for (int a = 0; a < 2 * v.nd; ++a) {
+      int ia; double ga;
+      con_grad(v, j, a, &ia, &ga);
+      rhs[ia] -= lam * ga;
+      for (int b = 0; b < 2 * v.nd; ++b) {
+        int ib; double gb;
+        con_grad(v, j, b, &ib, &gb);
+        if (ib <= ia) Kp[cs[ib] + ia - ib] += (Real) (v.w * ga * gb);
+      }
+    }
+  }
+}
+// -0.5 w sum_j (A_j s)^2: the constraint rows' share of the predicted decrease
+CTK_COLD double con_quadratic(const ConView v, const double* s) {
+  double out = 0.;
+  for (int j = 0; j < v.n_con; ++j) {
+    double as = 0.;
+    for (int a = 0; a < 2 * v.nd; ++a) {
+      int ia; double ga;
+      con_grad(v, j, a, &ia, &ga);
+      as += ga * s[ia];
+    }
+    out -= 0.5 * v.w * as * as;
+  }
+  return out;
+}
+
 // compile-time configuration of a kernel instance
 template <class Real_, int ND_, bool ISO_, int FAM_, bool SZ_, bool EX_>
 struct Config {
@@ -227,7 +326,7 @@ struct ClusterSolver {
   int shared_columns;            // parameter columns (besides background) shared within the cluster
   const void* frame;
   double fmax_;
-  int evals, accums, outers, n_entries, n_pair_entries;
+  int evals, accums, grad_accums, outers, n_entries, n_pair_entries;
   // residual statistics of the last evaluate()
   double sum_r, n_valid;
   // augmented Lagrangian (multipliers and distances live in shared memory, see CON())
@@ -313,16 +412,13 @@ struct ClusterSolver {
     }
   }
 
-  // per-feature bounds from the tables (fitfunc.py:538-551); fmax/fmin skip NaN like np.fmax/fmin
   CTK_DEV double bound_low(double p, int c) const {
-    double v = fmax(fmax(p - a.prob.bounds_diff[0][c], p * (1. - a.prob.bounds_rel[0][c])),
-                    a.prob.bounds_abs[0][c]);
-    return v == v ? v : -INFINITY;
+    return bound_from_tables(p, a.prob.bounds_diff[0][c], a.prob.bounds_rel[0][c],
+                             a.prob.bounds_abs[0][c], 0);
   }
   CTK_DEV double bound_high(double p, int c) const {
-    double v = fmin(fmin(p + a.prob.bounds_diff[1][c], p * (1. + a.prob.bounds_rel[1][c])),
-                    a.prob.bounds_abs[1][c]);
-    return v == v ? v : INFINITY;
+    return bound_from_tables(p, a.prob.bounds_diff[1][c], a.prob.bounds_rel[1][c],
+                             a.prob.bounds_abs[1][c], 1);
   }
 
   // ---- variables, start vector and bounds (refine.py:361-364, fitfunc.py:207-263, 552-558) ------
@@ -771,17 +867,19 @@ struct ClusterSolver {
 
   // ---- normal equations from the caches of the last evaluate() ---------------------------------
   // H = sum m m^T (packed lower, column-major), RHS = sum m r  (= -gradient of 0.5 sum r^2)
-  CTK_DEV_BIG void accumulate() {
-    ++accums;
+  // grad_only: refresh only RHS (the gradient); H and its factor are kept from the last full pass
+  // (chord iteration, used close to the minimum where H has stopped changing).
+  CTK_DEV_BIG void accumulate(bool grad_only) {
+    if (grad_only) ++grad_accums; else ++accums;
     Real* H = Hm();
     double* rhs = RHS();
     const int nt = CS()[V];
-    for (int t = lane; t < nt; t += CTK_WARP) H[t] = 0;
+    if (!grad_only) for (int t = lane; t < nt; t += CTK_WARP) H[t] = 0;
     for (int v = lane; v < V; v += CTK_WARP) rhs[v] = 0.;
     warp_sync();
     const int* cv = CV();
     const int vb = cv[0];
-    if (vb >= 0 && lane == 0) { H[pk(vb, vb)] = (Real) n_valid; rhs[vb] = sum_r; }
+    if (vb >= 0 && lane == 0) { if (!grad_only) H[pk(vb, vb)] = (Real) n_valid; rhs[vb] = sum_r; }
     warp_sync();
     const uint32_t* flist = FLIST();
     const Real* fe = FE();
@@ -803,19 +901,29 @@ struct ClusterSolver {
         Geo g = geometry(e, f);
         Real m[LD];
         model_derivs(g, f, ge[t], m);
-        int k = 0;
+        if (grad_only) {
 #pragma unroll
-        for (int u = 0; u < LD; ++u) {
-          acc[LT + u] += m[u];
-          acc[LT + LD + u] += m[u] * r;
+          for (int u = 0; u < LD; ++u) acc[LT + LD + u] += m[u] * r;
+        } else {
+          int k = 0;
 #pragma unroll
-          for (int w = 0; w <= u; ++w) acc[k++] += m[u] * m[w];
+          for (int u = 0; u < LD; ++u) {
+            acc[LT + u] += m[u];
+            acc[LT + LD + u] += m[u] * r;
+#pragma unroll
+            for (int w = 0; w <= u; ++w) acc[k++] += m[u] * m[w];
+          }
         }
       }
+      if (grad_only) {
 #pragma unroll
-      for (int k = 0; k < LT + 2 * LD; ++k) acc[k] = warp_sum(acc[k]);
+        for (int k = LT + LD; k < LT + 2 * LD; ++k) acc[k] = warp_sum(acc[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < LT + 2 * LD; ++k) acc[k] = warp_sum(acc[k]);
+      }
       // every lane now holds every sum; lane k adds entry k to its target
-      for (int k = lane; k < LT + 2 * LD; k += CTK_WARP) {
+      for (int k = (grad_only ? LT + LD : 0) + lane; k < LT + 2 * LD; k += CTK_WARP) {
         const int target = sidx[i * a.lay.sidx_stride + k];
         if (target >= 0) {
           const Real val = pick(acc, k);
@@ -824,6 +932,7 @@ struct ClusterSolver {
       }
       warp_sync();
     }
+    if (grad_only) return;
     // cross blocks over the pixels two features share
     const uint32_t* pairs = PAIRS();
     const int* phdr = PHDR();
@@ -878,63 +987,15 @@ struct ClusterSolver {
     }
   }
 
-  // ---- distance constraints (constraints.py:59-99) as augmented-Lagrangian rows ----------------
-  // constraint j couples features (p, q): dimer (0,1); trimer (0,1), (1,2), (0,2)
-  CTK_DEV void con_pair(int j, int& p, int& q) const {
-    p = (j == 1) ? 1 : 0;
-    q = (n == 2 || j == 0) ? 1 : 2;
-  }
-  CTK_DEV int pos_var(int k, int i) const { return CV()[i * P + 2 + k]; }
-  CTK_DEV double con_value(const double* x, int j) const {
-    int p, q;
-    con_pair(j, p, q);
-    const double* dist = CON() + 3;
-    double s = 0.;
-#pragma unroll
-    for (int k = 0; k < ND; ++k) {
-      double d = (x[pos_var(k, p)] - x[pos_var(k, q)]) / dist[k];
-      s += d * d;
-    }
-    return 1. - s;
-  }
-  CTK_DEV double penalty(const double* x) const {
-    double v = 0.;
-    for (int j = 0; j < n_con; ++j) {
-      double c = con_value(x, j);
-      v += CON()[j] * c + 0.5 * pen_w * c * c;
-    }
+  // ---- distance constraints as augmented-Lagrangian rows: thin views on the cold helpers -------
+  CTK_DEV ConView con_view(const double* x) const {
+    ConView v;
+    v.x = x; v.cv = CV(); v.con = CON(); v.n = n; v.P = P; v.nd = ND; v.n_con = n_con; v.w = pen_w;
     return v;
   }
+  CTK_DEV double penalty(const double* x) const { return n_con ? con_penalty(con_view(x)) : 0.; }
   CTK_DEV double con_violation(const double* x) const {
-    double v = 0.;
-    for (int j = 0; j < n_con; ++j) v = fmax(v, fabs(con_value(x, j)));
-    return v;
-  }
-  // gradient of constraint j: entry u (< 2 ND) belongs to variable idx, value g
-  CTK_DEV void con_grad(const double* x, int j, int u, int& idx, double& g) const {
-    int p, q;
-    con_pair(j, p, q);
-    const int k = u >> 1;
-    const double dist = CON()[3 + k];
-    const double d = (x[pos_var(k, p)] - x[pos_var(k, q)]) / (dist * dist);
-    idx = pos_var(k, (u & 1) ? q : p);
-    g = (u & 1) ? 2. * d : -2. * d;
-  }
-  // add w A^T A to the packed matrix Kp and -(mu + w c) A^T to rhs (one lane)
-  CTK_DEV void add_constraint_rows(const double* x, Real* Kp, double* rhs) const {
-    for (int j = 0; j < n_con; ++j) {
-      const double lam = CON()[j] + pen_w * con_value(x, j);
-      for (int u = 0; u < 2 * ND; ++u) {
-        int iu; double gu;
-        con_grad(x, j, u, iu, gu);
-        rhs[iu] -= lam * gu;
-        for (int v = 0; v < 2 * ND; ++v) {
-          int iv; double gv;
-          con_grad(x, j, v, iv, gv);
-          if (iv <= iu) Kp[pk(iu, iv)] += (Real) (pen_w * gu * gv);
-        }
-      }
-    }
+    return n_con ? ctk::con_violation(con_view(x)) : 0.;
   }
 
   // ---- damped, bound-aware step --------------------------------------------------------------------
@@ -942,7 +1003,8 @@ struct ClusterSolver {
   // active set, adds lambda*diag, factorises (Cholesky, column-major packed, every lane works on the
   // trailing block) with the forward substitution folded in, then back-substitutes.  On return D()
   // holds the step.  Returns false on breakdown.
-  CTK_DEV_BIG bool solve(double lambda, double* rhs_full) {
+  // reuse: keep the factor of the previous call (same active set required, else refactorise).
+  CTK_DEV_BIG bool solve(double lambda, double* rhs_full, bool reuse) {
     const Real* H = Hm();
     Real* Kf = Lm();
     double* d = D();
@@ -953,53 +1015,76 @@ struct ClusterSolver {
     const uint16_t* rc = RC();
     const double *x = X(), *lo = LO(), *hi = HI();
     const int nt = cs[V];
-    for (int t = lane; t < nt; t += CTK_WARP) Kf[t] = H[t];
     for (int v = lane; v < V; v += CTK_WARP) rhs_full[v] = RHS()[v];
     warp_sync();
-    if (n_con > 0) {
-      if (lane == 0) add_constraint_rows(x, Kf, rhs_full);
-      warp_sync();
-    }
-    double dmax = 0.;
-    for (int v = lane; v < V; v += CTK_WARP) dmax = fmax(dmax, (double) Kf[cs[v]]);
-    dmax = warp_max_d(dmax);
-    const double floor_ = fmax(dmax * 1e-14, 1e-300);
-    for (int v = lane; v < V; v += CTK_WARP) {
-      const double g = rhs_full[v];
-      const bool frozen = (x[v] <= lo[v] && g < 0.) || (x[v] >= hi[v] && g > 0.) || !(lo[v] < hi[v]);
-      act[v] = frozen ? 1 : 0;
-      const double s = 1. / sqrt(fmax((double) Kf[cs[v]], floor_));
-      sc[v] = s;
-      d[v] = frozen ? 0. : g * s;
-    }
-    warp_sync();
-    // scaled, damped system: (S K S + lambda I)(S^-1 step) = S rhs; frozen rows become identity
-    const Real lam1 = (Real) (1. + lambda);
-    for (int t = lane; t < nt; t += CTK_WARP) {
-      const int r = rc[t] & 0xff, c = rc[t] >> 8;
-      Real v;
-      if (act[r] || act[c]) v = (r == c) ? (Real) 1 : (Real) 0;
-      else if (r == c) v = lam1;
-      else v = Kf[t] * (Real) (sc[r] * sc[c]);
-      Kf[t] = v;
-    }
-    warp_sync();
-    for (int j = 0; j < V; ++j) {
-      const int cj = cs[j];
-      const Real piv = Kf[cj];
-      if (!(piv > (Real) 1e-7)) return false;              // also catches NaN
-      const Real inv = fast_rsqrt(piv);
-      const double yj = d[j] * (double) inv;               // forward substitution, row j
-      warp_sync();
-      for (int r = j + lane; r < V; r += CTK_WARP) Kf[cj + r - j] *= inv;
-      if (lane == 0) { idg[j] = inv; d[j] = yj; }
-      warp_sync();
-      for (int t = cs[j + 1] + lane; t < nt; t += CTK_WARP) {
-        const int r = rc[t] & 0xff, c = rc[t] >> 8;
-        Kf[t] -= Kf[cj + r - j] * Kf[cj + c - j];
+    if (reuse) {
+      // chord step: same matrix, same scaling, new right-hand side; the frozen set must not move
+      bool moved = false;
+      for (int v = lane; v < V; v += CTK_WARP) {
+        const double g = rhs_full[v];
+        const bool frozen = (x[v] <= lo[v] && g < 0.) || (x[v] >= hi[v] && g > 0.) || !(lo[v] < hi[v]);
+        moved |= frozen != (act[v] != 0);
+        d[v] = frozen ? 0. : g * sc[v];
       }
-      for (int r = j + 1 + lane; r < V; r += CTK_WARP) d[r] -= (double) Kf[cj + r - j] * yj;
+      if (warp_any(moved)) reuse = false;
       warp_sync();
+    }
+    if (reuse) {
+      for (int j = 0; j < V; ++j) {                        // forward substitution with L
+        const double yj = d[j] * (double) idg[j];
+        warp_sync();
+        if (lane == 0) d[j] = yj;
+        for (int r = j + 1 + lane; r < V; r += CTK_WARP) d[r] -= (double) Kf[cs[j] + r - j] * yj;
+        warp_sync();
+      }
+    } else {
+      for (int t = lane; t < nt; t += CTK_WARP) Kf[t] = H[t];
+      warp_sync();
+      if (n_con > 0) {
+        if (lane == 0) con_add_rows(con_view(x), Kf, cs, rhs_full);
+        warp_sync();
+      }
+      double dmax = 0.;
+      for (int v = lane; v < V; v += CTK_WARP) dmax = fmax(dmax, (double) Kf[cs[v]]);
+      dmax = warp_max_d(dmax);
+      const double floor_ = fmax(dmax * 1e-14, 1e-300);
+      for (int v = lane; v < V; v += CTK_WARP) {
+        const double g = rhs_full[v];
+        const bool frozen = (x[v] <= lo[v] && g < 0.) || (x[v] >= hi[v] && g > 0.) || !(lo[v] < hi[v]);
+        act[v] = frozen ? 1 : 0;
+        const double s = 1. / sqrt(fmax((double) Kf[cs[v]], floor_));
+        sc[v] = s;
+        d[v] = frozen ? 0. : g * s;
+      }
+      warp_sync();
+      // scaled, damped system: (S K S + lambda I)(S^-1 step) = S rhs; frozen rows become identity
+      const Real lam1 = (Real) (1. + lambda);
+      for (int t = lane; t < nt; t += CTK_WARP) {
+        const int r = rc[t] & 0xff, c = rc[t] >> 8;
+        Real v;
+        if (act[r] || act[c]) v = (r == c) ? (Real) 1 : (Real) 0;
+        else if (r == c) v = lam1;
+        else v = Kf[t] * (Real) (sc[r] * sc[c]);
+        Kf[t] = v;
+      }
+      warp_sync();
+      for (int j = 0; j < V; ++j) {
+        const int cj = cs[j];
+        const Real piv = Kf[cj];
+        if (!(piv > (Real) 1e-7)) return false;              // also catches NaN
+        const Real inv = fast_rsqrt(piv);
+        const double yj = d[j] * (double) inv;               // forward substitution, row j
+        warp_sync();
+        for (int r = j + lane; r < V; r += CTK_WARP) Kf[cj + r - j] *= inv;
+        if (lane == 0) { idg[j] = inv; d[j] = yj; }
+        warp_sync();
+        for (int t = cs[j + 1] + lane; t < nt; t += CTK_WARP) {
+          const int r = rc[t] & 0xff, c = rc[t] >> 8;
+          Kf[t] -= Kf[cj + r - j] * Kf[cj + c - j];
+        }
+        for (int r = j + 1 + lane; r < V; r += CTK_WARP) d[r] -= (double) Kf[cj + r - j] * yj;
+        warp_sync();
+      }
     }
     for (int j = V - 1; j >= 0; --j) {                     // back substitution with L^T
       const double zj = d[j] * (double) idg[j];
@@ -1026,15 +1111,7 @@ struct ClusterSolver {
     for (int u = lane; u < V; u += CTK_WARP) acc += s[u] * rhs_full[u];
     acc = warp_sum(acc);
     // constraint rows: the gradient part is already in rhs_full; add -0.5 w (A s)^2
-    for (int j = 0; j < n_con; ++j) {
-      double as = 0.;
-      for (int u = 0; u < 2 * ND; ++u) {
-        int iu; double gu;
-        con_grad(X(), j, u, iu, gu);
-        as += gu * s[iu];
-      }
-      acc -= 0.5 * pen_w * as * as;
-    }
+    if (n_con > 0) acc += con_quadratic(con_view(X()), s);
     return acc;
   }
 
@@ -1070,13 +1147,16 @@ struct ClusterSolver {
     double c_prev = 0.;
     int al_rounds = 0, rejects = 0;
     double prev_small_step = INFINITY;
-    bool first = true, need_eval = true;
+    // chord iterations: once the steps are small the normal matrix has stopped changing, so only the
+    // gradient is refreshed and the previous factor is reused (unconstrained clusters only)
+    const double chord_tol = a.prob.chord_tol;
+    bool first = true, force = true, need_eval = true, chord_next = false;
     for (int it = 0; it <= a.prob.lm_max_iter; ++it) {
       if (need_eval) {
         const double fdt = evaluate(xt);
         const double fat = fdt + (first ? 0. : penalty(xt));
         bool accept;
-        if (first) {
+        if (force) {
           if (!finite_d(fdt)) return CTK_FAIL_NUMERIC;
           accept = true;
         } else {
@@ -1104,6 +1184,15 @@ struct ClusterSolver {
               *f_data = fd;
               return (n_con == 0 || con_violation(x) <= 1e-6) ? CTK_OK : CTK_FAIL_NO_CONVERGENCE;
             }
+            if (chord_next) {
+              // the step from the stale matrix failed: rebuild everything at x (the caches hold the
+              // rejected point, so x is evaluated again)
+              for (int v = lane; v < V; v += CTK_WARP) xt[v] = x[v];
+              warp_sync();
+              force = true;
+              chord_next = false;
+              continue;
+            }
           }
         }
         if (accept) {
@@ -1111,7 +1200,10 @@ struct ClusterSolver {
           warp_sync();
           fd = fdt;
           fa = fat;
-          accumulate();
+          const bool cheap = !force && n_con == 0 && worst < chord_tol;
+          accumulate(cheap);
+          chord_next = cheap;
+          force = false;
           if (first && n_con > 0) {
             // penalty weight relative to the curvature of the data term in the position variables
             double hmax = 0.;
@@ -1129,7 +1221,7 @@ struct ClusterSolver {
         }
       }
       need_eval = true;
-      if (!solve(lambda, rhs_full)) {
+      if (!solve(lambda, rhs_full, chord_next)) {
         lambda = fmax(lambda * 10., 1e-8);
         if (++rejects > 60) { *f_data = fd; return CTK_FAIL_NUMERIC; }
         need_eval = false;
@@ -1162,7 +1254,10 @@ struct ClusterSolver {
           *f_data = fd;
           return CTK_OK;
         }
-        if (lane == 0) for (int j = 0; j < n_con; ++j) CON()[j] += pen_w * con_value(x, j);
+        if (lane == 0) {
+          const ConView cvw = con_view(x);
+          for (int j = 0; j < n_con; ++j) CON()[j] += pen_w * con_value(cvw, j);
+        }
         warp_sync();
         if (al_rounds > 0 && cv > 0.25 * c_prev && pen_w < 1e6 * pen_w0) pen_w *= 10.;
         c_prev = cv;
@@ -1185,7 +1280,7 @@ struct ClusterSolver {
     const int fidx = a.cluster_frame[cluster];
     frame = a.frames[fidx];
     fmax_ = a.frame_max[fidx];
-    evals = accums = outers = n_entries = n_pair_entries = 0;
+    evals = accums = grad_accums = outers = n_entries = n_pair_entries = 0;
     M = 0;
     V = 0;
     int status = CTK_OK;
@@ -1274,7 +1369,8 @@ struct ClusterSolver {
       int32_t* st = a.stats_out + (int64_t) cluster * CTK_STATS;
       st[CTK_STAT_EVALS] = evals; st[CTK_STAT_ACCUMS] = accums; st[CTK_STAT_OUTER] = outers;
       st[CTK_STAT_PIXELS] = M; st[CTK_STAT_ENTRIES] = n_entries;
-      st[CTK_STAT_PAIR_ENTRIES] = n_pair_entries; st[CTK_STAT_VARS] = V; st[7] = 0;
+      st[CTK_STAT_PAIR_ENTRIES] = n_pair_entries; st[CTK_STAT_VARS] = V;
+      st[CTK_STAT_GRAD_ACCUMS] = grad_accums;
     }
     warp_sync();
   }

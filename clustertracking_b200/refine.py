@@ -9,6 +9,7 @@ include/ctk.h): everything inside the reference's ``for _, f_iter in iterable`` 
 There is no CPU fallback: options the CUDA solver does not carry raise ``NotImplementedError``.
 """
 import logging
+import os
 import warnings
 
 import numpy as np
@@ -24,6 +25,8 @@ logger = logging.getLogger(__name__)
 # clusters are launched in bins of at most this many features (shared memory is sized per bin)
 _BINS = (1, 2, 3, 4, 6, 8, 12, 16, 24, 32)
 _FRAME_BATCH_BYTES = 1 << 30          # frames resident on the device per batch
+# scaled step below which the factorised normal matrix is reused (chord iterations)
+_CHORD_TOL = float(os.environ.get('CTK_CHORD_TOL', 0.02))
 
 
 class Plan(object):
@@ -101,7 +104,8 @@ def _solver_options(kwargs, compute_default):
     """``**kwargs`` of the reference go to scipy.optimize.minimize (refine.py:225-228, 242-244).
     The CUDA solver honours ``options['maxiter']``; ``tol`` only matters to SLSQP and is accepted
     and ignored (the device solver always converges tighter than SLSQP's default).  Extra keys:
-    ``precision`` ('float32' | 'float64' pixel arithmetic) and ``xtol`` (step tolerance)."""
+    ``precision`` ('float32' | 'float64' pixel arithmetic), ``xtol`` (step tolerance) and
+    ``chord_tol`` (scaled step size below which the factorised normal matrix is reused)."""
     kwargs = dict(kwargs)
     method = kwargs.pop('method', 'SLSQP')
     if method != 'SLSQP':
@@ -112,11 +116,13 @@ def _solver_options(kwargs, compute_default):
     options.pop('disp', None)
     precision = kwargs.pop('precision', compute_default)
     xtol = float(kwargs.pop('xtol', 0.))
+    chord_tol = float(kwargs.pop('chord_tol', _CHORD_TOL))
     if kwargs or options:
         raise TypeError("unsupported keyword arguments: %r" % sorted(list(kwargs) + list(options)))
     if precision not in ('float32', 'float64'):
         raise ValueError("precision must be 'float32' or 'float64'")
-    return lm_max_iter, (_lib.COMPUTE_F64 if precision == 'float64' else _lib.COMPUTE_F32), xtol
+    return (lm_max_iter, (_lib.COMPUTE_F64 if precision == 'float64' else _lib.COMPUTE_F32), xtol,
+            chord_tol)
 
 
 def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mode=None,
@@ -124,7 +130,7 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
             noise_size=None, threshold=None, max_iter=10, max_shift=1, max_rms_dev=1.,
             residual_factor=100000., compute_error=False, **kwargs):
     """Host half of ``refine_leastsq``: returns a :class:`Plan` (no GPU work)."""
-    lm_max_iter, compute_dtype, xtol = _solver_options(kwargs, 'float32')
+    lm_max_iter, compute_dtype, xtol, chord_tol = _solver_options(kwargs, 'float32')
     if pos_columns is None:
         pos_columns = guess_pos_columns(f)
     if compute_error:
@@ -207,7 +213,7 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
     prob.compute_dtype = compute_dtype
     prob.max_iter, prob.lm_max_iter = int(max_iter), lm_max_iter
     prob.max_shift, prob.max_rms_dev = float(max_shift), float(max_rms_dev)
-    prob.residual_factor, prob.xtol = float(residual_factor), xtol
+    prob.residual_factor, prob.xtol, prob.chord_tol = float(residual_factor), xtol, chord_tol
     mask = 0
     if cons['dimer'] is not None:
         mask |= _lib.CONSTRAINT_DIMER

@@ -66,7 +66,8 @@ enum {
   CTK_STAT_PIXELS = 3,        /* union-mask pixels M of the last pixel set    refine.py:47       */
   CTK_STAT_ENTRIES = 4,       /* sum over features of mask pixels (last pixel set)               */
   CTK_STAT_PAIR_ENTRIES = 5,  /* pixels shared by two features, summed over pairs                */
-  CTK_STAT_VARS = 6           /* free variables V                                                */
+  CTK_STAT_VARS = 6,          /* free variables V                                                */
+  CTK_STAT_GRAD_ACCUMS = 7    /* gradient-only accumulations (chord iterations, factor reused)   */
 };
 
 /* library error codes (return values) */
@@ -94,6 +95,8 @@ typedef struct {
   double  max_rms_dev;        /* refine.py:391-394 */
   double  residual_factor;    /* refine.py:354, 379 */
   double  xtol;               /* inner solver step tolerance; <= 0 selects the default      */
+  double  chord_tol;          /* reuse the factorised normal matrix once the scaled step is
+                                 below this (0 = never); only the gradient is refreshed then  */
   int32_t constraint_mask;    /* OR of CTK_CONSTRAINT_*                                     */
   int32_t reserved0;
   double  dimer_dist[3];      /* constraints.py:70-76, per axis */
