@@ -7,11 +7,16 @@ python ``set`` upstream receives (find.py:87-91).  That order is replayed in C f
 of the result (``ctk_pairs_set_order``; no python objects), the union step runs in C
 (``ctk_label_clusters``) instead of the reference's dict-of-sets loop (find.py:12-60), frames are
 cut from one stable sort instead of a pandas ``groupby`` + ``concat``, and frames are processed by
-a small thread pool (scipy's kd-tree and the ctypes calls release the GIL).
+a persistent pool of worker PROCESSES when the video is long (scipy's kd-tree holds the GIL, so
+threads do not help); positions and labels travel through shared memory.
 """
+import atexit
 import os
-from concurrent.futures import ThreadPoolExecutor
+import pickle
+import subprocess
+import sys
 from itertools import chain
+from multiprocessing import shared_memory
 
 import numpy as np
 from scipy.spatial import cKDTree
@@ -71,31 +76,141 @@ def find_iter(f, separation, pos_columns=None, t_column='frame'):
         yield frame_no, part
 
 
-def label_frames(pos, starts, stops, separation):
-    """Per-frame labels for frame-sorted positions: -> (cluster ids with the running offset of
-    find.py:127-128 applied, cluster sizes, permutation that sorts the rows by (frame, cluster)
-    keeping the row order inside a cluster -- the group order of refine.py:336)."""
-    n_frames = len(starts)
-    cluster = np.empty(len(pos), dtype=np.int64)
-    size = np.empty(len(pos), dtype=np.int64)
-    by_cluster = np.empty(len(pos), dtype=np.int64)
+_POOL = None
+_POOL_MIN_FRAMES = 64
 
-    def work(k):
-        a, b = starts[k], stops[k]
+
+def _pool_workers():
+    env = os.environ.get('CTK_FIND_WORKERS')
+    if env is not None:
+        return max(0, int(env))
+    return min(16, os.cpu_count() or 1)
+
+
+class _WorkerPool(object):
+    """Persistent worker processes, each a fresh interpreter running
+    ``python -m clustertracking_b200._find_worker`` (no fork of this process, no re-import of the
+    caller's ``__main__``, no CUDA state).  Tasks and replies are pickles on the workers' pipes;
+    the bulk data travels through shared memory."""
+
+    def __init__(self, n):
+        env = dict(os.environ)
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        env['PYTHONPATH'] = root + os.pathsep + env.get('PYTHONPATH', '')
+        env['CTK_FIND_WORKERS'] = '0'
+        for var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+            env[var] = '1'
+        self.procs = [subprocess.Popen([sys.executable, '-m', 'clustertracking_b200._find_worker'],
+                                       stdin=subprocess.PIPE, stdout=subprocess.PIPE, env=env)
+                      for _ in range(n)]
+
+    def __len__(self):
+        return len(self.procs)
+
+    def run(self, tasks):
+        """One task per worker (len(tasks) <= len(self)); returns the replies in order."""
+        for proc, task in zip(self.procs, tasks):
+            pickle.dump(task, proc.stdin)
+            proc.stdin.flush()
+        replies = []
+        for proc, _ in zip(self.procs, tasks):
+            reply = pickle.load(proc.stdout)
+            if isinstance(reply, Exception):
+                raise reply
+            replies.append(reply)
+        return replies
+
+    def close(self):
+        for proc in self.procs:
+            try:
+                proc.stdin.close()
+                proc.terminate()
+            except Exception:
+                pass
+        self.procs = []
+
+
+def _get_pool():
+    global _POOL
+    workers = _pool_workers()
+    if workers < 2:
+        return None
+    if _POOL is None or any(p.poll() is not None for p in _POOL.procs):
+        if _POOL is not None:
+            _POOL.close()
+        _POOL = _WorkerPool(workers)
+        atexit.register(_close_pool)
+    return _POOL
+
+
+def _close_pool():
+    global _POOL
+    if _POOL is not None:
+        _POOL.close()
+        _POOL = None
+
+
+def _label_range(pos, ranges, separation, cluster, size, by_cluster):
+    """Label the frames ``ranges`` = [(a, b), ...] of frame-sorted ``pos`` into the output arrays;
+    returns the per-frame label spans (max label + 1)."""
+    spans = []
+    for a, b in ranges:
         ids, sizes = _label_frame(pos[a:b], separation)
         cluster[a:b] = ids
         size[a:b] = sizes
         by_cluster[a:b] = a + np.argsort(ids, kind='stable')
-        return int(ids.max()) + 1 if b > a else 0
+        spans.append(int(ids.max()) + 1 if b > a else 0)
+    return spans
 
-    _replay_is_exact()                      # decide the path once, before threads start
-    workers = min(32, os.cpu_count() or 1, max(1, n_frames // 4))
-    if workers > 1:
-        with ThreadPoolExecutor(workers) as pool:
-            spans = list(pool.map(work, range(n_frames)))
+
+def _pool_task(args):
+    in_name, out_name, n, ndim, ranges, separation = args
+    shm_in = shared_memory.SharedMemory(name=in_name)
+    shm_out = shared_memory.SharedMemory(name=out_name)
+    for shm in (shm_in, shm_out):        # the parent owns the segments: do not track them here
+        try:
+            from multiprocessing import resource_tracker
+            resource_tracker.unregister(shm._name, 'shared_memory')
+        except Exception:
+            pass
+    try:
+        pos = np.ndarray((n, ndim), dtype=np.float64, buffer=shm_in.buf)
+        out = np.ndarray((3, n), dtype=np.int64, buffer=shm_out.buf)
+        return _label_range(pos, ranges, separation, out[0], out[1], out[2])
+    finally:
+        shm_in.close()
+        shm_out.close()
+
+
+def label_frames(pos, starts, stops, separation):
+    """Per-frame labels for frame-sorted positions: -> (cluster ids with the running offset of
+    find.py:127-128 applied, cluster sizes, permutation that sorts the rows by (frame, cluster)
+    keeping the row order inside a cluster -- the group order of refine.py:336)."""
+    n_frames, n = len(starts), len(pos)
+    ranges = list(zip((int(a) for a in starts), (int(b) for b in stops)))
+    pool = _get_pool() if n_frames >= _POOL_MIN_FRAMES else None
+    if pool is None:
+        cluster = np.empty(n, dtype=np.int64)
+        size = np.empty(n, dtype=np.int64)
+        by_cluster = np.empty(n, dtype=np.int64)
+        spans = _label_range(pos, ranges, separation, cluster, size, by_cluster)
     else:
-        spans = [work(k) for k in range(n_frames)]
-    offsets = np.concatenate(([0], np.cumsum(spans)[:-1]))
+        shm_in = shared_memory.SharedMemory(create=True, size=max(1, pos.nbytes))
+        shm_out = shared_memory.SharedMemory(create=True, size=max(1, 3 * n * 8))
+        try:
+            np.ndarray(pos.shape, dtype=np.float64, buffer=shm_in.buf)[:] = pos
+            per_task = max(1, -(-n_frames // len(pool)))
+            tasks = [(shm_in.name, shm_out.name, n, pos.shape[1], ranges[k:k + per_task], separation)
+                     for k in range(0, n_frames, per_task)]
+            spans = [s for part in pool.run(tasks) for s in part]
+            out = np.ndarray((3, n), dtype=np.int64, buffer=shm_out.buf)
+            cluster, size, by_cluster = out[0].copy(), out[1].copy(), out[2].copy()
+        finally:
+            shm_in.close()
+            shm_in.unlink()
+            shm_out.close()
+            shm_out.unlink()
+    offsets = np.concatenate(([0], np.cumsum(spans)[:-1])).astype(np.int64)
     cluster += np.repeat(offsets, np.asarray(stops) - np.asarray(starts))
     return cluster, size, by_cluster
 

@@ -24,7 +24,7 @@ logger = logging.getLogger(__name__)
 
 # clusters are launched in bins of at most this many features (shared memory is sized per bin)
 _BINS = (1, 2, 3, 4, 6, 8, 12, 16, 24, 32)
-_FRAME_BATCH_BYTES = 1 << 30          # frames resident on the device per batch
+_FRAME_BATCH_BYTES = 128 << 20        # frames per upload batch (uploads overlap the kernels)
 # scaled step below which the factorised normal matrix is reused (chord iterations)
 _CHORD_TOL = float(os.environ.get('CTK_CHORD_TOL', 0.02))
 
@@ -269,18 +269,23 @@ def run_bins(sizes, cluster_ids, status, launch):
 
 
 def finalize(plan, result):
-    """Write the fitted parameters and ``cost`` into the DataFrame (refine.py:408-427)."""
+    """Write the fitted parameters and ``cost`` into the DataFrame (refine.py:408-427).  The device
+    already copies the input parameters through for failed clusters, so the whole table is written
+    with one scatter per column."""
     f, ff = plan.f, plan.ff
     sizes = plan.cluster_sizes()
-    ok_rows = np.repeat(result.status == 0, sizes)
-    values = np.ascontiguousarray(f[ff.params].values, dtype=np.float64)
-    values[plan.order[ok_rows]] = result.params_out[ok_rows]
+    ok = result.status == 0
+    block = np.empty((len(ff.params), len(f)), dtype=np.float64)
+    block[:, plan.order] = result.params_out.T
+    if not ok.all():                       # belt and braces: failed clusters keep their input exactly
+        rows = np.repeat(~ok, sizes)
+        block[:, plan.order[rows]] = plan.params_in[rows].T
     for j, col in enumerate(ff.params):
-        f[col] = values[:, j]
+        f[col] = block[j]
     cost = np.empty(len(f), dtype=np.float64)
-    cost[plan.order] = np.repeat(np.where(result.status == 0, result.cost, np.nan), sizes)
+    cost[plan.order] = np.repeat(np.where(ok, result.cost, np.nan), sizes)
     f['cost'] = cost
-    failed = np.flatnonzero(result.status != 0)
+    failed = np.flatnonzero(~ok)
     if len(failed):
         first_row = plan.order[plan.cluster_offset[:-1][failed]]
         ids = f['cluster'].values[first_row]
@@ -467,18 +472,40 @@ class DeviceSession(object):
 
 
 def execute_cuda(plan, device=None):
-    """Run the plan on the current (or given) CUDA device through the C ABI.  Frames are staged
-    through pinned host memory in batches of about 1 GiB."""
+    """Run the plan on the current (or given) CUDA device through the C ABI.
+
+    Frames go to the device in batches on a separate copy stream, so the upload of batch k+1
+    overlaps the kernels of batch k: straight from the reader's array when it has one (a DMA when
+    that memory is pinned), else frame by frame through a pinned staging buffer."""
     session = DeviceSession(plan, device)
     torch = session.torch
     per_batch = max(1, min(session.n_frames, _FRAME_BATCH_BYTES // max(session.frame_bytes, 1)))
-    staging = None
     with torch.cuda.device(session.dev):
-        for f0 in range(0, session.n_frames, per_batch):
-            f1 = min(session.n_frames, f0 + per_batch)
-            batch, staging = session.upload_frames(f0, f1, staging)
-            session.run_batch(batch)
-            torch.cuda.current_stream(session.dev).synchronize()   # staging is reused next batch
+        compute = torch.cuda.current_stream(session.dev)
+        direct = session._direct_view(0, session.n_frames) is not None
+        if direct:
+            copy_stream = torch.cuda.Stream(device=session.dev)
+            pending = []
+            for f0 in range(0, session.n_frames, per_batch):
+                f1 = min(session.n_frames, f0 + per_batch)
+                with torch.cuda.stream(copy_stream):
+                    view = session._direct_view(f0, f1)
+                    d_frames = torch.from_numpy(view).to(session.dev, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(copy_stream)
+                session.h2d_bytes += (f1 - f0) * session.frame_bytes
+                pending.append((f0, d_frames, done))
+            for f0, d_frames, done in pending:
+                compute.wait_event(done)
+                d_frames.record_stream(compute)
+                session.run_batch(session.attach_frames(d_frames, f0))
+        else:
+            staging = None
+            for f0 in range(0, session.n_frames, per_batch):
+                f1 = min(session.n_frames, f0 + per_batch)
+                batch, staging = session.upload_frames(f0, f1, staging)
+                session.run_batch(batch)
+                compute.synchronize()                    # staging is reused by the next batch
         result = session.download()
     result.session = session
     return result
