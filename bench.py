@@ -335,26 +335,32 @@ def run_ours(args):
     # ---- value: everything resident in HBM, C-ABI launches only ----------------------------------
     plan = ctb_refine.prepare(f0.copy(), reader, DIAMETER, precision=args.precision)
     session = ctb_refine.DeviceSession(plan, device)
-    batch = session.attach_frames(d_stack, 0)
+    session.frames.register(d_stack, 0)                 # frames are already resident
+    slices = session.schedule()                         # every size class once
+
+    def one_step(events=None):
+        session.frames.launch_frame_max(0, n_frames, events)
+        session.run(slices, events)
+
     for _ in range(max(3, args.warmup)):
-        session.run_batch(batch, retry=False)
+        one_step()
     torch.cuda.synchronize()
     stats = session.d_stats.cpu().numpy()
     status = session.d_status.cpu().numpy()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = session.launches
+    launches0 = session.launches + session.frames.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_events = []
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        session.run_batch(batch, retry=False, events=kernel_events)
+        one_step(kernel_events)
     ev1.record()
     barrier()
     resident_ms = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop()
-    gpu_launches = session.launches - launches0
+    gpu_launches = session.launches + session.frames.launches - launches0
     total_features = sum_over_ranks(n_features)
     value = total_features * args.steps / (resident_ms * 1e-3)
 

@@ -107,17 +107,18 @@ class _WorkerPool(object):
     def __len__(self):
         return len(self.procs)
 
-    def run(self, tasks):
-        """One task per worker (len(tasks) <= len(self)); returns the replies in order."""
+    def send(self, tasks):
+        """One task per worker (len(tasks) <= len(self))."""
         for proc, task in zip(self.procs, tasks):
             pickle.dump(task, proc.stdin)
             proc.stdin.flush()
-        replies = []
-        for proc, _ in zip(self.procs, tasks):
-            reply = pickle.load(proc.stdout)
+
+    def receive(self, n_tasks):
+        """Replies of the last ``send`` in order; an exception in a worker is re-raised."""
+        replies = [pickle.load(proc.stdout) for proc in self.procs[:n_tasks]]
+        for reply in replies:
             if isinstance(reply, Exception):
                 raise reply
-            replies.append(reply)
         return replies
 
     def close(self):
@@ -182,37 +183,53 @@ def _pool_task(args):
         shm_out.close()
 
 
+class _LabelJob(object):
+    """Labelling of all frames, possibly running in the worker pool while the caller does other
+    host work; ``result()`` waits and returns (cluster, cluster_size, by_cluster)."""
+
+    def __init__(self, pos, starts, stops, separation):
+        self.starts, self.stops = np.asarray(starts), np.asarray(stops)
+        n_frames, n = len(starts), len(pos)
+        ranges = list(zip((int(a) for a in starts), (int(b) for b in stops)))
+        self.pool = _get_pool() if n_frames >= _POOL_MIN_FRAMES else None
+        self.n = n
+        if self.pool is None:
+            self.cluster = np.empty(n, dtype=np.int64)
+            self.size = np.empty(n, dtype=np.int64)
+            self.by_cluster = np.empty(n, dtype=np.int64)
+            self.spans = _label_range(pos, ranges, separation, self.cluster, self.size,
+                                      self.by_cluster)
+            return
+        self.shm_in = shared_memory.SharedMemory(create=True, size=max(1, pos.nbytes))
+        self.shm_out = shared_memory.SharedMemory(create=True, size=max(1, 3 * n * 8))
+        np.ndarray(pos.shape, dtype=np.float64, buffer=self.shm_in.buf)[:] = pos
+        per_task = max(1, -(-n_frames // len(self.pool)))
+        self.tasks = [(self.shm_in.name, self.shm_out.name, n, pos.shape[1],
+                       ranges[k:k + per_task], separation) for k in range(0, n_frames, per_task)]
+        self.pool.send(self.tasks)
+
+    def result(self):
+        if self.pool is not None:
+            try:
+                spans = [s for part in self.pool.receive(len(self.tasks)) for s in part]
+                out = np.ndarray((3, self.n), dtype=np.int64, buffer=self.shm_out.buf)
+                self.cluster, self.size, self.by_cluster = out[0].copy(), out[1].copy(), out[2].copy()
+                self.spans = spans
+            finally:
+                for shm in (self.shm_in, self.shm_out):
+                    shm.close()
+                    shm.unlink()
+                self.pool = None
+        offsets = np.concatenate(([0], np.cumsum(self.spans)[:-1])).astype(np.int64)
+        cluster = self.cluster + np.repeat(offsets, self.stops - self.starts)
+        return cluster, self.size, self.by_cluster
+
+
 def label_frames(pos, starts, stops, separation):
     """Per-frame labels for frame-sorted positions: -> (cluster ids with the running offset of
     find.py:127-128 applied, cluster sizes, permutation that sorts the rows by (frame, cluster)
     keeping the row order inside a cluster -- the group order of refine.py:336)."""
-    n_frames, n = len(starts), len(pos)
-    ranges = list(zip((int(a) for a in starts), (int(b) for b in stops)))
-    pool = _get_pool() if n_frames >= _POOL_MIN_FRAMES else None
-    if pool is None:
-        cluster = np.empty(n, dtype=np.int64)
-        size = np.empty(n, dtype=np.int64)
-        by_cluster = np.empty(n, dtype=np.int64)
-        spans = _label_range(pos, ranges, separation, cluster, size, by_cluster)
-    else:
-        shm_in = shared_memory.SharedMemory(create=True, size=max(1, pos.nbytes))
-        shm_out = shared_memory.SharedMemory(create=True, size=max(1, 3 * n * 8))
-        try:
-            np.ndarray(pos.shape, dtype=np.float64, buffer=shm_in.buf)[:] = pos
-            per_task = max(1, -(-n_frames // len(pool)))
-            tasks = [(shm_in.name, shm_out.name, n, pos.shape[1], ranges[k:k + per_task], separation)
-                     for k in range(0, n_frames, per_task)]
-            spans = [s for part in pool.run(tasks) for s in part]
-            out = np.ndarray((3, n), dtype=np.int64, buffer=shm_out.buf)
-            cluster, size, by_cluster = out[0].copy(), out[1].copy(), out[2].copy()
-        finally:
-            shm_in.close()
-            shm_in.unlink()
-            shm_out.close()
-            shm_out.unlink()
-    offsets = np.concatenate(([0], np.cumsum(spans)[:-1])).astype(np.int64)
-    cluster += np.repeat(offsets, np.asarray(stops) - np.asarray(starts))
-    return cluster, size, by_cluster
+    return _LabelJob(pos, starts, stops, separation).result()
 
 
 def find_clusters(f, separation, pos_columns=None, t_column='frame'):
@@ -245,10 +262,11 @@ def cluster_table(f, separation, pos_columns=None, t_column='frame'):
     cuts = np.flatnonzero(sorted_frames[1:] != sorted_frames[:-1]) + 1
     starts = np.concatenate(([0], cuts)).astype(np.int64)
     stops = np.concatenate((cuts, [len(pos)])).astype(np.int64)
-    cluster, size, by_cluster = label_frames(pos, starts, stops, separation)
-    out = f.copy() if order is None else f.iloc[order].copy()
+    job = _LabelJob(pos, starts, stops, separation)          # may run in the worker pool ...
+    out = f.copy() if order is None else f.iloc[order].copy()   # ... while the copy is made
     if t_column not in f:
         out[t_column] = 0                                     # the copies keep the temporary column
+    cluster, size, by_cluster = job.result()
     out['cluster'] = cluster
     out['cluster_size'] = size
     return out, by_cluster

@@ -59,11 +59,12 @@ class Plan(object):
 
 
 class Result(object):
-    def __init__(self, plan):
-        self.params_out = plan.params_in.copy()
-        self.cost = np.full(plan.n_clusters, np.nan)
-        self.status = np.full(plan.n_clusters, -1, dtype=np.int32)
-        self.stats = np.zeros((plan.n_clusters, 8), dtype=np.int32)   # CTK_STAT_* counters
+    def __init__(self, plan, allocate=True):
+        if allocate:
+            self.params_out = plan.params_in.copy()
+            self.cost = np.full(plan.n_clusters, np.nan)
+            self.status = np.full(plan.n_clusters, -1, dtype=np.int32)
+            self.stats = np.zeros((plan.n_clusters, 8), dtype=np.int32)   # CTK_STAT_* counters
 
     @property
     def iters(self):
@@ -128,8 +129,12 @@ def _solver_options(kwargs, compute_default):
 def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mode=None,
             param_val=None, constraints=None, bounds=None, pos_columns=None, t_column='frame',
             noise_size=None, threshold=None, max_iter=10, max_shift=1, max_rms_dev=1.,
-            residual_factor=100000., compute_error=False, **kwargs):
-    """Host half of ``refine_leastsq``: returns a :class:`Plan` (no GPU work)."""
+            residual_factor=100000., compute_error=False, frames_hook=None, empty=np.empty,
+            **kwargs):
+    """Host half of ``refine_leastsq``: returns a :class:`Plan` (no GPU work).  ``frames_hook`` is
+    called with a :class:`FrameInfo` as soon as the frames of the call are known, i.e. before the
+    clustering: ``refine_leastsq`` uses it to start the uploads while the host is still busy.
+    ``empty(shape, dtype)`` allocates the packed parameter table (pinned memory in production)."""
     lm_max_iter, compute_dtype, xtol, chord_tol = _solver_options(kwargs, 'float32')
     if pos_columns is None:
         pos_columns = guess_pos_columns(f)
@@ -162,8 +167,17 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
         raise NotImplementedError("mask radius (diameter // 2) must be within [1, %d]"
                                   % _lib.CTK_MAX_RADIUS)
     cons = _constraints.parse(constraints, ndim)
+    if len(f) == 0:
+        raise ValueError("no features to refine")
 
+    info = FrameInfo(source, f[t_column].values, ndim)
+    if frames_hook is not None:
+        frames_hook(info)
+
+    import time as _time
+    _t0 = _time.perf_counter()
     f, order = cluster_table(f, separation, pos_columns, t_column)     # refine.py:297 (a copy)
+    _t1 = _time.perf_counter()
     if param_val is not None:                                          # refine.py:300-302
         for col in param_val:
             f[col] = param_val[col]
@@ -176,7 +190,6 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
     plan.f, plan.ff = f, ff
     # column order of the parameter table follows ff.params, but positions are read from the
     # user's pos_columns (refine.py:345 reads ff.params; they coincide for the default names)
-    params = np.ascontiguousarray(f[ff.params].values, dtype=np.float64)
 
     # (frame, cluster) groups in the order of f.groupby(['frame', 'cluster'])     refine.py:336
     # ``order`` lists the rows by (frame, cluster), row order kept inside a cluster
@@ -190,17 +203,16 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
     starts = np.flatnonzero(new_group)
     plan.order = order
     plan.cluster_offset = np.concatenate((starts, [n])).astype(np.int32)
-    frame_numbers, frame_index = np.unique(frames_s[starts], return_inverse=True)
-    plan.frame_numbers = [int(x) if float(x).is_integer() else x for x in frame_numbers]
-    plan.cluster_frame = frame_index.astype(np.int32)
-    plan.params_in = np.ascontiguousarray(params[order])
+    plan.frame_numbers = info.numbers
+    plan.cluster_frame = np.searchsorted(info.sorted_numbers, frames_s[starts]).astype(np.int32)
+    params_in = empty((n, len(ff.params)), np.float64)
+    for j, col in enumerate(ff.params):                                # packed, group order
+        params_in[:, j] = f[col].values[order]
+    plan.params_in = params_in
     plan.frame_source = source
-
-    first = np.asarray(source[plan.frame_numbers[0]])
-    plan.frame_shape = tuple(first.shape)
-    if len(plan.frame_shape) != ndim:
-        raise ValueError("frames must have %d dimensions" % ndim)
-    plan.pixel_dtype = first.dtype if first.dtype in _lib.PIXEL_CODES else np.dtype(np.float64)
+    plan.frame_shape = info.shape
+    plan.pixel_dtype = info.dtype
+    plan.frame_info = info
 
     prob = _lib.Problem()
     prob.ndim, prob.isotropic, prob.family = ndim, int(isotropic), ff.family
@@ -230,7 +242,30 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
             for j in range(_lib.CTK_MAX_PARAMS):
                 dst[side][j] = table[side, j] if j < len(ff.params) else np.nan
     plan.problem = prob
+    plan.timing = dict(cluster_ms=1e3 * (_t1 - _t0), pack_ms=1e3 * (_time.perf_counter() - _t1))
     return plan
+
+
+class FrameInfo(object):
+    """The frames one call touches: source, sorted unique frame numbers, shape and pixel type."""
+
+    def __init__(self, source, frame_column, ndim):
+        frames = np.asarray(frame_column)
+        if len(frames) > 1 and np.all(frames[1:] >= frames[:-1]):
+            uniq = frames[np.concatenate(([True], frames[1:] != frames[:-1]))]
+        else:
+            uniq = np.unique(frames)
+        self.source = source
+        self.sorted_numbers = uniq
+        self.numbers = [int(x) if float(x).is_integer() else x for x in uniq]
+        first = np.asarray(source[self.numbers[0]])
+        self.shape = tuple(first.shape)
+        if len(self.shape) != ndim:
+            raise ValueError("frames must have %d dimensions" % ndim)
+        self.dtype = first.dtype if first.dtype in _lib.PIXEL_CODES else np.dtype(np.float64)
+        # attribute names shared with Plan, so that load_frame() serves both
+        self.frame_source, self.frame_shape, self.pixel_dtype = source, self.shape, self.dtype
+        self.frame_numbers = self.numbers
 
 
 def load_frame(plan, frame_no):
@@ -300,12 +335,25 @@ def finalize(plan, result):
 # --------------------------------------------------------------------------------------------------
 # device execution
 # --------------------------------------------------------------------------------------------------
-class DeviceSession(object):
-    """Device-side state of one plan: feature-level buffers stay resident for the whole call, frames
-    are uploaded in batches through pinned host memory.  torch is used for device memory and the
-    stream only; all arithmetic happens inside libctk (C ABI, include/ctk.h)."""
+_PINNED = {}          # cached pinned host buffers for the result download (not thread-safe)
 
-    def __init__(self, plan, device=None):
+
+def _pinned_buffer(torch, key, nbytes):
+    """Reusable pinned staging buffer: pinning costs ~0.6 ms per MB, a pageable device->host copy
+    runs at ~2 GB/s, a pinned one at ~50 GB/s (measured on the B200 boxes)."""
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        _PINNED[key] = buf
+    return buf
+
+
+class FrameSet(object):
+    """The frames of one call on the device: a table of frame pointers and the per-frame maxima.
+    ``upload_async`` enqueues the copies batch by batch on a copy stream and the ``ctk_frame_max``
+    launches behind them; nothing blocks the host, so clustering and packing run meanwhile."""
+
+    def __init__(self, info, device=None):
         import torch
         self.torch = torch
         self.lib = _lib.load()
@@ -314,29 +362,133 @@ class DeviceSession(object):
                                "there is no CPU fallback")
         self.dev = (torch.device('cuda', torch.cuda.current_device()) if device is None
                     else torch.device(device))
-        self.plan = plan
-        self.sizes = plan.cluster_sizes()
-        self.n_frames = len(plan.frame_numbers)
-        self.n_pixels = int(np.prod(plan.frame_shape))
-        self.frame_bytes = self.n_pixels * np.dtype(plan.pixel_dtype).itemsize
-        self.shape_arr = (_lib.ctypes.c_int64 * 3)(
-            *(list(plan.frame_shape) + [1] * (3 - len(plan.frame_shape))))
+        self.info = info
+        self.n_frames = len(info.numbers)
+        self.n_pixels = int(np.prod(info.shape))
+        self.frame_bytes = self.n_pixels * np.dtype(info.dtype).itemsize
+        self.pixel_code = _lib.PIXEL_CODES[np.dtype(info.dtype)]
         self.torch_dtype = {
             np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.uint16,
             np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
             np.dtype(np.int16): torch.int16, np.dtype(np.int32): torch.int32,
-        }[np.dtype(plan.pixel_dtype)]
-        self.first_cluster_of_frame = np.searchsorted(plan.cluster_frame,
-                                                      np.arange(self.n_frames + 1))
+        }[np.dtype(info.dtype)]
+        self.launches = 0
+        self.h2d_bytes = 0
+        self.tensors = []                 # keeps the uploaded batches alive
+        with torch.cuda.device(self.dev):
+            self.d_ptrs = torch.zeros(self.n_frames, dtype=torch.int64, device=self.dev)
+            self.d_fmax = torch.empty(self.n_frames, dtype=torch.float64, device=self.dev)
+
+    def stream_ptr(self):
+        return _lib.ctypes.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _direct_view(self, f0, f1):
+        """Zero-copy host view of frames f0..f1-1 when the reader is backed by one contiguous array
+        of the right type (``reader.stack``); pinned memory then goes to the device by DMA."""
+        src = self.info.source
+        stack = getattr(src, 'stack', None)
+        first = getattr(src, 'first_frame', 0)
+        if not isinstance(stack, np.ndarray) or stack.dtype != self.info.dtype:
+            return None
+        if stack.shape[1:] != tuple(self.info.shape) or not stack.flags.c_contiguous:
+            return None
+        idx = np.asarray(self.info.numbers[f0:f1], dtype=np.int64) - first
+        if idx[0] < 0 or idx[-1] >= len(stack) or np.any(np.diff(idx) != 1):
+            return None
+        return stack[idx[0]:idx[-1] + 1]
+
+    def register(self, d_frames, f0):
+        """Frames f0 .. f0+n-1 are resident in ``d_frames`` [n, *frame_shape]."""
+        n = int(d_frames.shape[0])
+        ptrs = d_frames.data_ptr() + self.frame_bytes * np.arange(n, dtype=np.int64)
+        self.d_ptrs[f0:f0 + n] = self.torch.from_numpy(ptrs).to(self.dev)
+        self.tensors.append(d_frames)
+
+    def launch_frame_max(self, f0, n, events=None):
+        if events is not None:
+            start, stop = (self.torch.cuda.Event(enable_timing=True) for _ in range(2))
+            start.record()
+        _lib.check(self.lib.ctk_frame_max(self.d_ptrs.data_ptr() + 8 * f0, n, self.n_pixels,
+                                          self.pixel_code, self.d_fmax.data_ptr() + 8 * f0,
+                                          self.stream_ptr()), "ctk_frame_max")
+        self.launches += 1
+        if events is not None:
+            stop.record()
+            events.append(("frame_max", start, stop))
+
+    def upload_async(self):
+        """Allocate the device frames, upload the pointer table once (the only host-synchronous
+        step, done while the device is idle), then enqueue copy -> frame max per batch."""
+        torch = self.torch
+        per_batch = max(1, min(self.n_frames, _FRAME_BATCH_BYTES // max(self.frame_bytes, 1)))
+        cuts = list(range(0, self.n_frames, per_batch)) + [self.n_frames]
+        with torch.cuda.device(self.dev):
+            compute = torch.cuda.current_stream(self.dev)
+            copy_stream = torch.cuda.Stream(device=self.dev)
+            batches, ptrs = [], np.empty(self.n_frames, dtype=np.int64)
+            for f0, f1 in zip(cuts[:-1], cuts[1:]):
+                d_frames = torch.empty((f1 - f0,) + tuple(self.info.shape), dtype=self.torch_dtype,
+                                       device=self.dev)
+                ptrs[f0:f1] = d_frames.data_ptr() + self.frame_bytes * np.arange(f1 - f0, dtype=np.int64)
+                batches.append(d_frames)
+            self.d_ptrs.copy_(torch.from_numpy(ptrs))
+            self.tensors.extend(batches)
+            copy_stream.wait_stream(compute)
+            staging = None
+            for d_frames, f0, f1 in zip(batches, cuts[:-1], cuts[1:]):
+                n = f1 - f0
+                view = self._direct_view(f0, f1)
+                if view is None:
+                    if staging is None:
+                        staging = torch.empty((per_batch,) + tuple(self.info.shape),
+                                              dtype=self.torch_dtype, pin_memory=True)
+                    host = staging.numpy()
+                    copy_stream.synchronize()        # the previous batch has left the staging buffer
+                    for k in range(f0, f1):
+                        host[k - f0] = load_frame(self.info, self.info.numbers[k])
+                    src = staging[:n]
+                else:
+                    src = torch.from_numpy(view)
+                with torch.cuda.stream(copy_stream):
+                    d_frames.copy_(src, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(copy_stream)
+                self.h2d_bytes += n * self.frame_bytes
+                compute.wait_event(done)
+                self.launch_frame_max(f0, n)
+            if staging is not None:
+                copy_stream.synchronize()
+        return self
+
+
+class DeviceSession(object):
+    """Device-side state of one plan.  torch is used for device memory, streams and events only;
+    all arithmetic happens inside libctk (C ABI, include/ctk.h).
+
+    Everything is enqueued asynchronously on the current stream: one refine launch per size class
+    over all clusters of the call (work ids: expensive clusters first), no host synchronisation
+    until the results are downloaded.  Clusters whose pixel lists overflowed their size class
+    (status TOO_LARGE) are relaunched once with a larger capacity."""
+
+    def __init__(self, plan, device=None, frames=None):
+        self.frames = frames if frames is not None else FrameSet(plan.frame_info, device)
+        torch = self.torch = self.frames.torch
+        self.lib = self.frames.lib
+        self.dev = self.frames.dev
+        self.plan = plan
+        self.sizes = plan.cluster_sizes()
+        self.n_frames = self.frames.n_frames
+        self.shape_arr = (_lib.ctypes.c_int64 * 3)(
+            *(list(plan.frame_shape) + [1] * (3 - len(plan.frame_shape))))
         self.launches = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
-        self.host_status = np.full(plan.n_clusters, -1, dtype=np.int32)
         with torch.cuda.device(self.dev):
             dev = self.dev
             self.workspace = torch.empty(int(self.lib.ctk_refine_workspace_bytes()),
                                          dtype=torch.uint8, device=dev)
             self.d_offset = self._up(plan.cluster_offset)
+            self.d_cframe = self._up(plan.cluster_frame)
             self.d_params = self._up(plan.params_in)
             self.d_lo = self._up(plan.bounds_lo) if plan.bounds_lo is not None else None
             self.d_hi = self._up(plan.bounds_hi) if plan.bounds_hi is not None else None
@@ -348,71 +500,35 @@ class DeviceSession(object):
     def _up(self, array):
         t = self.torch.from_numpy(np.ascontiguousarray(array))
         self.h2d_bytes += t.numel() * t.element_size()
-        return t.to(self.dev, non_blocking=False)
+        return t.to(self.dev, non_blocking=t.is_pinned())
 
     def stream_ptr(self):
         return _lib.ctypes.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
 
-    def attach_frames(self, d_frames, f0):
-        """Describe a batch of frames already resident on the device: ``d_frames`` is a torch
-        tensor [n, *frame_shape] holding frames f0 .. f0 + n - 1 of the plan."""
-        torch = self.torch
-        n = int(d_frames.shape[0])
-        ptrs = d_frames.data_ptr() + self.frame_bytes * np.arange(n, dtype=np.int64)
-        batch = dict(frames=d_frames, f0=f0, n=n, d_ptrs=self._up(ptrs),
-                     d_fmax=torch.empty(n, dtype=torch.float64, device=self.dev),
-                     d_cframe=self._up(self.plan.cluster_frame - f0),
-                     c0=int(self.first_cluster_of_frame[f0]),
-                     c1=int(self.first_cluster_of_frame[f0 + n]))
-        ids = np.arange(batch['c0'], batch['c1'])
-        batch['bins'] = [(cap, sel, self._up(sel)) for cap, sel in bin_clusters(self.sizes, ids)]
-        return batch
+    def schedule(self):
+        """Work ids of every size class, concatenated and uploaded once: -> list of
+        (capacity, start, count) slices.  Inside a class the expensive clusters come first."""
+        sizes = self.sizes
+        caps = np.asarray(_BINS)
+        cls = np.searchsorted(caps, sizes)                     # size class of every cluster
+        runnable = cls < len(caps)
+        key = cls.astype(np.int64) * 64 + (63 - np.minimum(sizes, 63))
+        ids = np.flatnonzero(runnable)
+        ids = ids[np.argsort(key[ids], kind='stable')]
+        self.d_work = self._up(ids.astype(np.int32))
+        group = cls[ids]
+        cut = np.flatnonzero(np.concatenate(([True], group[1:] != group[:-1], [True])))
+        self.never_run = np.flatnonzero(~runnable)
+        return [(int(caps[group[a]]), int(a), int(b - a)) for a, b in zip(cut[:-1], cut[1:])]
 
-    def _direct_view(self, f0, f1):
-        """Zero-copy host view of frames f0..f1-1 when the reader is backed by one contiguous array
-        of the right type (``reader.stack``); pinned memory then goes to the device by DMA."""
-        src = self.plan.frame_source
-        stack = getattr(src, 'stack', None)
-        first = getattr(src, 'first_frame', 0)
-        numbers = self.plan.frame_numbers[f0:f1]
-        if not isinstance(stack, np.ndarray) or stack.dtype != self.plan.pixel_dtype:
-            return None
-        if stack.shape[1:] != tuple(self.plan.frame_shape) or not stack.flags.c_contiguous:
-            return None
-        idx = np.asarray(numbers, dtype=np.int64) - first
-        if idx[0] < 0 or idx[-1] >= len(stack) or np.any(np.diff(idx) != 1):
-            return None
-        return stack[idx[0]:idx[-1] + 1]
-
-    def upload_frames(self, f0, f1, staging=None):
-        """Copy frames f0..f1-1 of the plan's source to the device: straight from the reader's
-        array when it has one, else frame by frame through a pinned staging buffer."""
-        torch = self.torch
-        n = f1 - f0
-        view = self._direct_view(f0, f1)
-        if view is not None:
-            d_frames = torch.from_numpy(view).to(self.dev, non_blocking=True)
-            self.h2d_bytes += n * self.frame_bytes
-            return self.attach_frames(d_frames, f0), staging
-        if staging is None or staging.shape[0] < n:
-            staging = torch.empty((n,) + tuple(self.plan.frame_shape), dtype=self.torch_dtype,
-                                  pin_memory=True)
-        view = staging.numpy()
-        for k in range(f0, f1):
-            view[k - f0] = load_frame(self.plan, self.plan.frame_numbers[k])
-        d_frames = staging[:n].to(self.dev, non_blocking=True)
-        self.h2d_bytes += n * self.frame_bytes
-        return self.attach_frames(d_frames, f0), staging
-
-    def _launch(self, batch, cap, ids, d_ids, events=None):
-        prob = self.plan.problem
+    def launch_refine(self, cap, work_ptr, count, events=None):
         if events is not None:
             start, stop = (self.torch.cuda.Event(enable_timing=True) for _ in range(2))
             start.record()
         _lib.check(self.lib.ctk_refine_batch(
-            _lib.ctypes.byref(prob), batch['d_ptrs'].data_ptr(), self.shape_arr,
-            batch['d_fmax'].data_ptr(), len(ids), d_ids.data_ptr(), int(cap),
-            batch['d_cframe'].data_ptr(), self.d_offset.data_ptr(), self.d_params.data_ptr(),
+            _lib.ctypes.byref(self.plan.problem), self.frames.d_ptrs.data_ptr(), self.shape_arr,
+            self.frames.d_fmax.data_ptr(), count, work_ptr, int(cap), self.d_cframe.data_ptr(),
+            self.d_offset.data_ptr(), self.d_params.data_ptr(),
             self.d_lo.data_ptr() if self.d_lo is not None else None,
             self.d_hi.data_ptr() if self.d_hi is not None else None, self.d_out.data_ptr(),
             self.d_cost.data_ptr(), self.d_status.data_ptr(), self.d_stats.data_ptr(),
@@ -422,92 +538,79 @@ class DeviceSession(object):
             stop.record()
             events.append(("refine", start, stop))
 
-    def run_batch(self, batch, retry=True, events=None):
-        """Frame maxima, then one refine launch per size bin; clusters whose pixel lists overflowed
-        their bin (status TOO_LARGE) are relaunched once with a larger capacity.  ``events``: list
-        that receives (kind, start, stop) CUDA-event triples of every launch (bench.py)."""
-        prob = self.plan.problem
-        if events is not None:
-            start, stop = (self.torch.cuda.Event(enable_timing=True) for _ in range(2))
-            start.record()
-        _lib.check(self.lib.ctk_frame_max(batch['d_ptrs'].data_ptr(), batch['n'], self.n_pixels,
-                                          prob.pixel_dtype, batch['d_fmax'].data_ptr(),
-                                          self.stream_ptr()), "ctk_frame_max")
-        self.launches += 1
-        if events is not None:
-            stop.record()
-            events.append(("frame_max", start, stop))
-        for cap, ids, d_ids in batch['bins']:
-            self._launch(batch, cap, ids, d_ids, events)
-        ids = np.arange(batch['c0'], batch['c1'])
-        self.host_status[ids[self.sizes[ids] > _BINS[-1]]] = _lib.STATUS_TOO_LARGE
-        if not retry:
-            return
-        # one small device->host read decides whether anything has to be relaunched
-        status = self.d_status[batch['c0']:batch['c1']].cpu().numpy()
+    def run(self, slices, events=None):
+        """One refine launch per size class."""
+        for cap, start, count in slices:
+            self.launch_refine(cap, self.d_work.data_ptr() + 4 * start, count, events)
+
+    def retry_overflow(self):
+        """Relaunch, with a larger capacity, the clusters that overflowed their size class."""
+        status = self.d_status.cpu().numpy()
         self.d2h_bytes += status.nbytes
-        over = ids[(status == _lib.STATUS_TOO_LARGE) & (self.sizes[ids] <= _BINS[-1])]
+        over = np.flatnonzero((status == _lib.STATUS_TOO_LARGE) & (self.sizes <= _BINS[-1]))
+        self.retry_ids = []
         for cap in _BINS:
-            sel = over[(self.sizes[over] <= cap)]
+            sel = over[self.sizes[over] <= cap]
             over = over[self.sizes[over] > cap]
             bigger = [c for c in _BINS if c > cap]
             if len(sel) and bigger:
-                sel = np.ascontiguousarray(sel, dtype=np.int32)
-                self._launch(batch, bigger[min(1, len(bigger) - 1)], sel, self._up(sel))
+                d_sel = self._up(sel.astype(np.int32))
+                self.retry_ids.append(d_sel)
+                self.launch_refine(bigger[min(1, len(bigger) - 1)], d_sel.data_ptr(), len(sel))
 
-    def download(self):
-        result = Result(self.plan)
-        self.torch.cuda.current_stream(self.dev).synchronize()
-        result.params_out = self.d_out.cpu().numpy()
-        result.cost = self.d_cost.cpu().numpy()
-        status = self.d_status.cpu().numpy()
-        result.status = np.where(self.host_status == _lib.STATUS_TOO_LARGE, self.host_status, status)
-        result.stats = self.d_stats.cpu().numpy()
-        self.d2h_bytes += (result.params_out.nbytes + result.cost.nbytes + status.nbytes
-                           + result.stats.nbytes)
-        # clusters that never ran (too many features) keep their input parameters
-        never = np.repeat(result.status == _lib.STATUS_TOO_LARGE, self.sizes)
-        result.params_out[never] = self.plan.params_in[never]
+    def download(self, want_stats=True):
+        """Results through cached pinned buffers.  The arrays of the returned Result are views of
+        those buffers: they stay valid until the next ``download`` of this process."""
+        torch = self.torch
+        plan = self.plan
+        result = Result(plan, allocate=False)
+        result.stats = None
+        stream = torch.cuda.current_stream(self.dev)
+        pieces = [("params", self.d_out, np.float64, plan.params_in.shape),
+                  ("cost", self.d_cost, np.float64, (plan.n_clusters,)),
+                  ("status", self.d_status, np.int32, (plan.n_clusters,))]
+        if want_stats:
+            pieces.append(("stats", self.d_stats, np.int32, (plan.n_clusters, 8)))
+        out = {}
+        for name, tensor, dtype, shape in pieces:
+            nbytes = tensor.numel() * tensor.element_size()
+            buf = _pinned_buffer(torch, name, nbytes)[:nbytes]
+            buf.copy_(tensor.view(torch.uint8).reshape(-1), non_blocking=True)
+            out[name] = buf.numpy().view(dtype).reshape(shape)
+            self.d2h_bytes += nbytes
+        stream.synchronize()
+        result.params_out, result.cost, result.status = out["params"], out["cost"], out["status"]
+        if want_stats:
+            result.stats = out["stats"]
+        if len(self.never_run):               # too many features for the kernel: never launched
+            result.status[self.never_run] = _lib.STATUS_TOO_LARGE
+            rows = np.repeat(result.status == _lib.STATUS_TOO_LARGE, self.sizes)
+            result.params_out[rows] = plan.params_in[rows]
         return result
 
 
-def execute_cuda(plan, device=None):
-    """Run the plan on the current (or given) CUDA device through the C ABI.
-
-    Frames go to the device in batches on a separate copy stream, so the upload of batch k+1
-    overlaps the kernels of batch k: straight from the reader's array when it has one (a DMA when
-    that memory is pinned), else frame by frame through a pinned staging buffer."""
-    session = DeviceSession(plan, device)
+def execute_cuda(plan, device=None, want_stats=True, frames=None):
+    """Run the plan on the current (or given) CUDA device through the C ABI.  ``frames``: a
+    :class:`FrameSet` whose uploads were started earlier (else they are started here)."""
+    import time as _time
+    _t0 = _time.perf_counter()
+    if frames is None:
+        frames = FrameSet(plan.frame_info, device).upload_async()
+    session = DeviceSession(plan, frames=frames)
     torch = session.torch
-    per_batch = max(1, min(session.n_frames, _FRAME_BATCH_BYTES // max(session.frame_bytes, 1)))
     with torch.cuda.device(session.dev):
-        compute = torch.cuda.current_stream(session.dev)
-        direct = session._direct_view(0, session.n_frames) is not None
-        if direct:
-            copy_stream = torch.cuda.Stream(device=session.dev)
-            pending = []
-            for f0 in range(0, session.n_frames, per_batch):
-                f1 = min(session.n_frames, f0 + per_batch)
-                with torch.cuda.stream(copy_stream):
-                    view = session._direct_view(f0, f1)
-                    d_frames = torch.from_numpy(view).to(session.dev, non_blocking=True)
-                    done = torch.cuda.Event()
-                    done.record(copy_stream)
-                session.h2d_bytes += (f1 - f0) * session.frame_bytes
-                pending.append((f0, d_frames, done))
-            for f0, d_frames, done in pending:
-                compute.wait_event(done)
-                d_frames.record_stream(compute)
-                session.run_batch(session.attach_frames(d_frames, f0))
-        else:
-            staging = None
-            for f0 in range(0, session.n_frames, per_batch):
-                f1 = min(session.n_frames, f0 + per_batch)
-                batch, staging = session.upload_frames(f0, f1, staging)
-                session.run_batch(batch)
-                compute.synchronize()                    # staging is reused by the next batch
-        result = session.download()
+        slices = session.schedule()
+        _t1 = _time.perf_counter()
+        session.run(slices)
+        _t2 = _time.perf_counter()
+        session.retry_overflow()
+        _t3 = _time.perf_counter()
+        result = session.download(want_stats)
+    session.launches += frames.launches
+    session.h2d_bytes += frames.h2d_bytes
     result.session = session
+    result.timing = dict(session_ms=1e3 * (_t1 - _t0), enqueue_ms=1e3 * (_t2 - _t1),
+                         wait_ms=1e3 * (_t3 - _t2), download_ms=1e3 * (_time.perf_counter() - _t3))
     return result
 
 
@@ -534,11 +637,20 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
     """
     import time
     t0 = time.perf_counter()
+    started = []          # the uploads start as soon as the frames are known, before the clustering
+
+    def pinned_empty(shape, dtype):
+        import torch
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        return _pinned_buffer(torch, "params_in", nbytes)[:nbytes].numpy().view(dtype).reshape(shape)
+
     plan = prepare(f, reader, diameter, separation, fit_function, param_mode, param_val,
                    constraints, bounds, pos_columns, t_column, noise_size, threshold, max_iter,
-                   max_shift, max_rms_dev, residual_factor, compute_error, **kwargs)
+                   max_shift, max_rms_dev, residual_factor, compute_error,
+                   frames_hook=lambda info: started.append(FrameSet(info).upload_async()),
+                   empty=pinned_empty, **kwargs)
     t1 = time.perf_counter()
-    result = execute_cuda(plan)
+    result = execute_cuda(plan, want_stats=False, frames=started[0])
     t2 = time.perf_counter()
     out = finalize(plan, result)
     t3 = time.perf_counter()
@@ -546,7 +658,7 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
     LAST_CALL.update(h2d_bytes=result.session.h2d_bytes, d2h_bytes=result.session.d2h_bytes,
                      launches=result.session.launches,
                      phases_ms=dict(prepare=1e3 * (t1 - t0), device=1e3 * (t2 - t1),
-                                    finalize=1e3 * (t3 - t2)))
+                                    finalize=1e3 * (t3 - t2), **plan.timing, **result.timing))
     return out
 
 

@@ -37,7 +37,9 @@ def _worker(rank, world, port, out_dir):
     import torch.distributed as dist
     import emul_backend
     from clustertracking_b200 import parallel, refine
-    refine.execute_cuda = lambda plan, device=None: _with_session(emul_backend.execute(plan))
+    refine.FrameSet = _NoFrames          # no GPU here: the emulated solver reads the host frames
+    refine._pinned_buffer = lambda torch, key, nbytes: torch.empty(max(nbytes, 1), dtype=torch.uint8)
+    refine.execute_cuda = lambda plan, device=None, **kw: _with_session(emul_backend.execute(plan))
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank,
                             world_size=world)
     reader, f0 = _video()
@@ -46,12 +48,21 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+class _NoFrames(object):
+    def __init__(self, info, device=None):
+        pass
+
+    def upload_async(self):
+        return self
+
+
 class _Session(object):
     h2d_bytes = d2h_bytes = launches = 0
 
 
 def _with_session(result):
     result.session = _Session()
+    result.timing = {}
     return result
 
 
