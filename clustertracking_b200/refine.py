@@ -29,6 +29,30 @@ _FRAME_BATCH_BYTES = 128 << 20        # frames per upload batch (uploads overlap
 _CHORD_TOL = float(os.environ.get('CTK_CHORD_TOL', 0.02))
 
 
+_THREADS = None
+
+
+def _parallel(fn, items):
+    """Run ``fn`` over ``items`` on a small thread pool (numpy's take/put loops release the GIL)."""
+    global _THREADS
+    items = list(items)
+    if len(items) < 2:
+        for item in items:
+            fn(item)
+        return
+    if _THREADS is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _THREADS = ThreadPoolExecutor(min(8, os.cpu_count() or 1))
+    list(_THREADS.map(fn, items))
+
+
+def _spans(n, target=1 << 18):
+    """Row ranges of about ``target`` rows."""
+    k = max(1, min(8, n // target))
+    cuts = np.linspace(0, n, k + 1).astype(np.int64)
+    return list(zip(cuts[:-1], cuts[1:]))
+
+
 class Plan(object):
     """Everything ``refine_leastsq`` knows after the host-side preparation; plain numpy.
 
@@ -206,8 +230,15 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
     plan.frame_numbers = info.numbers
     plan.cluster_frame = np.searchsorted(info.sorted_numbers, frames_s[starts]).astype(np.int32)
     params_in = empty((n, len(ff.params)), np.float64)
-    for j, col in enumerate(ff.params):                                # packed, group order
-        params_in[:, j] = f[col].values[order]
+    columns = [np.asarray(f[col].values, dtype=np.float64) for col in ff.params]
+
+    def gather(span):                                                  # packed, group order
+        a, b = span
+        rows = order[a:b]
+        for j, col in enumerate(columns):
+            params_in[a:b, j] = col[rows]
+
+    _parallel(gather, _spans(n))
     plan.params_in = params_in
     plan.frame_source = source
     plan.frame_shape = info.shape
@@ -311,10 +342,16 @@ def finalize(plan, result):
     sizes = plan.cluster_sizes()
     ok = result.status == 0
     block = np.empty((len(ff.params), len(f)), dtype=np.float64)
-    block[:, plan.order] = result.params_out.T
+    source = result.params_out
     if not ok.all():                       # belt and braces: failed clusters keep their input exactly
         rows = np.repeat(~ok, sizes)
-        block[:, plan.order[rows]] = plan.params_in[rows].T
+        source = source.copy()
+        source[rows] = plan.params_in[rows]
+
+    def scatter(j):
+        block[j, plan.order] = source[:, j]
+
+    _parallel(scatter, range(len(ff.params)))
     for j, col in enumerate(ff.params):
         f[col] = block[j]
     cost = np.empty(len(f), dtype=np.float64)
