@@ -37,7 +37,7 @@ class Problem(ctypes.Structure):
         ("max_rms_dev", ctypes.c_double), ("residual_factor", ctypes.c_double),
         ("xtol", ctypes.c_double), ("chord_tol", ctypes.c_double),
         ("constraint_mask", ctypes.c_int32),
-        ("reserved0", ctypes.c_int32), ("dimer_dist", ctypes.c_double * 3),
+        ("capacity_mode", ctypes.c_int32), ("dimer_dist", ctypes.c_double * 3),
         ("trimer_dist", ctypes.c_double * 3),
         ("bounds_abs", (ctypes.c_double * CTK_MAX_PARAMS) * 2),
         ("bounds_diff", (ctypes.c_double * CTK_MAX_PARAMS) * 2),

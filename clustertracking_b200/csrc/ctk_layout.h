@@ -83,7 +83,7 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
   // Capacities.  The largest launch class provisions for the rigorous worst case; smaller classes
   // provision for what clusters of that size typically need and rely on the relaunch of overflowing
   // clusters (status CTK_FAIL_TOO_LARGE) with a larger class.
-  const bool rigorous = n_max >= CTK_MAX_CLUSTER_FEATURES;
+  const bool rigorous = n_max >= CTK_MAX_CLUSTER_FEATURES || p.capacity_mode == 1;
   const int f_bound = mask_capacity(p.radius, nd);
   int f_typ = mask_typical(p.radius, nd) + 2;
   if (f_typ > f_bound) f_typ = f_bound;

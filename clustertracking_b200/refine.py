@@ -308,6 +308,15 @@ def load_frame(plan, frame_no):
     return np.ascontiguousarray(image, dtype=plan.pixel_dtype)
 
 
+def rigorous_problem(problem):
+    """Copy of the problem struct that sizes shared memory for the worst case (relaunches)."""
+    import ctypes
+    clone = _lib.Problem()
+    ctypes.memmove(ctypes.byref(clone), ctypes.byref(problem), ctypes.sizeof(_lib.Problem))
+    clone.capacity_mode = 1
+    return clone
+
+
 def bin_clusters(sizes, cluster_ids):
     """-> list of (capacity, ids) with ids sorted by descending size (expensive clusters first)."""
     out = []
@@ -322,16 +331,16 @@ def bin_clusters(sizes, cluster_ids):
 
 
 def run_bins(sizes, cluster_ids, status, launch):
-    """Launch every bin; clusters that overflowed their bin's capacity (status TOO_LARGE) are retried
-    once in the next larger bin.  ``launch(capacity, ids)`` must fill ``status[ids]``."""
+    """Launch every bin; clusters that overflowed their bin's typical-case capacity (status
+    TOO_LARGE) are relaunched once with rigorous capacities.  ``launch(capacity, ids, rigorous)``
+    must fill ``status[ids]``."""
     too_big = cluster_ids[sizes[cluster_ids] > _BINS[-1]]
     status[too_big] = _lib.STATUS_TOO_LARGE
     for cap, ids in bin_clusters(sizes, cluster_ids):
-        launch(cap, ids)
+        launch(cap, ids, False)
         retry = ids[status[ids] == _lib.STATUS_TOO_LARGE]
-        bigger = [c for c in _BINS if c > cap]
-        if len(retry) and bigger:
-            launch(bigger[min(1, len(bigger) - 1)], retry)
+        if len(retry):
+            launch(cap, retry, True)              # same class, rigorous capacities
 
 
 def finalize(plan, result):
@@ -505,7 +514,7 @@ class DeviceSession(object):
     Everything is enqueued asynchronously on the current stream: one refine launch per size class
     over all clusters of the call (work ids: expensive clusters first), no host synchronisation
     until the results are downloaded.  Clusters whose pixel lists overflowed their size class
-    (status TOO_LARGE) are relaunched once with a larger capacity."""
+    (status TOO_LARGE) are relaunched once with rigorous capacities."""
 
     def __init__(self, plan, device=None, frames=None):
         self.frames = frames if frames is not None else FrameSet(plan.frame_info, device)
@@ -548,7 +557,9 @@ class DeviceSession(object):
         sizes = self.sizes
         caps = np.asarray(_BINS)
         cls = np.searchsorted(caps, sizes)                     # size class of every cluster
-        runnable = cls < len(caps)
+        fits = np.array([self.lib.ctk_refine_shared_bytes(_lib.ctypes.byref(self.plan.problem),
+                                                          int(c)) > 0 for c in caps] + [False])
+        runnable = fits[np.minimum(cls, len(caps))]
         key = cls.astype(np.int64) * 64 + (63 - np.minimum(sizes, 63))
         ids = np.flatnonzero(runnable)
         ids = ids[np.argsort(key[ids], kind='stable')]
@@ -558,12 +569,13 @@ class DeviceSession(object):
         self.never_run = np.flatnonzero(~runnable)
         return [(int(caps[group[a]]), int(a), int(b - a)) for a, b in zip(cut[:-1], cut[1:])]
 
-    def launch_refine(self, cap, work_ptr, count, events=None):
+    def launch_refine(self, cap, work_ptr, count, events=None, problem=None):
         if events is not None:
             start, stop = (self.torch.cuda.Event(enable_timing=True) for _ in range(2))
             start.record()
         _lib.check(self.lib.ctk_refine_batch(
-            _lib.ctypes.byref(self.plan.problem), self.frames.d_ptrs.data_ptr(), self.shape_arr,
+            _lib.ctypes.byref(problem if problem is not None else self.plan.problem),
+            self.frames.d_ptrs.data_ptr(), self.shape_arr,
             self.frames.d_fmax.data_ptr(), count, work_ptr, int(cap), self.d_cframe.data_ptr(),
             self.d_offset.data_ptr(), self.d_params.data_ptr(),
             self.d_lo.data_ptr() if self.d_lo is not None else None,
@@ -586,14 +598,16 @@ class DeviceSession(object):
         self.d2h_bytes += status.nbytes
         over = np.flatnonzero((status == _lib.STATUS_TOO_LARGE) & (self.sizes <= _BINS[-1]))
         self.retry_ids = []
+        if not len(over):
+            return
+        rigorous = rigorous_problem(self.plan.problem)
         for cap in _BINS:
             sel = over[self.sizes[over] <= cap]
             over = over[self.sizes[over] > cap]
-            bigger = [c for c in _BINS if c > cap]
-            if len(sel) and bigger:
+            if len(sel) and self.lib.ctk_refine_shared_bytes(_lib.ctypes.byref(rigorous), cap) > 0:
                 d_sel = self._up(sel.astype(np.int32))
                 self.retry_ids.append(d_sel)
-                self.launch_refine(bigger[min(1, len(bigger) - 1)], d_sel.data_ptr(), len(sel))
+                self.launch_refine(cap, d_sel.data_ptr(), len(sel), problem=rigorous)
 
     def download(self, want_stats=True):
         """Results through cached pinned buffers.  The arrays of the returned Result are views of

@@ -98,7 +98,9 @@ typedef struct {
   double  chord_tol;          /* reuse the factorised normal matrix once the scaled step is
                                  below this (0 = never); only the gradient is refreshed then  */
   int32_t constraint_mask;    /* OR of CTK_CONSTRAINT_*                                     */
-  int32_t reserved0;
+  int32_t capacity_mode;      /* 0: size the per-cluster shared memory for the typical cluster of
+                                 the class (overflow -> CTK_FAIL_TOO_LARGE, relaunch with 1);
+                                 1: size it for the rigorous worst case                      */
   double  dimer_dist[3];      /* constraints.py:70-76, per axis */
   double  trimer_dist[3];     /* constraints.py:93-99, per axis */
   /* Bounds tables of FitFunctions.validate_bounds (fitfunc.py:492-533), [0] = lower, [1] = upper,
@@ -142,7 +144,8 @@ size_t ctk_refine_shared_bytes(const ctk_problem_t* prob, int32_t max_cluster_fe
  *   n_work          number of clusters to process in this launch
  *   d_work_ids      [n_work] cluster indices to process (NULL = 0..n_work-1); put expensive first
  *   max_cluster_features  capacity of this launch; clusters with more features (or whose pixel
- *                   lists overflow the derived capacity) get CTK_FAIL_TOO_LARGE
+ *                   lists overflow the derived capacity, see prob->capacity_mode) get
+ *                   CTK_FAIL_TOO_LARGE
  *   d_cluster_frame [n_clusters] index into d_frames
  *   d_cluster_offset[n_clusters + 1] feature ranges; features of a cluster are consecutive rows
  *   d_params_in     [n_features, P] float64 row-major, columns as in `modes`   (refine.py:345)

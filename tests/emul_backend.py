@@ -57,10 +57,11 @@ def execute(plan):
     shape = (ctypes.c_int64 * 3)(*(list(plan.frame_shape) + [1] * (3 - len(plan.frame_shape))))
     sizes = plan.cluster_sizes()
 
-    def launch(cap, ids):
+    def launch(cap, ids, rigorous):
         ids = np.ascontiguousarray(ids, dtype=np.int32)
+        problem = _refine.rigorous_problem(plan.problem) if rigorous else plan.problem
         code = handle.ctk_emul_refine_batch(
-            ctypes.byref(plan.problem), ptrs.ctypes.data, shape, fmax.ctypes.data, len(ids),
+            ctypes.byref(problem), ptrs.ctypes.data, shape, fmax.ctypes.data, len(ids),
             ids.ctypes.data, int(cap), plan.cluster_frame.ctypes.data,
             plan.cluster_offset.ctypes.data, plan.params_in.ctypes.data,
             plan.bounds_lo.ctypes.data if plan.bounds_lo is not None else None,

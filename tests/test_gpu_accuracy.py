@@ -1,0 +1,241 @@
+"""GPU restatement of the reference's own accuracy suite (clustertracking/tests/test_refine.py):
+12 model/geometry combinations x {noise-free, S/N 10, S/N 3} x {const, var signal, var size},
+dimers (free, shared signal, constrained), trimers (constrained), and the overlapping-features test
+of TestMultiple.  Images are drawn with ``clustertracking_b200.artificial`` (same drawing rule as the
+reference's generator), seeded; thresholds are the reference's (test_refine.py:37-50).
+Also size-independent properties on a full-size config-2 frame."""
+import zlib
+
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SIGNAL = 160
+NOISE_IMPERFECT, NOISE_NOISY = 16, 48
+CASES = {                                         # name: (feat, ndim, size, feat kwargs, pos_diff, size_dev)
+    'gauss2D': ('gauss', 2, 4., {}, 0.5, 0.2), 'gauss2D_a': ('gauss', 2, (5., 3.), {}, 0.5, 0.2),
+    'gauss3D': ('gauss', 3, 4., {}, 0.5, 0.2), 'gauss3D_a': ('gauss', 3, (3., 5., 5.), {}, 0.5, 0.2),
+    'disc2D': ('disc', 2, 4., dict(disc_size=0.5), 0.5, 0.2),
+    'disc2D_a': ('disc', 2, (5., 3.), dict(disc_size=0.5), 0.5, 0.2),
+    'disc3D': ('disc', 3, 4., dict(disc_size=0.5), 0.5, 0.2),
+    'disc3D_a': ('disc', 3, (3., 5., 5.), dict(disc_size=0.5), 0.5, 0.2),
+    'ring2D': ('ring', 2, 4., dict(thickness=0.2), 0.25, 0.05),
+    'ring2D_a': ('ring', 2, (5., 3.), dict(thickness=0.2), 0.25, 0.05),
+    'ring3D': ('ring', 3, 4., dict(thickness=0.2), 0.25, 0.05),
+    'ring3D_a': ('ring', 3, (3., 5., 5.), dict(thickness=0.2), 0.25, 0.05),
+}
+
+
+class Setup(object):
+    def __init__(self, name, seed):
+        from clustertracking_b200.utils import validate_tuple
+        self.feat, self.ndim, size, self.kw, self.pos_diff, self.size_dev = CASES[name]
+        self.size = validate_tuple(size, self.ndim)
+        self.diameter = tuple(int(s * 4) for s in self.size)        # test_refine.py:56
+        self.separation = tuple(d * 2 for d in self.diameter)
+        self.isotropic = len(set(self.diameter)) == 1
+        self.pos_columns = ['z', 'y', 'x'][-self.ndim:]
+        self.size_columns = ['size'] if self.isotropic else ['size_z', 'size_y', 'size_x'][-self.ndim:]
+        self.rng = np.random.RandomState(seed)
+        self.repeats = 20
+
+    def grid(self, separation):
+        n_side = int(self.repeats ** (1. / self.ndim) + 0.9999)
+        axes = np.meshgrid(*[np.arange(0, s * n_side, s) for s in separation], indexing='ij')
+        pos = np.array([a.ravel() for a in axes], dtype=float).T[:self.repeats] + self.separation
+        pos += self.rng.random_sample(pos.shape) - 0.5
+        shape = tuple(np.max(pos, axis=0).astype(int) + np.array(self.separation))
+        return pos, shape
+
+    def noisy(self, image, noise):
+        if noise > 0:
+            image = np.clip(image.astype(np.int64) + self.rng.poisson(noise, image.shape), 0, 255)
+        return image.astype(np.uint8)
+
+    def features(self, noise, signal_dev, size_dev):
+        """test_refine.py:84-127."""
+        from clustertracking_b200 import artificial
+        pos, shape = self.grid(self.separation)
+        n = len(pos)
+        signal = SIGNAL * (self.rng.uniform(1 - signal_dev, 1 + signal_dev, n) if signal_dev else np.ones(n))
+        scale = self.rng.uniform(1 - size_dev, 1 + size_dev, (n, 1)) if size_dev else np.ones((n, 1))
+        size = np.array([self.size]) * scale
+        image = np.zeros(shape, dtype=np.uint8)
+        for p, s, sz in zip(pos, signal, size):
+            artificial.draw_feature(image, p, tuple(sz), s, self.feat, **self.kw)
+        return self.noisy(image, noise), pos, signal, size
+
+    def clusters(self, cluster_size, noise, signal_dev):
+        """test_refine.py:129-187 with hard_radius 1."""
+        from clustertracking_b200 import artificial
+        separation = [int(sep + 2 * s) for sep, s in zip(self.separation, self.size)]
+        centres, shape = self.grid(separation)
+        n = len(centres)
+        signal = SIGNAL * (self.rng.uniform(1 - signal_dev, 1 + signal_dev, n) if signal_dev else np.ones(n))
+        image = np.zeros(shape, dtype=np.uint8)
+        coords = []
+        for c, s in zip(centres, signal):
+            angle = self.rng.uniform(0, 2 * np.pi, 1 if self.ndim == 2 else 3)
+            tmpl = np.dot(_TEMPLATES[self.ndim][cluster_size], _rotation(self.ndim, angle).T)
+            members = tmpl * np.array(self.size)[None, :] + c[None, :]
+            for p in members:
+                artificial.draw_feature(image, p, self.size, s, self.feat, **self.kw)
+            coords.extend(members)
+        return self.noisy(image, noise), np.array(coords), np.repeat(signal, cluster_size)
+
+    def start(self, pos, noise, cluster_size=None):
+        """test_refine.py:259-270 and 189-203: start points inside an ellipsoid of pos_diff*size."""
+        n = len(pos)
+        reach = np.array(self.size) * self.pos_diff
+        dev = (self.rng.random_sample((10 * n, self.ndim)) - 0.5) * reach * 2
+        dev = dev[np.sum((dev / reach) ** 2, axis=1) <= 1][:n]
+        f0 = pd.DataFrame(pos + dev, columns=self.pos_columns)
+        f0['signal'] = float(SIGNAL)
+        for col, s in zip(self.size_columns, self.size):
+            f0[col] = float(s)
+        f0['background'] = noise / 2
+        return f0
+
+    def refine(self, image, f0, **kwargs):
+        import clustertracking_b200 as ctb
+        out = ctb.refine_leastsq(f0, image, self.diameter, fit_function=self.feat,
+                                 param_val=dict(self.kw), pos_columns=self.pos_columns, **kwargs)
+        assert not np.isnan(out['cost'].values).any()
+        return out
+
+
+def _rotation(ndim, angle):
+    if ndim == 2:
+        c, s = np.cos(angle[0]), np.sin(angle[0])
+        return np.array([[c, -s], [s, c]])
+    s1, s2, s3 = np.sin(angle)
+    c1, c2, c3 = np.cos(angle)
+    return np.array([[c1 * c2, c1 * s2 * s3 - c3 * s1, s1 * s3 + c1 * c3 * s2],
+                     [c2 * s1, c1 * c3 + s1 * s2 * s3, c3 * s1 * s2 - c1 * s3],
+                     [-s2, c2 * s3, c2 * c3]])
+
+
+_TEMPLATES = {                                                     # artificial.py:180-194
+    2: {2: np.array([[0, -1], [0, 1]], float),
+        3: np.array([[0, 1], [-0.5 * np.sqrt(3), -0.5], [0.5 * np.sqrt(3), -0.5]]) * 2 / 3 * np.sqrt(3)},
+    3: {2: np.array([[0, 0, -1], [0, 0, 1]], float),
+        3: np.array([[0, 0, 2 / np.sqrt(3)], [-1, 0, -1 / np.sqrt(3)], [1, 0, -1 / np.sqrt(3)]])},
+}
+
+
+def _seed(*key):
+    return zlib.crc32(repr(key).encode()) % 100000
+
+
+def _rms(a):
+    return float(np.sqrt(np.mean(np.asarray(a) ** 2)))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("noise,precision", [(0, 0.01), (NOISE_IMPERFECT, 0.05), (NOISE_NOISY, 0.1)])
+@pytest.mark.parametrize("mode", ['const', 'var_signal', 'var_size', 'var'])
+def test_single_features(name, noise, precision, mode):
+    """test_refine.py:598-688."""
+    su = Setup(name, seed=_seed(name, noise, mode))
+    signal_dev = 0.2 if 'signal' in mode or mode == 'var' else 0.
+    size_dev = su.size_dev if 'size' in mode or mode == 'var' else 0.
+    image, pos, signal, size = su.features(noise, signal_dev, size_dev)
+    f0 = su.start(pos, noise)
+    pm = dict(signal='var' if signal_dev else 'const', size='var' if size_dev else 'const')
+    out = su.refine(image, f0, param_mode=pm)
+    assert _rms(out[su.pos_columns].values - pos) < precision
+    if noise == 0:
+        if signal_dev:
+            assert _rms(1 - out['signal'].values / signal) < 0.01
+        else:
+            assert _rms(1 - out['signal'].values / signal) < 1e-7           # const means const
+        if size_dev:
+            assert _rms(1 - out[su.size_columns].values / size) < 0.01
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("kind", ['dimer', 'dimer_shared_signal', 'dimer_constrained',
+                                  'trimer_constrained'])
+def test_clusters(name, kind):
+    """test_refine.py:690-751 (noise-free): free dimers, 'cluster' signal, constrained dimers/trimers."""
+    import clustertracking_b200 as ctb
+    su = Setup(name, seed=_seed(name, kind))
+    k = 3 if kind.startswith('trimer') else 2
+    image, pos, signal = su.clusters(k, 0, 0.2)
+    f0 = su.start(pos, 0)
+    kwargs = dict(param_mode=dict(signal='var', size='const'))
+    if kind == 'dimer_shared_signal':
+        kwargs = dict(param_mode=dict(signal='cluster', size='const'))
+    if kind.endswith('constrained'):
+        maker = ctb.constraints.dimer if k == 2 else ctb.constraints.trimer
+        kwargs['constraints'] = maker(2 * np.array(su.size), su.ndim)
+    out = su.refine(image, f0, **kwargs)
+    assert (out['cluster_size'].values <= k).all()
+    dev = out[su.pos_columns].values - pos
+    assert _rms(dev) < 0.01                                      # precision_perfect
+    if kind.endswith('constrained'):
+        p = out[su.pos_columns].values.reshape(-1, k, su.ndim)
+        for a in range(k):
+            for b in range(a + 1, k):
+                d = np.sqrt(np.sum(((p[:, a] - p[:, b]) / (2 * np.array(su.size))) ** 2, axis=1))
+                assert np.abs(d - 1).max() < 1e-6
+
+
+def test_multiple_overlapping():
+    """TestMultiple.test_multiple_simple_sparse / overlapping (test_refine.py:884-922): 7 px start
+    error, diameter 21, separation 24; every feature ends within 0.1 px of the truth."""
+    import clustertracking_b200 as ctb
+    from clustertracking_b200 import artificial
+    rng = np.random.RandomState(7)
+    for count, spacing in ((10, 24), (60, 15)):
+        pos = []
+        while len(pos) < count:
+            cand = rng.uniform(21, 256 - 21, 2)
+            if all(np.linalg.norm(cand - p) >= spacing for p in pos):
+                pos.append(cand)
+        pos = np.array(pos)
+        image = artificial.draw_features((256, 256), pos, 5.25, 200.)
+        f0 = pd.DataFrame(pos + rng.random_sample(pos.shape) * 7, columns=['y', 'x'])
+        f0['signal'] = 200.
+        f0['size'] = 5.25
+        out = ctb.refine_leastsq(f0, image, 21, 24)
+        ok = out['cluster_size'].values <= 32            # larger clusters fail loudly (documented)
+        assert np.isfinite(out['cost'].values[ok]).all()
+        assert np.isnan(out['cost'].values[~ok]).all()
+        assert np.abs(out[['y', 'x']].values[ok] - pos[ok]).max() < 0.1
+
+
+def test_full_size_frame_properties():
+    """Full-size config-2 frame (1024x1024, ~2100 features): every cluster converges; shifting image
+    and coordinates by whole pixels shifts the answer by exactly that amount (the pixel sets are
+    translation invariant).  (Refining a refined result is NOT idempotent, here or upstream: the
+    masks are re-centred on the new start points.)"""
+    import clustertracking_b200 as ctb
+    from clustertracking_b200 import artificial
+    frame, f0, truth = artificial.clustered_frame((1024, 1024), seed=11)
+    out = ctb.refine_leastsq(f0, frame, 11)
+    assert len(out) > 1900 and not np.isnan(out['cost'].values).any()
+    assert _rms(out[['y', 'x']].values - truth) < 0.1             # S/N ~ 15 data
+    shifted = np.zeros((1040, 1056), dtype=np.uint8)
+    shifted[16:, 32:] = frame
+    f1 = f0.copy()
+    f1['y'] += 16
+    f1['x'] += 32
+    moved = ctb.refine_leastsq(f1, shifted, 11)
+    assert np.abs(moved['y'].values - 16 - out['y'].values).max() < 2e-5
+    assert np.abs(moved['x'].values - 32 - out['x'].values).max() < 2e-5
+    assert np.array_equal(moved['cluster'].values, out['cluster'].values)
+
+
+def test_pixel_types_agree():
+    """uint8, uint16, float32 and float64 frames with the same values give the same fit."""
+    import clustertracking_b200 as ctb
+    from clustertracking_b200 import artificial
+    frame, f0, _ = artificial.clustered_frame((256, 256), seed=5)
+    ref = ctb.refine_leastsq(f0, frame, 11)
+    for dtype in (np.uint16, np.float32, np.float64, np.int16, np.int32):
+        out = ctb.refine_leastsq(f0, frame.astype(dtype), 11)
+        assert np.abs(out[['y', 'x', 'signal', 'cost']].values
+                      - ref[['y', 'x', 'signal', 'cost']].values).max() < 1e-6
