@@ -84,7 +84,9 @@ def _pool_workers():
     env = os.environ.get('CTK_FIND_WORKERS')
     if env is not None:
         return max(0, int(env))
-    return min(16, os.cpu_count() or 1)
+    # one process per GPU shares the host: split the cores between the local ranks
+    local_ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1') or 1))
+    return min(16, max(1, (os.cpu_count() or 1) // local_ranks))
 
 
 class _WorkerPool(object):
