@@ -9,8 +9,16 @@ namespace ctk {
 
 // Persistent warps, one cluster per warp at a time; clusters are handed out by an atomic counter so
 // that clusters of different cost do not leave the other warps of a block idle.
+#ifndef CTK_BLOCK_WARPS
+#define CTK_BLOCK_WARPS 4      // warps (clusters in flight) per block
+#endif
+#ifndef CTK_MIN_BLOCKS
+#define CTK_MIN_BLOCKS 4       // resident blocks per SM the register budget is sized for
+#endif
+
 template <class C>
-__global__ void __launch_bounds__(128, 4) refine_kernel(const BatchArgs a) {
+__global__ void __launch_bounds__(32 * CTK_BLOCK_WARPS, CTK_MIN_BLOCKS)
+refine_kernel(const BatchArgs a) {
   ClusterSolver<C> solver(a, (uint32_t) (threadIdx.x >> 5) * (uint32_t) a.lay.total);
   for (;;) {
     int w = 0;
@@ -42,7 +50,7 @@ int launch_refine(const BatchArgs& args, cudaStream_t stream, char* err, size_t 
              args.lay.n_max, per_warp, smem_max);
     return CTK_E_CAPACITY;
   }
-  int warps = 4;
+  int warps = CTK_BLOCK_WARPS;
   while (warps > 1 && warps * per_warp > smem_max / 2) warps >>= 1;   // keep >= 2 blocks per SM
   while (warps > 1 && warps * per_warp > smem_max) warps >>= 1;
   const int smem = warps * per_warp;

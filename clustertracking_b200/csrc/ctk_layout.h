@@ -118,6 +118,9 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
   lay->sidx_stride = ld_max * (ld_max + 1) / 2 + 2 * ld_max;
   lay->o_sidx = take(n_max * lay->sidx_stride * 4);
   lay->o_con = take(8 * 8);
+  lay->o_cmode = take(p.n_params * 4);
+  lay->o_cbase = take(p.n_params * 4);
+  lay->o_ctab = take(p.n_params * 6 * 8);
   lay->o_mc = take(n_max * 3 * 8);
   lay->o_fi = take(n_max * FI_STRIDE * 4);
   lay->o_fr = take(n_max * FR_STRIDE * rb);

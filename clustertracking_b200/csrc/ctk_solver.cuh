@@ -141,6 +141,8 @@ struct Layout {
   int o_sidx;              // [n_max, sidx_stride] scatter targets of a feature's local block
   int sidx_stride;
   int o_con;               // multipliers mu[3], distances[3], penalty weight
+  int o_cmode, o_cbase;    // [P] column modes / first variable of each column
+  int o_ctab;              // [P, 6] bounds tables (diff, rel, abs) x (lower, upper)
   int o_mc, o_fi, o_fr;
   int o_tab;      // aliases o_fe (tables are dead once the lists are built)
   int o_fe;
@@ -335,10 +337,10 @@ struct ClusterSolver {
 
 #ifdef CTK_EMUL
   CTK_DEV ClusterSolver(const BatchArgs& args, char* smem)
-      : a(args), lane(lane_id()), sm_(smem), cached_V(-1) {}
+      : a(args), lane(lane_id()), sm_(smem), cached_V(-1) { init_column_tables(); }
 #else
   CTK_DEV ClusterSolver(const BatchArgs& args, uint32_t smem_offset)
-      : a(args), lane(lane_id()), sm_off(smem_offset), cached_V(-1) {}
+      : a(args), lane(lane_id()), sm_off(smem_offset), cached_V(-1) { init_column_tables(); }
 #endif
 
   // ---- typed views ------------------------------------------------------------------------------
@@ -362,6 +364,9 @@ struct ClusterSolver {
   CTK_DEV int* CV() const { return reinterpret_cast<int*>(slice() + a.lay.o_cv); }
   CTK_DEV int* SIDX() const { return reinterpret_cast<int*>(slice() + a.lay.o_sidx); }
   CTK_DEV double* CON() const { return dvec(a.lay.o_con); }        // mu[0..2], dist[3..5]
+  CTK_DEV int* CMODE() const { return reinterpret_cast<int*>(slice() + a.lay.o_cmode); }
+  CTK_DEV int* CBASE() const { return reinterpret_cast<int*>(slice() + a.lay.o_cbase); }
+  CTK_DEV double* CTAB() const { return dvec(a.lay.o_ctab); }
   CTK_DEV double* MC() const { return dvec(a.lay.o_mc); }
   CTK_DEV int* FI() const { return reinterpret_cast<int*>(slice() + a.lay.o_fi); }
   CTK_DEV Real* FR() const { return reinterpret_cast<Real*>(slice() + a.lay.o_fr); }
@@ -412,61 +417,75 @@ struct ClusterSolver {
     }
   }
 
-  CTK_DEV double bound_low(double p, int c) const {
-    return bound_from_tables(p, a.prob.bounds_diff[0][c], a.prob.bounds_rel[0][c],
-                             a.prob.bounds_abs[0][c], 0);
-  }
-  CTK_DEV double bound_high(double p, int c) const {
-    return bound_from_tables(p, a.prob.bounds_diff[1][c], a.prob.bounds_rel[1][c],
-                             a.prob.bounds_abs[1][c], 1);
-  }
-
-  // ---- variables, start vector and bounds (refine.py:361-364, fitfunc.py:207-263, 552-558) ------
-  CTK_DEV_BIG int setup_variables() {
-    // variable numbering: columns in order; a 'var' column takes n entries, a 'cluster' column one
-    int v = 0;
-    int* cv = CV();
+  // Per-launch column tables in shared memory (modes and the bounds tables), filled once per warp:
+  // the per-cluster set-up then runs as plain loops over (feature, column) instead of code
+  // unrolled per column.
+  CTK_DEV void init_column_tables() {
+    int* cmode = CMODE();
+    double* ctab = CTAB();
 #pragma unroll
     for (int c = 0; c < P; ++c) {
-      const int m = mode(c);
-      for (int i = lane; i < n; i += CTK_WARP)
-        cv[i * P + c] = m == CTK_MODE_VAR ? v + i : (m == CTK_MODE_CLUSTER ? v : -1);
-      v += m == CTK_MODE_VAR ? n : (m == CTK_MODE_CLUSTER ? 1 : 0);
+      if (lane == 0) {
+        cmode[c] = a.prob.modes[c];
+        ctab[c * 6 + 0] = a.prob.bounds_diff[0][c]; ctab[c * 6 + 1] = a.prob.bounds_rel[0][c];
+        ctab[c * 6 + 2] = a.prob.bounds_abs[0][c];  ctab[c * 6 + 3] = a.prob.bounds_diff[1][c];
+        ctab[c * 6 + 4] = a.prob.bounds_rel[1][c];  ctab[c * 6 + 5] = a.prob.bounds_abs[1][c];
+      }
     }
-    V = v;
     shared_columns = 0;
 #pragma unroll
     for (int c = 1; c < P; ++c) shared_columns += mode(c) == CTK_MODE_CLUSTER ? 1 : 0;
+    warp_sync();
+  }
+
+  CTK_DEV_BIG int setup_variables() {
+    // variable numbering: columns in order; a 'var' column takes n entries, a 'cluster' column one
+    int* cv = CV();
+    const int* cmode = CMODE();
+    int* cbase = CBASE();
+    const double* ctab = CTAB();
+    int v = 0;
+    for (int c = 0; c < P; ++c) {
+      const int m = cmode[c];
+      if (lane == 0) cbase[c] = v;
+      v += m == CTK_MODE_VAR ? n : (m == CTK_MODE_CLUSTER ? 1 : 0);
+    }
+    V = v;
     if (V > a.lay.v_max || V > 255) return CTK_FAIL_TOO_LARGE;
+    warp_sync();
     const double* pin = a.params_in + (int64_t)feat0 * P;
     const bool tables = a.lo_in == nullptr;            // bounds from the problem's tables
     const double* lin = tables ? nullptr : a.lo_in + (int64_t)feat0 * P;
     const double* hin = tables ? nullptr : a.hi_in + (int64_t)feat0 * P;
-    bool bad = false;
-    for (int t = lane; t < n * P; t += CTK_WARP) bad |= !finite_d(pin[t]);
-    if (warp_any(bad)) return CTK_FAIL_NONFINITE;
-    warp_sync();
     double *x0 = X0(), *lo = LO(), *hi = HI();
-#pragma unroll
-    for (int c = 0; c < P; ++c) {
-      const int m = mode(c);
+    bool bad = false;
+    for (int t = lane; t < n * P; t += CTK_WARP) {
+      const int i = t / P, c = t - i * P;
+      const int m = cmode[c];
+      const double p = pin[t];
+      bad |= !finite_d(p);
+      cv[t] = m == CTK_MODE_VAR ? cbase[c] + i : (m == CTK_MODE_CLUSTER ? cbase[c] : -1);
       if (m == CTK_MODE_VAR) {
-        for (int i = lane; i < n; i += CTK_WARP) {
-          const int vi = cv[i * P + c];
-          x0[vi] = pin[i * P + c];
-          lo[vi] = tables ? bound_low(pin[i * P + c], c) : lin[i * P + c];
-          hi[vi] = tables ? bound_high(pin[i * P + c], c) : hin[i * P + c];
-        }
-      } else if (m == CTK_MODE_CLUSTER && lane == 0) {   // shared entry: mean start, widest bound
-        double s = 0., l = INFINITY, h = -INFINITY;
-        for (int i = 0; i < n; ++i) {
-          s += pin[i * P + c];
-          l = fmin(l, tables ? bound_low(pin[i * P + c], c) : lin[i * P + c]);
-          h = fmax(h, tables ? bound_high(pin[i * P + c], c) : hin[i * P + c]);
-        }
-        const int vi = cv[c];
-        x0[vi] = s / n; lo[vi] = l; hi[vi] = h;
+        const int vi = cbase[c] + i;
+        const double* tb = ctab + c * 6;
+        x0[vi] = p;
+        lo[vi] = tables ? bound_from_tables(p, tb[0], tb[1], tb[2], 0) : lin[t];
+        hi[vi] = tables ? bound_from_tables(p, tb[3], tb[4], tb[5], 1) : hin[t];
       }
+    }
+    if (warp_any(bad)) return CTK_FAIL_NONFINITE;
+    for (int c = lane; c < P; c += CTK_WARP) {
+      if (cmode[c] != CTK_MODE_CLUSTER) continue;       // shared entry: mean start, widest bound
+      const double* tb = ctab + c * 6;
+      double s = 0., l = INFINITY, h = -INFINITY;
+      for (int i = 0; i < n; ++i) {
+        const double p = pin[i * P + c];
+        s += p;
+        l = fmin(l, tables ? bound_from_tables(p, tb[0], tb[1], tb[2], 0) : lin[i * P + c]);
+        h = fmax(h, tables ? bound_from_tables(p, tb[3], tb[4], tb[5], 1) : hin[i * P + c]);
+      }
+      const int vi = cbase[c];
+      x0[vi] = s / n; lo[vi] = l; hi[vi] = h;
     }
     warp_sync();
     bad = false;
@@ -1047,12 +1066,12 @@ struct ClusterSolver {
       double dmax = 0.;
       for (int v = lane; v < V; v += CTK_WARP) dmax = fmax(dmax, (double) Kf[cs[v]]);
       dmax = warp_max_d(dmax);
-      const double floor_ = fmax(dmax * 1e-14, 1e-300);
+      const double floor_ = fmax(dmax * 1e-14, 1e-30);
       for (int v = lane; v < V; v += CTK_WARP) {
         const double g = rhs_full[v];
         const bool frozen = (x[v] <= lo[v] && g < 0.) || (x[v] >= hi[v] && g > 0.) || !(lo[v] < hi[v]);
         act[v] = frozen ? 1 : 0;
-        const double s = 1. / sqrt(fmax((double) Kf[cs[v]], floor_));
+        const double s = (double) fast_rsqrt((Real) fmax((double) Kf[cs[v]], floor_));
         sc[v] = s;
         d[v] = frozen ? 0. : g * s;
       }
@@ -1237,8 +1256,8 @@ struct ClusterSolver {
         xt[v] = t;
         const double s = t - x[v];
         d[v] = s;
-        const double scale = is_pos_var(v) ? 1. : fmax(1., fabs(x[v]));
-        worst = fmax(worst, fabs(s) / scale);
+        const float scale = is_pos_var(v) ? 1.f : fmaxf(1.f, fabsf((float) x[v]));
+        worst = fmax(worst, (double) (fabsf((float) s) / scale));
       }
       worst = warp_max_d(worst);
       warp_sync();
