@@ -11,6 +11,7 @@ import numpy as np
 
 CTK_MAX_PARAMS = 12
 CTK_MAX_CLUSTER_FEATURES = 32
+CTK_MAX_BIG_FEATURES = 256
 CTK_MAX_RADIUS = 30
 
 MODE_CONST, MODE_VAR, MODE_CLUSTER = 0, 1, 3
@@ -56,6 +57,7 @@ _PROTOTYPES = {
     "ctk_frame_max": (ctypes.c_int, [_vp, _i32, _i64, _i32, _vp, _vp]),
     "ctk_refine_workspace_bytes": (_sz, []),
     "ctk_refine_shared_bytes": (_sz, [ctypes.POINTER(Problem), _i32]),
+    "ctk_refine_workspace_bytes_for": (_sz, [ctypes.POINTER(Problem), _i32]),
     "ctk_refine_batch": (ctypes.c_int, [ctypes.POINTER(Problem), _vp, ctypes.POINTER(_i64), _vp,
                                         _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp]),

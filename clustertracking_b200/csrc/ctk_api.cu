@@ -97,10 +97,27 @@ int ctk_frame_max(const void* const* d_frames, int32_t n_frames, int64_t n_pixel
 
 size_t ctk_refine_workspace_bytes(void) { return 256; }
 
+namespace {
+// number of concurrently processed large clusters: bounded by 2 GiB of workspace
+int big_block_count(const ctk::Layout& lay) {
+  long long n = (2LL << 30) / (lay.total > 0 ? lay.total : 1);
+  return (int) (n < 4 ? 4 : (n > 148 ? 148 : n));
+}
+}  // namespace
+
+size_t ctk_refine_workspace_bytes_for(const ctk_problem_t* prob, int32_t max_cluster_features) {
+  if (!prob || ctk::validate_problem(*prob)) return 0;
+  ctk::Layout lay;
+  if (!ctk::compute_layout(*prob, max_cluster_features, &lay)) return 0;
+  if (max_cluster_features <= CTK_MAX_CLUSTER_FEATURES) return 256;
+  return 256 + (size_t) big_block_count(lay) * (size_t) lay.total;
+}
+
 size_t ctk_refine_shared_bytes(const ctk_problem_t* prob, int32_t max_cluster_features) {
   if (!prob || ctk::validate_problem(*prob)) return 0;
   ctk::Layout lay;
   if (!ctk::compute_layout(*prob, max_cluster_features, &lay)) return 0;
+  if (max_cluster_features > CTK_MAX_CLUSTER_FEATURES) return 0;   // no shared memory: workspace
   return lay.total <= 227 * 1024 ? (size_t) lay.total : 0;
 }
 
@@ -143,12 +160,18 @@ int ctk_refine_batch(const ctk_problem_t* prob, const void* const* d_frames,
   a.counter = static_cast<int32_t*>(d_workspace);
   if (!ctk::compute_layout(*prob, max_cluster_features, &a.lay))
     return fail(CTK_E_CAPACITY, "ctk_refine_batch: max_cluster_features %d out of range [1, %d]",
-                max_cluster_features, CTK_MAX_CLUSTER_FEATURES);
+                max_cluster_features, CTK_MAX_BIG_FEATURES);
+  const bool big = max_cluster_features > CTK_MAX_CLUSTER_FEATURES;
+  if (big) {
+    a.big_workspace = static_cast<char*>(d_workspace) + 256;
+    a.big_blocks = big_block_count(a.lay);
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CTK_CUDA(cudaMemsetAsync(d_workspace, 0, sizeof(int32_t), st));
   Launcher launcher{&a, st, 0};
-  bool found = prob->compute_dtype == CTK_COMPUTE_F64 ? ctk::dispatch_config<double>(*prob, launcher)
-                                                      : ctk::dispatch_config<float>(*prob, launcher);
+  bool found = prob->compute_dtype == CTK_COMPUTE_F64
+                   ? ctk::dispatch_config<double>(*prob, launcher, big)
+                   : ctk::dispatch_config<float>(*prob, launcher, big);
   if (!found) return fail(CTK_E_UNSUPPORTED, "ctk_refine_batch: no kernel instance for this problem");
   return launcher.result;
 }

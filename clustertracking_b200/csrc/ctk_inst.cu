@@ -19,4 +19,10 @@ CTK_INST_GEOM(true, false)
 CTK_INST_GEOM(false, true)
 CTK_INST_GEOM(true, true)
 #endif
+// large-cluster instances: every derivative slot, global-memory workspace
+#define CTK_INST_BIG(ND, ISO)                                                                 \
+  template int launch_refine<Config<CTK_INST_REAL, ND, ISO, CTK_INST_FAM, true,               \
+                                    CTK_INST_FAM != CTK_FAMILY_GAUSS, true> >(                \
+      const BatchArgs&, cudaStream_t, char*, size_t);
+CTK_INST_BIG(2, true) CTK_INST_BIG(2, false) CTK_INST_BIG(3, true) CTK_INST_BIG(3, false)
 }  // namespace ctk

@@ -44,6 +44,15 @@ int launch_refine(const BatchArgs& args, cudaStream_t stream, char* err, size_t 
   CTK_LAUNCH_CUDA(cudaGetDevice(&dev));
   CTK_LAUNCH_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   CTK_LAUNCH_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  auto kernel_big = refine_kernel<C>;
+  if (C::BIG) {
+    // large clusters: one warp per block, arrays in the global workspace (args.big_blocks slices)
+    int grid = args.big_blocks < args.n_work ? args.big_blocks : args.n_work;
+    if (grid < 1) grid = 1;
+    kernel_big<<<grid, 32, 0, stream>>>(args);
+    CTK_LAUNCH_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int per_warp = args.lay.total;
   if (per_warp > smem_max) {
     snprintf(err, err_len, "a cluster of %d features needs %d B of shared memory (limit %d B)",

@@ -66,9 +66,11 @@ inline int mask_typical(const int32_t* radius, int ndim) {
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // Fills `lay` for clusters of up to n_max features.  Returns false on an invalid request.
+// n_max > CTK_MAX_CLUSTER_FEATURES selects the large-cluster layout (global-memory workspace).
 inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
   memset(lay, 0, sizeof(*lay));
-  if (n_max < 1 || n_max > CTK_MAX_CLUSTER_FEATURES) return false;
+  if (n_max < 1 || n_max > CTK_MAX_BIG_FEATURES) return false;
+  const bool big = n_max > CTK_MAX_CLUSTER_FEATURES;
   const int nd = p.ndim;
   int v_max = 0;
   for (int c = 0; c < p.n_params; ++c) {
@@ -76,7 +78,7 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
     else if (p.modes[c] == CTK_MODE_CLUSTER) v_max += 1;
   }
   if (v_max < 1) v_max = 1;
-  if (v_max > 255) return false;                        // packed (row, column) bytes
+  if (v_max > (big ? 65535 : 255)) return false;        // packed (row, column) fields
   const int rb = p.compute_dtype == CTK_COMPUTE_F64 ? 8 : 4;
   lay->n_max = n_max;
   lay->v_max = v_max;
@@ -84,18 +86,25 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
   // provision for what clusters of that size typically need and rely on the relaunch of overflowing
   // clusters (status CTK_FAIL_TOO_LARGE) with a larger class.
   const bool rigorous = n_max >= CTK_MAX_CLUSTER_FEATURES || p.capacity_mode == 1;
+  const int entry_bytes = big ? 8 : 4;
+  lay->mask_words = big ? (n_max + 31) / 32 : 1;
   const int f_bound = mask_capacity(p.radius, nd);
   int f_typ = mask_typical(p.radius, nd) + 2;
   if (f_typ > f_bound) f_typ = f_bound;
   lay->f_cap = rigorous ? f_bound : f_typ;
   if (lay->f_cap > 16384) return false;
+  if (big && (long long) n_max * lay->f_cap > (1 << 24)) return false;
   lay->m_cap = n_max * lay->f_cap;
   if (!rigorous && n_max >= 3) lay->m_cap = (3 * n_max * lay->f_cap + 3) / 4 + 8;
-  if (lay->m_cap > 16384) lay->m_cap = 16384;          // pixel index is packed in 14 bits
+  if (!big && lay->m_cap > 16384) lay->m_cap = 16384;  // pixel index is packed in 14 bits
   lay->pair_cap = n_max > 1 ? n_max * lay->f_cap : 1;
   if (!rigorous && n_max >= 3) lay->pair_cap = (3 * n_max * lay->f_cap + 4) / 5;
   int np = n_max * (n_max - 1) / 2;
   lay->npair_cap = np < 1 ? 1 : (np < 4 * n_max ? np : 4 * n_max);
+  if (big) {                      // percolated clusters: several features per pixel are common
+    lay->pair_cap = 4 * lay->m_cap;
+    lay->npair_cap = np < 24 * n_max ? np : 24 * n_max;
+  }
   lay->tab_stride = 0;
   for (int k = 0; k < 3; ++k) {
     lay->tab_len[k] = k < nd ? 2 * p.radius[k] + 3 : 0;
@@ -112,7 +121,7 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
   lay->o_lo = take(v_max * 8);
   lay->o_hi = take(v_max * 8);
   lay->o_cs = take((v_max + 1) * 4);
-  lay->o_rc = take(v_max * (v_max + 1) / 2 * 2);
+  lay->o_rc = take(v_max * (v_max + 1) / 2 * (big ? 4 : 2));
   lay->o_cv = take(n_max * p.n_params * 4);
   const int ld_max = p.n_params - 1;
   lay->sidx_stride = ld_max * (ld_max + 1) / 2 + 2 * ld_max;
@@ -137,7 +146,9 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
   lay->o_L = take(v_max * (v_max + 1) / 2 * rb);
   lay->o_idg = take(v_max * rb);
   lay->o_pbits = scratch;
-  if (o - scratch < lay->m_cap * 4) o = align_up(scratch + lay->m_cap * 4, 16);
+  if (o - scratch < lay->m_cap * 4 * lay->mask_words)
+    o = align_up(scratch + lay->m_cap * 4 * lay->mask_words, 16);
+  lay->o_tmpw = take(big ? 32 * lay->mask_words * 4 : 16);
   // pixel lists
   const int tab_bytes = n_max * lay->tab_stride * 8;
   const int fe_bytes = n_max * lay->f_cap * rb;
@@ -146,7 +157,7 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
   lay->o_pval = take(lay->m_cap * px_bytes);
   lay->o_pr = take(lay->m_cap * (rb > 4 ? rb : 4));
   lay->o_pcrd = lay->o_pr;                 // box coordinates are dead once the lists exist
-  lay->o_flist = take(n_max * lay->f_cap * 4);
+  lay->o_flist = take(n_max * lay->f_cap * entry_bytes);
   lay->o_pairs = take(lay->pair_cap * 4);
   lay->o_phdr = take(lay->npair_cap * 16);
   lay->total = align_up(o, 128);
@@ -180,8 +191,23 @@ inline const char* validate_problem(const ctk_problem_t& p) {
 // Runs `fn.template operator()<Config>()` for the kernel instance matching the problem.
 // size_free / extra_free select the instances that carry derivative slots for those columns.
 template <class Real, class Fn>
-inline bool dispatch_config(const ctk_problem_t& p, Fn&& fn) {
+inline bool dispatch_config(const ctk_problem_t& p, Fn&& fn, bool big = false) {
   const int nd = p.ndim;
+  if (big) {
+    // large clusters: one instance per (geometry, family) that carries every derivative slot;
+    // constant columns are simply not scattered
+#define CTK_BIG_CASE(ND, ISO, FAM)                                                            \
+  if (nd == ND && (p.isotropic != 0) == ISO && p.family == FAM) {                             \
+    fn.template operator()<Config<Real, ND, ISO, FAM, true, FAM != CTK_FAMILY_GAUSS, true> >(); \
+    return true;                                                                              \
+  }
+#define CTK_BIG_GEOM(FAM) CTK_BIG_CASE(2, true, FAM) CTK_BIG_CASE(2, false, FAM)              \
+                          CTK_BIG_CASE(3, true, FAM) CTK_BIG_CASE(3, false, FAM)
+    CTK_BIG_GEOM(CTK_FAMILY_GAUSS) CTK_BIG_GEOM(CTK_FAMILY_RING) CTK_BIG_GEOM(CTK_FAMILY_DISC)
+#undef CTK_BIG_GEOM
+#undef CTK_BIG_CASE
+    return false;
+  }
   const int ns = p.isotropic ? 1 : nd;
   bool size_free = false;
   for (int k = 0; k < ns; ++k) size_free |= p.modes[2 + nd + k] != CTK_MODE_CONST;

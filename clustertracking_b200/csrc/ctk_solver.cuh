@@ -141,6 +141,8 @@ struct Layout {
   int o_sidx;              // [n_max, sidx_stride] scatter targets of a feature's local block
   int sidx_stride;
   int o_con;               // multipliers mu[3], distances[3], penalty weight
+  int mask_words;          // 32-bit words of the per-pixel feature mask (1 unless BIG)
+  int o_tmpw;              // [warp lanes, mask_words] staging of a pixel's mask words (BIG)
   int o_cmode, o_cbase;    // [P] column modes / first variable of each column
   int o_ctab;              // [P, 6] bounds tables (diff, rel, abs) x (lower, upper)
   int o_mc, o_fi, o_fr;
@@ -165,6 +167,21 @@ CTK_DEV uint32_t pack_entry(int p, int o0, int o1, int o2) {
 }
 CTK_DEV int entry_pixel(uint32_t e) { return (int)(e & 0x3fffu); }
 CTK_DEV int entry_off(uint32_t e, int k) { return (int)((e >> (14 + 6 * k)) & 0x3fu) - 32; }
+// large-cluster variant: 32-bit pixel index | three 8-bit offsets (biased +128)
+CTK_DEV uint64_t pack_entry64(int p, int o0, int o1, int o2) {
+  return (uint64_t)(uint32_t)p | ((uint64_t)(uint32_t)(o0 + 128) << 32) |
+         ((uint64_t)(uint32_t)(o1 + 128) << 40) | ((uint64_t)(uint32_t)(o2 + 128) << 48);
+}
+CTK_DEV int entry_pixel(uint64_t e) { return (int)(uint32_t)(e & 0xffffffffu); }
+CTK_DEV int entry_off(uint64_t e, int k) { return (int)((e >> (32 + 8 * k)) & 0xffu) - 128; }
+template <bool BIG> struct EntryOf { typedef uint32_t type; typedef uint16_t rc_type; };
+template <> struct EntryOf<true> { typedef uint64_t type; typedef uint32_t rc_type; };
+CTK_DEV uint16_t rc_pack(int r, int c, uint16_t) { return (uint16_t)(r | (c << 8)); }
+CTK_DEV uint32_t rc_pack(int r, int c, uint32_t) { return (uint32_t)r | ((uint32_t)c << 16); }
+CTK_DEV int rc_row(uint16_t v) { return v & 0xff; }
+CTK_DEV int rc_col(uint16_t v) { return v >> 8; }
+CTK_DEV int rc_row(uint32_t v) { return (int)(v & 0xffffu); }
+CTK_DEV int rc_col(uint32_t v) { return (int)(v >> 16); }
 
 // ------------------------------------------------------------------------------------------------
 // kernel arguments
@@ -186,6 +203,8 @@ struct BatchArgs {
   int32_t* status_out;
   int32_t* stats_out;        // [n_clusters, CTK_STATS] counters, see ctk.h
   int32_t* counter;
+  char* big_workspace;       // BIG kernels: one slice of lay.total bytes per block
+  int big_blocks;            // number of slices
   Layout lay;
 };
 
@@ -283,9 +302,13 @@ CTK_COLD double con_quadratic(const ConView v, const double* s) {
 }
 
 // compile-time configuration of a kernel instance
-template <class Real_, int ND_, bool ISO_, int FAM_, bool SZ_, bool EX_>
+template <class Real_, int ND_, bool ISO_, int FAM_, bool SZ_, bool EX_, bool BIG_ = false>
 struct Config {
   typedef Real_ Real;
+  // BIG: clusters of more than 32 features.  Same algorithm, but the per-cluster arrays live in a
+  // global-memory workspace instead of shared memory, the per-pixel feature mask has several
+  // words, and the packed indices are wider.
+  static const bool BIG = BIG_;
   static const int ND = ND_;
   static const bool ISO = ISO_;
   static const int FAM = FAM_;
@@ -301,6 +324,8 @@ struct Config {
 template <class C>
 struct ClusterSolver {
   typedef typename C::Real Real;
+  typedef typename EntryOf<C::BIG>::type Entry;
+  typedef typename EntryOf<C::BIG>::rc_type RcT;
   enum { ND = C::ND, P = C::P, LD = C::LD, LT = C::LT, NS = C::NS };
 
   // Kernel arguments BY VALUE: with every access at a compile-time index the compiler keeps them
@@ -316,6 +341,7 @@ struct ClusterSolver {
 #else
   uint32_t sm_off;
   CTK_DEV char* slice() const {
+    if (C::BIG) return a.big_workspace + (size_t) blockIdx.x * (size_t) a.lay.total;
     extern __shared__ __align__(128) char ctk_smem[];
     return ctk_smem + sm_off;
   }
@@ -360,7 +386,8 @@ struct ClusterSolver {
   CTK_DEV Real* Lm() const { return reinterpret_cast<Real*>(slice() + a.lay.o_L); }
   CTK_DEV Real* IDG() const { return reinterpret_cast<Real*>(slice() + a.lay.o_idg); }
   CTK_DEV int* CS() const { return reinterpret_cast<int*>(slice() + a.lay.o_cs); }
-  CTK_DEV uint16_t* RC() const { return reinterpret_cast<uint16_t*>(slice() + a.lay.o_rc); }
+  CTK_DEV RcT* RC() const { return reinterpret_cast<RcT*>(slice() + a.lay.o_rc); }
+  CTK_DEV int NW() const { return C::BIG ? a.lay.mask_words : 1; }
   CTK_DEV int* CV() const { return reinterpret_cast<int*>(slice() + a.lay.o_cv); }
   CTK_DEV int* SIDX() const { return reinterpret_cast<int*>(slice() + a.lay.o_sidx); }
   CTK_DEV double* CON() const { return dvec(a.lay.o_con); }        // mu[0..2], dist[3..5]
@@ -375,7 +402,7 @@ struct ClusterSolver {
   CTK_DEV Real* PR() const { return reinterpret_cast<Real*>(slice() + a.lay.o_pr); }
   CTK_DEV uint32_t* PBITS() const { return reinterpret_cast<uint32_t*>(slice() + a.lay.o_pbits); }
   CTK_DEV uint32_t* PCRD() const { return reinterpret_cast<uint32_t*>(slice() + a.lay.o_pcrd); }
-  CTK_DEV uint32_t* FLIST() const { return reinterpret_cast<uint32_t*>(slice() + a.lay.o_flist); }
+  CTK_DEV Entry* FLIST() const { return reinterpret_cast<Entry*>(slice() + a.lay.o_flist); }
   CTK_DEV uint32_t* PAIRS() const { return reinterpret_cast<uint32_t*>(slice() + a.lay.o_pairs); }
   CTK_DEV int* PHDR() const { return reinterpret_cast<int*>(slice() + a.lay.o_phdr); }
 
@@ -451,7 +478,7 @@ struct ClusterSolver {
       v += m == CTK_MODE_VAR ? n : (m == CTK_MODE_CLUSTER ? 1 : 0);
     }
     V = v;
-    if (V > a.lay.v_max || V > 255) return CTK_FAIL_TOO_LARGE;
+    if (V > a.lay.v_max || V > (C::BIG ? 65535 : 255)) return CTK_FAIL_TOO_LARGE;
     warp_sync();
     const double* pin = a.params_in + (int64_t)feat0 * P;
     const bool tables = a.lo_in == nullptr;            // bounds from the problem's tables
@@ -497,12 +524,12 @@ struct ClusterSolver {
     // packed-index tables (depend on V only; consecutive clusters of a launch mostly share V)
     if (V != cached_V) {
       int* cs = CS();
-      uint16_t* rc = RC();
+      RcT* rc = RC();
       for (int c = lane; c <= V; c += CTK_WARP) cs[c] = c * V - c * (c - 1) / 2;
       warp_sync();
       for (int t = lane; t < V * V; t += CTK_WARP) {
         int r = t / V, c = t - r * V;
-        if (r >= c) rc[cs[c] + r - c] = (uint16_t) (r | (c << 8));
+        if (r >= c) rc[cs[c] + r - c] = rc_pack(r, c, RcT());
       }
       cached_V = V;
     }
@@ -529,6 +556,32 @@ struct ClusterSolver {
     }
     warp_sync();
     return CTK_OK;
+  }
+
+  // ellipse test of box pixel c against feature i from the separable tables (refine.py:43-44)
+  CTK_DEV bool covers(int i, const int (&c)[3], const int* fi, const double* tab) const {
+    const int* f = fi + i * FI_STRIDE;
+    const double* tb = tab + i * a.lay.tab_stride;
+    double s = 0.;
+    bool in = true;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      int e = c[k] - f[FI_TS + k];
+      in = in && (e >= 0) && (e < a.lay.tab_len[k]);
+      if (in) s = (k == 0) ? tb[e] : dadd(s, tb[e]);
+      tb += a.lay.tab_len[k];
+    }
+    return in && s <= 1.0;
+  }
+  CTK_DEV static bool covered(const uint32_t* pbits, int p, int i, int nw) {
+    if (!C::BIG) return (pbits[p] >> i) & 1u;
+    return (pbits[(size_t) p * nw + (i >> 5)] >> (i & 31)) & 1u;
+  }
+  CTK_DEV static void store_entry(uint32_t* dst, int p, int o0, int o1, int o2) {
+    *dst = pack_entry(p, o0, o1, o2);
+  }
+  CTK_DEV static void store_entry(uint64_t* dst, int p, int o0, int o1, int o2) {
+    *dst = pack_entry64(p, o0, o1, o2);
   }
 
   // ---- pixel set (refine.py:28-58, masks.py:30-68) ----------------------------------------------
@@ -566,7 +619,7 @@ struct ClusterSolver {
     }
     if (total <= 0 || total > (int64_t) 1 << 30) return CTK_FAIL_TOO_LARGE;
 #pragma unroll
-    for (int k = 0; k < ND; ++k) if (bdim[k] > 1023) return CTK_FAIL_TOO_LARGE;
+    for (int k = 0; k < ND; ++k) if (!C::BIG && bdim[k] > 1023) return CTK_FAIL_TOO_LARGE;
     warp_sync();
     // separable tables: tab[i][k][e] = (((ts + e) - (c - origin)) / r)^2, float64, numpy's order
     double* tab = TAB();
@@ -598,29 +651,30 @@ struct ClusterSolver {
     warp_sync();
     // walk the box in C order, ballot-compact the union
     uint32_t *pbits = PBITS(), *pcrd = PCRD();
+    const int nw = NW();
+    uint32_t* tmpw = reinterpret_cast<uint32_t*>(slice() + a.lay.o_tmpw) + lane * nw;   // BIG only
     int count = 0;
     const int itotal = (int) total;
     for (int q0 = 0; q0 < itotal; q0 += CTK_WARP) {
       int q = q0 + lane;
-      uint32_t bits = 0u;
+      uint32_t bits = 0u;            // the mask itself (one word), or "any word set" (BIG)
       int c[3] = {0, 0, 0};
       if (q < itotal) {
         int rem = q;
 #pragma unroll
         for (int k = ND - 1; k >= 0; --k) { c[k] = rem % bdim[k]; rem /= bdim[k]; }
-        for (int i = 0; i < n; ++i) {
-          const int* f = fi + i * FI_STRIDE;
-          const double* tb = tab + i * a.lay.tab_stride;
-          double s = 0.;
-          bool in = true;
-#pragma unroll
-          for (int k = 0; k < ND; ++k) {
-            int e = c[k] - f[FI_TS + k];
-            in = in && (e >= 0) && (e < a.lay.tab_len[k]);
-            if (in) s = (k == 0) ? tb[e] : dadd(s, tb[e]);
-            tb += a.lay.tab_len[k];
+        if (!C::BIG) {
+          for (int i = 0; i < n; ++i)
+            if (covers(i, c, fi, tab)) bits |= (1u << i);
+        } else {
+          for (int w = 0; w < nw; ++w) {
+            uint32_t word = 0u;
+            const int i1 = min(n, 32 * w + 32);
+            for (int i = 32 * w; i < i1; ++i)
+              if (covers(i, c, fi, tab)) word |= (1u << (i & 31));
+            tmpw[w] = word;
+            bits |= word;
           }
-          if (in && s <= 1.0) bits |= (1u << i);
         }
       }
       uint32_t ball = ballot(bits != 0u);
@@ -631,8 +685,13 @@ struct ClusterSolver {
 #pragma unroll
           for (int k = 0; k < ND; ++k) gi = gi * a.shape[k] + (blo[k] + c[k]);
           stage_pixel(gi, pos);
-          pbits[pos] = bits;
-          pcrd[pos] = (uint32_t) c[0] | ((uint32_t) c[1] << 10) | ((uint32_t) c[2] << 20);
+          if (!C::BIG) {
+            pbits[pos] = bits;
+            pcrd[pos] = (uint32_t) c[0] | ((uint32_t) c[1] << 10) | ((uint32_t) c[2] << 20);
+          } else {
+            for (int w = 0; w < nw; ++w) pbits[(size_t) pos * nw + w] = tmpw[w];
+            pcrd[pos] = (uint32_t) q;              // linear box index, decoded when needed
+          }
         }
       }
       count += popc(ball);
@@ -641,7 +700,7 @@ struct ClusterSolver {
     if (M > a.lay.m_cap || M == 0) return M == 0 ? CTK_FAIL_OUT_OF_IMAGE : CTK_FAIL_TOO_LARGE;
     warp_sync();
     // per-feature pixel lists, in union order
-    uint32_t* flist = FLIST();
+    Entry* flist = FLIST();
     bool overflow = false;
     for (int i = 0; i < n; ++i) {
       const int* f = fi + i * FI_STRIDE;
@@ -651,15 +710,23 @@ struct ClusterSolver {
       int cnt = 0;
       for (int p0 = 0; p0 < M; p0 += CTK_WARP) {
         int p = p0 + lane;
-        bool has = (p < M) && ((pbits[p] >> i) & 1u);
+        bool has = (p < M) && covered(pbits, p, i, nw);
         uint32_t ball = ballot(has);
         if (has) {
           int t = cnt + popc(ball & lanemask_lt());
           if (t < a.lay.f_cap) {
             uint32_t crd = pcrd[p];
-            int o0 = (int) (crd & 1023u) - oc[0], o1 = (int) ((crd >> 10) & 1023u) - oc[1],
-                o2 = (int) ((crd >> 20) & 1023u) - oc[2];
-            flist[i * a.lay.f_cap + t] = pack_entry(p, o0, ND > 1 ? o1 : 0, ND > 2 ? o2 : 0);
+            int o[3] = {0, 0, 0};
+            if (!C::BIG) {
+              o[0] = (int) (crd & 1023u); o[1] = (int) ((crd >> 10) & 1023u);
+              o[2] = (int) ((crd >> 20) & 1023u);
+            } else {
+              int rem = (int) crd;
+#pragma unroll
+              for (int k = ND - 1; k >= 0; --k) { o[k] = rem % bdim[k]; rem /= bdim[k]; }
+            }
+            store_entry(flist + (size_t) i * a.lay.f_cap + t, p, o[0] - oc[0],
+                        ND > 1 ? o[1] - oc[1] : 0, ND > 2 ? o[2] - oc[2] : 0);
           }
         }
         cnt += popc(ball);
@@ -684,7 +751,7 @@ struct ClusterSolver {
           apart |= abs(f_i[FI_CI + k] - f_j[FI_CI + k]) > 2 * a.prob.radius[k] + 2;
         if (apart) continue;
         const int cnt_j = f_j[FI_CNT];
-        const uint32_t* fl_j = flist + j * a.lay.f_cap;
+        const Entry* fl_j = flist + j * a.lay.f_cap;
         int cnt = 0;
         for (int t0 = 0; t0 < cnt_i; t0 += CTK_WARP) {
           int t = t0 + lane;
@@ -692,7 +759,7 @@ struct ClusterSolver {
           bool has = false;
           if (t < cnt_i) {
             p = entry_pixel(flist[i * a.lay.f_cap + t]);
-            has = (pbits[p] >> j) & 1u;
+            has = covered(pbits, p, j, nw);
           }
           uint32_t ball = ballot(has);
           if (has) {
@@ -761,7 +828,7 @@ struct ClusterSolver {
 
   // geometry of one (pixel, feature): q_k = (x_k - c_k)/size_k, r2 = sum q_k^2, d2 = pixel dist^2
   struct Geo { Real q[3], r2, d2; };
-  CTK_DEV Geo geometry(uint32_t e, const Feat& f) const {
+  CTK_DEV Geo geometry(Entry e, const Feat& f) const {
     Geo g;
     g.r2 = 0; g.d2 = 0;
 #pragma unroll
@@ -843,16 +910,16 @@ struct ClusterSolver {
     Real* pr = PR();
     for (int p = lane; p < M; p += CTK_WARP) pr[p] = 0;
     warp_sync();
-    const uint32_t* flist = FLIST();
+    const Entry* flist = FLIST();
     Real* fe = FE();
     const int* fi = FI();
     for (int i = 0; i < n; ++i) {
       const Feat f = feat(i);
       const int cnt = fi[i * FI_STRIDE + FI_CNT];
-      const uint32_t* fl = flist + i * a.lay.f_cap;
+      const Entry* fl = flist + i * a.lay.f_cap;
       Real* ge = fe + i * a.lay.f_cap;
       for (int t = lane; t < cnt; t += CTK_WARP) {
-        uint32_t e = fl[t];
+        Entry e = fl[t];
         Geo g = geometry(e, f);
         bool drop;
         Real gv = model_value(g, f, drop);
@@ -900,7 +967,7 @@ struct ClusterSolver {
     const int vb = cv[0];
     if (vb >= 0 && lane == 0) { if (!grad_only) H[pk(vb, vb)] = (Real) n_valid; rhs[vb] = sum_r; }
     warp_sync();
-    const uint32_t* flist = FLIST();
+    const Entry* flist = FLIST();
     const Real* fe = FE();
     const Real* pr = PR();
     const int* fi = FI();
@@ -908,13 +975,13 @@ struct ClusterSolver {
     for (int i = 0; i < n; ++i) {
       const Feat f = feat(i);
       const int cnt = fi[i * FI_STRIDE + FI_CNT];
-      const uint32_t* fl = flist + i * a.lay.f_cap;
+      const Entry* fl = flist + i * a.lay.f_cap;
       const Real* ge = fe + i * a.lay.f_cap;
       Real acc[LT + 2 * LD];       // [LT] m_u m_w, [LD] m_u, [LD] m_u r
 #pragma unroll
       for (int k = 0; k < LT + 2 * LD; ++k) acc[k] = 0;
       for (int t = lane; t < cnt; t += CTK_WARP) {
-        uint32_t e = fl[t];
+        Entry e = fl[t];
         Real r = pr[entry_pixel(e)];
         if (!(r == r)) continue;
         Geo g = geometry(e, f);
@@ -958,7 +1025,7 @@ struct ClusterSolver {
     for (int q = 0; q < npairs; ++q) {
       const int i = phdr[q * 4], j = phdr[q * 4 + 1], start = phdr[q * 4 + 2], cnt = phdr[q * 4 + 3];
       const Feat f_i = feat(i), f_j = feat(j);
-      const uint32_t *fl_i = flist + i * a.lay.f_cap, *fl_j = flist + j * a.lay.f_cap;
+      const Entry *fl_i = flist + i * a.lay.f_cap, *fl_j = flist + j * a.lay.f_cap;
       const Real *ge_i = fe + i * a.lay.f_cap, *ge_j = fe + j * a.lay.f_cap;
       Real B[LD * LD];
 #pragma unroll
@@ -966,7 +1033,7 @@ struct ClusterSolver {
       for (int t = lane; t < cnt; t += CTK_WARP) {
         uint32_t pe = pairs[start + t];
         int ti = (int) (pe & 0xffffu), tj = (int) (pe >> 16);
-        uint32_t ei = fl_i[ti], ej = fl_j[tj];
+        Entry ei = fl_i[ti], ej = fl_j[tj];
         Real r = pr[entry_pixel(ei)];
         if (!(r == r)) continue;
         Real mi[LD], mj[LD];
@@ -1031,7 +1098,7 @@ struct ClusterSolver {
     Real* idg = IDG();
     int* act = ACT();
     const int* cs = CS();
-    const uint16_t* rc = RC();
+    const RcT* rc = RC();
     const double *x = X(), *lo = LO(), *hi = HI();
     const int nt = cs[V];
     for (int v = lane; v < V; v += CTK_WARP) rhs_full[v] = RHS()[v];
@@ -1079,7 +1146,7 @@ struct ClusterSolver {
       // scaled, damped system: (S K S + lambda I)(S^-1 step) = S rhs; frozen rows become identity
       const Real lam1 = (Real) (1. + lambda);
       for (int t = lane; t < nt; t += CTK_WARP) {
-        const int r = rc[t] & 0xff, c = rc[t] >> 8;
+        const int r = rc_row(rc[t]), c = rc_col(rc[t]);
         Real v;
         if (act[r] || act[c]) v = (r == c) ? (Real) 1 : (Real) 0;
         else if (r == c) v = lam1;
@@ -1098,7 +1165,7 @@ struct ClusterSolver {
         if (lane == 0) { idg[j] = inv; d[j] = yj; }
         warp_sync();
         for (int t = cs[j + 1] + lane; t < nt; t += CTK_WARP) {
-          const int r = rc[t] & 0xff, c = rc[t] >> 8;
+          const int r = rc_row(rc[t]), c = rc_col(rc[t]);
           Kf[t] -= Kf[cj + r - j] * Kf[cj + c - j];
         }
         for (int r = j + 1 + lane; r < V; r += CTK_WARP) d[r] -= (double) Kf[cj + r - j] * yj;
@@ -1120,11 +1187,11 @@ struct ClusterSolver {
   // predicted decrease of the (augmented) objective for step s: rhs.s - 0.5 s^T K s
   CTK_DEV_BIG double predicted(const double* s, const double* rhs_full) const {
     const Real* H = Hm();
-    const uint16_t* rc = RC();
+    const RcT* rc = RC();
     const int nt = CS()[V];
     double acc = 0.;
     for (int t = lane; t < nt; t += CTK_WARP) {
-      const int r = rc[t] & 0xff, c = rc[t] >> 8;
+      const int r = rc_row(rc[t]), c = rc_col(rc[t]);
       acc -= (r == c ? 0.5 : 1.) * (double) H[t] * s[r] * s[c];
     }
     for (int u = lane; u < V; u += CTK_WARP) acc += s[u] * rhs_full[u];
@@ -1310,7 +1377,8 @@ struct ClusterSolver {
     V = 0;
     int status = CTK_OK;
     double cost = NAN;
-    if (n <= 0 || n > a.lay.n_max || n > CTK_MAX_CLUSTER_FEATURES) status = CTK_FAIL_TOO_LARGE;
+    if (n <= 0 || n > a.lay.n_max || (!C::BIG && n > CTK_MAX_CLUSTER_FEATURES))
+      status = CTK_FAIL_TOO_LARGE;
     if (status == CTK_OK) status = setup_variables();
     // constraints apply to clusters of exactly their size, with free per-feature positions
     n_con = 0;

@@ -23,10 +23,11 @@ from .utils import guess_pos_columns, is_isotropic, validate_tuple
 logger = logging.getLogger(__name__)
 
 # clusters are launched in bins of at most this many features (shared memory is sized per bin)
-_BINS = (1, 2, 3, 4, 6, 8, 12, 16, 24, 32)
+_BINS = (1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 64, 128, 256)   # > 32: large-cluster kernels (workspace)
 _FRAME_BATCH_BYTES = 128 << 20        # frames per upload batch (uploads overlap the kernels)
 # scaled step below which the factorised normal matrix is reused (chord iterations)
 _CHORD_TOL = float(os.environ.get('CTK_CHORD_TOL', 0.02))
+_BIG_WORKSPACE_LIMIT = 8 << 30         # device scratch a large-cluster launch may take
 
 
 _THREADS = None
@@ -339,7 +340,7 @@ def run_bins(sizes, cluster_ids, status, launch):
     for cap, ids in bin_clusters(sizes, cluster_ids):
         launch(cap, ids, False)
         retry = ids[status[ids] == _lib.STATUS_TOO_LARGE]
-        if len(retry):
+        if len(retry) and cap < _lib.CTK_MAX_CLUSTER_FEATURES:
             launch(cap, retry, True)              # same class, rigorous capacities
 
 
@@ -529,6 +530,7 @@ class DeviceSession(object):
         self.launches = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.big_workspaces = {}
         with torch.cuda.device(self.dev):
             dev = self.dev
             self.workspace = torch.empty(int(self.lib.ctk_refine_workspace_bytes()),
@@ -557,8 +559,11 @@ class DeviceSession(object):
         sizes = self.sizes
         caps = np.asarray(_BINS)
         cls = np.searchsorted(caps, sizes)                     # size class of every cluster
-        fits = np.array([self.lib.ctk_refine_shared_bytes(_lib.ctypes.byref(self.plan.problem),
-                                                          int(c)) > 0 for c in caps] + [False])
+        prob = _lib.ctypes.byref(self.plan.problem)
+        fits = np.array([(self.lib.ctk_refine_shared_bytes(prob, int(c)) > 0
+                          if c <= _lib.CTK_MAX_CLUSTER_FEATURES else
+                          0 < self.lib.ctk_refine_workspace_bytes_for(prob, int(c)) <= _BIG_WORKSPACE_LIMIT)
+                         for c in caps] + [False])
         runnable = fits[np.minimum(cls, len(caps))]
         key = cls.astype(np.int64) * 64 + (63 - np.minimum(sizes, 63))
         ids = np.flatnonzero(runnable)
@@ -581,11 +586,22 @@ class DeviceSession(object):
             self.d_lo.data_ptr() if self.d_lo is not None else None,
             self.d_hi.data_ptr() if self.d_hi is not None else None, self.d_out.data_ptr(),
             self.d_cost.data_ptr(), self.d_status.data_ptr(), self.d_stats.data_ptr(),
-            self.workspace.data_ptr(), self.stream_ptr()), "ctk_refine_batch")
+            self._workspace_for(cap).data_ptr(), self.stream_ptr()), "ctk_refine_batch")
         self.launches += 1
         if events is not None:
             stop.record()
             events.append(("refine", start, stop))
+
+    def _workspace_for(self, cap):
+        """Small classes share one scratch word; a large-cluster class gets its own workspace."""
+        if cap <= _lib.CTK_MAX_CLUSTER_FEATURES:
+            return self.workspace
+        if cap not in self.big_workspaces:
+            nbytes = int(self.lib.ctk_refine_workspace_bytes_for(
+                _lib.ctypes.byref(self.plan.problem), int(cap)))
+            self.big_workspaces[cap] = self.torch.empty(nbytes, dtype=self.torch.uint8,
+                                                        device=self.dev)
+        return self.big_workspaces[cap]
 
     def run(self, slices, events=None):
         """One refine launch per size class."""
@@ -596,12 +612,13 @@ class DeviceSession(object):
         """Relaunch, with a larger capacity, the clusters that overflowed their size class."""
         status = self.d_status.cpu().numpy()
         self.d2h_bytes += status.nbytes
-        over = np.flatnonzero((status == _lib.STATUS_TOO_LARGE) & (self.sizes <= _BINS[-1]))
+        over = np.flatnonzero((status == _lib.STATUS_TOO_LARGE) &
+                              (self.sizes <= _lib.CTK_MAX_CLUSTER_FEATURES))
         self.retry_ids = []
         if not len(over):
             return
         rigorous = rigorous_problem(self.plan.problem)
-        for cap in _BINS:
+        for cap in [c for c in _BINS if c <= _lib.CTK_MAX_CLUSTER_FEATURES]:
             sel = over[self.sizes[over] <= cap]
             over = over[self.sizes[over] > cap]
             if len(sel) and self.lib.ctk_refine_shared_bytes(_lib.ctypes.byref(rigorous), cap) > 0:

@@ -29,7 +29,9 @@ extern "C" {
 
 #define CTK_VERSION 100          /* major*10000 + minor*100 + patch */
 #define CTK_MAX_PARAMS 12        /* background, signal, <=3 pos, <=3 size, <=1 extra (+ spare) */
-#define CTK_MAX_CLUSTER_FEATURES 32   /* features per cluster handled by the warp-per-cluster kernel */
+#define CTK_MAX_CLUSTER_FEATURES 32   /* features per cluster of the shared-memory kernels */
+#define CTK_MAX_BIG_FEATURES 256      /* features per cluster of the large-cluster kernels (per-cluster
+                                         arrays in a global-memory workspace, see ctk_refine_batch) */
 #define CTK_MAX_RADIUS 30        /* mask radius per axis (pixel offsets are packed in 6 bits) */
 
 /* parameter modes, same codes as fitfunc.py:9-11 (2 = 'global' is out of scope) */
@@ -123,8 +125,14 @@ const char* ctk_last_error(void);
 int ctk_frame_max(const void* const* d_frames, int32_t n_frames, int64_t n_pixels,
                   int32_t pixel_dtype, double* d_max_out, void* stream);
 
-/* Bytes of scratch `ctk_refine_batch` needs in `d_workspace`. */
+/* Bytes of scratch `ctk_refine_batch` needs in `d_workspace` for launches with
+ * max_cluster_features <= CTK_MAX_CLUSTER_FEATURES. */
 size_t ctk_refine_workspace_bytes(void);
+
+/* Bytes of scratch a launch with this capacity needs.  Above CTK_MAX_CLUSTER_FEATURES the
+ * per-cluster arrays (pixel lists, normal matrix, ...) live in this workspace instead of shared
+ * memory; 0 = the request is out of range. */
+size_t ctk_refine_workspace_bytes_for(const ctk_problem_t* prob, int32_t max_cluster_features);
 
 /* Shared memory (bytes per cluster) a launch with this capacity would use, or 0 when it does not
  * fit the device limit (227 KB on sm_100a).  Lets the caller bin clusters by size. */
@@ -155,7 +163,7 @@ size_t ctk_refine_shared_bytes(const ctk_problem_t* prob, int32_t max_cluster_fe
  *   d_cost_out      [n_clusters] rms_dev, NaN on failure                      (refine.py:379, 427)
  *   d_status_out    [n_clusters] CTK_OK or CTK_FAIL_*
  *   d_stats_out     [n_clusters, CTK_STATS] int32 counters (CTK_STAT_*), for accounting
- *   d_workspace     ctk_refine_workspace_bytes() bytes of device scratch
+ *   d_workspace     ctk_refine_workspace_bytes_for(prob, max_cluster_features) bytes of device scratch
  */
 int ctk_refine_batch(const ctk_problem_t* prob,
                      const void* const* d_frames, const int64_t* frame_shape,

@@ -58,8 +58,9 @@ extern "C" int ctk_emul_refine_batch(const ctk_problem_t* prob, const void* cons
   a.stats_out = iters_out;
   if (!ctk::compute_layout(*prob, max_cluster_features, &a.lay)) return CTK_E_CAPACITY;
   RunAll run{&a};
-  bool ok = prob->compute_dtype == CTK_COMPUTE_F64 ? ctk::dispatch_config<double>(*prob, run)
-                                                   : ctk::dispatch_config<float>(*prob, run);
+  const bool big = max_cluster_features > CTK_MAX_CLUSTER_FEATURES;
+  bool ok = prob->compute_dtype == CTK_COMPUTE_F64 ? ctk::dispatch_config<double>(*prob, run, big)
+                                                   : ctk::dispatch_config<float>(*prob, run, big);
   return ok ? 0 : CTK_E_UNSUPPORTED;
 }
 

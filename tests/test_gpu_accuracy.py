@@ -189,7 +189,7 @@ def test_multiple_overlapping():
     import clustertracking_b200 as ctb
     from clustertracking_b200 import artificial
     rng = np.random.RandomState(7)
-    for count, spacing in ((10, 24), (60, 15)):
+    for count, spacing in ((10, 24), (100, 15)):
         pos = []
         while len(pos) < count:
             cand = rng.uniform(21, 256 - 21, 2)
@@ -201,10 +201,10 @@ def test_multiple_overlapping():
         f0['signal'] = 200.
         f0['size'] = 5.25
         out = ctb.refine_leastsq(f0, image, 21, 24)
-        ok = out['cluster_size'].values <= 32            # larger clusters fail loudly (documented)
-        assert np.isfinite(out['cost'].values[ok]).all()
-        assert np.isnan(out['cost'].values[~ok]).all()
-        assert np.abs(out[['y', 'x']].values[ok] - pos[ok]).max() < 0.1
+        if count == 100:                                  # percolates into one large cluster
+            assert out['cluster_size'].values.max() > 32
+        assert np.isfinite(out['cost'].values).all()
+        assert np.abs(out[['y', 'x']].values - pos).max() < 0.1
 
 
 def test_full_size_frame_properties():

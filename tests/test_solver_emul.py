@@ -66,15 +66,39 @@ def test_failure_statuses():
     assert got['y'].values[1] == 500.            # failed fits keep their parameters
 
 
-def test_cluster_larger_than_capacity_fails_loudly():
+def test_cluster_larger_than_every_capacity_fails_loudly():
     import pandas as pd
     rng = np.random.RandomState(0)
-    n = 40
-    f = pd.DataFrame(dict(y=30 + rng.uniform(-4, 4, n), x=30 + rng.uniform(-4, 4, n),
+    n = 300                                   # above CTK_MAX_BIG_FEATURES
+    f = pd.DataFrame(dict(y=60 + rng.uniform(-30, 30, n), x=60 + rng.uniform(-30, 30, n),
                           signal=50., size=2.))
-    img = rng.randint(0, 50, (64, 64)).astype(np.uint8)
+    img = rng.randint(0, 50, (128, 128)).astype(np.uint8)
     got, plan = emul_backend.refine_leastsq(f, img, 9)
     assert plan.n_clusters == 1 and np.isnan(got['cost'].values).all()
+    assert (got['y'].values == f['y'].values).all()
+
+
+def test_large_cluster_path():
+    """More than 32 overlapping features percolate into one cluster (TestMultiple,
+    tests/test_refine.py:913-922): the large-cluster kernels (global workspace, multi-word pixel
+    masks) take it; every feature ends within 0.1 px of the truth."""
+    import pandas as pd
+    from clustertracking_b200 import artificial
+    rng = np.random.RandomState(7)
+    pos = []
+    while len(pos) < 70:
+        cand = rng.uniform(21, 200 - 21, 2)
+        if all(np.linalg.norm(cand - p) >= 15 for p in pos):
+            pos.append(cand)
+    pos = np.array(pos)
+    image = artificial.draw_features((200, 200), pos, 5.25, 200.)
+    f0 = pd.DataFrame(pos + rng.random_sample(pos.shape) * 7, columns=['y', 'x'])
+    f0['signal'] = 200.
+    f0['size'] = 5.25
+    got, plan = emul_backend.refine_leastsq(f0, image, 21, separation=24)
+    assert plan.cluster_sizes().max() > 32
+    assert np.isfinite(got['cost'].values).all()
+    assert np.abs(got[['y', 'x']].values - pos).max() < 0.1
 
 
 def test_edge_clipped_and_overlapping_masks():
