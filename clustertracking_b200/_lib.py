@@ -18,7 +18,7 @@ MODE_CONST, MODE_VAR, MODE_CLUSTER = 0, 1, 3
 PIXEL_CODES = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2,
                np.dtype(np.float64): 3, np.dtype(np.int16): 4, np.dtype(np.int32): 5}
 COMPUTE_F32, COMPUTE_F64 = 0, 1
-CONSTRAINT_DIMER, CONSTRAINT_TRIMER = 1, 2
+CONSTRAINT_DIMER, CONSTRAINT_TRIMER, CONSTRAINT_TETRAMER = 1, 2, 4
 
 STATUS_NAMES = {0: 'ok', 1: 'non-finite initial parameters', 2: 'cluster outside of the image',
                 3: 'solver did not converge', 4: 'rms deviation above max_rms_dev',
@@ -40,6 +40,7 @@ class Problem(ctypes.Structure):
         ("constraint_mask", ctypes.c_int32),
         ("capacity_mode", ctypes.c_int32), ("dimer_dist", ctypes.c_double * 3),
         ("trimer_dist", ctypes.c_double * 3),
+        ("tetramer_dist", ctypes.c_double * 3),
         ("bounds_abs", (ctypes.c_double * CTK_MAX_PARAMS) * 2),
         ("bounds_diff", (ctypes.c_double * CTK_MAX_PARAMS) * 2),
         ("bounds_rel", (ctypes.c_double * CTK_MAX_PARAMS) * 2),

@@ -1,7 +1,7 @@
 """Distance constraints of the refine path (reference: clustertracking/constraints.py:59-137).
 
 The reference hands python callables to SLSQP, which differentiates them numerically.  On the GPU
-the dimer / trimer constraints are built into the solver (augmented-Lagrangian rows), so the dicts
+the dimer / trimer / tetramer constraints are built into the solver (augmented-Lagrangian rows), so the dicts
 returned here are *descriptors*: ``refine_leastsq`` recognises them by their ``fun`` and reads the
 distances from ``args``.  They keep the reference's keys (``type``, ``cluster_size``, ``fun``,
 ``args``) and the callables evaluate the same expressions, so user code that inspects or calls them
@@ -29,7 +29,8 @@ def _trimer_fun(x, dist, ndim):
 
 
 def _tetramer_fun(x, dist, ndim):
-    """constraints.py:102-125.  Not built into the CUDA solver yet."""
+    """2D: the four shortest of the six pair distances (the sides of a square); 3D: all six
+    (constraints.py:102-125)."""
     pos = x[..., 2:2 + ndim]
     terms = [1 - _pair_term(pos, a, b, dist)
              for a, b in ((0, 1), (1, 2), (0, 2), (1, 3), (0, 3), (2, 3))]
@@ -52,8 +53,8 @@ def trimer(dist, ndim=2):
 
 
 def tetramer(dist, ndim=2):
-    """Descriptor for clusters of 4 (constraints.py:127-137); ``refine_leastsq`` rejects it with
-    NotImplementedError until the CUDA solver carries it."""
+    """Constrain clusters of 4: a square in 2D (4 constraints), a tetrahedron in 3D (6)
+    (constraints.py:127-137)."""
     if ndim not in (2, 3):
         raise NotImplementedError
     dist = np.array(validate_tuple(dist, ndim), dtype=np.float64)
@@ -66,17 +67,20 @@ def parse(constraints, ndim):
     Accepts this module's descriptors and the reference's own (recognised by function name, so
     dicts built by ``clustertracking.constraints`` work unchanged).  Anything the CUDA solver does
     not carry raises NotImplementedError: there is no CPU fallback."""
-    out = dict(dimer=None, trimer=None)
+    out = dict(dimer=None, trimer=None, tetramer=None)
     if not constraints:
         return out
     for cons in constraints:
         name = getattr(cons.get('fun', None), '__name__', '')
         size = cons.get('cluster_size', None)
-        kind = {('_dimer_fun', 2): 'dimer', ('_trimer_fun', 3): 'trimer'}.get((name, size))
+        kind = {('_dimer_fun', 2): 'dimer', ('_trimer_fun', 3): 'trimer',
+                ('_tetramer_fun', 4): 'tetramer', ('_tetramer_fun_2d', 4): 'tetramer',
+                ('_tetramer_fun_3d', 4): 'tetramer'}.get((name, size))
         if kind is None or cons.get('type', 'eq') != 'eq':
             raise NotImplementedError(
                 "constraint %r (cluster_size=%r) is not available in the CUDA solver; supported: "
-                "constraints.dimer, constraints.trimer" % (name or cons.get('fun'), size))
+                "constraints.dimer, constraints.trimer, constraints.tetramer"
+                % (name or cons.get('fun'), size))
         dist = np.asarray(validate_tuple(cons['args'][0] if np.ndim(cons['args'][0]) == 0
                                          else tuple(cons['args'][0]), ndim), dtype=np.float64)
         if out[kind] is not None and not np.array_equal(out[kind], dist):

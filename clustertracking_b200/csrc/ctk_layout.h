@@ -126,7 +126,7 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
   const int ld_max = p.n_params - 1;
   lay->sidx_stride = ld_max * (ld_max + 1) / 2 + 2 * ld_max;
   lay->o_sidx = take(n_max * lay->sidx_stride * 4);
-  lay->o_con = take(8 * 8);
+  lay->o_con = take(16 * 8);
   lay->o_cmode = take(p.n_params * 4);
   lay->o_cbase = take(p.n_params * 4);
   lay->o_ctab = take(p.n_params * 6 * 8);
@@ -185,6 +185,9 @@ inline const char* validate_problem(const ctk_problem_t& p) {
     for (int k = 0; k < p.ndim; ++k) if (!(p.dimer_dist[k] > 0.)) return "dimer distance must be > 0";
   if (p.constraint_mask & CTK_CONSTRAINT_TRIMER)
     for (int k = 0; k < p.ndim; ++k) if (!(p.trimer_dist[k] > 0.)) return "trimer distance must be > 0";
+  if (p.constraint_mask & CTK_CONSTRAINT_TETRAMER)
+    for (int k = 0; k < p.ndim; ++k)
+      if (!(p.tetramer_dist[k] > 0.)) return "tetramer distance must be > 0";
   return nullptr;
 }
 

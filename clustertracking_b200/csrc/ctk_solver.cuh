@@ -222,7 +222,7 @@ CTK_COLD double bound_from_tables(double p, double diff, double rel, double ab, 
 }
 
 // Distance constraints (constraints.py:59-99).  Constraint j couples features (p, q): dimer (0,1);
-// trimer (0,1), (1,2), (0,2).  con[0..2] multipliers, con[3..5] distances per axis.
+// trimer (0,1), (1,2), (0,2); tetramer see con_pair.  con[0..5] multipliers, con[6..8] distances.
 struct ConView {
   const double* x;
   const int* cv;        // [n, P] variable index of (feature, column)
@@ -231,19 +231,37 @@ struct ConView {
   double w;             // penalty weight
 };
 CTK_COLD int con_pos_var(const ConView v, int k, int i) { return v.cv[i * v.P + 2 + k]; }
+// squared distance of features p, q in units of the constraint distance
+CTK_COLD double con_dist2(const ConView v, int p, int q) {
+  double s = 0.;
+  for (int k = 0; k < v.nd; ++k) {
+    double d = (v.x[con_pos_var(v, k, p)] - v.x[con_pos_var(v, k, q)]) / v.con[6 + k];
+    s += d * d;
+  }
+  return s;
+}
+// Feature pair of constraint j.  dimer (0,1); trimer (0,1),(1,2),(0,2) (constraints.py:79-83);
+// tetramer in 3D: all six pairs (constraints.py:117-125); tetramer in 2D: the four SHORTEST of the
+// six pair distances, i.e. the sides of the square (constraints.py:102-114).
 CTK_COLD void con_pair(const ConView v, int j, int* p, int* q) {
-  *p = (j == 1) ? 1 : 0;
-  *q = (v.n == 2 || j == 0) ? 1 : 2;
+  const int pa[6] = {0, 1, 0, 1, 0, 2}, pb[6] = {1, 2, 2, 3, 3, 3};
+  if (v.n == 4 && v.nd == 2) {
+    double d[6];
+    int order[6];
+    for (int a = 0; a < 6; ++a) { d[a] = con_dist2(v, pa[a], pb[a]); order[a] = a; }
+    for (int a = 1; a < 6; ++a)                      // insertion sort, stable
+      for (int b = a; b > 0 && d[order[b]] < d[order[b - 1]]; --b) {
+        int t = order[b]; order[b] = order[b - 1]; order[b - 1] = t;
+      }
+    j = order[j];
+  }
+  *p = pa[j];
+  *q = pb[j];
 }
 CTK_COLD double con_value(const ConView v, int j) {
   int p, q;
   con_pair(v, j, &p, &q);
-  double s = 0.;
-  for (int k = 0; k < v.nd; ++k) {
-    double d = (v.x[con_pos_var(v, k, p)] - v.x[con_pos_var(v, k, q)]) / v.con[3 + k];
-    s += d * d;
-  }
-  return 1. - s;
+  return 1. - con_dist2(v, p, q);
 }
 CTK_COLD double con_penalty(const ConView v) {
   double out = 0.;
@@ -263,7 +281,7 @@ CTK_COLD void con_grad(const ConView v, int j, int u, int* idx, double* g) {
   int p, q;
   con_pair(v, j, &p, &q);
   const int k = u >> 1;
-  const double dist = v.con[3 + k];
+  const double dist = v.con[6 + k];
   const double d = (v.x[con_pos_var(v, k, p)] - v.x[con_pos_var(v, k, q)]) / (dist * dist);
   *idx = con_pos_var(v, k, (u & 1) ? q : p);
   *g = (u & 1) ? 2. * d : -2. * d;
@@ -390,7 +408,7 @@ struct ClusterSolver {
   CTK_DEV int NW() const { return C::BIG ? a.lay.mask_words : 1; }
   CTK_DEV int* CV() const { return reinterpret_cast<int*>(slice() + a.lay.o_cv); }
   CTK_DEV int* SIDX() const { return reinterpret_cast<int*>(slice() + a.lay.o_sidx); }
-  CTK_DEV double* CON() const { return dvec(a.lay.o_con); }        // mu[0..2], dist[3..5]
+  CTK_DEV double* CON() const { return dvec(a.lay.o_con); }        // mu[0..5], dist[6..8]
   CTK_DEV int* CMODE() const { return reinterpret_cast<int*>(slice() + a.lay.o_cmode); }
   CTK_DEV int* CBASE() const { return reinterpret_cast<int*>(slice() + a.lay.o_cbase); }
   CTK_DEV double* CTAB() const { return dvec(a.lay.o_ctab); }
@@ -1224,7 +1242,7 @@ struct ClusterSolver {
     double *x = X(), *xt = XT(), *d = D();
     double* rhs_full = dvec(a.lay.o_rhsf);            // rhs incl. constraint terms, before freezing
     double lambda = 1e-3, nu = 2.;
-    if (lane == 0) for (int j = 0; j < 3; ++j) CON()[j] = 0.;
+    if (lane == 0) for (int j = 0; j < 6; ++j) CON()[j] = 0.;
     for (int v = lane; v < V; v += CTK_WARP) xt[v] = x[v];
     warp_sync();
     pen_w = 0.;
@@ -1301,7 +1319,7 @@ struct ClusterSolver {
             hmax = warp_max_d(hmax);
             double a2 = 0.;
 #pragma unroll
-            for (int k = 0; k < ND; ++k) a2 = fmax(a2, 8. / (CON()[3 + k] * CON()[3 + k]));
+            for (int k = 0; k < ND; ++k) a2 = fmax(a2, 8. / (CON()[6 + k] * CON()[6 + k]));
             pen_w = pen_w0 = 100. * fmax(hmax, 1e-30) / a2;
             fa = fd + penalty(x);
             c_prev = con_violation(x);
@@ -1390,13 +1408,19 @@ struct ClusterSolver {
         n_con = 1;
         if (lane == 0) {
 #pragma unroll
-          for (int k = 0; k < ND; ++k) CON()[3 + k] = a.prob.dimer_dist[k];
+          for (int k = 0; k < ND; ++k) CON()[6 + k] = a.prob.dimer_dist[k];
+        }
+      } else if (pos_var && n == 4 && (a.prob.constraint_mask & CTK_CONSTRAINT_TETRAMER)) {
+        n_con = ND == 2 ? 4 : 6;
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < ND; ++k) CON()[6 + k] = a.prob.tetramer_dist[k];
         }
       } else if (pos_var && n == 3 && (a.prob.constraint_mask & CTK_CONSTRAINT_TRIMER)) {
         n_con = 3;
         if (lane == 0) {
 #pragma unroll
-          for (int k = 0; k < ND; ++k) CON()[3 + k] = a.prob.trimer_dist[k];
+          for (int k = 0; k < ND; ++k) CON()[6 + k] = a.prob.trimer_dist[k];
         }
       }
     }

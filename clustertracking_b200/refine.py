@@ -267,6 +267,10 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
         mask |= _lib.CONSTRAINT_TRIMER
         for k in range(ndim):
             prob.trimer_dist[k] = cons['trimer'][k]
+    if cons['tetramer'] is not None:
+        mask |= _lib.CONSTRAINT_TETRAMER
+        for k in range(ndim):
+            prob.tetramer_dist[k] = cons['tetramer'][k]
     prob.constraint_mask = mask
     for which, table in zip(("bounds_abs", "bounds_diff", "bounds_rel"), tables):
         dst = getattr(prob, which)
@@ -698,7 +702,7 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
 
     * ``fit_function``: 'gauss', 'ring' or 'disc' (custom dicts and 'inv_series_<n>' raise);
     * ``param_mode`` values 'const', 'var', 'cluster' ('global' raises);
-    * ``constraints``: ``constraints.dimer`` / ``constraints.trimer`` descriptors (others raise);
+    * ``constraints``: ``constraints.dimer`` / ``trimer`` / ``tetramer`` descriptors (others raise);
     * ``noise_size`` and ``compute_error`` raise ``NotImplementedError``;
     * ``**kwargs``: ``options=dict(maxiter=...)`` caps the inner iterations; ``tol`` is accepted and
       ignored; ``precision='float64'`` switches the pixel arithmetic from float32 to float64.

@@ -43,8 +43,8 @@ enum { CTK_PIXEL_U8 = 0, CTK_PIXEL_U16 = 1, CTK_PIXEL_F32 = 2, CTK_PIXEL_F64 = 3
        CTK_PIXEL_I16 = 4, CTK_PIXEL_I32 = 5 };
 /* arithmetic of the pixel pass (normal equations, factorisation and parameters are always f64) */
 enum { CTK_COMPUTE_F32 = 0, CTK_COMPUTE_F64 = 1 };
-/* equality constraints, constraints.py:59-99; applied to clusters of exactly that size */
-enum { CTK_CONSTRAINT_DIMER = 1, CTK_CONSTRAINT_TRIMER = 2 };
+/* equality constraints, constraints.py:59-137; applied to clusters of exactly that size */
+enum { CTK_CONSTRAINT_DIMER = 1, CTK_CONSTRAINT_TRIMER = 2, CTK_CONSTRAINT_TETRAMER = 4 };
 
 /* per-cluster status (status_out).  0 = success; anything else = the reference's RefineException
  * path: cost NaN, parameters copied through unchanged. */
@@ -105,6 +105,7 @@ typedef struct {
                                  1: size it for the rigorous worst case                      */
   double  dimer_dist[3];      /* constraints.py:70-76, per axis */
   double  trimer_dist[3];     /* constraints.py:93-99, per axis */
+  double  tetramer_dist[3];   /* constraints.py:127-137, per axis (2D: square, 3D: tetrahedron) */
   /* Bounds tables of FitFunctions.validate_bounds (fitfunc.py:492-533), [0] = lower, [1] = upper,
    * NaN = no bound.  Used when d_bounds_lo / d_bounds_hi are NULL: per feature and column
    *   low  = fmax(fmax(p - diff[0], p * (1 - rel[0])), abs[0]), NaN -> -inf

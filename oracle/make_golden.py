@@ -198,7 +198,7 @@ class _Video(object):
 
 
 def golden_refine(ct):
-    from clustertracking.constraints import dimer, trimer
+    from clustertracking.constraints import dimer, trimer, tetramer
     from clustertracking.artificial import feat_gauss, feat_ring, feat_disc, draw_cluster
     rng = np.random.RandomState(1234)
 
@@ -340,9 +340,53 @@ def golden_refine(ct):
     _refine_case(ct, "refine_gauss2d_video", np.array(stack), f0, 11, {}, frames=video)
 
 
+def golden_tetramer(ct):
+    """Tetramers: square in 2D (four shortest distances), tetrahedron in 3D (all six)
+    (constraints.py:102-137, tests/test_refine.py:753-765)."""
+    from clustertracking.constraints import tetramer
+    from clustertracking.artificial import feat_gauss, draw_cluster
+    rng = np.random.RandomState(4321)
+
+    def grid_positions(shape, pitch, margin, jitter):
+        axes = [np.arange(margin, s - margin + 1e-9, pitch) for s in shape]
+        pos = np.array([g.ravel() for g in np.meshgrid(*axes, indexing='ij')], float).T
+        return pos + rng.uniform(-jitter, jitter, pos.shape)
+
+    def start_frame(pos, err, cols, **const):
+        f0 = pd.DataFrame(pos + rng.uniform(-err, err, pos.shape), columns=cols)
+        for k, v in const.items():
+            f0[k] = v
+        return f0
+
+    shape = (150, 150)
+    centres = grid_positions(shape, 48, 28, 2)
+    image = np.zeros(shape, dtype=np.uint8)
+    pos = []
+    for c in centres:
+        pos.extend(draw_cluster(image, c, (4., 4.), 4, 1., rng.uniform(0, 2 * np.pi),
+                                max_value=float(rng.uniform(128, 192)), feat_func=feat_gauss))
+    pos = np.array(pos)
+    image = np.clip(image + rng.poisson(6, shape), 0, 255).astype(np.uint8)
+    f0 = start_frame(pos, 0.8, ['y', 'x'], signal=160., size=4., background=3.)
+    _refine_case(ct, "refine_tetramer2d_constrained", image, f0, 16,
+                 dict(constraints=tetramer(8.0, 2)), constraint=("tetramer", 8.0))
+    shape = (40, 72, 72)
+    centres = grid_positions(shape, 36, 18, 1)
+    image = np.zeros(shape, dtype=np.uint8)
+    pos = []
+    for c in centres:
+        pos.extend(draw_cluster(image, c, (3., 4., 4.), 4, 1., rng.uniform(0, 2 * np.pi, 3),
+                                max_value=160., feat_func=feat_gauss))
+    pos = np.array(pos)
+    f0 = start_frame(pos, 0.7, ['z', 'y', 'x'], signal=150., size_z=3., size_y=4., size_x=4.)
+    _refine_case(ct, "refine_tetramer3d_constrained", image, f0, (12, 16, 16),
+                 dict(constraints=tetramer((6., 8., 8.), 3)), constraint=("tetramer", (6., 8., 8.)))
+
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ct = ref_loader.load()
-    only = sys.argv[1:] or ["fitfunc", "pixels", "clusters", "refine"]
+    only = sys.argv[1:] or ["fitfunc", "pixels", "clusters", "refine", "tetramer"]
     for part in only:
         globals()["golden_" + part](ct)

@@ -45,8 +45,36 @@ def _compare(got, want, pos_tol, rel_tol):
             assert_allclose(got[col].values, want[col].values, rtol=rel_tol, atol=1e-9, err_msg=col)
 
 
+# The 2D tetramer constraint is built on a sort of the six pair distances (constraints.py:102-114),
+# which SLSQP differentiates numerically; the reference stops at slightly sub-optimal points there
+# (and fails two of four clusters at tol=1e-12), so that fixture gets its own test below.
+STRICT = [n for n in golden_io.names("refine_") if n != "refine_tetramer2d_constrained"]
+
+
+def check_tetramer2d(got, d):
+    """Constraint met to 1e-6, cost not above the reference's, positions within 2e-2 px (that
+    residue is the reference's: its cost is higher by up to 3e-4 relative on these clusters)."""
+    want = golden_io.frame(d, "ref_")
+    assert_array_equal(got['cluster'].values, want['cluster'].values)
+    assert not np.isnan(got['cost'].values).any()
+    assert (got['cost'].values <= want['cost'].values * (1 + 1e-6)).all()
+    assert_allclose(got[['y', 'x']].values, want[['y', 'x']].values, rtol=0, atol=2e-2)
+    for _, g in got.groupby('cluster'):
+        p = g[['y', 'x']].values
+        d2 = sorted(np.sum(((p[a] - p[b]) / 8.) ** 2) for a in range(4) for b in range(a + 1, 4))
+        assert max(abs(1 - x) for x in d2[:4]) < 1e-6
+
+
 @pytest.mark.parametrize("precision", ["float32", "float64"])
-@pytest.mark.parametrize("name", golden_io.names("refine_"))
+def test_cuda_tetramer2d(precision):
+    import clustertracking_b200 as ctb
+    d = golden_io.load("refine_tetramer2d_constrained")
+    f0, reader, diameter, kwargs = golden_io.refine_inputs(d, ctb.constraints)
+    check_tetramer2d(ctb.refine_leastsq(f0, reader, diameter, precision=precision, **kwargs), d)
+
+
+@pytest.mark.parametrize("precision", ["float32", "float64"])
+@pytest.mark.parametrize("name", STRICT)
 def test_cuda_matches_reference_golden(name, precision):
     import clustertracking_b200 as ctb
     d = golden_io.load(name)

@@ -31,8 +31,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_problem_struct_matches_header_size():
-    # ctk_problem_t: 4 + 12 + 3 + 4 int32, 5 doubles, 2 int32, 6 doubles, 3 x 2 x 12 doubles
-    assert ctypes.sizeof(_lib.Problem) == (4 + 12 + 3 + 4) * 4 + 4 + 5 * 8 + 2 * 4 + 6 * 8 + 72 * 8
+    # ctk_problem_t: 4 + 12 + 3 + 4 int32, 5 doubles, 2 int32, 9 doubles, 3 x 2 x 12 doubles
+    assert ctypes.sizeof(_lib.Problem) == (4 + 12 + 3 + 4) * 4 + 4 + 5 * 8 + 2 * 4 + 9 * 8 + 72 * 8
 
 
 def test_shared_bytes_query_needs_no_gpu():
@@ -123,8 +123,6 @@ def test_unsupported_options_raise():
         refine.prepare(f.copy(), img, 9, noise_size=1)
     with pytest.raises(NotImplementedError):
         refine.prepare(f.copy(), img, 9, compute_error=True)
-    with pytest.raises(NotImplementedError):
-        refine.prepare(f.copy(), img, 9, constraints=ctb.constraints.tetramer(4.))
     with pytest.raises(NotImplementedError):
         refine.prepare(f.copy(), img, 9, constraints=[dict(type='eq', fun=lambda x: x)])
     with pytest.raises(ValueError):

@@ -12,9 +12,10 @@ from numpy.testing import assert_allclose, assert_array_equal
 import golden_io
 import emul_backend
 import clustertracking_b200 as ctb
-from test_gpu_parity import _compare, POS_TOL, REL_TOL, POS_TOL_TIGHT, REL_TOL_TIGHT
+from test_gpu_parity import (_compare, check_tetramer2d, POS_TOL, REL_TOL, POS_TOL_TIGHT,
+                             REL_TOL_TIGHT, STRICT)
 
-CASES = golden_io.names("refine_")
+CASES = STRICT
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -37,6 +38,13 @@ def test_emulated_solver_float64(name):
         warnings.simplefilter("ignore")
         got, _ = emul_backend.refine_leastsq(f0, reader, diameter, precision='float64', **kwargs)
     _compare(got, golden_io.frame(d, "tight_"), 1e-6, 1e-6)
+
+
+def test_emulated_tetramer2d():
+    d = golden_io.load("refine_tetramer2d_constrained")
+    f0, reader, diameter, kwargs = golden_io.refine_inputs(d, ctb.constraints)
+    got, _ = emul_backend.refine_leastsq(f0, reader, diameter, **kwargs)
+    check_tetramer2d(got, d)
 
 
 def test_constraints_are_satisfied():
