@@ -62,6 +62,9 @@ _PROTOTYPES = {
     "ctk_refine_batch": (ctypes.c_int, [ctypes.POINTER(Problem), _vp, ctypes.POINTER(_i64), _vp,
                                         _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp]),
+    "ctk_refine_batch_chained": (ctypes.c_int, [ctypes.POINTER(Problem), _vp, ctypes.POINTER(_i64),
+                                                _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "ctk_label_clusters": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "ctk_pairs_set_order": (ctypes.c_int, [_vp, _i64, _vp]),
 }

@@ -128,6 +128,21 @@ int ctk_refine_batch(const ctk_problem_t* prob, const void* const* d_frames,
                      const double* d_params_in, const double* d_bounds_lo, const double* d_bounds_hi,
                      double* d_params_out, double* d_cost_out, int32_t* d_status_out,
                      int32_t* d_stats_out, void* d_workspace, void* stream) {
+  return ctk_refine_batch_chained(prob, d_frames, frame_shape, d_frame_max, n_work, d_work_ids,
+                                  max_cluster_features, d_cluster_frame, d_cluster_offset,
+                                  d_params_in, d_bounds_lo, d_bounds_hi, d_params_out, d_cost_out,
+                                  d_status_out, d_stats_out, d_workspace, nullptr, nullptr, 0, stream);
+}
+
+int ctk_refine_batch_chained(const ctk_problem_t* prob, const void* const* d_frames,
+                             const int64_t* frame_shape, const double* d_frame_max, int32_t n_work,
+                             const int32_t* d_work_ids, int32_t max_cluster_features,
+                             const int32_t* d_cluster_frame, const int32_t* d_cluster_offset,
+                             const double* d_params_in, const double* d_bounds_lo,
+                             const double* d_bounds_hi, double* d_params_out, double* d_cost_out,
+                             int32_t* d_status_out, int32_t* d_stats_out, void* d_workspace,
+                             const int32_t* d_n_work, int32_t* d_overflow,
+                             int32_t overflow_capacity, void* stream) {
   if (!prob) return fail(CTK_E_INVALID, "ctk_refine_batch: prob is NULL");
   if (const char* why = ctk::validate_problem(*prob)) return fail(CTK_E_INVALID, "ctk_refine_batch: %s", why);
   if (n_work < 0) return fail(CTK_E_INVALID, "ctk_refine_batch: n_work < 0");
@@ -158,6 +173,10 @@ int ctk_refine_batch(const ctk_problem_t* prob, const void* const* d_frames,
   a.status_out = d_status_out;
   a.stats_out = d_stats_out;
   a.counter = static_cast<int32_t*>(d_workspace);
+  if (overflow_capacity < 0) return fail(CTK_E_INVALID, "ctk_refine_batch: overflow_capacity < 0");
+  a.n_work_dev = d_n_work;
+  a.overflow = overflow_capacity > 0 ? d_overflow : nullptr;
+  a.overflow_cap = overflow_capacity;
   if (!ctk::compute_layout(*prob, max_cluster_features, &a.lay))
     return fail(CTK_E_CAPACITY, "ctk_refine_batch: max_cluster_features %d out of range [1, %d]",
                 max_cluster_features, CTK_MAX_BIG_FEATURES);
@@ -168,6 +187,7 @@ int ctk_refine_batch(const ctk_problem_t* prob, const void* const* d_frames,
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CTK_CUDA(cudaMemsetAsync(d_workspace, 0, sizeof(int32_t), st));
+  if (a.overflow) CTK_CUDA(cudaMemsetAsync(a.overflow, 0, sizeof(int32_t), st));
   Launcher launcher{&a, st, 0};
   bool found = prob->compute_dtype == CTK_COMPUTE_F64
                    ? ctk::dispatch_config<double>(*prob, launcher, big)

@@ -20,11 +20,13 @@ template <class C>
 __global__ void __launch_bounds__(32 * CTK_BLOCK_WARPS, CTK_MIN_BLOCKS)
 refine_kernel(const BatchArgs a) {
   ClusterSolver<C> solver(a, (uint32_t) (threadIdx.x >> 5) * (uint32_t) a.lay.total);
+  int n_work = a.n_work;
+  if (a.n_work_dev) n_work = min(n_work, *a.n_work_dev);   // e.g. the overflow list of a previous launch
   for (;;) {
     int w = 0;
     if ((threadIdx.x & 31) == 0) w = atomicAdd(a.counter, 1);
     w = __shfl_sync(0xffffffffu, w, 0);
-    if (w >= a.n_work) break;
+    if (w >= n_work) break;
     solver.run(a.work_ids ? a.work_ids[w] : w);
   }
 }

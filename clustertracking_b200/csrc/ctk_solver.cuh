@@ -203,6 +203,9 @@ struct BatchArgs {
   int32_t* status_out;
   int32_t* stats_out;        // [n_clusters, CTK_STATS] counters, see ctk.h
   int32_t* counter;
+  int32_t* overflow;         // optional [1 + overflow_cap]: ids of clusters that ended TOO_LARGE
+  int overflow_cap;
+  const int32_t* n_work_dev; // optional device-side work count (<= n_work)
   char* big_workspace;       // BIG kernels: one slice of lay.total bytes per block
   int big_blocks;            // number of slices
   Layout lay;
@@ -1488,6 +1491,10 @@ struct ClusterSolver {
       st[CTK_STAT_PIXELS] = M; st[CTK_STAT_ENTRIES] = n_entries;
       st[CTK_STAT_PAIR_ENTRIES] = n_pair_entries; st[CTK_STAT_VARS] = V;
       st[CTK_STAT_GRAD_ACCUMS] = grad_accums;
+      if (status == CTK_FAIL_TOO_LARGE && a.overflow != nullptr) {
+        const int k = atomic_next(a.overflow);
+        if (k < a.overflow_cap) a.overflow[1 + k] = cluster;
+      }
     }
     warp_sync();
   }

@@ -519,7 +519,7 @@ class DeviceSession(object):
     Everything is enqueued asynchronously on the current stream: one refine launch per size class
     over all clusters of the call (work ids: expensive clusters first), no host synchronisation
     until the results are downloaded.  Clusters whose pixel lists overflowed their size class
-    (status TOO_LARGE) are relaunched once with rigorous capacities."""
+    (status TOO_LARGE) are relaunched once with rigorous capacities from a device-side list."""
 
     def __init__(self, plan, device=None, frames=None):
         self.frames = frames if frames is not None else FrameSet(plan.frame_info, device)
@@ -559,16 +559,29 @@ class DeviceSession(object):
 
     def schedule(self):
         """Work ids of every size class, concatenated and uploaded once: -> list of
-        (capacity, start, count) slices.  Inside a class the expensive clusters come first."""
+        (capacity, start, count) slices.  Inside a class the expensive clusters come first.
+        A class whose per-cluster arrays do not fit the shared memory (large masks) runs in the
+        first large-cluster class instead (global-memory workspace)."""
         sizes = self.sizes
         caps = np.asarray(_BINS)
         cls = np.searchsorted(caps, sizes)                     # size class of every cluster
         prob = _lib.ctypes.byref(self.plan.problem)
-        fits = np.array([(self.lib.ctk_refine_shared_bytes(prob, int(c)) > 0
-                          if c <= _lib.CTK_MAX_CLUSTER_FEATURES else
-                          0 < self.lib.ctk_refine_workspace_bytes_for(prob, int(c)) <= _BIG_WORKSPACE_LIMIT)
+        self.rigorous = rigorous_problem(self.plan.problem)
+        rig = _lib.ctypes.byref(self.rigorous)
+        small = caps <= _lib.CTK_MAX_CLUSTER_FEATURES
+        fits = np.array([(self.lib.ctk_refine_shared_bytes(prob, int(c)) > 0 if c <= _lib.CTK_MAX_CLUSTER_FEATURES
+                          else 0 < self.lib.ctk_refine_workspace_bytes_for(prob, int(c)) <= _BIG_WORKSPACE_LIMIT)
                          for c in caps] + [False])
-        runnable = fits[np.minimum(cls, len(caps))]
+        # classes whose typical-case capacities can overflow, and whether the rigorous ones fit
+        self.retry_fits = {int(c): self.lib.ctk_refine_shared_bytes(rig, int(c)) > 0
+                           for c in caps[small]}
+        first_big = int(np.flatnonzero(~small)[0])
+        self.big_fallback = int(caps[first_big]) if fits[first_big] else None
+        cls = np.minimum(cls, len(caps))
+        spill = small[np.minimum(cls, len(caps) - 1)] & ~fits[cls] & (cls < len(caps))
+        if self.big_fallback is not None:
+            cls = np.where(spill, first_big, cls)
+        runnable = fits[cls]
         key = cls.astype(np.int64) * 64 + (63 - np.minimum(sizes, 63))
         ids = np.flatnonzero(runnable)
         ids = ids[np.argsort(key[ids], kind='stable')]
@@ -576,13 +589,24 @@ class DeviceSession(object):
         group = cls[ids]
         cut = np.flatnonzero(np.concatenate(([True], group[1:] != group[:-1], [True])))
         self.never_run = np.flatnonzero(~runnable)
-        return [(int(caps[group[a]]), int(a), int(b - a)) for a, b in zip(cut[:-1], cut[1:])]
+        slices = [(int(caps[group[a]]), int(a), int(b - a)) for a, b in zip(cut[:-1], cut[1:])]
+        # one overflow list [count, ids...] per small class: filled by the class's launch, consumed by
+        # its relaunch with rigorous capacities -- no host round trip in between
+        self.overflow_at = {}
+        words = 0
+        for cap, _, count in slices:
+            if cap <= _lib.CTK_MAX_CLUSTER_FEATURES:
+                self.overflow_at[cap] = (words, count)
+                words += 1 + count
+        self.d_overflow = self.torch.zeros(max(words, 1), dtype=self.torch.int32, device=self.dev)
+        return slices
 
-    def launch_refine(self, cap, work_ptr, count, events=None, problem=None):
+    def launch_refine(self, cap, work_ptr, count, events=None, problem=None, n_work_ptr=None,
+                      overflow_ptr=None, overflow_cap=0):
         if events is not None:
             start, stop = (self.torch.cuda.Event(enable_timing=True) for _ in range(2))
             start.record()
-        _lib.check(self.lib.ctk_refine_batch(
+        _lib.check(self.lib.ctk_refine_batch_chained(
             _lib.ctypes.byref(problem if problem is not None else self.plan.problem),
             self.frames.d_ptrs.data_ptr(), self.shape_arr,
             self.frames.d_fmax.data_ptr(), count, work_ptr, int(cap), self.d_cframe.data_ptr(),
@@ -590,7 +614,8 @@ class DeviceSession(object):
             self.d_lo.data_ptr() if self.d_lo is not None else None,
             self.d_hi.data_ptr() if self.d_hi is not None else None, self.d_out.data_ptr(),
             self.d_cost.data_ptr(), self.d_status.data_ptr(), self.d_stats.data_ptr(),
-            self._workspace_for(cap).data_ptr(), self.stream_ptr()), "ctk_refine_batch")
+            self._workspace_for(cap).data_ptr(), n_work_ptr, overflow_ptr, int(overflow_cap),
+            self.stream_ptr()), "ctk_refine_batch_chained")
         self.launches += 1
         if events is not None:
             stop.record()
@@ -608,27 +633,25 @@ class DeviceSession(object):
         return self.big_workspaces[cap]
 
     def run(self, slices, events=None):
-        """One refine launch per size class."""
+        """One refine launch per size class; behind it, for the classes provisioned for the typical
+        case, the relaunch of the clusters that overflowed (device-side list, usually empty or a
+        percent of the class): with rigorous capacities if those fit the shared memory, else in the
+        first large-cluster class."""
+        base = self.d_overflow.data_ptr()
         for cap, start, count in slices:
-            self.launch_refine(cap, self.d_work.data_ptr() + 4 * start, count, events)
-
-    def retry_overflow(self):
-        """Relaunch, with a larger capacity, the clusters that overflowed their size class."""
-        status = self.d_status.cpu().numpy()
-        self.d2h_bytes += status.nbytes
-        over = np.flatnonzero((status == _lib.STATUS_TOO_LARGE) &
-                              (self.sizes <= _lib.CTK_MAX_CLUSTER_FEATURES))
-        self.retry_ids = []
-        if not len(over):
-            return
-        rigorous = rigorous_problem(self.plan.problem)
-        for cap in [c for c in _BINS if c <= _lib.CTK_MAX_CLUSTER_FEATURES]:
-            sel = over[self.sizes[over] <= cap]
-            over = over[self.sizes[over] > cap]
-            if len(sel) and self.lib.ctk_refine_shared_bytes(_lib.ctypes.byref(rigorous), cap) > 0:
-                d_sel = self._up(sel.astype(np.int32))
-                self.retry_ids.append(d_sel)
-                self.launch_refine(cap, d_sel.data_ptr(), len(sel), problem=rigorous)
+            at = self.overflow_at.get(cap)
+            if at is None:
+                self.launch_refine(cap, self.d_work.data_ptr() + 4 * start, count, events)
+                continue
+            lst = base + 4 * at[0]
+            self.launch_refine(cap, self.d_work.data_ptr() + 4 * start, count, events,
+                               overflow_ptr=lst, overflow_cap=count)
+            if self.retry_fits.get(cap):
+                if cap < _lib.CTK_MAX_CLUSTER_FEATURES:       # the largest class is rigorous already
+                    self.launch_refine(cap, lst + 4, count, events, problem=self.rigorous,
+                                       n_work_ptr=lst)
+            elif self.big_fallback is not None:
+                self.launch_refine(self.big_fallback, lst + 4, count, events, n_work_ptr=lst)
 
     def download(self, want_stats=True):
         """Results through cached pinned buffers.  The arrays of the returned Result are views of
@@ -675,8 +698,7 @@ def execute_cuda(plan, device=None, want_stats=True, frames=None):
         _t1 = _time.perf_counter()
         session.run(slices)
         _t2 = _time.perf_counter()
-        session.retry_overflow()
-        _t3 = _time.perf_counter()
+        _t3 = _t2
         result = session.download(want_stats)
     session.launches += frames.launches
     session.h2d_bytes += frames.h2d_bytes

@@ -175,6 +175,26 @@ int ctk_refine_batch(const ctk_problem_t* prob,
                      double* d_params_out, double* d_cost_out, int32_t* d_status_out,
                      int32_t* d_stats_out, void* d_workspace, void* stream);
 
+/* ctk_refine_batch with two device-side hooks, so that overflowing clusters can be relaunched
+ * without a host round trip:
+ *   d_n_work        optional device int32: the launch processes min(n_work, *d_n_work) work items
+ *                   (n_work still sizes the grid).  Typically the count word of an overflow list.
+ *   d_overflow      optional device int32 [1 + overflow_capacity]: word 0 is reset to 0 at the
+ *                   start of the launch (stream-ordered) and counts the clusters that ended with
+ *                   CTK_FAIL_TOO_LARGE; their indices are appended at words 1.. (order unspecified).
+ *                   A follow-up launch with prob->capacity_mode = 1, d_work_ids = d_overflow + 1 and
+ *                   d_n_work = d_overflow refines exactly those clusters. */
+int ctk_refine_batch_chained(const ctk_problem_t* prob,
+                     const void* const* d_frames, const int64_t* frame_shape,
+                     const double* d_frame_max,
+                     int32_t n_work, const int32_t* d_work_ids, int32_t max_cluster_features,
+                     const int32_t* d_cluster_frame, const int32_t* d_cluster_offset,
+                     const double* d_params_in, const double* d_bounds_lo, const double* d_bounds_hi,
+                     double* d_params_out, double* d_cost_out, int32_t* d_status_out,
+                     int32_t* d_stats_out, void* d_workspace,
+                     const int32_t* d_n_work, int32_t* d_overflow, int32_t overflow_capacity,
+                     void* stream);
+
 /* Host helper (no GPU): cluster labels of one frame from the close pairs, visiting the pairs in the
  * given order with the reference's "the label of a's cluster survives" rule (find.py:41-48, 84-93).
  *   pairs [n_pairs, 2] int64; labels_out, sizes_out [n] int64 */
