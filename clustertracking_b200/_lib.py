@@ -67,6 +67,9 @@ _PROTOTYPES = {
                                                 _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "ctk_label_clusters": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "ctk_pairs_set_order": (ctypes.c_int, [_vp, _i64, _vp]),
+    "ctk_query_pairs": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i64, _vp]),
+    "ctk_cluster_frames": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp,
+                                          _vp]),
 }
 
 
@@ -112,3 +115,40 @@ def pairs_set_order(pairs):
     check(load().ctk_pairs_set_order(pairs.ctypes.data, len(pairs), order.ctypes.data),
           "ctk_pairs_set_order")
     return pairs[order]
+
+
+def query_pairs(data):
+    """Host helper ``ctk_query_pairs``: close pairs (distance <= 1) of ``data`` [n, ndim] in the order
+    of ``scipy.spatial.cKDTree(data).query_pairs(1, output_type='ndarray')``."""
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    n, ndim = data.shape
+    count = ctypes.c_int64(0)
+    lib = load()
+    capacity = max(16, 4 * n)
+    while True:
+        out = np.empty((capacity, 2), dtype=np.int64)
+        code = lib.ctk_query_pairs(data.ctypes.data, n, ndim, out.ctypes.data, capacity,
+                                   ctypes.byref(count))
+        if code == -4:                      # CTK_E_CAPACITY: count holds the size needed
+            capacity = int(count.value)
+            continue
+        check(code, "ctk_query_pairs")
+        return out[:count.value]
+
+
+def cluster_frames(pos, starts, stops, separation, n_threads):
+    """Host helper ``ctk_cluster_frames`` -> (cluster, size, by_cluster, spans), int64 arrays."""
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    n, ndim = pos.shape
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    stops = np.ascontiguousarray(stops, dtype=np.int64)
+    separation = np.ascontiguousarray(separation, dtype=np.float64)
+    cluster = np.empty(n, dtype=np.int64)
+    size = np.empty(n, dtype=np.int64)
+    by_cluster = np.empty(n, dtype=np.int64)
+    spans = np.zeros(len(starts), dtype=np.int64)
+    check(load().ctk_cluster_frames(pos.ctypes.data, n, ndim, starts.ctypes.data, stops.ctypes.data,
+                                    len(starts), separation.ctypes.data, int(n_threads),
+                                    cluster.ctypes.data, size.ctypes.data, by_cluster.ctypes.data,
+                                    spans.ctypes.data), "ctk_cluster_frames")
+    return cluster, size, by_cluster, spans

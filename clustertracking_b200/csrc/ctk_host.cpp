@@ -108,3 +108,371 @@ extern "C" int ctk_pairs_set_order(const int64_t* pairs, int64_t n_pairs, int64_
     if (s.item >= 0) order_out[out++] = s.item;
   return out == n_pairs ? 0 : CTK_E_INVALID;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Cluster labelling of a whole video on host threads (find.py:72-129).
+//
+// The reference obtains the close pairs of a frame from scipy.spatial.cKDTree.query_pairs and its
+// label VALUES depend on the order in which that call reports the pairs (see above).  To label a
+// video without one python call per frame, the few hundred lines below restate the published
+// algorithm of scipy's kd-tree for exactly the call the reference makes -- cKDTree(data) with the
+// default leafsize 16, compact nodes and median splits (scipy/spatial/ckdtree/src/build.cxx),
+// query_pairs(r=1, p=2, eps=0) (query_pairs.cxx with the rectangle-distance tracker of
+// rectangle.h) -- so that the pairs come out in the same order.  scipy is a third-party dependency
+// of the reference (unpinned, `setup.py:22`); find.py verifies this restatement against the
+// installed scipy once per process and uses scipy itself if they ever disagree.
+// ------------------------------------------------------------------------------------------------
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <thread>
+
+namespace {
+
+struct KdNode {
+  int split_dim;          // -1: leaf
+  double split;
+  int start, end;
+  int less, greater;
+  double lo[3], hi[3];    // leaves: tight bounds of the points (exact pruning, see PairQuery)
+};
+
+// A point in tree order.  scipy permutes an index array with std::nth_element and an indirect
+// comparison; permuting the records themselves with the same comparison results gives the same
+// permutation (the algorithm only sees the outcomes of the comparisons) without the indirection.
+struct KdPoint { double c[3]; int64_t idx; };
+
+struct KdTree {
+  int n, m;
+  std::vector<KdPoint> pts;
+  std::vector<KdNode> nodes;
+  double mins[3], maxes[3];
+
+  // data [n, m]; every coordinate is divided by scale[k] (numpy's pos / separation)
+  void init(const double* data, int n_, int m_, const double* scale) {
+    n = n_; m = m_;
+    pts.resize(n);
+    for (int i = 0; i < n; ++i) {
+      KdPoint& p = pts[i];
+      p.idx = i;
+      for (int k = 0; k < 3; ++k)
+        p.c[k] = k < m ? (scale ? data[(int64_t) i * m + k] / scale[k] : data[(int64_t) i * m + k]) : 0.;
+    }
+    nodes.clear();
+    nodes.reserve(n / 4 + 8);
+    for (int k = 0; k < m; ++k) { mins[k] = maxes[k] = n ? pts[0].c[k] : 0.; }
+    for (int i = 1; i < n; ++i)
+      for (int k = 0; k < m; ++k) {
+        const double v = pts[i].c[k];
+        maxes[k] = maxes[k] > v ? maxes[k] : v;
+        mins[k] = mins[k] < v ? mins[k] : v;
+      }
+    if (n > 0) build(0, n);
+  }
+
+  int build(int start, int end) {
+    const int node_index = (int) nodes.size();
+    nodes.push_back(KdNode{-1, 0., start, end, -1, -1, {0., 0., 0.}, {0., 0., 0.}});
+    // bounds over the node's points (scipy's compact nodes recompute them for the split decision)
+    double mx[3], mn[3];
+    for (int k = 0; k < m; ++k) { mx[k] = pts[start].c[k]; mn[k] = pts[start].c[k]; }
+    for (int j = start + 1; j < end; ++j)
+      for (int k = 0; k < m; ++k) {
+        const double v = pts[j].c[k];
+        mx[k] = mx[k] > v ? mx[k] : v;
+        mn[k] = mn[k] < v ? mn[k] : v;
+      }
+    for (int k = 0; k < m; ++k) { nodes[node_index].lo[k] = mn[k]; nodes[node_index].hi[k] = mx[k]; }
+    if (end - start <= 16) return node_index;
+    int d = 0;
+    double size = 0.;
+    for (int k = 0; k < m; ++k)
+      if (mx[k] - mn[k] > size) { d = k; size = mx[k] - mn[k]; }
+    if (mx[d] == mn[d]) return node_index;            // all points identical: leaf
+    // median split
+    const int half = (end - start) / 2;
+    std::nth_element(pts.begin() + start, pts.begin() + start + half, pts.begin() + end,
+                     [d](const KdPoint& a, const KdPoint& b) { return a.c[d] < b.c[d]; });
+    double split = pts[start + half].c[d];
+    // a median equal to the node's minimum would leave the lower side empty: scipy then splits
+    // just above it, so that every point equal to the minimum goes to the lower side
+    if (split == mn[d]) split = std::nextafter(split, HUGE_VAL);
+    int p = start, q = end - 1;
+    while (p <= q) {
+      if (pts[p].c[d] < split) ++p;
+      else if (pts[q].c[d] >= split) --q;
+      else { std::swap(pts[p], pts[q]); ++p; --q; }
+    }
+    const int l = build(start, p);
+    const int g = build(p, end);
+    KdNode& nd = nodes[node_index];
+    nd.split_dim = d;
+    nd.split = split;
+    nd.less = l;
+    nd.greater = g;
+    return node_index;
+  }
+};
+
+// rectangle-rectangle distance tracker for p = 2 (squared distances), eps = 0
+struct RectTracker {
+  int m;
+  double r1mn[3], r1mx[3], r2mn[3], r2mx[3];
+  double min_d, max_d, upper, limit;
+  struct Item { int which, dim; double min_d, max_d, mn, mx; };
+  std::vector<Item> stack;
+
+  void interval(int k, double* mn, double* mx) const {
+    *mn = std::fmax(0., std::fmax(r1mn[k] - r2mx[k], r2mn[k] - r1mx[k]));
+    *mx = std::fmax(r1mx[k] - r2mn[k], r2mx[k] - r1mn[k]);
+  }
+  void rect_rect(double* mn, double* mx) const {
+    *mn = 0.; *mx = 0.;
+    for (int k = 0; k < m; ++k) {
+      double a, b;
+      interval(k, &a, &b);
+      *mn += a * a;
+      *mx += b * b;
+    }
+  }
+  void init(const KdTree& t, double r) {
+    m = t.m;
+    for (int k = 0; k < m; ++k) {
+      r1mn[k] = r2mn[k] = t.mins[k];
+      r1mx[k] = r2mx[k] = t.maxes[k];
+    }
+    upper = r * r;
+    rect_rect(&min_d, &max_d);
+    limit = max_d;
+    stack.clear();
+  }
+  void push(int which, bool less, int dim, double split) {
+    double* mn = which == 1 ? r1mn : r2mn;
+    double* mx = which == 1 ? r1mx : r2mx;
+    stack.push_back(Item{which, dim, min_d, max_d, mn[dim], mx[dim]});
+    double min1, max1, min2, max2;
+    interval(dim, &min1, &max1);
+    min1 *= min1; max1 *= max1;
+    if (less) mx[dim] = split; else mn[dim] = split;
+    interval(dim, &min2, &max2);
+    min2 *= min2; max2 *= max2;
+    bool sub = (min1 != 0 && min1 < limit) || max1 < limit;
+    sub = sub || (min2 != 0 && min2 < limit) || max2 < limit;
+    sub = sub || min_d < limit || max_d < limit;
+    if (sub) rect_rect(&min_d, &max_d);
+    else { min_d += (min2 - min1); max_d += (max2 - max1); }
+  }
+  void pop() {
+    const Item it = stack.back();
+    stack.pop_back();
+    min_d = it.min_d; max_d = it.max_d;
+    if (it.which == 1) { r1mn[it.dim] = it.mn; r1mx[it.dim] = it.mx; }
+    else { r2mn[it.dim] = it.mn; r2mx[it.dim] = it.mx; }
+  }
+};
+
+struct PairQuery {
+  const KdTree* t;
+  RectTracker tr;
+  std::vector<int64_t>* out;      // flat (i, j), i < j
+
+  void add(int64_t i, int64_t j) {
+    if (i > j) std::swap(i, j);
+    out->push_back(i);
+    out->push_back(j);
+  }
+  void no_checking(int n1, int n2) {
+    const KdNode& a = t->nodes[n1];
+    const KdNode& b = t->nodes[n2];
+    if (a.split_dim == -1) {
+      if (b.split_dim == -1) {
+        for (int i = a.start; i < a.end; ++i) {
+          const int min_j = n1 == n2 ? i + 1 : b.start;
+          for (int j = min_j; j < b.end; ++j) add(t->pts[i].idx, t->pts[j].idx);
+        }
+      } else {
+        no_checking(n1, b.less);
+        no_checking(n1, b.greater);
+      }
+    } else if (n1 == n2) {
+      no_checking(a.less, b.less);
+      no_checking(a.less, b.greater);
+      no_checking(a.greater, b.greater);
+    } else {
+      no_checking(a.less, n2);
+      no_checking(a.greater, n2);
+    }
+  }
+  // scipy tests every point pair of two leaves; pairs that cannot be close are skipped here with
+  // bounds that are exact lower bounds of the same floating-point sum (monotone rounding), so the
+  // pairs reported and their order do not change
+  void leaves(int n1, int n2) {
+    const KdNode& a = t->nodes[n1];
+    const KdNode& b = t->nodes[n2];
+    const int m = t->m;
+    const double upper = tr.upper;
+    if (n1 != n2) {
+      double s = 0.;
+      for (int k = 0; k < m; ++k) {
+        const double g = std::fmax(0., std::fmax(a.lo[k] - b.hi[k], b.lo[k] - a.hi[k]));
+        s += g * g;
+      }
+      if (s > upper) return;
+    }
+    const KdPoint* pts = t->pts.data();
+    for (int i = a.start; i < a.end; ++i) {
+      const KdPoint& u = pts[i];
+      if (n1 != n2) {
+        double s = 0.;
+        for (int k = 0; k < m; ++k) {
+          const double g = std::fmax(0., std::fmax(u.c[k] - b.hi[k], b.lo[k] - u.c[k]));
+          s += g * g;
+        }
+        if (s > upper) continue;
+      }
+      const int min_j = n1 == n2 ? i + 1 : b.start;
+      for (int j = min_j; j < b.end; ++j) {
+        const KdPoint& v = pts[j];
+        double s = 0.;
+        for (int k = 0; k < m; ++k) { const double d = u.c[k] - v.c[k]; s += d * d; }
+        if (s <= upper) add(u.idx, v.idx);
+      }
+    }
+  }
+  void checking(int n1, int n2) {
+    if (tr.min_d > tr.upper) return;
+    if (tr.max_d < tr.upper) { no_checking(n1, n2); return; }
+    const KdNode& a = t->nodes[n1];
+    const KdNode& b = t->nodes[n2];
+    if (a.split_dim == -1) {
+      if (b.split_dim == -1) {
+        leaves(n1, n2);
+      } else {
+        tr.push(2, true, b.split_dim, b.split);
+        checking(n1, b.less);
+        tr.pop();
+        tr.push(2, false, b.split_dim, b.split);
+        checking(n1, b.greater);
+        tr.pop();
+      }
+    } else if (b.split_dim == -1) {
+      tr.push(1, true, a.split_dim, a.split);
+      checking(a.less, n2);
+      tr.pop();
+      tr.push(1, false, a.split_dim, a.split);
+      checking(a.greater, n2);
+      tr.pop();
+    } else {
+      tr.push(1, true, a.split_dim, a.split);
+      tr.push(2, true, b.split_dim, b.split);
+      checking(a.less, b.less);
+      tr.pop();
+      tr.push(2, false, b.split_dim, b.split);
+      checking(a.less, b.greater);
+      tr.pop();
+      tr.pop();
+      tr.push(1, false, a.split_dim, a.split);
+      if (n1 != n2) {
+        tr.push(2, true, b.split_dim, b.split);
+        checking(a.greater, b.less);
+        tr.pop();
+      }
+      tr.push(2, false, b.split_dim, b.split);
+      checking(a.greater, b.greater);
+      tr.pop();
+      tr.pop();
+    }
+  }
+};
+
+// per-thread scratch of the frame labelling
+struct FrameScratch {
+  std::vector<int64_t> pairs, order, ordered, count;
+  KdTree tree;
+  PairQuery query;
+};
+
+}  // namespace
+
+extern "C" int ctk_query_pairs(const double* data, int64_t n, int32_t ndim, int64_t* pairs_out,
+                               int64_t capacity, int64_t* n_pairs_out) {
+  if (n < 0 || ndim < 1 || ndim > 3 || (n > 0 && !data) || !n_pairs_out) return CTK_E_INVALID;
+  KdTree tree;
+  tree.init(data, (int) n, ndim, nullptr);
+  std::vector<int64_t> pairs;
+  PairQuery q;
+  q.t = &tree;
+  q.out = &pairs;
+  q.tr.init(tree, 1.0);
+  if (n > 0) q.checking(0, 0);
+  *n_pairs_out = (int64_t) pairs.size() / 2;
+  if (pairs_out) {
+    if ((int64_t) pairs.size() / 2 > capacity) return CTK_E_CAPACITY;
+    std::copy(pairs.begin(), pairs.end(), pairs_out);
+  }
+  return 0;
+}
+
+extern "C" int ctk_cluster_frames(const double* pos, int64_t n, int32_t ndim, const int64_t* starts,
+                                  const int64_t* stops, int64_t n_frames, const double* separation,
+                                  int32_t n_threads, int64_t* cluster_out, int64_t* size_out,
+                                  int64_t* by_cluster_out, int64_t* span_out) {
+  if (n < 0 || n_frames < 0 || ndim < 1 || ndim > 3 || !separation) return CTK_E_INVALID;
+  if (n_frames == 0) return 0;
+  if (!pos || !starts || !stops || !cluster_out || !size_out || !by_cluster_out || !span_out)
+    return CTK_E_INVALID;
+  for (int64_t f = 0; f < n_frames; ++f)
+    if (starts[f] < 0 || stops[f] < starts[f] || stops[f] > n || stops[f] - starts[f] > (1 << 30))
+      return CTK_E_INVALID;
+  std::atomic<int64_t> next(0);
+  std::atomic<int> failed(0);
+  auto worker = [&]() {
+    FrameScratch s;
+    for (;;) {
+      const int64_t f = next.fetch_add(1);
+      if (f >= n_frames) break;
+      const int64_t a = starts[f], b = stops[f];
+      const int cnt = (int) (b - a);
+      if (cnt == 0) { span_out[f] = 0; continue; }
+      s.tree.init(pos + a * ndim, cnt, ndim, separation);
+      s.pairs.clear();
+      s.query.t = &s.tree;
+      s.query.out = &s.pairs;
+      s.query.tr.init(s.tree, 1.0);
+      s.query.checking(0, 0);
+      const int64_t np = (int64_t) s.pairs.size() / 2;
+      s.order.resize(np);
+      s.ordered.resize(2 * np);
+      if (ctk_pairs_set_order(s.pairs.data(), np, s.order.data()) != 0) { failed = 1; continue; }
+      for (int64_t k = 0; k < np; ++k) {
+        s.ordered[2 * k] = s.pairs[2 * s.order[k]];
+        s.ordered[2 * k + 1] = s.pairs[2 * s.order[k] + 1];
+      }
+      if (ctk_label_clusters(s.ordered.data(), np, cnt, cluster_out + a, size_out + a) != 0) {
+        failed = 1;
+        continue;
+      }
+      // stable argsort of the labels (counting sort: labels are point indices of the frame)
+      s.count.assign((size_t) cnt + 1, 0);
+      int64_t top = 0;
+      for (int i = 0; i < cnt; ++i) {
+        const int64_t id = cluster_out[a + i];
+        ++s.count[id + 1];
+        top = id > top ? id : top;
+      }
+      for (int i = 0; i < cnt; ++i) s.count[i + 1] += s.count[i];
+      for (int i = 0; i < cnt; ++i) by_cluster_out[a + s.count[cluster_out[a + i]]++] = a + i;
+      span_out[f] = top + 1;
+    }
+  };
+  int nt = n_threads < 1 ? 1 : n_threads;
+  if (nt > n_frames) nt = (int) n_frames;
+  if (nt == 1) {
+    worker();
+  } else {
+    std::vector<std::thread> pool;
+    for (int k = 0; k < nt; ++k) pool.emplace_back(worker);
+    for (auto& th : pool) th.join();
+  }
+  return failed ? CTK_E_INVALID : 0;
+}

@@ -7,8 +7,9 @@ python ``set`` upstream receives (find.py:87-91).  That order is replayed in C f
 of the result (``ctk_pairs_set_order``; no python objects), the union step runs in C
 (``ctk_label_clusters``) instead of the reference's dict-of-sets loop (find.py:12-60), frames are
 cut from one stable sort instead of a pandas ``groupby`` + ``concat``, and frames are processed by
-a persistent pool of worker PROCESSES when the video is long (scipy's kd-tree holds the GIL, so
-threads do not help); positions and labels travel through shared memory.
+host threads inside libctk (``ctk_cluster_frames``), which restates scipy's kd-tree for this one
+call so that the pairs come out in scipy's order; the restatement is verified against the installed
+scipy once per process, and scipy itself (in worker processes for long videos) is the fallback.
 """
 import atexit
 import os
@@ -48,6 +49,28 @@ def _replay_is_exact():
             ok = ok and np.array_equal(_pairs_via_set(tree), _pairs_via_replay(tree))
         _replay_checked = bool(ok)
     return _replay_checked
+
+
+_native_checked = None      # None = not checked yet, True = ctk_query_pairs reproduces scipy's order
+
+
+def _native_is_exact():
+    """One-time self check of the kd-tree restatement in libctk (ctk_query_pairs) against the
+    installed scipy: same pairs in the same order on random, integer-grid and duplicate-heavy data.
+    If scipy ever changes its traversal the labelling falls back to scipy itself."""
+    global _native_checked
+    if _native_checked is None:
+        rng = np.random.RandomState(54321)
+        ok = _replay_is_exact()
+        cases = [rng.uniform(0, 30, (900, 2)), rng.uniform(0, 9, (700, 3)),
+                 rng.randint(0, 200, (800, 2)) / 11., rng.randint(0, 60, (600, 3)) / [9., 13., 13.],
+                 rng.randint(0, 4, (300, 2)) * 0.5, rng.uniform(0, 0.6, (40, 2))]
+        for data in cases:
+            data = np.ascontiguousarray(data, dtype=np.float64)
+            want = cKDTree(data).query_pairs(1, output_type='ndarray')
+            ok = ok and np.array_equal(want, _lib.query_pairs(data))
+        _native_checked = bool(ok)
+    return _native_checked
 
 
 def _label_frame(pos, separation):
@@ -186,15 +209,38 @@ def _pool_task(args):
 
 
 class _LabelJob(object):
-    """Labelling of all frames, possibly running in the worker pool while the caller does other
-    host work; ``result()`` waits and returns (cluster, cluster_size, by_cluster)."""
+    """Labelling of all frames, running on host threads inside libctk (ctk_cluster_frames; ctypes
+    releases the GIL) while the caller does other host work; ``result()`` waits and returns
+    (cluster, cluster_size, by_cluster).  If the library's kd-tree restatement does not reproduce
+    the installed scipy (self check), scipy itself is used: in worker processes for long videos."""
 
     def __init__(self, pos, starts, stops, separation):
         self.starts, self.stops = np.asarray(starts), np.asarray(stops)
         n_frames, n = len(starts), len(pos)
+        self.pool = None
+        self.thread = None
+        self.n = n
+        if os.environ.get('CTK_FIND_NATIVE', '1') != '0' and _native_is_exact():
+            self.error = None
+            args = (np.ascontiguousarray(pos, dtype=np.float64), self.starts.astype(np.int64),
+                    self.stops.astype(np.int64), separation, max(1, _pool_workers()))
+
+            def work():
+                try:
+                    self.cluster, self.size, self.by_cluster, spans = _lib.cluster_frames(*args)
+                    self.spans = spans.tolist()
+                except Exception as exc:       # re-raised in result()
+                    self.error = exc
+
+            if n_frames >= 8:
+                import threading
+                self.thread = threading.Thread(target=work)
+                self.thread.start()
+            else:
+                work()
+            return
         ranges = list(zip((int(a) for a in starts), (int(b) for b in stops)))
         self.pool = _get_pool() if n_frames >= _POOL_MIN_FRAMES else None
-        self.n = n
         if self.pool is None:
             self.cluster = np.empty(n, dtype=np.int64)
             self.size = np.empty(n, dtype=np.int64)
@@ -211,6 +257,11 @@ class _LabelJob(object):
         self.pool.send(self.tasks)
 
     def result(self):
+        if self.thread is not None:
+            self.thread.join()
+            self.thread = None
+        if getattr(self, 'error', None) is not None:
+            raise self.error
         if self.pool is not None:
             try:
                 spans = [s for part in self.pool.receive(len(self.tasks)) for s in part]

@@ -207,6 +207,27 @@ int ctk_label_clusters(const int64_t* pairs, int64_t n_pairs, int64_t n,
  * which fixes its cluster label values.  order_out [n_pairs] = insertion indices in iteration order. */
 int ctk_pairs_set_order(const int64_t* pairs, int64_t n_pairs, int64_t* order_out);
 
+/* Host helper (no GPU): the close pairs scipy.spatial.cKDTree(data).query_pairs(1,
+ * output_type='ndarray') reports, in the same order (find.py:87; restatement of scipy's kd-tree for
+ * this one call, verified against the installed scipy by find.py).  data [n, ndim] float64;
+ * pairs_out [capacity, 2] may be NULL to query the count only. */
+int ctk_query_pairs(const double* data, int64_t n, int32_t ndim, int64_t* pairs_out,
+                    int64_t capacity, int64_t* n_pairs_out);
+
+/* Host helper (no GPU): find_clusters for a whole video on host threads (find.py:72-129).
+ *   pos [n, ndim] float64, rows sorted by frame; frame f owns rows starts[f] .. stops[f]-1
+ *   separation [ndim]; n_threads worker threads (frames are independent)
+ *   cluster_out [n]    label of every row, local to its frame (caller adds the running offset of
+ *                      find.py:127-128 from span_out)
+ *   size_out [n]       cluster_size
+ *   by_cluster_out [n] row permutation that lists every frame's rows by label, original order kept
+ *                      inside a label (the group order of refine.py:336)
+ *   span_out [n_frames] largest label of the frame + 1 */
+int ctk_cluster_frames(const double* pos, int64_t n, int32_t ndim, const int64_t* starts,
+                       const int64_t* stops, int64_t n_frames, const double* separation,
+                       int32_t n_threads, int64_t* cluster_out, int64_t* size_out,
+                       int64_t* by_cluster_out, int64_t* span_out);
+
 #ifdef __cplusplus
 }
 #endif
