@@ -278,6 +278,58 @@ class _LabelJob(object):
         return cluster, self.size, self.by_cluster
 
 
+class ChunkLabeller(object):
+    """Labels a frame-sorted video chunk by chunk on a background thread, so that the caller can
+    pack and launch chunk k while chunk k+1 is being labelled.  ``frame_cuts`` = frame indices at
+    which the chunks begin and end (len K+1).  ``get(k)`` waits for chunk k and returns, for its
+    rows, (labels local to each frame, cluster sizes, permutation that lists the chunk's rows by
+    (frame, label) as indices into the chunk, per-frame label spans).
+
+    Without the verified native labelling (see ``_native_is_exact``) everything is one chunk
+    labelled through scipy."""
+
+    def __init__(self, pos, starts, stops, frame_cuts, separation):
+        import threading
+        self.native = os.environ.get('CTK_FIND_NATIVE', '1') != '0' and _native_is_exact()
+        self.starts, self.stops = np.asarray(starts, np.int64), np.asarray(stops, np.int64)
+        self.frame_cuts = list(frame_cuts) if self.native else [0, len(starts)]
+        self.results = [None] * (len(self.frame_cuts) - 1)
+        self.events = [threading.Event() for _ in self.results]
+        self.error = None
+        if not self.native:
+            job = _LabelJob(pos, starts, stops, separation)
+            job.result()
+            self.results[0] = (job.cluster, job.size, job.by_cluster, np.asarray(job.spans, np.int64))
+            self.events[0].set()
+            return
+        workers = max(1, _pool_workers())
+
+        def work():
+            try:
+                for k, (fa, fb) in enumerate(zip(self.frame_cuts[:-1], self.frame_cuts[1:])):
+                    a = int(self.starts[fa]) if fb > fa else 0
+                    b = int(self.stops[fb - 1]) if fb > fa else 0
+                    self.results[k] = _lib.cluster_frames(pos[a:b], self.starts[fa:fb] - a,
+                                                          self.stops[fa:fb] - a, separation, workers)
+                    self.events[k].set()
+            except Exception as exc:
+                self.error = exc
+                for ev in self.events:
+                    ev.set()
+
+        self.thread = threading.Thread(target=work, daemon=True)
+        self.thread.start()
+
+    def __len__(self):
+        return len(self.results)
+
+    def get(self, k):
+        self.events[k].wait()
+        if self.error is not None:
+            raise self.error
+        return self.results[k]
+
+
 def label_frames(pos, starts, stops, separation):
     """Per-frame labels for frame-sorted positions: -> (cluster ids with the running offset of
     find.py:127-128 applied, cluster sizes, permutation that sorts the rows by (frame, cluster)

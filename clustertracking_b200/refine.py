@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 from . import constraints as _constraints
-from .find import cluster_table, find_clusters
+from .find import ChunkLabeller, cluster_table, find_clusters
 from .fitfunc import FitFunctions
 from .utils import guess_pos_columns, is_isotropic, validate_tuple
 
@@ -151,15 +151,19 @@ def _solver_options(kwargs, compute_default):
             chord_tol)
 
 
-def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mode=None,
-            param_val=None, constraints=None, bounds=None, pos_columns=None, t_column='frame',
-            noise_size=None, threshold=None, max_iter=10, max_shift=1, max_rms_dev=1.,
-            residual_factor=100000., compute_error=False, frames_hook=None, empty=np.empty,
-            **kwargs):
-    """Host half of ``refine_leastsq``: returns a :class:`Plan` (no GPU work).  ``frames_hook`` is
-    called with a :class:`FrameInfo` as soon as the frames of the call are known, i.e. before the
-    clustering: ``refine_leastsq`` uses it to start the uploads while the host is still busy.
-    ``empty(shape, dtype)`` allocates the packed parameter table (pinned memory in production)."""
+class Prepared(object):
+    """What ``refine_leastsq`` knows before the clustering: the validated arguments, the model
+    (``ff``), the filled problem struct and the frames of the call."""
+
+
+def prepare_common(f, reader, diameter, separation=None, fit_function='gauss', param_mode=None,
+                   param_val=None, constraints=None, bounds=None, pos_columns=None,
+                   t_column='frame', noise_size=None, threshold=None, max_iter=10, max_shift=1,
+                   max_rms_dev=1., residual_factor=100000., compute_error=False, frames_hook=None,
+                   **kwargs):
+    """Argument handling of refine.py:242-315 (no clustering, no GPU work) -> :class:`Prepared`.
+    ``frames_hook`` is called with the :class:`FrameInfo` as soon as the frames of the call are
+    known: ``refine_leastsq`` uses it to start the uploads while the host is still busy."""
     lm_max_iter, compute_dtype, xtol, chord_tol = _solver_options(kwargs, 'float32')
     if pos_columns is None:
         pos_columns = guess_pos_columns(f)
@@ -198,53 +202,7 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
     info = FrameInfo(source, f[t_column].values, ndim)
     if frames_hook is not None:
         frames_hook(info)
-
-    import time as _time
-    _t0 = _time.perf_counter()
-    f, order = cluster_table(f, separation, pos_columns, t_column)     # refine.py:297 (a copy)
-    _t1 = _time.perf_counter()
-    if param_val is not None:                                          # refine.py:300-302
-        for col in param_val:
-            f[col] = param_val[col]
-    for col in ff.params:                                              # refine.py:303-305
-        if col not in f.columns:
-            f[col] = ff.default[col]
     tables = ff.validate_bounds(bounds, radius=radius)                 # refine.py:315
-
-    plan = Plan()
-    plan.f, plan.ff = f, ff
-    # column order of the parameter table follows ff.params, but positions are read from the
-    # user's pos_columns (refine.py:345 reads ff.params; they coincide for the default names)
-
-    # (frame, cluster) groups in the order of f.groupby(['frame', 'cluster'])     refine.py:336
-    # ``order`` lists the rows by (frame, cluster), row order kept inside a cluster
-    frames_s, cluster_s = f[t_column].values[order], f['cluster'].values[order]
-    n = len(order)
-    if n == 0:
-        raise ValueError("no features to refine")
-    new_group = np.empty(n, dtype=bool)
-    new_group[0] = True
-    new_group[1:] = (frames_s[1:] != frames_s[:-1]) | (cluster_s[1:] != cluster_s[:-1])
-    starts = np.flatnonzero(new_group)
-    plan.order = order
-    plan.cluster_offset = np.concatenate((starts, [n])).astype(np.int32)
-    plan.frame_numbers = info.numbers
-    plan.cluster_frame = np.searchsorted(info.sorted_numbers, frames_s[starts]).astype(np.int32)
-    params_in = empty((n, len(ff.params)), np.float64)
-    columns = [np.asarray(f[col].values, dtype=np.float64) for col in ff.params]
-
-    def gather(span):                                                  # packed, group order
-        a, b = span
-        rows = order[a:b]
-        for j, col in enumerate(columns):
-            params_in[a:b, j] = col[rows]
-
-    _parallel(gather, _spans(n))
-    plan.params_in = params_in
-    plan.frame_source = source
-    plan.frame_shape = info.shape
-    plan.pixel_dtype = info.dtype
-    plan.frame_info = info
 
     prob = _lib.Problem()
     prob.ndim, prob.isotropic, prob.family = ndim, int(isotropic), ff.family
@@ -253,7 +211,7 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
         prob.modes[j] = m
     for k, r in enumerate(radius):
         prob.radius[k] = r
-    prob.pixel_dtype = _lib.PIXEL_CODES[np.dtype(plan.pixel_dtype)]
+    prob.pixel_dtype = _lib.PIXEL_CODES[np.dtype(info.dtype)]
     prob.compute_dtype = compute_dtype
     prob.max_iter, prob.lm_max_iter = int(max_iter), lm_max_iter
     prob.max_shift, prob.max_rms_dev = float(max_shift), float(max_rms_dev)
@@ -277,7 +235,72 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
         for side in range(2):
             for j in range(_lib.CTK_MAX_PARAMS):
                 dst[side][j] = table[side, j] if j < len(ff.params) else np.nan
-    plan.problem = prob
+
+    pre = Prepared()
+    pre.ff, pre.problem, pre.info = ff, prob, info
+    pre.pos_columns, pre.t_column, pre.separation = list(pos_columns), t_column, separation
+    pre.param_val, pre.ndim = param_val, ndim
+    return pre
+
+
+def _plan_for(pre, order, cluster_offset, cluster_frame, params_in):
+    plan = Plan()
+    plan.ff, plan.problem = pre.ff, pre.problem
+    plan.order, plan.cluster_offset, plan.cluster_frame = order, cluster_offset, cluster_frame
+    plan.params_in = params_in
+    info = pre.info
+    plan.frame_numbers, plan.frame_source = info.numbers, info.source
+    plan.frame_shape, plan.pixel_dtype, plan.frame_info = info.shape, info.dtype, info
+    return plan
+
+
+def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mode=None,
+            param_val=None, constraints=None, bounds=None, pos_columns=None, t_column='frame',
+            noise_size=None, threshold=None, max_iter=10, max_shift=1, max_rms_dev=1.,
+            residual_factor=100000., compute_error=False, frames_hook=None, empty=np.empty,
+            **kwargs):
+    """Host half of ``refine_leastsq`` for the whole table at once: returns a :class:`Plan` (no GPU
+    work).  ``empty(shape, dtype)`` allocates the packed parameter table."""
+    pre = prepare_common(f, reader, diameter, separation, fit_function, param_mode, param_val,
+                         constraints, bounds, pos_columns, t_column, noise_size, threshold,
+                         max_iter, max_shift, max_rms_dev, residual_factor, compute_error,
+                         frames_hook=frames_hook, **kwargs)
+    ff, info = pre.ff, pre.info
+    import time as _time
+    _t0 = _time.perf_counter()
+    f, order = cluster_table(f, pre.separation, pre.pos_columns, t_column)   # refine.py:297 (a copy)
+    _t1 = _time.perf_counter()
+    if param_val is not None:                                          # refine.py:300-302
+        for col in param_val:
+            f[col] = param_val[col]
+    for col in ff.params:                                              # refine.py:303-305
+        if col not in f.columns:
+            f[col] = ff.default[col]
+
+    # (frame, cluster) groups in the order of f.groupby(['frame', 'cluster'])     refine.py:336
+    # ``order`` lists the rows by (frame, cluster), row order kept inside a cluster
+    frames_s, cluster_s = f[t_column].values[order], f['cluster'].values[order]
+    n = len(order)
+    if n == 0:
+        raise ValueError("no features to refine")
+    new_group = np.empty(n, dtype=bool)
+    new_group[0] = True
+    new_group[1:] = (frames_s[1:] != frames_s[:-1]) | (cluster_s[1:] != cluster_s[:-1])
+    starts = np.flatnonzero(new_group)
+    params_in = empty((n, len(ff.params)), np.float64)
+    columns = [np.asarray(f[col].values, dtype=np.float64) for col in ff.params]
+
+    def gather(span):                                                  # packed, group order
+        a, b = span
+        rows = order[a:b]
+        for j, col in enumerate(columns):
+            params_in[a:b, j] = col[rows]
+
+    _parallel(gather, _spans(n))
+    plan = _plan_for(pre, order, np.concatenate((starts, [n])).astype(np.int32),
+                     np.searchsorted(info.sorted_numbers, frames_s[starts]).astype(np.int32),
+                     params_in)
+    plan.f = f
     plan.timing = dict(cluster_ms=1e3 * (_t1 - _t0), pack_ms=1e3 * (_time.perf_counter() - _t1))
     return plan
 
@@ -708,6 +731,57 @@ def execute_cuda(plan, device=None, want_stats=True, frames=None):
     return result
 
 
+class Pending(object):
+    """A launched chunk: the kernels and the result copies are enqueued; ``result()`` waits for the
+    copies (an event, not a device-wide synchronisation) and returns the :class:`Result`."""
+
+    def __init__(self, session, result, event):
+        self.session, self._result, self.event = session, result, event
+
+    def result(self):
+        if self.event is not None:
+            self.event.synchronize()
+            self.event = None
+        res = self._result
+        session = self.session
+        if len(session.never_run):            # too many features for any kernel: never launched
+            res.status[session.never_run] = _lib.STATUS_TOO_LARGE
+            rows = np.repeat(res.status == _lib.STATUS_TOO_LARGE, session.sizes)
+            res.params_out[rows] = session.plan.params_in[rows]
+        return res
+
+
+def launch_cuda(plan, frames, out_params, out_cost, out_status):
+    """Enqueue one plan on the current CUDA device (uploads, one launch per size class, result
+    copies into the given pinned host arrays) and return a :class:`Pending` without waiting."""
+    session = DeviceSession(plan, frames=frames)
+    torch = session.torch
+    with torch.cuda.device(session.dev):
+        session.run(session.schedule())
+        result = Result(plan, allocate=False)
+        result.stats = None
+        for tensor, dst in ((session.d_out, out_params), (session.d_cost, out_cost),
+                            (session.d_status, out_status)):
+            host = torch.from_numpy(dst)
+            host.copy_(tensor.view(host.dtype).reshape(host.shape), non_blocking=True)
+            session.d2h_bytes += dst.nbytes
+        event = torch.cuda.Event()
+        event.record()
+    result.params_out, result.cost, result.status = out_params, out_cost, out_status
+    result.session = session
+    return Pending(session, result, event)
+
+
+_CHUNK_ROWS = int(os.environ.get('CTK_CHUNK_ROWS', 1 << 18))   # features per pipeline chunk
+_MAX_CHUNKS = 16
+
+
+def _pinned_array(key, shape, dtype):
+    import torch
+    nbytes = max(1, int(np.prod(shape)) * np.dtype(dtype).itemsize)
+    return _pinned_buffer(torch, key, nbytes)[:nbytes].numpy().view(dtype).reshape(shape)
+
+
 def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', param_mode=None,
                    param_val=None, constraints=None, bounds=None, pos_columns=None,
                    t_column='frame', noise_size=None, threshold=None, max_iter=10, max_shift=1,
@@ -730,29 +804,155 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
       ignored; ``precision='float64'`` switches the pixel arithmetic from float32 to float64.
     """
     import time
+    import pandas as pd
     t0 = time.perf_counter()
     started = []          # the uploads start as soon as the frames are known, before the clustering
+    pre = prepare_common(f, reader, diameter, separation, fit_function, param_mode, param_val,
+                         constraints, bounds, pos_columns, t_column, noise_size, threshold,
+                         max_iter, max_shift, max_rms_dev, residual_factor, compute_error,
+                         frames_hook=lambda info: started.append(FrameSet(info).upload_async()),
+                         **kwargs)
+    ff, info = pre.ff, pre.info
+    frameset = started[0]
+    P = len(ff.params)
 
-    def pinned_empty(shape, dtype):
-        import torch
-        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        return _pinned_buffer(torch, "params_in", nbytes)[:nbytes].numpy().view(dtype).reshape(shape)
-
-    plan = prepare(f, reader, diameter, separation, fit_function, param_mode, param_val,
-                   constraints, bounds, pos_columns, t_column, noise_size, threshold, max_iter,
-                   max_shift, max_rms_dev, residual_factor, compute_error,
-                   frames_hook=lambda info: started.append(FrameSet(info).upload_async()),
-                   empty=pinned_empty, **kwargs)
+    # ---- frame-sorted view of the table (find.py:122-129: the result is sorted by frame) ----------
+    frames_col = f[t_column].values
+    n = len(f)
+    if n > 1 and not np.all(frames_col[1:] >= frames_col[:-1]):
+        order0 = np.argsort(frames_col, kind='stable')
+        base = f.iloc[order0]
+        frames_col = frames_col[order0]
+    else:
+        order0, base = None, f
+    pos = np.ascontiguousarray(base[pre.pos_columns].values, dtype=np.float64)
+    cuts = np.flatnonzero(frames_col[1:] != frames_col[:-1]) + 1
+    starts = np.concatenate(([0], cuts)).astype(np.int64)
+    stops = np.concatenate((cuts, [n])).astype(np.int64)
+    n_frames = len(starts)
+    # chunks of whole frames with about _CHUNK_ROWS features each
+    k_chunks = int(max(1, min(_MAX_CHUNKS, n // max(1, _CHUNK_ROWS), n_frames)))
+    frame_cuts = np.unique(np.searchsorted(starts, np.linspace(0, n, k_chunks + 1)[1:-1]))
+    frame_cuts = [0] + [int(c) for c in frame_cuts if 0 < c < n_frames] + [n_frames]
+    separation = np.asarray(validate_tuple(pre.separation, pre.ndim), dtype=np.float64)
+    labeller = ChunkLabeller(pos, starts, stops, frame_cuts, separation)
+    frame_cuts = labeller.frame_cuts
     t1 = time.perf_counter()
-    result = execute_cuda(plan, want_stats=False, frames=started[0])
+
+    # ---- parameter columns: from the table, from param_val, or the model's defaults ---------------
+    sources = []                                   # per column: 1-D float64 array or a scalar
+    for col in ff.params:
+        if param_val is not None and col in param_val:
+            sources.append(float(param_val[col]))
+        elif col in base.columns:
+            sources.append(np.asarray(base[col].values, dtype=np.float64))
+        else:
+            sources.append(float(ff.default[col]))
+    params_in = _pinned_array("params_in", (n, P), np.float64)     # packed, group order
+    out_params = _pinned_array("params", (n, P), np.float64)
+    out_cost = _pinned_array("cost", (n,), np.float64)             # one entry per cluster (<= n)
+    out_status = _pinned_array("status", (n,), np.int32)
+    block = np.empty((P, n), dtype=np.float64)                     # fitted columns, table order
+    cost = np.empty(n, dtype=np.float64)
+    cluster = np.empty(n, dtype=np.int64)
+    csize = np.empty(n, dtype=np.int64)
+    frame_of_row = np.repeat(np.arange(n_frames, dtype=np.int32), stops - starts)
+    chunks = []                                    # (a, b, order_c, plan, pending, c0)
+    totals = dict(h2d=0, d2h=0, launches=0, failed=0)
+    next_id, c0 = 0, 0
+
+    def finish(chunk):
+        a, b, order_c, plan, pending, _ = chunk
+        res = pending.result()
+        sizes = plan.cluster_sizes()
+        ok = res.status == 0
+        src = res.params_out
+        if not ok.all():                  # belt and braces: failed clusters keep their input exactly
+            rows = np.repeat(~ok, sizes)
+            src[rows] = plan.params_in[rows]
+
+        def scatter(j):
+            block[j, order_c] = src[:, j]
+
+        _parallel(scatter, range(P))
+        cost[order_c] = np.repeat(np.where(ok, res.cost, np.nan), sizes)
+        failed = np.flatnonzero(~ok)
+        for c in failed[:max(0, 20 - totals['failed'])]:
+            logger.warning("RefineException: cluster %d: %s",
+                           int(cluster[order_c[plan.cluster_offset[c]]]),
+                           _lib.STATUS_NAMES.get(int(res.status[c]), "status %d" % res.status[c]))
+        totals['failed'] += len(failed)
+        session = res.session
+        totals['h2d'] += session.h2d_bytes
+        totals['d2h'] += session.d2h_bytes
+        totals['launches'] += session.launches
+
+    for k, (fa, fb) in enumerate(zip(frame_cuts[:-1], frame_cuts[1:])):
+        a, b = int(starts[fa]), int(stops[fb - 1])
+        local, size, by_cluster, spans = labeller.get(k)
+        counts = stops[fa:fb] - starts[fa:fb]
+        offsets = next_id + np.concatenate(([0], np.cumsum(spans)[:-1]))    # find.py:127-128
+        next_id += int(np.sum(spans))
+        np.add(local, np.repeat(offsets, counts), out=cluster[a:b])
+        csize[a:b] = size
+        order_c = by_cluster + a                   # rows by (frame, cluster): refine.py:336
+        cl_s = cluster[order_c]
+        new_group = np.empty(b - a, dtype=bool)
+        new_group[0] = True
+        np.not_equal(cl_s[1:], cl_s[:-1], out=new_group[1:])   # labels are unique over frames
+        g_starts = np.flatnonzero(new_group)
+        m = b - a
+        chunk_in = params_in[a:b]
+
+        def gather(span, order_c=order_c, chunk_in=chunk_in):
+            u, v = span
+            rows = order_c[u:v]
+            for j, src in enumerate(sources):
+                chunk_in[u:v, j] = src[rows] if isinstance(src, np.ndarray) else src
+
+        _parallel(gather, _spans(m, 1 << 16))
+        plan = _plan_for(pre, order_c, np.concatenate((g_starts, [m])).astype(np.int32),
+                         frame_of_row[order_c[g_starts]], chunk_in)
+        n_c = len(g_starts)
+        pending = launch_cuda(plan, frameset, out_params[a:b], out_cost[c0:c0 + n_c],
+                              out_status[c0:c0 + n_c])
+        chunks.append((a, b, order_c, plan, pending, c0))
+        c0 += n_c
+        if k > 0:
+            finish(chunks[k - 1])                  # while the device works on chunk k
     t2 = time.perf_counter()
-    out = finalize(plan, result)
+    finish(chunks[-1])
+    if totals['failed'] > 20:
+        logger.warning("RefineException: ... and %d more clusters failed", totals['failed'] - 20)
     t3 = time.perf_counter()
+
+    # ---- the result table: a frame-sorted copy of f with the new columns (refine.py:296-305) -------
+    data = {}
+    fitted = {col: block[j] for j, col in enumerate(ff.params)}
+    for col in base.columns:
+        if col in fitted:
+            data[col] = fitted[col]
+        elif param_val is not None and col in param_val:
+            data[col] = np.full(n, param_val[col])
+        else:
+            data[col] = np.array(base[col].values)          # an independent copy, like f.copy()
+    data['cluster'] = cluster
+    data['cluster_size'] = csize
+    if param_val is not None:
+        for col in param_val:
+            if col not in data:
+                data[col] = fitted[col] if col in fitted else np.full(n, param_val[col])
+    for col in ff.params:
+        if col not in data:
+            data[col] = fitted[col]
+    data['cost'] = cost
+    out = pd.DataFrame(data, index=base.index, copy=False)
+    t4 = time.perf_counter()
     LAST_CALL.clear()
-    LAST_CALL.update(h2d_bytes=result.session.h2d_bytes, d2h_bytes=result.session.d2h_bytes,
-                     launches=result.session.launches,
-                     phases_ms=dict(prepare=1e3 * (t1 - t0), device=1e3 * (t2 - t1),
-                                    finalize=1e3 * (t3 - t2), **plan.timing, **result.timing))
+    LAST_CALL.update(h2d_bytes=totals['h2d'] + frameset.h2d_bytes, d2h_bytes=totals['d2h'],
+                     launches=totals['launches'] + frameset.launches, chunks=len(chunks),
+                     phases_ms=dict(setup=1e3 * (t1 - t0), chunks=1e3 * (t2 - t1),
+                                    last_chunk=1e3 * (t3 - t2), table=1e3 * (t4 - t3)))
     return out
 
 

@@ -195,3 +195,68 @@ def test_frame_column_is_added_in_place_like_the_reference():
     plan = refine.prepare(f, img, 9)
     assert 'frame' in f and (f['frame'] == 0).all()          # refine.py:279
     assert list(plan.f.columns[:7]) == ['y', 'x', 'signal', 'size', 'frame', 'cluster', 'cluster_size']
+
+
+# ---- the chunked pipeline of refine_leastsq (host logic; the solver is the one-lane emulation) -----
+class _NoFrames(object):
+    h2d_bytes = launches = 0
+
+    def __init__(self, info, device=None):
+        pass
+
+    def upload_async(self):
+        return self
+
+
+class _Done(object):
+    def __init__(self, result):
+        self._result = result
+
+    def result(self):
+        return self._result
+
+
+def _emulated_launch(plan, frames, out_params, out_cost, out_status):
+    import emul_backend
+    result = emul_backend.execute(plan)
+    out_params[...], out_cost[...], out_status[...] = result.params_out, result.cost, result.status
+    result.params_out, result.cost, result.status = out_params, out_cost, out_status
+    result.session = type("S", (), dict(h2d_bytes=0, d2h_bytes=0, launches=0))()
+    return _Done(result)
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_pipelined_chunks_equal_whole_table(monkeypatch, shuffle):
+    import torch
+    import emul_backend
+    from clustertracking_b200 import artificial
+    stack, rows = [], []
+    for t in range(6):
+        frame, f0, _ = artificial.clustered_frame((96, 96), pitch=44, seed=70 + t)
+        f0['frame'] = 2 * t + 1
+        f0['tag'] = np.arange(len(f0)) + 100 * t                # a column the fit does not touch
+        stack.append(frame)
+        rows.append(f0)
+    reader = {2 * t + 1: stack[t] for t in range(6)}
+
+    class Reader(dict):
+        frame_shape = (96, 96)
+
+    reader = Reader(reader)
+    f = pd.concat(rows, ignore_index=True)
+    if shuffle:
+        f = f.sample(frac=1., random_state=3)
+    want, _ = emul_backend.refine_leastsq(f.copy(), reader, 11, param_val=dict(size=2.75))
+    monkeypatch.setattr(refine, "FrameSet", _NoFrames)
+    monkeypatch.setattr(refine, "_pinned_buffer",
+                        lambda torch_, key, nbytes: torch.empty(max(nbytes, 1), dtype=torch.uint8))
+    monkeypatch.setattr(refine, "launch_cuda", _emulated_launch)
+    monkeypatch.setattr(refine, "_CHUNK_ROWS", 8)
+    got = refine.refine_leastsq(f.copy(), reader, 11, param_val=dict(size=2.75))
+    assert refine.LAST_CALL["chunks"] > 2
+    assert list(got.columns) == list(want.columns)
+    assert_array_equal(got.index.values, want.index.values)
+    for col in want.columns:
+        assert got[col].dtype == want[col].dtype, col
+        assert_array_equal(got[col].values, want[col].values, err_msg=col)
+    got.loc[got.index[0], 'x'] = 1.0                            # the result is writable

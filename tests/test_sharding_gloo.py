@@ -39,7 +39,7 @@ def _worker(rank, world, port, out_dir):
     from clustertracking_b200 import parallel, refine
     refine.FrameSet = _NoFrames          # no GPU here: the emulated solver reads the host frames
     refine._pinned_buffer = lambda torch, key, nbytes: torch.empty(max(nbytes, 1), dtype=torch.uint8)
-    refine.execute_cuda = lambda plan, device=None, **kw: _with_session(emul_backend.execute(plan))
+    refine.launch_cuda = _emulated_launch
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank,
                             world_size=world)
     reader, f0 = _video()
@@ -49,6 +49,8 @@ def _worker(rank, world, port, out_dir):
 
 
 class _NoFrames(object):
+    h2d_bytes = launches = 0
+
     def __init__(self, info, device=None):
         pass
 
@@ -60,10 +62,22 @@ class _Session(object):
     h2d_bytes = d2h_bytes = launches = 0
 
 
-def _with_session(result):
+class _Done(object):
+    def __init__(self, result):
+        self._result = result
+
+    def result(self):
+        return self._result
+
+
+def _emulated_launch(plan, frames, out_params, out_cost, out_status):
+    """Stand-in for ``refine.launch_cuda``: the one-lane host build of the device solver."""
+    import emul_backend
+    result = emul_backend.execute(plan)
+    out_params[...], out_cost[...], out_status[...] = result.params_out, result.cost, result.status
+    result.params_out, result.cost, result.status = out_params, out_cost, out_status
     result.session = _Session()
-    result.timing = {}
-    return result
+    return _Done(result)
 
 
 def test_two_rank_sharding_matches_single_process(tmp_path):
