@@ -67,6 +67,11 @@ _PROTOTYPES = {
                                                 _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "ctk_label_clusters": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "ctk_pairs_set_order": (ctypes.c_int, [_vp, _i64, _vp]),
+    "ctk_group_chunk": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp,
+                                       _vp, _vp, _vp]),
+    "ctk_gather_rows": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _i32]),
+    "ctk_scatter_rows": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp,
+                                        _i32, _vp]),
     "ctk_query_pairs": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i64, _vp]),
     "ctk_cluster_frames": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp,
                                           _vp]),
@@ -152,3 +157,55 @@ def cluster_frames(pos, starts, stops, separation, n_threads):
                                     cluster.ctypes.data, size.ctypes.data, by_cluster.ctypes.data,
                                     spans.ctypes.data), "ctk_cluster_frames")
     return cluster, size, by_cluster, spans
+
+
+def group_chunk(local, by_cluster, starts, stops, spans, next_id, row_base, frame_base, cluster_out):
+    """``ctk_group_chunk`` -> (order, group_offset int32 [g + 1], group_frame int32 [g], next_id);
+    ``cluster_out`` (int64 [m], a view into the table's cluster column) is filled in place."""
+    m = len(local)
+    order = np.empty(m, dtype=np.int64)
+    goff = np.empty(m + 1, dtype=np.int32)
+    gframe = np.empty(max(m, 1), dtype=np.int32)
+    n_groups, nxt = ctypes.c_int64(0), ctypes.c_int64(0)
+    assert cluster_out.flags.c_contiguous and cluster_out.dtype == np.int64
+    check(load().ctk_group_chunk(local.ctypes.data, by_cluster.ctypes.data, starts.ctypes.data,
+                                 stops.ctypes.data, spans.ctypes.data, len(starts), int(next_id),
+                                 int(row_base), int(frame_base), cluster_out.ctypes.data,
+                                 order.ctypes.data, goff.ctypes.data, gframe.ctypes.data,
+                                 ctypes.byref(n_groups), ctypes.byref(nxt)), "ctk_group_chunk")
+    g = n_groups.value
+    return order, goff[:g + 1], gframe[:g], nxt.value
+
+
+def gather_rows(sources, rows, out, n_threads):
+    """``ctk_gather_rows``: out[r, j] = sources[j][rows[r]] (array) or sources[j] (scalar)."""
+    n_cols = len(sources)
+    ptrs = (ctypes.c_void_p * n_cols)()
+    scalars = (ctypes.c_double * n_cols)()
+    for j, src in enumerate(sources):
+        if isinstance(src, np.ndarray):
+            assert src.dtype == np.float64 and src.flags.c_contiguous
+            ptrs[j] = src.ctypes.data
+        else:
+            ptrs[j] = None
+            scalars[j] = float(src)
+    assert out.flags.c_contiguous and out.dtype == np.float64 and rows.dtype == np.int64
+    check(load().ctk_gather_rows(ptrs, scalars, rows.ctypes.data, len(rows), n_cols,
+                                 out.ctypes.data, int(n_threads)), "ctk_gather_rows")
+
+
+def scatter_rows(params, params_in, rows, group_offset, group_cost, group_status, block, cost_out,
+                 n_threads):
+    """``ctk_scatter_rows``: write one chunk back into the table-order column block [P, N] and the
+    cost column; returns the number of failed clusters."""
+    n_cols = block.shape[0]
+    ptrs = (ctypes.c_void_p * n_cols)(*[block[j].ctypes.data for j in range(n_cols)])
+    failed = ctypes.c_int64(0)
+    for arr in (params, params_in, rows, group_offset, group_cost, group_status, block, cost_out):
+        assert arr.flags.c_contiguous
+    check(load().ctk_scatter_rows(params.ctypes.data, params_in.ctypes.data, rows.ctypes.data,
+                                  len(rows), n_cols, group_offset.ctypes.data,
+                                  group_cost.ctypes.data, group_status.ctypes.data,
+                                  len(group_status), ptrs, cost_out.ctypes.data, int(n_threads),
+                                  ctypes.byref(failed)), "ctk_scatter_rows")
+    return failed.value

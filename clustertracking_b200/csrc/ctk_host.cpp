@@ -476,3 +476,107 @@ extern "C" int ctk_cluster_frames(const double* pos, int64_t n, int32_t ndim, co
   }
   return failed ? CTK_E_INVALID : 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Packing helpers of the host pipeline (refine.py:336-345, 426-427): plain loops on host threads
+// in place of numpy fancy indexing on one core.
+// ------------------------------------------------------------------------------------------------
+namespace {
+template <class Fn>
+void parallel_ranges(int64_t n, int n_threads, Fn&& fn) {
+  int nt = n_threads < 1 ? 1 : n_threads;
+  if (n < (int64_t) nt * 8192) nt = (int) (n / 8192) + 1;
+  if (nt <= 1) { fn((int64_t) 0, n); return; }
+  std::vector<std::thread> pool;
+  const int64_t step = (n + nt - 1) / nt;
+  for (int k = 0; k < nt; ++k) {
+    const int64_t a = k * step, b = a + step < n ? a + step : n;
+    if (a >= b) break;
+    pool.emplace_back([=, &fn]() { fn(a, b); });
+  }
+  for (auto& th : pool) th.join();
+}
+}  // namespace
+
+// Running cluster ids, group order and group table of one labelled chunk of frames.
+//   local_labels, by_cluster [m]  outputs of ctk_cluster_frames for the chunk (chunk-local rows)
+//   starts, stops [n_frames]       chunk-local row range of each frame; spans [n_frames]
+//   next_id                        running offset of find.py:127-128 before this chunk
+//   row_base                       table row of the chunk's first row; frame_base: index of its first frame
+//   cluster_out [m] labels with the running offset; order_out [m] table rows by (frame, cluster);
+//   group_offset_out [m + 1] int32; group_frame_out [m] int32; *n_groups_out; *next_id_out
+extern "C" int ctk_group_chunk(const int64_t* local_labels, const int64_t* by_cluster,
+                               const int64_t* starts, const int64_t* stops, const int64_t* spans,
+                               int64_t n_frames, int64_t next_id, int64_t row_base,
+                               int32_t frame_base, int64_t* cluster_out, int64_t* order_out,
+                               int32_t* group_offset_out, int32_t* group_frame_out,
+                               int64_t* n_groups_out, int64_t* next_id_out) {
+  if (n_frames < 0 || !n_groups_out || !next_id_out) return CTK_E_INVALID;
+  int64_t groups = 0;
+  for (int64_t f = 0; f < n_frames; ++f) {
+    const int64_t a = starts[f], b = stops[f];
+    for (int64_t i = a; i < b; ++i) cluster_out[i] = local_labels[i] + next_id;
+    int64_t prev = -1;
+    for (int64_t i = a; i < b; ++i) {
+      const int64_t row = by_cluster[i];
+      order_out[i] = row + row_base;
+      const int64_t label = local_labels[row];
+      if (label != prev) {
+        group_offset_out[groups] = (int32_t) i;
+        group_frame_out[groups] = frame_base + (int32_t) f;
+        ++groups;
+        prev = label;
+      }
+    }
+    next_id += spans[f];
+  }
+  group_offset_out[groups] = n_frames ? (int32_t) stops[n_frames - 1] : 0;
+  *n_groups_out = groups;
+  *next_id_out = next_id;
+  return 0;
+}
+
+// out[r, j] = columns[j] ? columns[j][rows[r]] : scalars[j]
+extern "C" int ctk_gather_rows(const double* const* columns, const double* scalars,
+                               const int64_t* rows, int64_t n, int32_t n_cols, double* out,
+                               int32_t n_threads) {
+  if (n < 0 || n_cols < 1 || !columns || !scalars || (n > 0 && (!rows || !out))) return CTK_E_INVALID;
+  parallel_ranges(n, n_threads, [=](int64_t a, int64_t b) {
+    for (int64_t r = a; r < b; ++r) {
+      const int64_t row = rows[r];
+      double* dst = out + r * n_cols;
+      for (int j = 0; j < n_cols; ++j) dst[j] = columns[j] ? columns[j][row] : scalars[j];
+    }
+  });
+  return 0;
+}
+
+// Write-back of one chunk (refine.py:408-427): columns[j][rows[r]] = params[r, j] for clusters with
+// status 0, the untouched input (params_in) for failed ones; cost_out[rows[r]] = the cluster's cost
+// or NaN.  Returns the number of failed clusters in *n_failed_out.
+extern "C" int ctk_scatter_rows(const double* params, const double* params_in, const int64_t* rows,
+                                int64_t n, int32_t n_cols, const int32_t* group_offset,
+                                const double* group_cost, const int32_t* group_status,
+                                int64_t n_groups, double* const* columns, double* cost_out,
+                                int32_t n_threads, int64_t* n_failed_out) {
+  if (n < 0 || n_cols < 1 || n_groups < 0 || !columns || !cost_out || !n_failed_out)
+    return CTK_E_INVALID;
+  std::atomic<int64_t> failed(0);
+  parallel_ranges(n_groups, n_threads, [=, &failed](int64_t a, int64_t b) {
+    int64_t bad = 0;
+    for (int64_t g = a; g < b; ++g) {
+      const bool ok = group_status[g] == 0;
+      const double cost = ok ? group_cost[g] : NAN;
+      const double* src = ok ? params : params_in;
+      bad += ok ? 0 : 1;
+      for (int64_t r = group_offset[g]; r < group_offset[g + 1]; ++r) {
+        const int64_t row = rows[r];
+        for (int j = 0; j < n_cols; ++j) columns[j][row] = src[r * n_cols + j];
+        cost_out[row] = cost;
+      }
+    }
+    failed += bad;
+  });
+  *n_failed_out = failed.load();
+  return 0;
+}

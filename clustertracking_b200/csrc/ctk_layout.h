@@ -88,8 +88,17 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
   const bool rigorous = n_max >= CTK_MAX_CLUSTER_FEATURES || p.capacity_mode == 1;
   const int entry_bytes = big ? 8 : 4;
   lay->mask_words = big ? (n_max + 31) / 32 : 1;
-  const int f_bound = mask_capacity(p.radius, nd);
-  int f_typ = mask_typical(p.radius, nd) + 2;
+  // the two mask sizes only depend on the radii: remember the last answer (one launch per size
+  // class asks again with the same problem)
+  static thread_local int memo_key[4] = {-1, -1, -1, -1}, memo_bound = 0, memo_typ = 0;
+  const int key[4] = {nd, p.radius[0], nd > 1 ? p.radius[1] : 0, nd > 2 ? p.radius[2] : 0};
+  if (memcmp(key, memo_key, sizeof(key)) != 0) {
+    memo_bound = mask_capacity(p.radius, nd);
+    memo_typ = mask_typical(p.radius, nd);
+    memcpy(memo_key, key, sizeof(key));
+  }
+  const int f_bound = memo_bound;
+  int f_typ = memo_typ + 2;
   if (f_typ > f_bound) f_typ = f_bound;
   lay->f_cap = rigorous ? f_bound : f_typ;
   if (lay->f_cap > 16384) return false;

@@ -422,6 +422,45 @@ def _pinned_buffer(torch, key, nbytes):
     return buf
 
 
+class _PinnedArena(object):
+    """Bump allocator over one cached pinned buffer for the small per-launch uploads (cluster
+    offsets, frame indices, work ids).  A pageable source would make every ``.to(device)`` wait for
+    the kernels already queued on the stream; from pinned memory the copies are asynchronous.
+    ``reset()`` is called at the start of a ``refine_leastsq`` call, after the previous call has
+    synchronised, so the memory is not reused while a copy is in flight."""
+
+    def __init__(self):
+        self.offset = 0
+        self.fallback = []
+
+    def reset(self):
+        self.offset = 0
+        self.fallback = []
+
+    def stage(self, torch, array):
+        """-> pinned torch tensor holding a copy of ``array`` (1-D view of its bytes as its dtype)."""
+        array = np.ascontiguousarray(array)
+        nbytes = array.nbytes
+        buf = _PINNED.get("arena")
+        if buf is None:
+            buf = _pinned_buffer(torch, "arena", 64 << 20)
+        start = (self.offset + 255) & ~255
+        if start + nbytes > buf.numel():          # does not fit: a one-off pinned tensor
+            t = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+            self.fallback.append(t)
+            view = t[:nbytes]
+        else:
+            view = buf[start:start + nbytes]
+            self.offset = start + nbytes
+        host = view.numpy().view(array.dtype).reshape(array.shape)
+        host[...] = array
+        return torch.from_numpy(host)
+
+
+_ARENA = _PinnedArena()
+_FITS_CACHE = {}      # (problem bytes) -> per-class capacity answers of the library
+
+
 class FrameSet(object):
     """The frames of one call on the device: a table of frame pointers and the per-frame maxima.
     ``upload_async`` enqueues the copies batch by batch on a copy stream and the ``ctk_frame_max``
@@ -574,8 +613,10 @@ class DeviceSession(object):
 
     def _up(self, array):
         t = self.torch.from_numpy(np.ascontiguousarray(array))
+        if not t.is_pinned() and self.torch.cuda.is_available():
+            t = _ARENA.stage(self.torch, array)
         self.h2d_bytes += t.numel() * t.element_size()
-        return t.to(self.dev, non_blocking=t.is_pinned())
+        return t.to(self.dev, non_blocking=True)
 
     def stream_ptr(self):
         return _lib.ctypes.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
@@ -588,16 +629,23 @@ class DeviceSession(object):
         sizes = self.sizes
         caps = np.asarray(_BINS)
         cls = np.searchsorted(caps, sizes)                     # size class of every cluster
-        prob = _lib.ctypes.byref(self.plan.problem)
         self.rigorous = rigorous_problem(self.plan.problem)
-        rig = _lib.ctypes.byref(self.rigorous)
         small = caps <= _lib.CTK_MAX_CLUSTER_FEATURES
-        fits = np.array([(self.lib.ctk_refine_shared_bytes(prob, int(c)) > 0 if c <= _lib.CTK_MAX_CLUSTER_FEATURES
-                          else 0 < self.lib.ctk_refine_workspace_bytes_for(prob, int(c)) <= _BIG_WORKSPACE_LIMIT)
-                         for c in caps] + [False])
+        key = bytes(self.plan.problem)
+        if key not in _FITS_CACHE:                 # the capacity queries only depend on the problem
+            prob = _lib.ctypes.byref(self.plan.problem)
+            rig = _lib.ctypes.byref(self.rigorous)
+            fits = np.array([(self.lib.ctk_refine_shared_bytes(prob, int(c)) > 0
+                              if c <= _lib.CTK_MAX_CLUSTER_FEATURES else
+                              0 < self.lib.ctk_refine_workspace_bytes_for(prob, int(c)) <= _BIG_WORKSPACE_LIMIT)
+                             for c in caps] + [False])
+            retry_fits = {int(c): self.lib.ctk_refine_shared_bytes(rig, int(c)) > 0
+                          for c in caps[small]}
+            if len(_FITS_CACHE) > 64:
+                _FITS_CACHE.clear()
+            _FITS_CACHE[key] = (fits, retry_fits)
         # classes whose typical-case capacities can overflow, and whether the rigorous ones fit
-        self.retry_fits = {int(c): self.lib.ctk_refine_shared_bytes(rig, int(c)) > 0
-                           for c in caps[small]}
+        fits, self.retry_fits = _FITS_CACHE[key]
         first_big = int(np.flatnonzero(~small)[0])
         self.big_fallback = int(caps[first_big]) if fits[first_big] else None
         cls = np.minimum(cls, len(caps))
@@ -605,7 +653,7 @@ class DeviceSession(object):
         if self.big_fallback is not None:
             cls = np.where(spill, first_big, cls)
         runnable = fits[cls]
-        key = cls.astype(np.int64) * 64 + (63 - np.minimum(sizes, 63))
+        key = (cls * 64 + (63 - np.minimum(sizes, 63))).astype(np.uint16)   # 16 bits: radix sort
         ids = np.flatnonzero(runnable)
         ids = ids[np.argsort(key[ids], kind='stable')]
         self.d_work = self._up(ids.astype(np.int32))
@@ -712,6 +760,7 @@ def execute_cuda(plan, device=None, want_stats=True, frames=None):
     :class:`FrameSet` whose uploads were started earlier (else they are started here)."""
     import time as _time
     _t0 = _time.perf_counter()
+    _ARENA.reset()
     if frames is None:
         frames = FrameSet(plan.frame_info, device).upload_async()
     session = DeviceSession(plan, frames=frames)
@@ -806,6 +855,7 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
     import time
     import pandas as pd
     t0 = time.perf_counter()
+    _ARENA.reset()
     started = []          # the uploads start as soon as the frames are known, before the clustering
     pre = prepare_common(f, reader, diameter, separation, fit_function, param_mode, param_val,
                          constraints, bounds, pos_columns, t_column, noise_size, threshold,
@@ -845,7 +895,7 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
         if param_val is not None and col in param_val:
             sources.append(float(param_val[col]))
         elif col in base.columns:
-            sources.append(np.asarray(base[col].values, dtype=np.float64))
+            sources.append(np.ascontiguousarray(base[col].values, dtype=np.float64))
         else:
             sources.append(float(ff.default[col]))
     params_in = _pinned_array("params_in", (n, P), np.float64)     # packed, group order
@@ -856,70 +906,57 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
     cost = np.empty(n, dtype=np.float64)
     cluster = np.empty(n, dtype=np.int64)
     csize = np.empty(n, dtype=np.int64)
-    frame_of_row = np.repeat(np.arange(n_frames, dtype=np.int32), stops - starts)
     chunks = []                                    # (a, b, order_c, plan, pending, c0)
     totals = dict(h2d=0, d2h=0, launches=0, failed=0)
     next_id, c0 = 0, 0
 
+    threads = max(1, min(8, (os.cpu_count() or 2) // 2))
+
     def finish(chunk):
         a, b, order_c, plan, pending, _ = chunk
         res = pending.result()
-        sizes = plan.cluster_sizes()
-        ok = res.status == 0
-        src = res.params_out
-        if not ok.all():                  # belt and braces: failed clusters keep their input exactly
-            rows = np.repeat(~ok, sizes)
-            src[rows] = plan.params_in[rows]
-
-        def scatter(j):
-            block[j, order_c] = src[:, j]
-
-        _parallel(scatter, range(P))
-        cost[order_c] = np.repeat(np.where(ok, res.cost, np.nan), sizes)
-        failed = np.flatnonzero(~ok)
-        for c in failed[:max(0, 20 - totals['failed'])]:
-            logger.warning("RefineException: cluster %d: %s",
-                           int(cluster[order_c[plan.cluster_offset[c]]]),
-                           _lib.STATUS_NAMES.get(int(res.status[c]), "status %d" % res.status[c]))
-        totals['failed'] += len(failed)
+        n_failed = _lib.scatter_rows(res.params_out, plan.params_in, order_c, plan.cluster_offset,
+                                     res.cost, res.status, block, cost, threads)
+        if n_failed:
+            failed = np.flatnonzero(res.status != 0)
+            for c in failed[:max(0, 20 - totals['failed'])]:
+                logger.warning("RefineException: cluster %d: %s",
+                               int(cluster[order_c[plan.cluster_offset[c]]]),
+                               _lib.STATUS_NAMES.get(int(res.status[c]), "status %d" % res.status[c]))
+            totals['failed'] += n_failed
         session = res.session
         totals['h2d'] += session.h2d_bytes
         totals['d2h'] += session.d2h_bytes
         totals['launches'] += session.launches
 
+    lap = dict(label_wait=0., index=0., gather=0., launch=0., finish=0.)
     for k, (fa, fb) in enumerate(zip(frame_cuts[:-1], frame_cuts[1:])):
         a, b = int(starts[fa]), int(stops[fb - 1])
+        _ta = time.perf_counter()
         local, size, by_cluster, spans = labeller.get(k)
-        counts = stops[fa:fb] - starts[fa:fb]
-        offsets = next_id + np.concatenate(([0], np.cumsum(spans)[:-1]))    # find.py:127-128
-        next_id += int(np.sum(spans))
-        np.add(local, np.repeat(offsets, counts), out=cluster[a:b])
+        _tb = time.perf_counter()
         csize[a:b] = size
-        order_c = by_cluster + a                   # rows by (frame, cluster): refine.py:336
-        cl_s = cluster[order_c]
-        new_group = np.empty(b - a, dtype=bool)
-        new_group[0] = True
-        np.not_equal(cl_s[1:], cl_s[:-1], out=new_group[1:])   # labels are unique over frames
-        g_starts = np.flatnonzero(new_group)
-        m = b - a
+        # running ids (find.py:127-128), rows by (frame, cluster) and the group table (refine.py:336)
+        order_c, g_offset, g_frame, next_id = _lib.group_chunk(
+            local, by_cluster, starts[fa:fb] - a, stops[fa:fb] - a, np.asarray(spans, np.int64),
+            next_id, a, fa, cluster[a:b])
         chunk_in = params_in[a:b]
-
-        def gather(span, order_c=order_c, chunk_in=chunk_in):
-            u, v = span
-            rows = order_c[u:v]
-            for j, src in enumerate(sources):
-                chunk_in[u:v, j] = src[rows] if isinstance(src, np.ndarray) else src
-
-        _parallel(gather, _spans(m, 1 << 16))
-        plan = _plan_for(pre, order_c, np.concatenate((g_starts, [m])).astype(np.int32),
-                         frame_of_row[order_c[g_starts]], chunk_in)
-        n_c = len(g_starts)
+        _tc = time.perf_counter()
+        _lib.gather_rows(sources, order_c, chunk_in, threads)
+        _td = time.perf_counter()
+        plan = _plan_for(pre, order_c, g_offset, g_frame, chunk_in)
+        n_c = len(g_frame)
         pending = launch_cuda(plan, frameset, out_params[a:b], out_cost[c0:c0 + n_c],
                               out_status[c0:c0 + n_c])
         chunks.append((a, b, order_c, plan, pending, c0))
         c0 += n_c
+        _te = time.perf_counter()
         if k > 0:
             finish(chunks[k - 1])                  # while the device works on chunk k
+        _tf = time.perf_counter()
+        for name, dt in (("label_wait", _tb - _ta), ("index", _tc - _tb), ("gather", _td - _tc),
+                         ("launch", _te - _td), ("finish", _tf - _te)):
+            lap[name] += 1e3 * dt
     t2 = time.perf_counter()
     finish(chunks[-1])
     if totals['failed'] > 20:
@@ -952,7 +989,7 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
     LAST_CALL.update(h2d_bytes=totals['h2d'] + frameset.h2d_bytes, d2h_bytes=totals['d2h'],
                      launches=totals['launches'] + frameset.launches, chunks=len(chunks),
                      phases_ms=dict(setup=1e3 * (t1 - t0), chunks=1e3 * (t2 - t1),
-                                    last_chunk=1e3 * (t3 - t2), table=1e3 * (t4 - t3)))
+                                    last_chunk=1e3 * (t3 - t2), table=1e3 * (t4 - t3), **lap))
     return out
 
 
