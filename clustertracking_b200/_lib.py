@@ -13,6 +13,7 @@ CTK_MAX_PARAMS = 12
 CTK_MAX_CLUSTER_FEATURES = 32
 CTK_MAX_BIG_FEATURES = 256
 CTK_MAX_RADIUS = 30
+CTK_MAX_TAPS = 33
 
 MODE_CONST, MODE_VAR, MODE_CLUSTER = 0, 1, 3
 PIXEL_CODES = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2,
@@ -44,6 +45,9 @@ class Problem(ctypes.Structure):
         ("bounds_abs", (ctypes.c_double * CTK_MAX_PARAMS) * 2),
         ("bounds_diff", (ctypes.c_double * CTK_MAX_PARAMS) * 2),
         ("bounds_rel", (ctypes.c_double * CTK_MAX_PARAMS) * 2),
+        ("lowpass", ctypes.c_int32), ("lowpass_half", ctypes.c_int32 * 3),
+        ("lowpass_threshold", ctypes.c_double),
+        ("lowpass_taps", (ctypes.c_double * CTK_MAX_TAPS) * 3),
     ]
 
 

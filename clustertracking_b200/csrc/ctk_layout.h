@@ -120,7 +120,9 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
     lay->tab_stride += lay->tab_len[k];
   }
   lay->real_bytes = rb;
-  const int px_bytes = p.pixel_dtype == CTK_PIXEL_U8 ? 1
+  // pixel values are staged in their native width, filtered values (lowpass) in the arithmetic type
+  const int px_bytes = p.lowpass ? rb
+                       : p.pixel_dtype == CTK_PIXEL_U8 ? 1
                        : (p.pixel_dtype == CTK_PIXEL_U16 || p.pixel_dtype == CTK_PIXEL_I16) ? 2
                        : p.pixel_dtype == CTK_PIXEL_F64 ? 8 : 4;
   int o = 0;
@@ -139,6 +141,7 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
   lay->o_cmode = take(p.n_params * 4);
   lay->o_cbase = take(p.n_params * 4);
   lay->o_ctab = take(p.n_params * 6 * 8);
+  lay->o_taps = take(p.lowpass ? 3 * CTK_MAX_TAPS * 8 : 0);
   lay->o_mc = take(n_max * 3 * 8);
   lay->o_fi = take(n_max * FI_STRIDE * 4);
   lay->o_fr = take(n_max * FR_STRIDE * rb);
@@ -189,6 +192,10 @@ inline const char* validate_problem(const ctk_problem_t& p) {
   if (p.compute_dtype != CTK_COMPUTE_F32 && p.compute_dtype != CTK_COMPUTE_F64)
     return "unknown compute dtype";
   if (p.max_iter < 1 || p.lm_max_iter < 1) return "iteration limits must be positive";
+  if (p.lowpass)
+    for (int k = 0; k < p.ndim; ++k)
+      if (p.lowpass_half[k] < -1 || 2 * p.lowpass_half[k] + 1 > CTK_MAX_TAPS)
+        return "lowpass kernel too wide (half width must be <= 16)";
   if (!(p.residual_factor > 0.)) return "residual_factor must be positive";
   if (p.constraint_mask & CTK_CONSTRAINT_DIMER)
     for (int k = 0; k < p.ndim; ++k) if (!(p.dimer_dist[k] > 0.)) return "dimer distance must be > 0";

@@ -145,6 +145,7 @@ struct Layout {
   int o_tmpw;              // [warp lanes, mask_words] staging of a pixel's mask words (BIG)
   int o_cmode, o_cbase;    // [P] column modes / first variable of each column
   int o_ctab;              // [P, 6] bounds tables (diff, rel, abs) x (lower, upper)
+  int o_taps;              // [3, CTK_MAX_TAPS] lowpass taps (only when the problem has a lowpass)
   int o_mc, o_fi, o_fr;
   int o_tab;      // aliases o_fe (tables are dead once the lists are built)
   int o_fe;
@@ -415,6 +416,7 @@ struct ClusterSolver {
   CTK_DEV int* CMODE() const { return reinterpret_cast<int*>(slice() + a.lay.o_cmode); }
   CTK_DEV int* CBASE() const { return reinterpret_cast<int*>(slice() + a.lay.o_cbase); }
   CTK_DEV double* CTAB() const { return dvec(a.lay.o_ctab); }
+  CTK_DEV double* TAPS() const { return dvec(a.lay.o_taps); }
   CTK_DEV double* MC() const { return dvec(a.lay.o_mc); }
   CTK_DEV int* FI() const { return reinterpret_cast<int*>(slice() + a.lay.o_fi); }
   CTK_DEV Real* FR() const { return reinterpret_cast<Real*>(slice() + a.lay.o_fr); }
@@ -444,8 +446,55 @@ struct ClusterSolver {
   template <class T> CTK_DEV static void copy_px(const void* src, int64_t i, void* dst, int p) {
     reinterpret_cast<T*>(dst)[p] = reinterpret_cast<const T*>(src)[i];
   }
-  CTK_DEV void stage_pixel(int64_t idx, int p) const {
+  // type of the staged values: the frame's own, or the arithmetic type when they are filtered
+  CTK_DEV int staged_dtype() const {
+    return a.prob.lowpass ? (sizeof(Real) == 4 ? CTK_PIXEL_F32 : CTK_PIXEL_F64) : a.prob.pixel_dtype;
+  }
+  CTK_DEV double frame_value(int64_t i) const {
+    switch (a.prob.pixel_dtype) {
+      case CTK_PIXEL_U8: return (double) reinterpret_cast<const uint8_t*>(frame)[i];
+      case CTK_PIXEL_U16: return (double) reinterpret_cast<const uint16_t*>(frame)[i];
+      case CTK_PIXEL_F32: return (double) reinterpret_cast<const float*>(frame)[i];
+      case CTK_PIXEL_F64: return reinterpret_cast<const double*>(frame)[i];
+      case CTK_PIXEL_I16: return (double) reinterpret_cast<const int16_t*>(frame)[i];
+      default: return (double) reinterpret_cast<const int32_t*>(frame)[i];
+    }
+  }
+  // Lowpass-filtered value of box pixel c (refine.py:36-40 -> preprocessing.py:39-44): gaussian taps
+  // along axis 0 first, then axis 1 (then 2), over the cluster's BOX with zeros beyond its edge, then
+  // the threshold cut.  Float64 like the reference.
+  CTK_DEV double lowpass_value(const int (&c)[3]) const {
+    const double* taps = TAPS();
+    int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}, hw[3] = {-1, -1, -1};
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      hw[k] = k == 0 ? a.prob.lowpass_half[0] : (k == 1 ? a.prob.lowpass_half[1] : a.prob.lowpass_half[2]);
+      if (hw[k] >= 0) { lo[k] = max(-hw[k], -c[k]); hi[k] = min(hw[k], bdim[k] - 1 - c[k]); }
+    }
+    double acc2 = 0.;
+    for (int d2 = lo[2]; d2 <= hi[2]; ++d2) {
+      double acc1 = 0.;
+      for (int d1 = lo[1]; d1 <= hi[1]; ++d1) {
+        double acc0 = 0.;
+        for (int d0 = lo[0]; d0 <= hi[0]; ++d0) {
+          const int d[3] = {d0, d1, d2};
+          int64_t gi = 0;
+#pragma unroll
+          for (int k = 0; k < ND; ++k) gi = gi * a.shape[k] + (blo[k] + c[k] + d[k]);
+          acc0 += (hw[0] >= 0 ? taps[d0 + hw[0]] : 1.) * frame_value(gi);
+        }
+        acc1 += (ND > 1 && hw[1] >= 0 ? taps[CTK_MAX_TAPS + d1 + hw[1]] : 1.) * acc0;
+      }
+      acc2 += (ND > 2 && hw[2] >= 0 ? taps[2 * CTK_MAX_TAPS + d2 + hw[2]] : 1.) * acc1;
+    }
+    return acc2 > a.prob.lowpass_threshold ? acc2 : 0.;
+  }
+  CTK_DEV void stage_pixel(int64_t idx, int p, const int (&c)[3]) const {
     void* dst = slice() + a.lay.o_pval;
+    if (a.prob.lowpass) {
+      reinterpret_cast<Real*>(dst)[p] = (Real) lowpass_value(c);
+      return;
+    }
     switch (a.prob.pixel_dtype) {
       case CTK_PIXEL_U8: copy_px<uint8_t>(frame, idx, dst, p); break;
       case CTK_PIXEL_U16: case CTK_PIXEL_I16: copy_px<uint16_t>(frame, idx, dst, p); break;
@@ -455,7 +504,7 @@ struct ClusterSolver {
   }
   CTK_DEV Real pixel_value(int p) const {
     const void* src = slice() + a.lay.o_pval;
-    switch (a.prob.pixel_dtype) {
+    switch (staged_dtype()) {
       case CTK_PIXEL_U8: return (Real) reinterpret_cast<const uint8_t*>(src)[p];
       case CTK_PIXEL_U16: return (Real) reinterpret_cast<const uint16_t*>(src)[p];
       case CTK_PIXEL_F32: return (Real) reinterpret_cast<const float*>(src)[p];
@@ -479,6 +528,14 @@ struct ClusterSolver {
         ctab[c * 6 + 2] = a.prob.bounds_abs[0][c];  ctab[c * 6 + 3] = a.prob.bounds_diff[1][c];
         ctab[c * 6 + 4] = a.prob.bounds_rel[1][c];  ctab[c * 6 + 5] = a.prob.bounds_abs[1][c];
       }
+    }
+    if (a.prob.lowpass) {
+      double* taps = TAPS();
+      // compile-time indices only: a run-time index into the kernel arguments would make the
+      // compiler copy them to local memory
+#pragma unroll
+      for (int t = 0; t < 3 * CTK_MAX_TAPS; ++t)
+        if (lane == t % CTK_WARP) taps[t] = a.prob.lowpass_taps[t / CTK_MAX_TAPS][t % CTK_MAX_TAPS];
     }
     shared_columns = 0;
 #pragma unroll
@@ -705,7 +762,7 @@ struct ClusterSolver {
           int64_t gi = 0;
 #pragma unroll
           for (int k = 0; k < ND; ++k) gi = gi * a.shape[k] + (blo[k] + c[k]);
-          stage_pixel(gi, pos);
+          stage_pixel(gi, pos, c);
           if (!C::BIG) {
             pbits[pos] = bits;
             pcrd[pos] = (uint32_t) c[0] | ((uint32_t) c[1] << 10) | ((uint32_t) c[2] << 20);

@@ -170,9 +170,6 @@ def prepare_common(f, reader, diameter, separation=None, fit_function='gauss', p
     if compute_error:
         raise NotImplementedError("compute_error (numdifftools Hessian, refine.py:400-406) is not "
                                   "available in the CUDA solver")
-    if noise_size is not None:
-        raise NotImplementedError("noise_size / threshold (lowpass on the sub-image, "
-                                  "refine.py:36-40) is not available in the CUDA solver yet")
     source, ndim = _normalise_reader(f, reader, t_column)
     assert ndim == len(pos_columns)
     if ndim not in (2, 3):
@@ -230,6 +227,25 @@ def prepare_common(f, reader, diameter, separation=None, fit_function='gauss', p
         for k in range(ndim):
             prob.tetramer_dist[k] = cons['tetramer'][k]
     prob.constraint_mask = mask
+    if noise_size is not None:                                         # refine.py:36-40
+        # lowpass of the cluster's sub-image: taps of trackpy.masks.gaussian_kernel(sigma, 4)
+        # (preprocessing.py:41-44); a size <= 0 leaves that axis unfiltered
+        prob.lowpass = 1
+        prob.lowpass_threshold = 0. if threshold is None else float(threshold)
+        for k, sigma in enumerate(validate_tuple(noise_size, ndim)):
+            if not sigma > 0:
+                prob.lowpass_half[k] = -1
+                continue
+            lw = int(4.0 * sigma + 0.5)
+            if 2 * lw + 1 > _lib.CTK_MAX_TAPS:
+                raise NotImplementedError("noise_size %r: the lowpass kernel is limited to a half "
+                                          "width of %d pixels" % (sigma, _lib.CTK_MAX_TAPS // 2))
+            x = np.arange(-lw, lw + 1)
+            taps = np.exp(x ** 2 / (-2 * sigma ** 2))
+            taps = taps / np.sum(taps)
+            prob.lowpass_half[k] = lw
+            for t, w in enumerate(taps):
+                prob.lowpass_taps[k][t] = w
     for which, table in zip(("bounds_abs", "bounds_diff", "bounds_rel"), tables):
         dst = getattr(prob, which)
         for side in range(2):
@@ -848,7 +864,7 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
     * ``fit_function``: 'gauss', 'ring' or 'disc' (custom dicts and 'inv_series_<n>' raise);
     * ``param_mode`` values 'const', 'var', 'cluster' ('global' raises);
     * ``constraints``: ``constraints.dimer`` / ``trimer`` / ``tetramer`` descriptors (others raise);
-    * ``noise_size`` and ``compute_error`` raise ``NotImplementedError``;
+    * ``compute_error`` raises ``NotImplementedError``;
     * ``**kwargs``: ``options=dict(maxiter=...)`` caps the inner iterations; ``tol`` is accepted and
       ignored; ``precision='float64'`` switches the pixel arithmetic from float32 to float64.
     """

@@ -33,6 +33,7 @@ extern "C" {
 #define CTK_MAX_BIG_FEATURES 256      /* features per cluster of the large-cluster kernels (per-cluster
                                          arrays in a global-memory workspace, see ctk_refine_batch) */
 #define CTK_MAX_RADIUS 30        /* mask radius per axis (pixel offsets are packed in 6 bits) */
+#define CTK_MAX_TAPS 33          /* taps of the lowpass kernel per axis: half width <= 16 */
 
 /* parameter modes, same codes as fitfunc.py:9-11 (2 = 'global' is out of scope) */
 enum { CTK_MODE_CONST = 0, CTK_MODE_VAR = 1, CTK_MODE_CLUSTER = 3 };
@@ -113,6 +114,14 @@ typedef struct {
   double  bounds_abs[2][CTK_MAX_PARAMS];
   double  bounds_diff[2][CTK_MAX_PARAMS];
   double  bounds_rel[2][CTK_MAX_PARAMS];
+  /* Lowpass of the cluster's sub-image before masking (`noise_size`, `threshold`; refine.py:36-40
+   * -> preprocessing.py:12-49): separable gaussian over the cluster's bounding box, zero padded at
+   * the BOX edge, then values <= threshold are set to 0. */
+  int32_t lowpass;              /* 0: off (noise_size is None) */
+  int32_t lowpass_half[3];      /* half width lw = int(4 sigma + 0.5) per axis; -1: axis not filtered */
+  double  lowpass_threshold;    /* refine.py:38-39: 0 when `threshold` is None */
+  double  lowpass_taps[3][CTK_MAX_TAPS];  /* trackpy.masks.gaussian_kernel(sigma, 4): normalised
+                                   exp(-x^2 / (2 sigma^2)), x = -lw .. lw; entry 0 = offset -lw */
 } ctk_problem_t;
 
 int ctk_version(void);

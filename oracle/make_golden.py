@@ -12,6 +12,7 @@ fitfunc_*   residual / jacobian values of ``FitFunctions.get_residual`` (fitfunc
 pixels_*    ``prepare_subimage`` pixel sets (refine.py:28-58) and ``slices_multiple`` boxes
 clusters_*  ``find_clusters`` labels (find.py:132-163)
 refine_*    ``refine_leastsq`` end to end (refine.py:82-452), default ``tol`` and ``tol=1e-12``
+lowpass_*   ``prepare_subimage`` with ``noise_size`` (refine.py:36-40, preprocessing.py:12-49)
 """
 import json
 import os
@@ -382,11 +383,65 @@ def golden_tetramer(ct):
     _refine_case(ct, "refine_tetramer3d_constrained", image, f0, (12, 16, 16),
                  dict(constraints=tetramer((6., 8., 8.), 3)), constraint=("tetramer", (6., 8., 8.)))
 
+def golden_lowpass(ct):
+    """``noise_size`` / ``threshold``: lowpass of the cluster sub-image (refine.py:36-40,
+    preprocessing.py:12-49), pixel sets and end-to-end fits."""
+    from clustertracking.refine import prepare_subimage
+    from clustertracking.artificial import feat_gauss
+    rng = np.random.RandomState(99)
+    # pixel values after the filter; boxes touching the image edge (zero padding at the BOX edge)
+    k = 0
+    for shape, radius, noise_size, threshold in (((40, 48), 5, 1, None), ((40, 48), (3, 6), (1, 1.5), 20),
+                                                 ((40, 48), 4, (0, 2), None),
+                                                 ((16, 30, 30), (3, 5, 5), (0.8, 1, 1), 5)):
+        ndim = len(shape)
+        image = rng.randint(0, 255, shape).astype(np.uint8)
+        for variant in range(3):
+            n = variant + 1
+            centre = np.array([rng.uniform(r + 1, s - r - 1) for r, s in
+                               zip(np.broadcast_to(radius, ndim), shape)])
+            coords = centre + rng.uniform(-1, 1, (n, ndim)) * np.broadcast_to(radius, ndim) * 1.2
+            if variant == 2:
+                coords[0] = 1.3                            # close to the image corner
+            vals, mesh, masks = prepare_subimage(coords, image, radius, noise_size, threshold)
+            save("lowpass_pixels_%02d" % k, image=image, radius=np.array(radius), coords=coords,
+                 values=np.asarray(vals), mesh=mesh, masks=masks,
+                 noise_size=np.array(noise_size, dtype=float),
+                 threshold=np.array(np.nan if threshold is None else threshold, dtype=float))
+            k += 1
+
+    def grid_positions(shape, pitch, margin, jitter):
+        axes = [np.arange(margin, s - margin + 1e-9, pitch) for s in shape]
+        pos = np.array([g.ravel() for g in np.meshgrid(*axes, indexing='ij')], float).T
+        return pos + rng.uniform(-jitter, jitter, pos.shape)
+
+    def start_frame(pos, err, cols, **const):
+        f0 = pd.DataFrame(pos + rng.uniform(-err, err, pos.shape), columns=cols)
+        for key, v in const.items():
+            f0[key] = v
+        return f0
+
+    centres = grid_positions((176, 176), 44, 22, 3)
+    ks = rng.randint(1, 6, len(centres))
+    pos, _ = _grow_clusters(rng, centres, ks, 5.5, 2)
+    signal = rng.uniform(80, 160, len(pos))
+    image = _draw((176, 176), pos, 2.75, signal, feat_gauss, 16, rng)
+    f0 = start_frame(pos, 0.5, ['y', 'x'], signal=120., size=2.75, background=4.)
+    _refine_case(ct, "refine_lowpass2d", image, f0, 11, dict(noise_size=1))
+    _refine_case(ct, "refine_lowpass2d_threshold", image, f0, 11,
+                 dict(noise_size=(1, 0.7), threshold=12, param_mode=dict(size='var')))
+    centres = grid_positions((28, 72, 72), 36, 14, 1)
+    ks = rng.randint(1, 3, len(centres))
+    pos, _ = _grow_clusters(rng, centres, ks, (4.5, 6.5, 6.5), 3)
+    image = _draw((28, 72, 72), pos, (2.25, 3.25, 3.25), 140., feat_gauss, 8, rng)
+    f0 = start_frame(pos, 0.5, ['z', 'y', 'x'], signal=120., size_z=2.25, size_y=3.25, size_x=3.25,
+                     background=2.)
+    _refine_case(ct, "refine_lowpass3d", image, f0, (9, 13, 13), dict(noise_size=(0.6, 1, 1)))
 
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ct = ref_loader.load()
-    only = sys.argv[1:] or ["fitfunc", "pixels", "clusters", "refine", "tetramer"]
+    only = sys.argv[1:] or ["fitfunc", "pixels", "clusters", "refine", "tetramer", "lowpass"]
     for part in only:
         globals()["golden_" + part](ct)

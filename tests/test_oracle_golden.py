@@ -124,6 +124,22 @@ def test_pixel_sets_match_reference(name):
     assert_array_equal(masks, d["masks"])
 
 
+@pytest.mark.parametrize("name", golden_io.names("lowpass_pixels_"))
+def test_lowpass_pixel_sets_match_reference(name):
+    """``noise_size`` / ``threshold``: the filter runs on the cluster's box, zero padded at the BOX
+    edge (refine.py:36-40, preprocessing.py:12-49)."""
+    d = golden_io.load(name)
+    radius = tuple(int(r) for r in np.atleast_1d(d["radius"]))
+    radius = radius if len(radius) > 1 else radius[0]
+    noise = tuple(float(v) for v in np.atleast_1d(d["noise_size"]))
+    noise = noise if len(noise) > 1 else noise[0]
+    threshold = None if np.isnan(d["threshold"]) else float(d["threshold"])
+    values, mesh, masks = oracle.cluster_pixels(d["coords"], d["image"], radius, noise, threshold)
+    assert_array_equal(values, d["values"])
+    assert_array_equal(mesh, d["mesh"])
+    assert_array_equal(masks, d["masks"])
+
+
 # ---- clustering (find.py:12-163) -------------------------------------------------------------
 @pytest.mark.parametrize("name", golden_io.names("clusters_"))
 def test_find_clusters_matches_reference(name):
