@@ -47,7 +47,7 @@ class Problem(ctypes.Structure):
         ("bounds_rel", (ctypes.c_double * CTK_MAX_PARAMS) * 2),
         ("lowpass", ctypes.c_int32), ("lowpass_half", ctypes.c_int32 * 3),
         ("lowpass_threshold", ctypes.c_double),
-        ("lowpass_taps", (ctypes.c_double * CTK_MAX_TAPS) * 3),
+        ("lowpass_sigma", ctypes.c_double * 3),
     ]
 
 

@@ -530,12 +530,27 @@ struct ClusterSolver {
       }
     }
     if (a.prob.lowpass) {
+      // taps of trackpy.masks.gaussian_kernel(sigma, truncate=4): exp(x^2 / (-2 sigma^2)) on
+      // [-lw, lw], normalised; CTK_MAX_TAPS <= 2 lanes' worth of entries per axis
       double* taps = TAPS();
-      // compile-time indices only: a run-time index into the kernel arguments would make the
-      // compiler copy them to local memory
 #pragma unroll
-      for (int t = 0; t < 3 * CTK_MAX_TAPS; ++t)
-        if (lane == t % CTK_WARP) taps[t] = a.prob.lowpass_taps[t / CTK_MAX_TAPS][t % CTK_MAX_TAPS];
+      for (int k = 0; k < ND; ++k) {
+        const int hw = k == 0 ? a.prob.lowpass_half[0] : (k == 1 ? a.prob.lowpass_half[1] : a.prob.lowpass_half[2]);
+        const double sg = k == 0 ? a.prob.lowpass_sigma[0] : (k == 1 ? a.prob.lowpass_sigma[1] : a.prob.lowpass_sigma[2]);
+        if (hw < 0) continue;
+        double part = 0.;
+#pragma unroll 1
+        for (int t = lane; t <= 2 * hw; t += CTK_WARP) {
+          const double x = (double) (t - hw);
+          const double w = exp(x * x / (-2. * sg * sg));
+          taps[k * CTK_MAX_TAPS + t] = w;
+          part += w;
+        }
+        const double total = warp_sum(part);
+        warp_sync();
+#pragma unroll 1
+        for (int t = lane; t <= 2 * hw; t += CTK_WARP) taps[k * CTK_MAX_TAPS + t] /= total;
+      }
     }
     shared_columns = 0;
 #pragma unroll
@@ -564,6 +579,7 @@ struct ClusterSolver {
     const double* hin = tables ? nullptr : a.hi_in + (int64_t)feat0 * P;
     double *x0 = X0(), *lo = LO(), *hi = HI();
     bool bad = false;
+#pragma unroll 1
     for (int t = lane; t < n * P; t += CTK_WARP) {
       const int i = t / P, c = t - i * P;
       const int m = cmode[c];
@@ -579,6 +595,7 @@ struct ClusterSolver {
       }
     }
     if (warp_any(bad)) return CTK_FAIL_NONFINITE;
+#pragma unroll 1
     for (int c = lane; c < P; c += CTK_WARP) {
       if (cmode[c] != CTK_MODE_CLUSTER) continue;       // shared entry: mean start, widest bound
       const double* tb = ctab + c * 6;
@@ -594,6 +611,7 @@ struct ClusterSolver {
     }
     warp_sync();
     bad = false;
+#pragma unroll 1
     for (int v2 = lane; v2 < V; v2 += CTK_WARP) {
       bad |= !(lo[v2] <= hi[v2]);
       x0[v2] = fmin(fmax(x0[v2], lo[v2]), hi[v2]);     // scipy clips the start into the box
@@ -603,8 +621,10 @@ struct ClusterSolver {
     if (V != cached_V) {
       int* cs = CS();
       RcT* rc = RC();
+#pragma unroll 1
       for (int c = lane; c <= V; c += CTK_WARP) cs[c] = c * V - c * (c - 1) / 2;
       warp_sync();
+#pragma unroll 1
       for (int t = lane; t < V * V; t += CTK_WARP) {
         int r = t / V, c = t - r * V;
         if (r >= c) rc[cs[c] + r - c] = rc_pack(r, c, RcT());
@@ -616,6 +636,7 @@ struct ClusterSolver {
     // background column, [LD] right-hand side entries
     int* sidx = SIDX();
     const int vb = cv[0];
+#pragma unroll 1
     for (int t = lane; t < n * (LT + 2 * LD); t += CTK_WARP) {
       const int i = t / (LT + 2 * LD), k = t - i * (LT + 2 * LD);
       int target = -1;
@@ -668,6 +689,7 @@ struct ClusterSolver {
     int* fi = FI();
     // integer centres (round half to even) and the in-bounds test of masks.py:42-46
     int mn[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, mx[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
+#pragma unroll 1
     for (int i = lane; i < n; i += CTK_WARP) {
       bool inb = true;
       int ci[3] = {0, 0, 0};
@@ -701,6 +723,7 @@ struct ClusterSolver {
     warp_sync();
     // separable tables: tab[i][k][e] = (((ts + e) - (c - origin)) / r)^2, float64, numpy's order
     double* tab = TAB();
+#pragma unroll 1
     for (int i = lane; i < n; i += CTK_WARP) {
 #pragma unroll
       for (int k = 0; k < ND; ++k) {
@@ -716,6 +739,7 @@ struct ClusterSolver {
 #pragma unroll
       for (int k = 0; k < ND; ++k) {
         const int len = a.lay.tab_len[k];
+#pragma unroll 1
         for (int t = lane; t < n * len; t += CTK_WARP) {
           const int i = t / len, e = t - i * len;
           const double crel = dsub(mc[i * 3 + k], (double) blo[k]);
@@ -879,6 +903,7 @@ struct ClusterSolver {
   CTK_DEV void load_features(const double* x) {
     Real* fr = FR();
     const int* fi = FI();
+#pragma unroll 1
     for (int i = lane; i < n; i += CTK_WARP) {
       Real* r = fr + i * FR_STRIDE;
       r[FR_S] = (Real) value_of(x, 1, i);
@@ -986,6 +1011,7 @@ struct ClusterSolver {
     ++evals;
     load_features(x);
     Real* pr = PR();
+#pragma unroll 1
     for (int p = lane; p < M; p += CTK_WARP) pr[p] = 0;
     warp_sync();
     const Entry* flist = FLIST();
@@ -996,6 +1022,7 @@ struct ClusterSolver {
       const int cnt = fi[i * FI_STRIDE + FI_CNT];
       const Entry* fl = flist + i * a.lay.f_cap;
       Real* ge = fe + i * a.lay.f_cap;
+#pragma unroll 1
       for (int t = lane; t < cnt; t += CTK_WARP) {
         Entry e = fl[t];
         Geo g = geometry(e, f);
@@ -1009,6 +1036,7 @@ struct ClusterSolver {
     }
     const Real bg = (Real) value_of(x, 0, 0);
     double acc = 0., sr = 0., nv = 0.;
+#pragma unroll 1
     for (int p = lane; p < M; p += CTK_WARP) {
       Real r = pixel_value(p) - bg - pr[p];
       pr[p] = r;
@@ -1029,6 +1057,47 @@ struct ClusterSolver {
     return v;
   }
 
+  // Warp reduction of the register array v[OFF .. OFF + CNT): a halving butterfly (each step a lane
+  // keeps one half of its entries and hands the other half to its partner) needs about CNT
+  // shuffles where CNT plain warp sums need 5 CNT.  The total of entry k ends up on one owning
+  // lane; f(k, total, owner) is called ONCE on every lane, in converged control flow.
+  template <int OFF, int CNT, int N, class F>
+  CTK_DEV void reduce_each(Real (&v)[N], F&& f) const {
+#ifdef CTK_EMUL
+    for (int k = 0; k < CNT; ++k) f(OFF + k, v[OFF + k], true);
+#else
+    static_assert(CNT >= 1 && CNT <= 32, "reduce_each: split longer arrays");
+    constexpr int KP = CNT <= 1 ? 1 : CNT <= 2 ? 2 : CNT <= 4 ? 4 : CNT <= 8 ? 8 : CNT <= 16 ? 16 : 32;
+    constexpr int STEPS = KP == 1 ? 0 : KP == 2 ? 1 : KP == 4 ? 2 : KP == 8 ? 3 : KP == 16 ? 4 : 5;
+    int index = 0;
+#pragma unroll
+    for (int st = 0; st < STEPS; ++st) {
+      const int h = KP >> (st + 1), m = 16 >> st;
+      const bool up = (lane & m) != 0;
+#pragma unroll
+      for (int i = 0; i < h; ++i) {
+        const Real lo = v[OFF + i];
+        const Real hi = (i + h < CNT) ? v[OFF + i + h] : (Real) 0;
+        v[OFF + i] = (up ? hi : lo) + shfl_xor(up ? lo : hi, m);
+      }
+      index += up ? h : 0;
+    }
+    Real r = v[OFF];
+#pragma unroll
+    for (int m = 16 / KP; m > 0; m >>= 1) r += shfl_xor(r, m);
+    f(OFF + index, r, (lane & (32 / KP - 1)) == 0 && index < CNT);
+#endif
+  }
+  template <int OFF, int CNT, int N, class F>
+  CTK_DEV void reduce_all(Real (&v)[N], F&& f) const {
+    if constexpr (CNT > 32) {
+      reduce_each<OFF, 32>(v, f);
+      reduce_all<OFF + 32, CNT - 32>(v, f);
+    } else {
+      reduce_each<OFF, CNT>(v, f);
+    }
+  }
+
   // ---- normal equations from the caches of the last evaluate() ---------------------------------
   // H = sum m m^T (packed lower, column-major), RHS = sum m r  (= -gradient of 0.5 sum r^2)
   // grad_only: refresh only RHS (the gradient); H and its factor are kept from the last full pass
@@ -1039,6 +1108,7 @@ struct ClusterSolver {
     double* rhs = RHS();
     const int nt = CS()[V];
     if (!grad_only) for (int t = lane; t < nt; t += CTK_WARP) H[t] = 0;
+#pragma unroll 1
     for (int v = lane; v < V; v += CTK_WARP) rhs[v] = 0.;
     warp_sync();
     const int* cv = CV();
@@ -1058,6 +1128,7 @@ struct ClusterSolver {
       Real acc[LT + 2 * LD];       // [LT] m_u m_w, [LD] m_u, [LD] m_u r
 #pragma unroll
       for (int k = 0; k < LT + 2 * LD; ++k) acc[k] = 0;
+#pragma unroll 1
       for (int t = lane; t < cnt; t += CTK_WARP) {
         Entry e = fl[t];
         Real r = pr[entry_pixel(e)];
@@ -1079,21 +1150,17 @@ struct ClusterSolver {
           }
         }
       }
-      if (grad_only) {
-#pragma unroll
-        for (int k = LT + LD; k < LT + 2 * LD; ++k) acc[k] = warp_sum(acc[k]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < LT + 2 * LD; ++k) acc[k] = warp_sum(acc[k]);
-      }
-      // every lane now holds every sum; lane k adds entry k to its target
-      for (int k = (grad_only ? LT + LD : 0) + lane; k < LT + 2 * LD; k += CTK_WARP) {
-        const int target = sidx[i * a.lay.sidx_stride + k];
+      // the owning lane of every sum adds it to its target
+      const int* sx = sidx + i * a.lay.sidx_stride;
+      auto add = [&](int k, Real val, bool owner) {
+        if (!owner) return;
+        const int target = sx[k];
         if (target >= 0) {
-          const Real val = pick(acc, k);
           if (k < LT + LD) H[target] += val; else rhs[target] += (double) val;
         }
-      }
+      };
+      if (grad_only) reduce_all<LT + LD, LD>(acc, add);
+      else reduce_all<0, LT + 2 * LD>(acc, add);
       warp_sync();
     }
     if (grad_only) return;
@@ -1108,6 +1175,7 @@ struct ClusterSolver {
       Real B[LD * LD];
 #pragma unroll
       for (int k = 0; k < LD * LD; ++k) B[k] = 0;
+#pragma unroll 1
       for (int t = lane; t < cnt; t += CTK_WARP) {
         uint32_t pe = pairs[start + t];
         int ti = (int) (pe & 0xffffu), tj = (int) (pe >> 16);
@@ -1122,31 +1190,29 @@ struct ClusterSolver {
 #pragma unroll
           for (int w = 0; w < LD; ++w) B[u * LD + w] += mi[u] * mj[w];
       }
-#pragma unroll
-      for (int k = 0; k < LD * LD; ++k) B[k] = warp_sum(B[k]);
       // entry (u, w) goes to (var(i,u), var(j,w)); two entries can share a target only when both
       // columns are shared within the cluster, so the adds go one lane at a time in that case
-      for (int k0 = 0; k0 < LD * LD; k0 += CTK_WARP) {
-        const int k = k0 + lane;
+      const bool serial = shared_columns > 1;
+      auto add = [&](int k, Real val, bool owner) {
         int target = -1;
-        Real val = 0;
-        if (k < LD * LD) {
+        if (owner) {
           const int u = k / LD, w = k - u * LD;
           const int vu = cv[i * P + slot_col(u)], vw = cv[j * P + slot_col(w)];
           if (vu >= 0 && vw >= 0) {
             target = pk_sym(vu, vw);
-            val = pick(B, k) * (vu == vw ? (Real) 2 : (Real) 1);
+            if (vu == vw) val *= (Real) 2;
           }
         }
-        if (shared_columns > 1) {
-          for (int turn = 0; turn < (LD * LD < CTK_WARP ? LD * LD : CTK_WARP); ++turn) {
-            if (turn == (k - k0) && target >= 0) H[target] += val;
+        if (serial) {
+          for (int turn = 0; turn < CTK_WARP; ++turn) {
+            if (turn == lane && target >= 0) H[target] += val;
             warp_sync();
           }
         } else if (target >= 0) {
           H[target] += val;
         }
-      }
+      };
+      reduce_all<0, LD * LD>(B, add);
       warp_sync();
     }
   }
@@ -1179,11 +1245,13 @@ struct ClusterSolver {
     const RcT* rc = RC();
     const double *x = X(), *lo = LO(), *hi = HI();
     const int nt = cs[V];
+#pragma unroll 1
     for (int v = lane; v < V; v += CTK_WARP) rhs_full[v] = RHS()[v];
     warp_sync();
     if (reuse) {
       // chord step: same matrix, same scaling, new right-hand side; the frozen set must not move
       bool moved = false;
+#pragma unroll 1
       for (int v = lane; v < V; v += CTK_WARP) {
         const double g = rhs_full[v];
         const bool frozen = (x[v] <= lo[v] && g < 0.) || (x[v] >= hi[v] && g > 0.) || !(lo[v] < hi[v]);
@@ -1198,10 +1266,12 @@ struct ClusterSolver {
         const double yj = d[j] * (double) idg[j];
         warp_sync();
         if (lane == 0) d[j] = yj;
+#pragma unroll 1
         for (int r = j + 1 + lane; r < V; r += CTK_WARP) d[r] -= (double) Kf[cs[j] + r - j] * yj;
         warp_sync();
       }
     } else {
+#pragma unroll 1
       for (int t = lane; t < nt; t += CTK_WARP) Kf[t] = H[t];
       warp_sync();
       if (n_con > 0) {
@@ -1209,9 +1279,11 @@ struct ClusterSolver {
         warp_sync();
       }
       double dmax = 0.;
+#pragma unroll 1
       for (int v = lane; v < V; v += CTK_WARP) dmax = fmax(dmax, (double) Kf[cs[v]]);
       dmax = warp_max_d(dmax);
       const double floor_ = fmax(dmax * 1e-14, 1e-30);
+#pragma unroll 1
       for (int v = lane; v < V; v += CTK_WARP) {
         const double g = rhs_full[v];
         const bool frozen = (x[v] <= lo[v] && g < 0.) || (x[v] >= hi[v] && g > 0.) || !(lo[v] < hi[v]);
@@ -1223,6 +1295,7 @@ struct ClusterSolver {
       warp_sync();
       // scaled, damped system: (S K S + lambda I)(S^-1 step) = S rhs; frozen rows become identity
       const Real lam1 = (Real) (1. + lambda);
+#pragma unroll 1
       for (int t = lane; t < nt; t += CTK_WARP) {
         const int r = rc_row(rc[t]), c = rc_col(rc[t]);
         Real v;
@@ -1239,13 +1312,16 @@ struct ClusterSolver {
         const Real inv = fast_rsqrt(piv);
         const double yj = d[j] * (double) inv;               // forward substitution, row j
         warp_sync();
+#pragma unroll 1
         for (int r = j + lane; r < V; r += CTK_WARP) Kf[cj + r - j] *= inv;
         if (lane == 0) { idg[j] = inv; d[j] = yj; }
         warp_sync();
+#pragma unroll 1
         for (int t = cs[j + 1] + lane; t < nt; t += CTK_WARP) {
           const int r = rc_row(rc[t]), c = rc_col(rc[t]);
           Kf[t] -= Kf[cj + r - j] * Kf[cj + c - j];
         }
+#pragma unroll 1
         for (int r = j + 1 + lane; r < V; r += CTK_WARP) d[r] -= (double) Kf[cj + r - j] * yj;
         warp_sync();
       }
@@ -1254,9 +1330,11 @@ struct ClusterSolver {
       const double zj = d[j] * (double) idg[j];
       warp_sync();
       if (lane == 0) d[j] = zj;
+#pragma unroll 1
       for (int r = lane; r < j; r += CTK_WARP) d[r] -= (double) Kf[cs[r] + j - r] * zj;
       warp_sync();
     }
+#pragma unroll 1
     for (int v = lane; v < V; v += CTK_WARP) d[v] *= sc[v];
     warp_sync();
     return true;
@@ -1268,10 +1346,12 @@ struct ClusterSolver {
     const RcT* rc = RC();
     const int nt = CS()[V];
     double acc = 0.;
+#pragma unroll 1
     for (int t = lane; t < nt; t += CTK_WARP) {
       const int r = rc_row(rc[t]), c = rc_col(rc[t]);
       acc -= (r == c ? 0.5 : 1.) * (double) H[t] * s[r] * s[c];
     }
+#pragma unroll 1
     for (int u = lane; u < V; u += CTK_WARP) acc += s[u] * rhs_full[u];
     acc = warp_sum(acc);
     // constraint rows: the gradient part is already in rhs_full; add -0.5 w (A s)^2
@@ -1303,6 +1383,7 @@ struct ClusterSolver {
     double* rhs_full = dvec(a.lay.o_rhsf);            // rhs incl. constraint terms, before freezing
     double lambda = 1e-3, nu = 2.;
     if (lane == 0) for (int j = 0; j < 6; ++j) CON()[j] = 0.;
+#pragma unroll 1
     for (int v = lane; v < V; v += CTK_WARP) xt[v] = x[v];
     warp_sync();
     pen_w = 0.;
@@ -1354,6 +1435,7 @@ struct ClusterSolver {
             if (chord_next) {
               // the step from the stale matrix failed: rebuild everything at x (the caches hold the
               // rejected point, so x is evaluated again)
+#pragma unroll 1
               for (int v = lane; v < V; v += CTK_WARP) xt[v] = x[v];
               warp_sync();
               force = true;
@@ -1363,6 +1445,7 @@ struct ClusterSolver {
           }
         }
         if (accept) {
+#pragma unroll 1
           for (int v = lane; v < V; v += CTK_WARP) x[v] = xt[v];
           warp_sync();
           fd = fdt;
@@ -1374,6 +1457,7 @@ struct ClusterSolver {
           if (first && n_con > 0) {
             // penalty weight relative to the curvature of the data term in the position variables
             double hmax = 0.;
+#pragma unroll 1
             for (int v = lane; v < V; v += CTK_WARP)
               if (is_pos_var(v)) hmax = fmax(hmax, (double) Hm()[CS()[v]]);
             hmax = warp_max_d(hmax);
@@ -1396,6 +1480,7 @@ struct ClusterSolver {
       }
       // trial point, projected on the box
       worst = 0.;
+#pragma unroll 1
       for (int v = lane; v < V; v += CTK_WARP) {
         const double t = fmin(fmax(x[v] + d[v], LO()[v]), HI()[v]);
         xt[v] = t;
@@ -1414,6 +1499,7 @@ struct ClusterSolver {
         if (n_con == 0) { *f_data = fd; return CTK_OK; }
         // take the (sub-tolerance) step: it carries the Newton correction towards c(x) = 0; the
         // data term is flat at this scale, so its caches stay valid
+#pragma unroll 1
         for (int v = lane; v < V; v += CTK_WARP) x[v] = xt[v];
         warp_sync();
         const double cv = con_violation(x);
@@ -1487,6 +1573,7 @@ struct ClusterSolver {
     double fd = 0.;
     if (status == CTK_OK) {
       double* mc = MC();
+#pragma unroll 1
       for (int i = lane; i < n; i += CTK_WARP) {
 #pragma unroll
         for (int k = 0; k < ND; ++k) mc[i * 3 + k] = a.params_in[(int64_t) (feat0 + i) * P + 2 + k];
@@ -1496,12 +1583,14 @@ struct ClusterSolver {
         ++outers;
         status = build_pixels();
         if (status != CTK_OK) break;
+#pragma unroll 1
         for (int v = lane; v < V; v += CTK_WARP) X()[v] = X0()[v];   // restart, refine.py:361-365
         warp_sync();
         status = minimise(&fd);
         if (status != CTK_OK) break;
         // accept when every feature stayed within max_shift of its mask centre, refine.py:383-385
         bool moved = false;
+#pragma unroll 1
         for (int i = lane; i < n; i += CTK_WARP) {
           double s = 0.;
 #pragma unroll
@@ -1514,6 +1603,7 @@ struct ClusterSolver {
         moved = warp_any(moved);
         if (!moved) break;
         warp_sync();
+#pragma unroll 1
         for (int i = lane; i < n; i += CTK_WARP) {
 #pragma unroll
           for (int k = 0; k < ND; ++k) mc[i * 3 + k] = value_of(X(), 2 + k, i);
@@ -1533,6 +1623,7 @@ struct ClusterSolver {
     if (n > 0) {
       const double* pin = a.params_in + (int64_t) feat0 * P;
       double* pout = a.params_out + (int64_t) feat0 * P;
+#pragma unroll 1
       for (int t = lane; t < n * P; t += CTK_WARP) {
         int i = t / P, c = t - i * P;
         double v = pin[t];

@@ -228,8 +228,8 @@ def prepare_common(f, reader, diameter, separation=None, fit_function='gauss', p
             prob.tetramer_dist[k] = cons['tetramer'][k]
     prob.constraint_mask = mask
     if noise_size is not None:                                         # refine.py:36-40
-        # lowpass of the cluster's sub-image: taps of trackpy.masks.gaussian_kernel(sigma, 4)
-        # (preprocessing.py:41-44); a size <= 0 leaves that axis unfiltered
+        # lowpass of the cluster's sub-image with the taps of trackpy.masks.gaussian_kernel(sigma, 4)
+        # (preprocessing.py:41-44, built on the device); a size <= 0 leaves that axis unfiltered
         prob.lowpass = 1
         prob.lowpass_threshold = 0. if threshold is None else float(threshold)
         for k, sigma in enumerate(validate_tuple(noise_size, ndim)):
@@ -240,12 +240,8 @@ def prepare_common(f, reader, diameter, separation=None, fit_function='gauss', p
             if 2 * lw + 1 > _lib.CTK_MAX_TAPS:
                 raise NotImplementedError("noise_size %r: the lowpass kernel is limited to a half "
                                           "width of %d pixels" % (sigma, _lib.CTK_MAX_TAPS // 2))
-            x = np.arange(-lw, lw + 1)
-            taps = np.exp(x ** 2 / (-2 * sigma ** 2))
-            taps = taps / np.sum(taps)
             prob.lowpass_half[k] = lw
-            for t, w in enumerate(taps):
-                prob.lowpass_taps[k][t] = w
+            prob.lowpass_sigma[k] = float(sigma)
     for which, table in zip(("bounds_abs", "bounds_diff", "bounds_rel"), tables):
         dst = getattr(prob, which)
         for side in range(2):

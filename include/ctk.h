@@ -120,8 +120,9 @@ typedef struct {
   int32_t lowpass;              /* 0: off (noise_size is None) */
   int32_t lowpass_half[3];      /* half width lw = int(4 sigma + 0.5) per axis; -1: axis not filtered */
   double  lowpass_threshold;    /* refine.py:38-39: 0 when `threshold` is None */
-  double  lowpass_taps[3][CTK_MAX_TAPS];  /* trackpy.masks.gaussian_kernel(sigma, 4): normalised
-                                   exp(-x^2 / (2 sigma^2)), x = -lw .. lw; entry 0 = offset -lw */
+  double  lowpass_sigma[3];     /* noise_size per axis; the device builds the taps of
+                                   trackpy.masks.gaussian_kernel(sigma, 4): exp(-x^2 / (2 sigma^2)),
+                                   x = -lw .. lw, normalised to sum 1 */
 } ctk_problem_t;
 
 int ctk_version(void);

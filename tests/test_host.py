@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_problem_struct_matches_header_size():
     # ctk_problem_t: 4 + 12 + 3 + 4 int32, 5 doubles, 2 int32, 9 doubles, 3 x 2 x 12 doubles
-    assert ctypes.sizeof(_lib.Problem) == (4 + 12 + 3 + 4) * 4 + 4 + 5 * 8 + 2 * 4 + 9 * 8 + 72 * 8 + 4 * 4 + 8 + 99 * 8
+    assert ctypes.sizeof(_lib.Problem) == (4 + 12 + 3 + 4) * 4 + 4 + 5 * 8 + 2 * 4 + 9 * 8 + 72 * 8 + 4 * 4 + 8 + 3 * 8
 
 
 def test_shared_bytes_query_needs_no_gpu():
@@ -123,7 +123,7 @@ def test_unsupported_options_raise():
         refine.prepare(f.copy(), img, 9, noise_size=5)      # taps wider than the device table
     plan = refine.prepare(f.copy(), img, 9, noise_size=(1, 0), threshold=3)
     assert plan.problem.lowpass == 1 and list(plan.problem.lowpass_half)[:2] == [4, -1]
-    assert plan.problem.lowpass_threshold == 3. and abs(sum(plan.problem.lowpass_taps[0]) - 1) < 1e-12
+    assert plan.problem.lowpass_threshold == 3. and plan.problem.lowpass_sigma[0] == 1.
     with pytest.raises(NotImplementedError):
         refine.prepare(f.copy(), img, 9, compute_error=True)
     with pytest.raises(NotImplementedError):
