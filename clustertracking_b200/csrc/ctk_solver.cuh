@@ -1204,6 +1204,7 @@ struct ClusterSolver {
           }
         }
         if (serial) {
+#pragma unroll 1
           for (int turn = 0; turn < CTK_WARP; ++turn) {
             if (turn == lane && target >= 0) H[target] += val;
             warp_sync();
