@@ -73,6 +73,7 @@ _PROTOTYPES = {
     "ctk_pairs_set_order": (ctypes.c_int, [_vp, _i64, _vp]),
     "ctk_group_chunk": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp,
                                        _vp, _vp, _vp]),
+    "ctk_schedule": (ctypes.c_int, [_vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "ctk_gather_rows": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _i32]),
     "ctk_scatter_rows": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp,
                                         _i32, _vp]),
@@ -213,3 +214,21 @@ def scatter_rows(params, params_in, rows, group_offset, group_cost, group_status
                                   len(group_status), ptrs, cost_out.ctypes.data, int(n_threads),
                                   ctypes.byref(failed)), "ctk_scatter_rows")
     return failed.value
+
+
+def schedule(cluster_offset, caps, class_target):
+    """``ctk_schedule`` -> (work ids grouped by target class with the expensive clusters first,
+    clusters per target class, ids that cannot run)."""
+    cluster_offset = np.ascontiguousarray(cluster_offset, dtype=np.int32)
+    caps = np.ascontiguousarray(caps, dtype=np.int32)
+    class_target = np.ascontiguousarray(class_target, dtype=np.int32)
+    n = len(cluster_offset) - 1
+    work = np.empty(max(n, 1), dtype=np.int32)
+    counts = np.zeros(len(caps), dtype=np.int64)
+    not_run = np.empty(max(n, 1), dtype=np.int32)
+    n_not = ctypes.c_int64(0)
+    check(load().ctk_schedule(cluster_offset.ctypes.data, n, caps.ctypes.data, len(caps),
+                              class_target.ctypes.data, work.ctypes.data, counts.ctypes.data,
+                              not_run.ctypes.data, ctypes.byref(n_not)), "ctk_schedule")
+    n_run = int(counts.sum())
+    return work[:n_run], counts, not_run[:n_not.value]

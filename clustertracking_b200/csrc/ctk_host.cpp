@@ -580,3 +580,40 @@ extern "C" int ctk_scatter_rows(const double* params, const double* params_in, c
   *n_failed_out = failed.load();
   return 0;
 }
+
+// Launch schedule of one plan: clusters sorted by (size class, size descending) with a counting
+// sort.  class_target[k] = class a cluster of class k runs in (k itself, a larger class when class
+// k's arrays do not fit shared memory) or -1 (cannot run).
+//   caps [n_caps] ascending capacities; work_ids_out [n_clusters]; class_count_out [n_caps] clusters
+//   scheduled per TARGET class (work ids are grouped by target class, ascending);
+//   not_run_out [n_clusters] ids that cannot run (count in *n_not_run_out)
+extern "C" int ctk_schedule(const int32_t* cluster_offset, int64_t n_clusters, const int32_t* caps,
+                            int32_t n_caps, const int32_t* class_target, int32_t* work_ids_out,
+                            int64_t* class_count_out, int32_t* not_run_out, int64_t* n_not_run_out) {
+  if (n_clusters < 0 || n_caps < 1 || n_caps > 64 || !cluster_offset || !caps || !class_target ||
+      !work_ids_out || !class_count_out || !not_run_out || !n_not_run_out)
+    return CTK_E_INVALID;
+  const int B = 64;                                   // size buckets inside a class
+  std::vector<int64_t> bucket((size_t) n_caps * B + 1, 0);
+  std::vector<int32_t> key((size_t) n_clusters);
+  int64_t not_run = 0;
+  for (int64_t c = 0; c < n_clusters; ++c) {
+    const int size = cluster_offset[c + 1] - cluster_offset[c];
+    int k = 0;
+    while (k < n_caps && caps[k] < size) ++k;
+    const int target = k < n_caps ? class_target[k] : -1;
+    if (target < 0) {
+      key[c] = -1;
+      not_run_out[not_run++] = (int32_t) c;
+      continue;
+    }
+    key[c] = target * B + (B - 1 - (size < B - 1 ? size : B - 1));
+    ++bucket[key[c] + 1];
+  }
+  for (size_t b = 1; b < bucket.size(); ++b) bucket[b] += bucket[b - 1];
+  for (int k = 0; k < n_caps; ++k) class_count_out[k] = bucket[(size_t) (k + 1) * B] - bucket[(size_t) k * B];
+  for (int64_t c = 0; c < n_clusters; ++c)
+    if (key[c] >= 0) work_ids_out[bucket[key[c]]++] = (int32_t) c;
+  *n_not_run_out = not_run;
+  return 0;
+}

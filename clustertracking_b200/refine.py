@@ -322,8 +322,15 @@ class FrameInfo(object):
 
     def __init__(self, source, frame_column, ndim):
         frames = np.asarray(frame_column)
-        if len(frames) > 1 and np.all(frames[1:] >= frames[:-1]):
-            uniq = frames[np.concatenate(([True], frames[1:] != frames[:-1]))]
+        self.run_starts = None                  # rows at which a new frame starts (sorted tables)
+        if len(frames) > 1:
+            change = frames[1:] != frames[:-1]
+            cuts = np.flatnonzero(change) + 1
+            # sorted <=> every change is an increase
+            if np.all(frames[cuts] > frames[cuts - 1]):
+                self.run_starts = np.concatenate(([0], cuts)).astype(np.int64)
+        if self.run_starts is not None:
+            uniq = frames[self.run_starts]
         else:
             uniq = np.unique(frames)
         self.source = source
@@ -638,9 +645,7 @@ class DeviceSession(object):
         (capacity, start, count) slices.  Inside a class the expensive clusters come first.
         A class whose per-cluster arrays do not fit the shared memory (large masks) runs in the
         first large-cluster class instead (global-memory workspace)."""
-        sizes = self.sizes
         caps = np.asarray(_BINS)
-        cls = np.searchsorted(caps, sizes)                     # size class of every cluster
         self.rigorous = rigorous_problem(self.plan.problem)
         small = caps <= _lib.CTK_MAX_CLUSTER_FEATURES
         key = bytes(self.plan.problem)
@@ -660,19 +665,17 @@ class DeviceSession(object):
         fits, self.retry_fits = _FITS_CACHE[key]
         first_big = int(np.flatnonzero(~small)[0])
         self.big_fallback = int(caps[first_big]) if fits[first_big] else None
-        cls = np.minimum(cls, len(caps))
-        spill = small[np.minimum(cls, len(caps) - 1)] & ~fits[cls] & (cls < len(caps))
-        if self.big_fallback is not None:
-            cls = np.where(spill, first_big, cls)
-        runnable = fits[cls]
-        key = (cls * 64 + (63 - np.minimum(sizes, 63))).astype(np.uint16)   # 16 bits: radix sort
-        ids = np.flatnonzero(runnable)
-        ids = ids[np.argsort(key[ids], kind='stable')]
-        self.d_work = self._up(ids.astype(np.int32))
-        group = cls[ids]
-        cut = np.flatnonzero(np.concatenate(([True], group[1:] != group[:-1], [True])))
-        self.never_run = np.flatnonzero(~runnable)
-        slices = [(int(caps[group[a]]), int(a), int(b - a)) for a, b in zip(cut[:-1], cut[1:])]
+        # class a cluster of class k runs in: k, the first large class when k's arrays do not fit
+        # the shared memory, or -1
+        target = np.where(fits[:len(caps)], np.arange(len(caps)),
+                          np.where(small & bool(self.big_fallback), first_big, -1)).astype(np.int32)
+        ids, counts, self.never_run = _lib.schedule(self.plan.cluster_offset, caps, target)
+        self.d_work = self._up(ids)
+        slices, at = [], 0
+        for k, count in enumerate(counts):
+            if count:
+                slices.append((int(caps[k]), at, int(count)))
+                at += int(count)
         # one overflow list [count, ids...] per small class: filled by the class's launch, consumed by
         # its relaunch with rigorous capacities -- no host round trip in between
         self.overflow_at = {}
@@ -881,16 +884,17 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
     # ---- frame-sorted view of the table (find.py:122-129: the result is sorted by frame) ----------
     frames_col = f[t_column].values
     n = len(f)
-    if n > 1 and not np.all(frames_col[1:] >= frames_col[:-1]):
+    if n > 1 and info.run_starts is None:
         order0 = np.argsort(frames_col, kind='stable')
         base = f.iloc[order0]
         frames_col = frames_col[order0]
+        cuts = np.flatnonzero(frames_col[1:] != frames_col[:-1]) + 1
+        starts = np.concatenate(([0], cuts)).astype(np.int64)
     else:
         order0, base = None, f
+        starts = info.run_starts if info.run_starts is not None else np.zeros(1, dtype=np.int64)
     pos = np.ascontiguousarray(base[pre.pos_columns].values, dtype=np.float64)
-    cuts = np.flatnonzero(frames_col[1:] != frames_col[:-1]) + 1
-    starts = np.concatenate(([0], cuts)).astype(np.int64)
-    stops = np.concatenate((cuts, [n])).astype(np.int64)
+    stops = np.concatenate((starts[1:], [n])).astype(np.int64)
     n_frames = len(starts)
     # chunks of whole frames with about _CHUNK_ROWS features each
     k_chunks = int(max(1, min(_MAX_CHUNKS, n // max(1, _CHUNK_ROWS), n_frames)))

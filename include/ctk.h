@@ -239,14 +239,18 @@ int ctk_cluster_frames(const double* pos, int64_t n, int32_t ndim, const int64_t
                        int64_t* by_cluster_out, int64_t* span_out);
 
 /* Host helpers (no GPU) of the packing pipeline: running cluster ids (find.py:127-128), group order
- * and group table (refine.py:336) of one labelled chunk of frames; the gather of the packed
- * parameter rows (refine.py:345); the write-back of the results (refine.py:408-427).  See
+ * and group table (refine.py:336) of one labelled chunk of frames; the launch schedule (clusters by
+ * size class, expensive first); the gather of the packed parameter rows (refine.py:345); the
+ * write-back of the results (refine.py:408-427).  See
  * ctk_host.cpp for the argument lists. */
 int ctk_group_chunk(const int64_t* local_labels, const int64_t* by_cluster, const int64_t* starts,
                     const int64_t* stops, const int64_t* spans, int64_t n_frames, int64_t next_id,
                     int64_t row_base, int32_t frame_base, int64_t* cluster_out, int64_t* order_out,
                     int32_t* group_offset_out, int32_t* group_frame_out, int64_t* n_groups_out,
                     int64_t* next_id_out);
+int ctk_schedule(const int32_t* cluster_offset, int64_t n_clusters, const int32_t* caps,
+                 int32_t n_caps, const int32_t* class_target, int32_t* work_ids_out,
+                 int64_t* class_count_out, int32_t* not_run_out, int64_t* n_not_run_out);
 int ctk_gather_rows(const double* const* columns, const double* scalars, const int64_t* rows,
                     int64_t n, int32_t n_cols, double* out, int32_t n_threads);
 int ctk_scatter_rows(const double* params, const double* params_in, const int64_t* rows, int64_t n,

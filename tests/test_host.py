@@ -263,3 +263,16 @@ def test_pipelined_chunks_equal_whole_table(monkeypatch, shuffle):
         assert got[col].dtype == want[col].dtype, col
         assert_array_equal(got[col].values, want[col].values, err_msg=col)
     got.loc[got.index[0], 'x'] = 1.0                            # the result is writable
+
+
+def test_schedule_groups_by_class_expensive_first():
+    sizes = np.array([1, 5, 2, 6, 300, 33, 2, 4, 40, 1])
+    offset = np.concatenate(([0], np.cumsum(sizes))).astype(np.int32)
+    caps = np.array(refine._BINS, dtype=np.int32)
+    target = np.arange(len(caps), dtype=np.int32)
+    target[list(caps).index(4)] = list(caps).index(64)        # class 4 does not fit: runs in class 64
+    ids, counts, not_run = _lib.schedule(offset, caps, target)
+    assert list(not_run) == [4]                               # 300 features: no class
+    by_cap = dict(zip(caps.tolist(), counts.tolist()))
+    assert by_cap[1] == 2 and by_cap[2] == 2 and by_cap[6] == 2 and by_cap[4] == 0 and by_cap[64] == 3
+    assert list(ids) == [0, 9, 2, 6, 3, 1, 8, 5, 7]           # per class: larger clusters first
