@@ -63,6 +63,7 @@ _PROTOTYPES = {
     "ctk_refine_workspace_bytes": (_sz, []),
     "ctk_refine_shared_bytes": (_sz, [ctypes.POINTER(Problem), _i32]),
     "ctk_refine_workspace_bytes_for": (_sz, [ctypes.POINTER(Problem), _i32]),
+    "ctk_refine_thread_kernel": (ctypes.c_int, [ctypes.POINTER(Problem), _i32]),
     "ctk_refine_batch": (ctypes.c_int, [ctypes.POINTER(Problem), _vp, ctypes.POINTER(_i64), _vp,
                                         _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp]),

@@ -3,7 +3,14 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <stdlib.h>
+
 #include "ctk_launch.h"
+#include "ctk_thread.cuh"
+
+namespace ctk {
+int launch_refine_threads(const BatchArgs& args, cudaStream_t stream, char* err, size_t err_len);
+}
 
 namespace {
 
@@ -121,6 +128,18 @@ size_t ctk_refine_shared_bytes(const ctk_problem_t* prob, int32_t max_cluster_fe
   return lay.total <= 227 * 1024 ? (size_t) lay.total : 0;
 }
 
+int ctk_refine_thread_kernel(const ctk_problem_t* prob, int32_t max_cluster_features) {
+  // Opt-in (CTK_THREAD_KERNEL=1): the thread-per-cluster kernel executes 2.4x fewer warp
+  // instructions per cluster than the warp-per-cluster kernel but its per-thread working set
+  // (entry lists, normal matrix and factor in local memory, ~8 KB touched per thread) overflows
+  // L1 and L2 at full occupancy, and it ends up 6 % slower on config 2.
+  const char* env = getenv("CTK_THREAD_KERNEL");
+  const bool on = env && env[0] == '1';
+  return prob && on && !ctk::validate_problem(*prob) &&
+                 ctk::thread_eligible(*prob, max_cluster_features)
+             ? 1 : 0;
+}
+
 int ctk_refine_batch(const ctk_problem_t* prob, const void* const* d_frames,
                      const int64_t* frame_shape, const double* d_frame_max, int32_t n_work,
                      const int32_t* d_work_ids, int32_t max_cluster_features,
@@ -188,6 +207,9 @@ int ctk_refine_batch_chained(const ctk_problem_t* prob, const void* const* d_fra
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CTK_CUDA(cudaMemsetAsync(d_workspace, 0, sizeof(int32_t), st));
   if (a.overflow) CTK_CUDA(cudaMemsetAsync(a.overflow, 0, sizeof(int32_t), st));
+  // small clusters of the default 2D gauss model: one thread per cluster (ctk_thread.cuh)
+  if (!big && ctk_refine_thread_kernel(prob, max_cluster_features))
+    return ctk::launch_refine_threads(a, st, g_error, sizeof(g_error));
   Launcher launcher{&a, st, 0};
   bool found = prob->compute_dtype == CTK_COMPUTE_F64
                    ? ctk::dispatch_config<double>(*prob, launcher, big)

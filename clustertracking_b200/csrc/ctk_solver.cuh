@@ -64,6 +64,7 @@ CTK_DEV uint32_t lanemask_lt() { return 0u; }
 template <class T> CTK_DEV T shfl_xor(T v, int) { return v; }
 template <class T> CTK_DEV T shfl(T v, int) { return v; }
 CTK_DEV int popc(uint32_t v) { return __builtin_popcount(v); }
+CTK_DEV int ctz(uint32_t v) { return __builtin_ctz(v); }
 CTK_DEV double dsub(double a, double b) { return a - b; }   // built with -ffp-contract=off
 CTK_DEV double ddiv(double a, double b) { return a / b; }
 CTK_DEV double dmul(double a, double b) { return a * b; }
@@ -78,6 +79,7 @@ CTK_DEV uint32_t lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
 template <class T> CTK_DEV T shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 template <class T> CTK_DEV T shfl(T v, int s) { return __shfl_sync(0xffffffffu, v, s); }
 CTK_DEV int popc(uint32_t v) { return __popc(v); }
+CTK_DEV int ctz(uint32_t v) { return __ffs((int) v) - 1; }
 // float64 without FMA contraction: the mask test must round exactly like numpy (refine.py:43)
 CTK_DEV double dsub(double a, double b) { return __dsub_rn(a, b); }
 CTK_DEV double ddiv(double a, double b) { return __ddiv_rn(a, b); }

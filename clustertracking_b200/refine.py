@@ -648,7 +648,7 @@ class DeviceSession(object):
         caps = np.asarray(_BINS)
         self.rigorous = rigorous_problem(self.plan.problem)
         small = caps <= _lib.CTK_MAX_CLUSTER_FEATURES
-        key = bytes(self.plan.problem)
+        key = bytes(self.plan.problem) + os.environ.get('CTK_THREAD_KERNEL', '0').encode()
         if key not in _FITS_CACHE:                 # the capacity queries only depend on the problem
             prob = _lib.ctypes.byref(self.plan.problem)
             rig = _lib.ctypes.byref(self.rigorous)
@@ -658,17 +658,23 @@ class DeviceSession(object):
                              for c in caps] + [False])
             retry_fits = {int(c): self.lib.ctk_refine_shared_bytes(rig, int(c)) > 0
                           for c in caps[small]}
+            # largest capacity the thread-per-cluster kernel takes (0: the problem does not qualify);
+            # it handles every size up to that in ONE launch, so those classes are merged
+            merged = max([int(c) for c in caps[small]
+                          if self.lib.ctk_refine_thread_kernel(prob, int(c))] + [0])
             if len(_FITS_CACHE) > 64:
                 _FITS_CACHE.clear()
-            _FITS_CACHE[key] = (fits, retry_fits)
+            _FITS_CACHE[key] = (fits, retry_fits, merged)
         # classes whose typical-case capacities can overflow, and whether the rigorous ones fit
-        fits, self.retry_fits = _FITS_CACHE[key]
+        fits, self.retry_fits, merged = _FITS_CACHE[key]
         first_big = int(np.flatnonzero(~small)[0])
         self.big_fallback = int(caps[first_big]) if fits[first_big] else None
         # class a cluster of class k runs in: k, the first large class when k's arrays do not fit
         # the shared memory, or -1
         target = np.where(fits[:len(caps)], np.arange(len(caps)),
                           np.where(small & bool(self.big_fallback), first_big, -1)).astype(np.int32)
+        if merged:
+            target[caps <= merged] = int(np.flatnonzero(caps == merged)[0])
         ids, counts, self.never_run = _lib.schedule(self.plan.cluster_offset, caps, target)
         self.d_work = self._up(ids)
         slices, at = [], 0

@@ -149,6 +149,15 @@ size_t ctk_refine_workspace_bytes_for(const ctk_problem_t* prob, int32_t max_clu
  * fit the device limit (227 KB on sm_100a).  Lets the caller bin clusters by size. */
 size_t ctk_refine_shared_bytes(const ctk_problem_t* prob, int32_t max_cluster_features);
 
+/* 1 when a launch with this problem and capacity runs the thread-per-cluster kernel (the
+ * reference's default model -- 2D isotropic gauss, signal and position free, constant size, no
+ * constraints, no lowpass -- and at most 8 features per cluster): such a launch takes clusters of
+ * ANY size up to max_cluster_features at full efficiency, so a caller should hand it all of them
+ * in one launch instead of one launch per size class.  0: the warp-per-cluster kernel runs.
+ * The thread-per-cluster kernel is opt-in (environment variable CTK_THREAD_KERNEL=1): on B200 its
+ * per-thread working set does not fit the caches and it is slightly slower than the warp kernel. */
+int ctk_refine_thread_kernel(const ctk_problem_t* prob, int32_t max_cluster_features);
+
 /* Refine a batch of clusters: the body of the reference's loop over (frame, cluster) groups
  * (refine.py:343-430) including the pixel-set construction (refine.py:28-58, masks.py:30-68), the
  * objective (fitfunc.py:421-489), the bounds (fitfunc.py:535-558), the dimer/trimer constraints

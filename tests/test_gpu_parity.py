@@ -84,3 +84,29 @@ def test_cuda_matches_reference_golden(name, precision):
         got = ctb.refine_leastsq(f0, reader, diameter, precision=precision, **kwargs)
     _compare(got, golden_io.frame(d, "ref_"), POS_TOL, REL_TOL)
     _compare(got, golden_io.frame(d, "tight_"), POS_TOL_TIGHT, REL_TOL_TIGHT)
+
+
+THREAD_CASES = ["refine_gauss2d_isolated", "refine_gauss2d_clusters", "refine_gauss2d_integer_start",
+                "refine_gauss2d_overlap_7px", "refine_gauss2d_video", "refine_failure_rms",
+                "refine_dimer2d_free", "refine_trimer2d_free"]
+
+
+@pytest.mark.parametrize("precision", ["float32", "float64"])
+@pytest.mark.parametrize("name", THREAD_CASES)
+def test_thread_per_cluster_kernel_matches_reference_golden(name, precision, monkeypatch):
+    """The opt-in thread-per-cluster kernel (csrc/ctk_thread.cuh, CTK_THREAD_KERNEL=1) on the cases
+    it takes: default 2D gauss model, clusters of up to 8 features; larger ones overflow to the warp
+    kernel through the device-side list."""
+    import clustertracking_b200 as ctb
+    from clustertracking_b200 import _lib
+    monkeypatch.setenv("CTK_THREAD_KERNEL", "1")
+    d = golden_io.load(name)
+    f0, reader, diameter, kwargs = golden_io.refine_inputs(d, ctb.constraints)
+    from clustertracking_b200 import refine as ctb_refine
+    plan = ctb_refine.prepare(f0.copy(), reader, diameter, precision=precision, **kwargs)
+    assert _lib.load().ctk_refine_thread_kernel(_lib.ctypes.byref(plan.problem), 8) == 1
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = ctb.refine_leastsq(f0, reader, diameter, precision=precision, **kwargs)
+    _compare(got, golden_io.frame(d, "ref_"), POS_TOL, REL_TOL)
+    _compare(got, golden_io.frame(d, "tight_"), POS_TOL_TIGHT, REL_TOL_TIGHT)
