@@ -78,6 +78,11 @@ _PROTOTYPES = {
     "ctk_gather_rows": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _i32]),
     "ctk_scatter_rows": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp,
                                         _i32, _vp]),
+    "ctk_find_workspace_bytes": (_sz, [_i32, _i64, _i32]),
+    "ctk_find_maxima": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_i64), _i32, _i32, _vp, ctypes.c_double,
+                                       _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "ctk_find_last_error": (ctypes.c_char_p, []),
+    "ctk_query_pairs_within": (ctypes.c_int, [_vp, _i64, _i32, ctypes.c_double, _vp, _i64, _vp]),
     "ctk_query_pairs": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i64, _vp]),
     "ctk_cluster_frames": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp,
                                           _vp]),
@@ -128,9 +133,9 @@ def pairs_set_order(pairs):
     return pairs[order]
 
 
-def query_pairs(data):
-    """Host helper ``ctk_query_pairs``: close pairs (distance <= 1) of ``data`` [n, ndim] in the order
-    of ``scipy.spatial.cKDTree(data).query_pairs(1, output_type='ndarray')``."""
+def query_pairs(data, r=1.0):
+    """Host helper ``ctk_query_pairs_within``: pairs of ``data`` [n, ndim] closer than ``r``; for
+    r = 1 in the order of ``scipy.spatial.cKDTree(data).query_pairs(1, output_type='ndarray')``."""
     data = np.ascontiguousarray(data, dtype=np.float64)
     n, ndim = data.shape
     count = ctypes.c_int64(0)
@@ -138,8 +143,8 @@ def query_pairs(data):
     capacity = max(16, 4 * n)
     while True:
         out = np.empty((capacity, 2), dtype=np.int64)
-        code = lib.ctk_query_pairs(data.ctypes.data, n, ndim, out.ctypes.data, capacity,
-                                   ctypes.byref(count))
+        code = lib.ctk_query_pairs_within(data.ctypes.data, n, ndim, float(r), out.ctypes.data,
+                                          capacity, ctypes.byref(count))
         if code == -4:                      # CTK_E_CAPACITY: count holds the size needed
             capacity = int(count.value)
             continue

@@ -44,7 +44,8 @@ def _source_hash(extra):
 
 
 def _jobs():
-    jobs = [("api", "ctk_api.cu", []), ("host", "ctk_host.cpp", []), ("thread", "ctk_thread.cu", [])]
+    jobs = [("api", "ctk_api.cu", []), ("host", "ctk_host.cpp", []), ("thread", "ctk_thread.cu", []),
+            ("find", "ctk_find.cu", [])]
     for real in ("float", "double"):
         for fam in (0, 1, 2):
             jobs.append(("inst_%s_%d" % (real, fam), "ctk_inst.cu",

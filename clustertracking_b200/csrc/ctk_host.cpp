@@ -396,14 +396,19 @@ struct FrameScratch {
 
 extern "C" int ctk_query_pairs(const double* data, int64_t n, int32_t ndim, int64_t* pairs_out,
                                int64_t capacity, int64_t* n_pairs_out) {
-  if (n < 0 || ndim < 1 || ndim > 3 || (n > 0 && !data) || !n_pairs_out) return CTK_E_INVALID;
+  return ctk_query_pairs_within(data, n, ndim, 1.0, pairs_out, capacity, n_pairs_out);
+}
+
+extern "C" int ctk_query_pairs_within(const double* data, int64_t n, int32_t ndim, double r,
+                                      int64_t* pairs_out, int64_t capacity, int64_t* n_pairs_out) {
+  if (n < 0 || ndim < 1 || ndim > 3 || (n > 0 && !data) || !n_pairs_out || !(r >= 0.)) return CTK_E_INVALID;
   KdTree tree;
   tree.init(data, (int) n, ndim, nullptr);
   std::vector<int64_t> pairs;
   PairQuery q;
   q.t = &tree;
   q.out = &pairs;
-  q.tr.init(tree, 1.0);
+  q.tr.init(tree, r);
   if (n > 0) q.checking(0, 0);
   *n_pairs_out = (int64_t) pairs.size() / 2;
   if (pairs_out) {

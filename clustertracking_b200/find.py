@@ -375,3 +375,124 @@ def cluster_table(f, separation, pos_columns=None, t_column='frame'):
     out['cluster'] = cluster
     out['cluster_size'] = size
     return out, by_cluster
+
+
+# --------------------------------------------------------------------------------------------------
+# feature finding: the step in front of the refinement (reference: clustertracking/find.py:166-277)
+# --------------------------------------------------------------------------------------------------
+def where_close(pos, separation, intensity=None):
+    """Indices of features closer than ``separation`` to another feature: of every close pair the
+    dimmer one (``intensity`` given) or the one nearer the top left (find.py:166-199).  The pairs
+    come from libctk's kd-tree (``ctk_query_pairs_within``); the result does not depend on their
+    order."""
+    if len(pos) == 0:
+        return []
+    pos = np.asarray(pos)
+    separation = validate_tuple(separation, pos.shape[1])
+    if any([s == 0 for s in separation]):
+        return []
+    pos_rescaled = pos / separation                                          # find.py:179
+    pairs = _lib.query_pairs(np.ascontiguousarray(pos_rescaled, dtype=np.float64), 1 - 1e-7)
+    if len(pairs) == 0:
+        return []
+    index_0, index_1 = pairs[:, 0], pairs[:, 1]
+    top_left = np.sum(pos_rescaled[index_0], 1) > np.sum(pos_rescaled[index_1], 1)
+    if intensity is None:
+        to_drop = np.where(top_left, index_1, index_0)
+    else:
+        intensity = np.asarray(intensity)
+        intensity_0, intensity_1 = intensity[index_0], intensity[index_1]
+        to_drop = np.where(intensity_0 > intensity_1, index_1, index_0)
+        ties = intensity_0 == intensity_1
+        to_drop[ties] = np.where(top_left, index_1, index_0)[ties]
+    return np.unique(to_drop)
+
+
+def drop_close(pos, separation, intensity=None):
+    """``pos`` without the features ``where_close`` names (find.py:202-207)."""
+    return np.delete(pos, where_close(pos, separation, intensity), axis=0)
+
+
+def _maxima_on_device(frames, size, percentile, margin):
+    """Maxima of a list of equally shaped integer frames on the current CUDA device through
+    ``ctk_find_maxima`` -> list of (positions int64 [k, ndim], pixel values int64 [k], threshold)."""
+    import torch
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("clustertracking_b200 needs a CUDA device (B200, sm_100a); "
+                           "there is no CPU fallback")
+    first = np.asarray(frames[0])
+    if first.dtype not in (np.dtype(np.uint8), np.dtype(np.uint16)):
+        raise NotImplementedError("grey_dilation on the GPU takes uint8 or uint16 frames, got %s"
+                                  % first.dtype)
+    ndim, shape = first.ndim, first.shape
+    if ndim not in (2, 3):
+        raise ValueError("only 2D and 3D images are supported")
+    dev = torch.device('cuda', torch.cuda.current_device())
+    stack = np.ascontiguousarray(np.stack([np.asarray(fr) for fr in frames]))
+    if stack.shape[1:] != shape:
+        raise ValueError("frames must have equal shapes")
+    tdtype = torch.uint8 if first.dtype == np.uint8 else torch.uint16
+    d_stack = torch.from_numpy(stack).to(dev)
+    n_frames, n_pixels = len(stack), int(np.prod(shape))
+    ptrs = d_stack.data_ptr() + stack[0].nbytes * np.arange(n_frames, dtype=np.int64)
+    d_ptrs = torch.from_numpy(ptrs).to(dev)
+    code = _lib.PIXEL_CODES[first.dtype]
+    d_ws = torch.empty(int(lib.ctk_find_workspace_bytes(n_frames, n_pixels, code)), dtype=torch.uint8,
+                       device=dev)
+    shape_arr = (_lib.ctypes.c_int64 * 3)(*(list(shape) + [1] * (3 - ndim)))
+    size_arr = (_lib.ctypes.c_int32 * 3)(*(list(size) + [1] * (3 - ndim)))
+    margin_arr = (_lib.ctypes.c_int32 * 3)(*(list(margin) + [0] * (3 - ndim)))
+    capacity = max(1024, n_pixels // 64)
+    while True:
+        d_coords = torch.empty((n_frames, capacity, ndim), dtype=torch.int32, device=dev)
+        d_values = torch.empty((n_frames, capacity), dtype=torch.int32, device=dev)
+        d_count = torch.empty(n_frames, dtype=torch.int32, device=dev)
+        d_thr = torch.empty(n_frames, dtype=torch.float64, device=dev)
+        rc = lib.ctk_find_maxima(d_ptrs.data_ptr(), n_frames, shape_arr, ndim, code, size_arr,
+                                 float(percentile), margin_arr, capacity, d_coords.data_ptr(),
+                                 d_values.data_ptr(), d_count.data_ptr(), d_thr.data_ptr(),
+                                 d_ws.data_ptr(), int(bool(np.all(ptrs % 4 == 0))),
+                                 _lib.ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        if rc != 0:
+            raise RuntimeError("ctk_find_maxima failed (%d): %s"
+                               % (rc, lib.ctk_find_last_error().decode()))
+        counts = d_count.cpu().numpy()
+        if counts.max(initial=0) <= capacity:
+            break
+        capacity = int(counts.max())
+    coords, values, thr = d_coords.cpu().numpy(), d_values.cpu().numpy(), d_thr.cpu().numpy()
+    del tdtype
+    return [(coords[k, :counts[k]].astype(np.int64), values[k, :counts[k]].astype(np.int64), thr[k])
+            for k in range(n_frames)]
+
+
+def grey_dilation_batch(frames, separation, percentile=64, margin=None, precise=True):
+    """``grey_dilation`` for a sequence of equally shaped frames, image work on the GPU in one
+    batch -> list of position arrays."""
+    frames = list(frames)
+    if not frames:
+        return []
+    ndim = np.asarray(frames[0]).ndim
+    separation = validate_tuple(separation, ndim)
+    if margin is None:
+        margin = tuple([int(s / 2) for s in separation])                     # find.py:246-247
+    margin = validate_tuple(margin, ndim)
+    size = [int(2 * s / np.sqrt(ndim)) for s in separation]                   # find.py:255
+    out = []
+    for pos, values, threshold in _maxima_on_device(frames, size, percentile, margin):
+        if np.isnan(threshold) or len(pos) == 0:
+            out.append(np.empty((0, ndim)))                                   # find.py:251-252, 262
+            continue
+        if precise:
+            pos = drop_close(pos, separation, values)                         # find.py:275-276
+        out.append(pos)
+    return out
+
+
+def grey_dilation(image, separation, percentile=64, margin=None, precise=True):
+    """Local maxima brighter than the given percentile of the non-black pixels, at least
+    ``separation`` apart -- same signature and result as the reference's ``grey_dilation``
+    (find.py:219-277).  The percentile, the dilation and the comparison run on the GPU
+    (``ctk_find_maxima``); uint8 and uint16 images."""
+    return grey_dilation_batch([image], separation, percentile, margin, precise)[0]

@@ -267,6 +267,37 @@ int ctk_scatter_rows(const double* params, const double* params_in, const int64_
                      const int32_t* group_status, int64_t n_groups, double* const* columns,
                      double* cost_out, int32_t n_threads, int64_t* n_failed_out);
 
+/* Local maxima of a batch of frames: the image part of clustertracking's grey_dilation
+ * (find.py:219-270), the step that produces the initial coordinates of the refinement:
+ *   threshold = np.percentile(image[image != 0], percentile)                 find.py:210-216
+ *   dilation  = scipy.ndimage.grey_dilation(image, size, mode='constant')    find.py:255-259
+ *   maxima    = (image == dilation) & (image > threshold), minus the pixels closer than `margin`
+ *               to an edge, listed in C order                                find.py:260-270
+ * (the pair-wise drop_close step, find.py:166-206, is host code).  Integer frames only
+ * (CTK_PIXEL_U8, CTK_PIXEL_U16).  HBM-bound streaming kernels, asynchronous on `stream`.
+ *   d_frames [n_frames] device pointers to C-contiguous frames; frame_shape [ndim], ndim 2 | 3
+ *   size [ndim]    box of the dilation, int(2 * separation / sqrt(ndim))     find.py:252
+ *   margin [ndim]  exclusion zone at the edges
+ *   capacity       maxima stored per frame
+ *   d_coords_out [n_frames, capacity, ndim] int32; d_values_out [n_frames, capacity] int32 (pixel
+ *   value of every maximum); d_count_out [n_frames] int32 number found (may exceed capacity: call
+ *   again with more room); d_threshold_out [n_frames] float64 (NaN: the frame is all black)
+ *   d_workspace    ctk_find_workspace_bytes(n_frames, pixels per frame, pixel_dtype) bytes
+ *   frames_aligned 1: every frame pointer is 4-byte aligned (enables the packed uint8 filter) */
+size_t ctk_find_workspace_bytes(int32_t n_frames, int64_t n_pixels, int32_t pixel_dtype);
+int ctk_find_maxima(const void* const* d_frames, int32_t n_frames, const int64_t* frame_shape,
+                    int32_t ndim, int32_t pixel_dtype, const int32_t* size, double percentile,
+                    const int32_t* margin, int32_t capacity, int32_t* d_coords_out,
+                    int32_t* d_values_out, int32_t* d_count_out, double* d_threshold_out,
+                    void* d_workspace, int32_t frames_aligned, void* stream);
+const char* ctk_find_last_error(void);
+
+/* ctk_query_pairs with a radius: pairs closer than `r` (the SET scipy's
+ * cKDTree(data, leafsize).query_pairs(r) reports for any leafsize; used by where_close,
+ * find.py:166-199, whose result does not depend on the order of the pairs). */
+int ctk_query_pairs_within(const double* data, int64_t n, int32_t ndim, double r,
+                           int64_t* pairs_out, int64_t capacity, int64_t* n_pairs_out);
+
 #ifdef __cplusplus
 }
 #endif

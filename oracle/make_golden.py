@@ -13,6 +13,7 @@ pixels_*    ``prepare_subimage`` pixel sets (refine.py:28-58) and ``slices_multi
 clusters_*  ``find_clusters`` labels (find.py:132-163)
 refine_*    ``refine_leastsq`` end to end (refine.py:82-452), default ``tol`` and ``tol=1e-12``
 lowpass_*   ``prepare_subimage`` with ``noise_size`` (refine.py:36-40, preprocessing.py:12-49)
+find_*      ``grey_dilation`` local maxima (find.py:166-277)
 """
 import json
 import os
@@ -437,11 +438,47 @@ def golden_lowpass(ct):
     f0 = start_frame(pos, 0.5, ['z', 'y', 'x'], signal=120., size_z=2.25, size_y=3.25, size_x=3.25,
                      background=2.)
     _refine_case(ct, "refine_lowpass3d", image, f0, (9, 13, 13), dict(noise_size=(0.6, 1, 1)))
+def golden_find(ct):
+    """``grey_dilation`` (find.py:219-277): local maxima above a percentile, margin, drop_close."""
+    from clustertracking.find import grey_dilation
+    rng = np.random.RandomState(77)
+
+    def blobs(shape, n, sigma, amp, noise, dtype):
+        """smooth random blobs + noise; plateaus and ties included on purpose (integer images)"""
+        img = np.zeros(shape, dtype=float)
+        grids = np.meshgrid(*[np.arange(s) for s in shape], indexing='ij')
+        for _ in range(n):
+            c = [rng.uniform(0, s) for s in shape]
+            r2 = sum(((g - ci) / sg) ** 2 for g, ci, sg in zip(grids, c, np.broadcast_to(sigma, len(shape))))
+            img += rng.uniform(0.4, 1.0) * amp * np.exp(-r2)
+        img += rng.poisson(noise, shape)
+        info = np.iinfo(dtype)
+        return np.clip(img, 0, info.max).astype(dtype)
+
+    cases = [
+        ("2d_u8", blobs((200, 240), 60, 3.0, 180, 6, np.uint8), dict(separation=11)),
+        ("2d_u8_even", blobs((160, 200), 50, 3.0, 200, 4, np.uint8), dict(separation=12, percentile=80)),
+        ("2d_u8_aniso", blobs((180, 150), 40, (4.0, 2.5), 180, 5, np.uint8),
+         dict(separation=(14, 9), margin=(3, 20))),
+        ("2d_u8_fast", blobs((150, 150), 40, 3.0, 160, 8, np.uint8), dict(separation=9, precise=False)),
+        ("2d_u16", blobs((128, 160), 30, 3.5, 3000, 40, np.uint16), dict(separation=13, percentile=50)),
+        ("2d_black", np.zeros((64, 64), np.uint8), dict(separation=9)),
+        ("2d_sparse", (rng.uniform(size=(90, 90)) > 0.995).astype(np.uint8) * 200, dict(separation=7)),
+        ("3d_u8", blobs((24, 64, 72), 25, (2.0, 3.0, 3.0), 180, 3, np.uint8), dict(separation=(7, 11, 11))),
+        ("3d_u8_margin", blobs((20, 50, 60), 20, 2.5, 200, 2, np.uint8),
+         dict(separation=9, margin=(2, 6, 6), percentile=90)),
+    ]
+    for name, image, kwargs in cases:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            pos = grey_dilation(image, **kwargs)
+        save("find_" + name, image=image, kwargs=np.array(json.dumps(kwargs)),
+             pos=np.asarray(pos, dtype=np.int64).reshape(-1, image.ndim))
 
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ct = ref_loader.load()
-    only = sys.argv[1:] or ["fitfunc", "pixels", "clusters", "refine", "tetramer", "lowpass"]
+    only = sys.argv[1:] or ["fitfunc", "pixels", "clusters", "refine", "tetramer", "lowpass", "find"]
     for part in only:
         globals()["golden_" + part](ct)

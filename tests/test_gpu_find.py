@@ -1,0 +1,59 @@
+"""GPU tests of the feature-finding step (``-m gpu``): ``clustertracking_b200.find.grey_dilation``
+(image work in ``ctk_find_maxima``) against the reference's own outputs (tests/golden/find_*.npz)
+and against the CPU oracle on a full-size frame.  Integer work: results must be identical."""
+import json
+
+import numpy as np
+import pytest
+from numpy.testing import assert_array_equal
+
+import golden_io
+
+pytestmark = pytest.mark.gpu
+
+
+def _kwargs(d):
+    kwargs = json.loads(str(d["kwargs"]))
+    for key in ("separation", "margin"):
+        if isinstance(kwargs.get(key), list):
+            kwargs[key] = tuple(kwargs[key])
+    return kwargs
+
+
+@pytest.mark.parametrize("name", golden_io.names("find_"))
+def test_grey_dilation_matches_reference_golden(name):
+    from clustertracking_b200 import find
+    d = golden_io.load(name)
+    got = find.grey_dilation(d["image"], **_kwargs(d))
+    assert_array_equal(np.asarray(got).reshape(-1, d["image"].ndim), d["pos"])
+
+
+def test_grey_dilation_batch_equals_single_frames():
+    from clustertracking_b200 import find
+    names = ["find_2d_u8_fast", "find_2d_u8_fast"]
+    d = golden_io.load(names[0])
+    image = d["image"]
+    flipped = np.ascontiguousarray(image[::-1])
+    out = find.grey_dilation_batch([image, flipped], **_kwargs(d))
+    assert_array_equal(out[0], d["pos"])
+    assert_array_equal(out[1], find.grey_dilation(flipped, **_kwargs(d)))
+
+
+def test_full_size_frame_equals_oracle():
+    """1024x1024 config-2 frame: identical maxima; and the maxima sit on the rendered features."""
+    from clustertracking_b200 import artificial, find
+    from oracle import find_oracle
+    frame, f0, truth = artificial.clustered_frame((1024, 1024), seed=3)
+    got = find.grey_dilation(frame, 5, percentile=90)
+    want = find_oracle.grey_dilation(frame, 5, percentile=90)
+    assert_array_equal(got, want)
+    assert len(got) > 1000
+    for dtype in (np.uint16,):
+        assert_array_equal(find.grey_dilation(frame.astype(dtype) * 3, 5, percentile=90),
+                           find_oracle.grey_dilation(frame.astype(dtype) * 3, 5, percentile=90))
+
+
+def test_unsupported_pixel_types_raise():
+    from clustertracking_b200 import find
+    with pytest.raises(NotImplementedError):
+        find.grey_dilation(np.zeros((32, 32), np.float32), 5)

@@ -276,3 +276,28 @@ def test_schedule_groups_by_class_expensive_first():
     by_cap = dict(zip(caps.tolist(), counts.tolist()))
     assert by_cap[1] == 2 and by_cap[2] == 2 and by_cap[6] == 2 and by_cap[4] == 0 and by_cap[64] == 3
     assert list(ids) == [0, 9, 2, 6, 3, 1, 8, 5, 7]           # per class: larger clusters first
+
+
+# ---- feature finding, host part --------------------------------------------------------------------
+def test_where_close_matches_oracle():
+    from clustertracking_b200 import find
+    from oracle import find_oracle
+    rng = np.random.RandomState(8)
+    for ndim, sep in ((2, 9), (2, (8, 12)), (3, (5, 9, 9))):
+        pos = rng.randint(0, 120, (400, ndim))
+        inten = rng.randint(50, 60, 400)                    # many ties
+        assert_array_equal(find.where_close(pos, sep, inten), find_oracle.where_close(pos, sep, inten))
+        assert_array_equal(find.where_close(pos, sep), find_oracle.where_close(pos, sep))
+        assert_array_equal(find.drop_close(pos, sep, inten),
+                           np.delete(pos, find_oracle.where_close(pos, sep, inten), axis=0))
+    assert find.where_close(np.empty((0, 2)), 5) == []
+
+
+def test_query_pairs_within_is_the_scipy_set():
+    from scipy.spatial import cKDTree
+    rng = np.random.RandomState(9)
+    for r in (1 - 1e-7, 0.5, 1.0, 2.0):
+        data = rng.randint(0, 60, (500, 2)) / 7.
+        want = cKDTree(data, 30).query_pairs(r, output_type='ndarray')
+        got = _lib.query_pairs(data, r)
+        assert set(map(tuple, got.tolist())) == set(map(tuple, want.tolist()))

@@ -189,3 +189,17 @@ def test_refine_matches_reference(name):
         if col in ('cluster', 'cluster_size', 'frame'):
             continue
         assert_allclose(got[col].values, want[col].values, rtol=tol, atol=tol, err_msg=col)
+
+
+# ---- feature finding (find.py:166-277) -----------------------------------------------------------
+@pytest.mark.parametrize("name", golden_io.names("find_"))
+def test_grey_dilation_oracle_matches_reference(name):
+    import json
+    from oracle import find_oracle
+    d = golden_io.load(name)
+    kwargs = json.loads(str(d["kwargs"]))
+    for key in ("separation", "margin"):
+        if isinstance(kwargs.get(key), list):
+            kwargs[key] = tuple(kwargs[key])
+    got = find_oracle.grey_dilation(d["image"], **kwargs)
+    assert_array_equal(np.asarray(got).reshape(-1, d["image"].ndim), d["pos"])
