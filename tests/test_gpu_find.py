@@ -57,3 +57,35 @@ def test_unsupported_pixel_types_raise():
     from clustertracking_b200 import find
     with pytest.raises(NotImplementedError):
         find.grey_dilation(np.zeros((32, 32), np.float32), 5)
+
+
+def test_find_then_refine_matches_oracle():
+    """BASELINE config 5 in miniature: integer pixel maxima from the find step are the start
+    coordinates of the refinement (the reference's documented pipeline, doc/source/api.rst:10-12);
+    both steps on the GPU against both steps of the CPU oracle.  Maxima that are not on a rendered
+    feature (noise peaks) are dropped first: fits of noise have many local minima and no solver
+    agrees with another on them."""
+    import warnings
+    import pandas as pd
+    from scipy.spatial import cKDTree
+    import clustertracking_b200 as ctb
+    from clustertracking_b200 import artificial, find
+    from oracle import cluster_oracle, find_oracle
+    frame, _, truth = artificial.clustered_frame((220, 220), pitch=44, size=2.75, noise=4, seed=21)
+    pos = find.grey_dilation(frame, 5, percentile=95, margin=6)
+    assert_array_equal(pos, find_oracle.grey_dilation(frame, 5, percentile=95, margin=6))
+    dist, _ = cKDTree(truth).query(pos)
+    pos = pos[dist < 1.5]
+    assert len(pos) >= 0.7 * len(truth)
+    f0 = pd.DataFrame(dict(y=pos[:, 0].astype(float), x=pos[:, 1].astype(float), signal=120., size=2.75))
+    got = ctb.refine_leastsq(f0.copy(), frame, 11)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = cluster_oracle.refine_leastsq(f0.copy(), frame, 11)
+    assert_array_equal(got['cluster'].values, want['cluster'].values)
+    both = ~np.isnan(got['cost'].values) & ~np.isnan(want['cost'].values)
+    assert both.mean() > 0.95
+    dpos = np.abs(got[['y', 'x']].values[both] - want[['y', 'x']].values[both]).max(axis=1)
+    # clusters with a missed member are ill-posed fits with flat directions, where SLSQP's default
+    # tolerance stops early: the bulk must agree to the contract, the tail to a tenth of a pixel
+    assert np.percentile(dpos, 90) < 1e-3 and dpos.max() < 0.1, (np.percentile(dpos, 90), dpos.max())
