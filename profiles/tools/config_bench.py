@@ -1,0 +1,125 @@
+"""Throughput and parity of the hot path on BASELINE configs 3 and 4 (parity-test configurations, not
+bench.py lines): python profiles/tools/config_bench.py [frames3] [stacks4]
+
+  config 3  2D 512x512, size 4, diameter 16, 60 dimers + 40 trimers per frame at bond 2*size;
+            constraints dimer(8) + trimer(8) (each applies to clusters of its own size), signal var
+  config 4  3D stacks 64x256x256, size (2.25, 3.25, 3.25), diameter (9, 13, 13), ~150 features per
+            stack in clusters of 1-4, per-axis size 'var'
+
+e2e = clustertracking_b200.refine_leastsq(DataFrame, host frames); parity against the CPU oracle
+(scipy SLSQP) on the first frame / stack; the CPU time of that sample gives the 1-core baseline."""
+import json, os, sys, time, warnings
+import numpy as np
+import pandas as pd
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import torch
+import clustertracking_b200 as ctb
+from clustertracking_b200 import artificial, constraints, refine
+from oracle import cluster_oracle
+
+
+def video(n_frames, shape, make_positions, draw_size, noise, columns, seed, **const):
+    rng = np.random.default_rng(seed)
+    stack, rows = [], []
+    for t in range(n_frames):
+        pos = make_positions(rng)
+        signal = rng.uniform(100., 180., len(pos))
+        stack.append(artificial.draw_features(shape, pos, draw_size, signal, noise=noise, rng=rng))
+        f0 = pd.DataFrame(pos + rng.uniform(-0.5, 0.5, pos.shape), columns=columns)
+        for key, val in const.items():
+            f0[key] = float(val)
+        f0['frame'] = t
+        rows.append(f0)
+    return artificial.FrameStack(np.ascontiguousarray(np.array(stack))), pd.concat(rows, ignore_index=True)
+
+
+def measure(name, reader, f0, diameter, oracle_constraints=None, **kwargs):
+    for _ in range(2):
+        ctb.refine_leastsq(f0, reader, diameter, **kwargs)
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(3):
+        t = time.perf_counter()
+        out = ctb.refine_leastsq(f0, reader, diameter, **kwargs)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t)
+    e2e = len(f0) / min(times)
+    # resident: kernels only
+    plan = refine.prepare(f0.copy(), reader, diameter, **kwargs)
+    res = refine.execute_cuda(plan)                       # uploads + warm-up
+    session = res.session
+    slices = session.schedule()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        session.run(slices)
+    b.record()
+    torch.cuda.synchronize()
+    resident = len(f0) * 3 / (a.elapsed_time(b) * 1e-3)
+    # parity + cpu baseline on the first frame
+    sub = f0[f0['frame'] == 0].copy()
+    okw = dict(kwargs)
+    if oracle_constraints is not None:
+        okw['constraints'] = oracle_constraints
+    t = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = cluster_oracle.refine_leastsq(sub.copy(), reader[0], diameter, **okw)
+    cpu = len(sub) / (time.perf_counter() - t)
+    got = out[out['frame'] == 0]
+    cols = [c for c in ('z', 'y', 'x') if c in got]
+    both = ~np.isnan(got['cost'].values) & ~np.isnan(want['cost'].values)
+    line = dict(config=name, frames=int(f0['frame'].nunique()), features=len(f0),
+                clusters=int(out['cluster'].nunique()), failed_features=int(np.isnan(out['cost']).sum()),
+                resident_features_per_s=resident, e2e_features_per_s=e2e, cpu_1core_features_per_s=cpu,
+                sample_features=len(sub), oracle_failed=int(np.isnan(want['cost']).sum()),
+                max_abs_dpos_px=float(np.abs(got[cols].values[both] - want[cols].values[both]).max()),
+                p99_abs_dpos_px=float(np.percentile(np.abs(got[cols].values[both] - want[cols].values[both]), 99)),
+                max_rel_dsignal=float(np.abs(got['signal'].values[both] / want['signal'].values[both] - 1).max()))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    n3 = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+    n4 = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+
+    def positions3(rng):
+        # rigid templates like artificial.py:144-185: dimers (two features one bond apart) and
+        # equilateral trimers at a random angle -- the shapes the constraints describe
+        centres = artificial.jittered_grid((512, 512), 48, 30, 4, rng)
+        centres = centres[rng.permutation(len(centres))[:100]]
+        pos = []
+        for k, c in enumerate(centres):
+            theta = rng.uniform(0, 2 * np.pi)
+            if k < 60:
+                offs = [(4.0, theta), (4.0, theta + np.pi)]
+            else:
+                offs = [(8.0 / np.sqrt(3.), theta + 2 * np.pi * m / 3) for m in range(3)]
+            pos.extend([c + r * np.array([np.sin(a), np.cos(a)]) for r, a in offs])
+        return np.array(pos)
+
+    reader, f0 = video(n3, (512, 512), positions3, 4.0, 6, ['y', 'x'], 3, signal=150., size=4., background=3.)
+    # the reference cannot take both constraint kinds in one call: the oracle gets
+    # them the same way this repository applies them, each to clusters of its own size
+    measure("config3: dimers + trimers, constraints dimer(8)+trimer(8), 2D 512x512", reader, f0, 16,
+            constraints=constraints.dimer(8.0) + constraints.trimer(8.0),
+            oracle_constraints=cluster_oracle.dimer(8.0, 2) + cluster_oracle.trimer(8.0, 2),
+            param_mode=dict(signal='var', size='const'))
+
+    def positions4(rng):
+        centres = artificial.jittered_grid((64, 256, 256), 30, 16, 3, rng)
+        centres = centres[rng.permutation(len(centres))[:60]]
+        counts = rng.integers(1, 5, len(centres))
+        pos, _ = artificial.grow_clusters(rng, centres, counts, (4.5, 6.5, 6.5), max_reach=None)
+        return pos
+
+    reader, f0 = video(n4, (64, 256, 256), positions4, (2.25, 3.25, 3.25), 4, ['z', 'y', 'x'], 4, signal=150.,
+                       size_z=2.25, size_y=3.25, size_x=3.25, background=2.)
+    measure("config4: 3D aniso stacks 64x256x256, clusters of 1-4, per-axis size var", reader, f0,
+            (9, 13, 13), param_mode=dict(signal='var', size='var'))
+
+
+if __name__ == "__main__":
+    main()
