@@ -76,8 +76,12 @@ _PROTOTYPES = {
                                        _vp, _vp, _vp]),
     "ctk_schedule": (ctypes.c_int, [_vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "ctk_gather_rows": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _i32]),
-    "ctk_scatter_rows": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp,
-                                        _i32, _vp]),
+    "ctk_scatter_rows": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp,
+                                        _vp, _i32, _vp]),
+    "ctk_cluster_pack_frames": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp, _vp,
+                                               _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
+    "ctk_concat_groups": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "ctk_apply_label_offsets": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "ctk_find_workspace_bytes": (_sz, [_i32, _i64, _i32]),
     "ctk_find_maxima": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_i64), _i32, _i32, _vp, ctypes.c_double,
                                        _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
@@ -206,16 +210,16 @@ def gather_rows(sources, rows, out, n_threads):
 
 
 def scatter_rows(params, params_in, rows, group_offset, group_cost, group_status, block, cost_out,
-                 n_threads):
+                 n_threads, row_base=0):
     """``ctk_scatter_rows``: write one chunk back into the table-order column block [P, N] and the
-    cost column; returns the number of failed clusters."""
+    cost column (table row = row_base + rows[r]); returns the number of failed clusters."""
     n_cols = block.shape[0]
     ptrs = (ctypes.c_void_p * n_cols)(*[block[j].ctypes.data for j in range(n_cols)])
     failed = ctypes.c_int64(0)
     for arr in (params, params_in, rows, group_offset, group_cost, group_status, block, cost_out):
         assert arr.flags.c_contiguous
     check(load().ctk_scatter_rows(params.ctypes.data, params_in.ctypes.data, rows.ctypes.data,
-                                  len(rows), n_cols, group_offset.ctypes.data,
+                                  int(row_base), len(rows), n_cols, group_offset.ctypes.data,
                                   group_cost.ctypes.data, group_status.ctypes.data,
                                   len(group_status), ptrs, cost_out.ctypes.data, int(n_threads),
                                   ctypes.byref(failed)), "ctk_scatter_rows")
@@ -238,3 +242,64 @@ def schedule(cluster_offset, caps, class_target):
                               not_run.ctypes.data, ctypes.byref(n_not)), "ctk_schedule")
     n_run = int(counts.sum())
     return work[:n_run], counts, not_run[:n_not.value]
+
+
+def column_pointers(sources):
+    """(pointer array, scalar array) describing table columns for the gather helpers: an ndarray
+    (float64, contiguous) or a constant per column.  Keep the returned objects alive during the call."""
+    n_cols = len(sources)
+    ptrs = (ctypes.c_void_p * n_cols)()
+    scalars = (ctypes.c_double * n_cols)()
+    for j, src in enumerate(sources):
+        if isinstance(src, np.ndarray):
+            assert src.dtype == np.float64 and src.flags.c_contiguous
+            ptrs[j] = src.ctypes.data
+        else:
+            ptrs[j] = None
+            scalars[j] = float(src)
+    return ptrs, scalars
+
+
+def cluster_pack_frames(pos, starts, stops, separation, n_threads, sources, row_base, params_out):
+    """``ctk_cluster_pack_frames`` -> (labels local to each frame, sizes, by_cluster, spans,
+    group counts per frame, group starts); ``params_out`` [n, P] receives the packed rows."""
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    n, ndim = pos.shape
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    stops = np.ascontiguousarray(stops, dtype=np.int64)
+    separation = np.ascontiguousarray(separation, dtype=np.float64)
+    cluster = np.empty(n, dtype=np.int64)
+    size = np.empty(n, dtype=np.int64)
+    by_cluster = np.empty(n, dtype=np.int64)
+    spans = np.zeros(len(starts), dtype=np.int64)
+    gcount = np.zeros(len(starts), dtype=np.int32)
+    gstart = np.empty(max(n, 1), dtype=np.int32)
+    ptrs, scalars = column_pointers(sources)
+    assert params_out.flags.c_contiguous and params_out.dtype == np.float64
+    check(load().ctk_cluster_pack_frames(
+        pos.ctypes.data, n, ndim, starts.ctypes.data, stops.ctypes.data, len(starts),
+        separation.ctypes.data, int(n_threads), cluster.ctypes.data, size.ctypes.data,
+        by_cluster.ctypes.data, spans.ctypes.data, ptrs, scalars, len(sources), int(row_base),
+        params_out.ctypes.data, gcount.ctypes.data, gstart.ctypes.data), "ctk_cluster_pack_frames")
+    return cluster, size, by_cluster, spans, gcount, gstart
+
+
+def concat_groups(starts, stops, gcount, gstart, frame_base):
+    """``ctk_concat_groups`` -> (group_offset int32 [g + 1], group_frame int32 [g])."""
+    total = int(gcount.sum())
+    goff = np.empty(total + 1, dtype=np.int32)
+    gframe = np.empty(max(total, 1), dtype=np.int32)
+    n_groups = ctypes.c_int64(0)
+    check(load().ctk_concat_groups(starts.ctypes.data, stops.ctypes.data, gcount.ctypes.data,
+                                   gstart.ctypes.data, len(starts), int(frame_base), goff.ctypes.data,
+                                   gframe.ctypes.data, ctypes.byref(n_groups)), "ctk_concat_groups")
+    return goff, gframe[:total]
+
+
+def apply_label_offsets(local, starts, stops, frame_offset, n_threads, out):
+    """``ctk_apply_label_offsets``: out[i] = local[i] + frame_offset[frame of row i]."""
+    for arr in (local, starts, stops, frame_offset, out):
+        assert arr.flags.c_contiguous and arr.dtype == np.int64
+    check(load().ctk_apply_label_offsets(local.ctypes.data, starts.ctypes.data, stops.ctypes.data,
+                                         frame_offset.ctypes.data, len(starts), int(n_threads),
+                                         out.ctypes.data), "ctk_apply_label_offsets")

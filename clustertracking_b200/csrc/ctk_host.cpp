@@ -394,6 +394,23 @@ struct FrameScratch {
 
 }  // namespace
 
+namespace {
+template <class Fn>
+void parallel_ranges(int64_t n, int n_threads, Fn&& fn) {
+  int nt = n_threads < 1 ? 1 : n_threads;
+  if (n < (int64_t) nt * 8192) nt = (int) (n / 8192) + 1;
+  if (nt <= 1) { fn((int64_t) 0, n); return; }
+  std::vector<std::thread> pool;
+  const int64_t step = (n + nt - 1) / nt;
+  for (int k = 0; k < nt; ++k) {
+    const int64_t a = k * step, b = a + step < n ? a + step : n;
+    if (a >= b) break;
+    pool.emplace_back([=, &fn]() { fn(a, b); });
+  }
+  for (auto& th : pool) th.join();
+}
+}  // namespace
+
 extern "C" int ctk_query_pairs(const double* data, int64_t n, int32_t ndim, int64_t* pairs_out,
                                int64_t capacity, int64_t* n_pairs_out) {
   return ctk_query_pairs_within(data, n, ndim, 1.0, pairs_out, capacity, n_pairs_out);
@@ -422,7 +439,29 @@ extern "C" int ctk_cluster_frames(const double* pos, int64_t n, int32_t ndim, co
                                   const int64_t* stops, int64_t n_frames, const double* separation,
                                   int32_t n_threads, int64_t* cluster_out, int64_t* size_out,
                                   int64_t* by_cluster_out, int64_t* span_out) {
+  return ctk_cluster_pack_frames(pos, n, ndim, starts, stops, n_frames, separation, n_threads,
+                                 cluster_out, size_out, by_cluster_out, span_out, nullptr, nullptr,
+                                 0, 0, nullptr, nullptr, nullptr);
+}
+
+// ctk_cluster_frames that also, while a frame's rows are hot in the worker's cache, (a) gathers the
+// packed parameter rows of the frame in (cluster, row) order (refine.py:345) and (b) writes the
+// frame's group table: group_count_out[f] clusters, the row (index into this call's rows) at which
+// each starts in group_start_out[starts[f] ...].
+//   columns [n_cols] table-order column arrays (NULL entry: the constant scalars[j]); the table row
+//   of this call's row i is row_base + i; params_out [n, n_cols] packed rows.  columns == NULL
+//   skips the gather; group_*_out == NULL skips the group table.
+extern "C" int ctk_cluster_pack_frames(const double* pos, int64_t n, int32_t ndim,
+                                       const int64_t* starts, const int64_t* stops, int64_t n_frames,
+                                       const double* separation, int32_t n_threads,
+                                       int64_t* cluster_out, int64_t* size_out,
+                                       int64_t* by_cluster_out, int64_t* span_out,
+                                       const double* const* columns, const double* scalars,
+                                       int32_t n_cols, int64_t row_base, double* params_out,
+                                       int32_t* group_count_out, int32_t* group_start_out) {
   if (n < 0 || n_frames < 0 || ndim < 1 || ndim > 3 || !separation) return CTK_E_INVALID;
+  if (columns && (n_cols < 1 || !scalars || !params_out)) return CTK_E_INVALID;
+  if ((group_count_out == nullptr) != (group_start_out == nullptr)) return CTK_E_INVALID;
   if (n_frames == 0) return 0;
   if (!pos || !starts || !stops || !cluster_out || !size_out || !by_cluster_out || !span_out)
     return CTK_E_INVALID;
@@ -438,7 +477,11 @@ extern "C" int ctk_cluster_frames(const double* pos, int64_t n, int32_t ndim, co
       if (f >= n_frames) break;
       const int64_t a = starts[f], b = stops[f];
       const int cnt = (int) (b - a);
-      if (cnt == 0) { span_out[f] = 0; continue; }
+      if (cnt == 0) {
+        span_out[f] = 0;
+        if (group_count_out) group_count_out[f] = 0;
+        continue;
+      }
       s.tree.init(pos + a * ndim, cnt, ndim, separation);
       s.pairs.clear();
       s.query.t = &s.tree;
@@ -468,6 +511,22 @@ extern "C" int ctk_cluster_frames(const double* pos, int64_t n, int32_t ndim, co
       for (int i = 0; i < cnt; ++i) s.count[i + 1] += s.count[i];
       for (int i = 0; i < cnt; ++i) by_cluster_out[a + s.count[cluster_out[a + i]]++] = a + i;
       span_out[f] = top + 1;
+      if (group_count_out) {                       // group starts: where the label changes
+        int groups = 0;
+        int64_t prev = -1;
+        for (int64_t k = a; k < b; ++k) {
+          const int64_t label = cluster_out[by_cluster_out[k]];
+          if (label != prev) { group_start_out[a + groups++] = (int32_t) k; prev = label; }
+        }
+        group_count_out[f] = groups;
+      }
+      if (columns) {                               // packed rows in (cluster, row) order
+        for (int64_t k = a; k < b; ++k) {
+          const int64_t row = row_base + by_cluster_out[k];
+          double* dst = params_out + k * n_cols;
+          for (int j = 0; j < n_cols; ++j) dst[j] = columns[j] ? columns[j][row] : scalars[j];
+        }
+      }
     }
   };
   int nt = n_threads < 1 ? 1 : n_threads;
@@ -486,22 +545,6 @@ extern "C" int ctk_cluster_frames(const double* pos, int64_t n, int32_t ndim, co
 // Packing helpers of the host pipeline (refine.py:336-345, 426-427): plain loops on host threads
 // in place of numpy fancy indexing on one core.
 // ------------------------------------------------------------------------------------------------
-namespace {
-template <class Fn>
-void parallel_ranges(int64_t n, int n_threads, Fn&& fn) {
-  int nt = n_threads < 1 ? 1 : n_threads;
-  if (n < (int64_t) nt * 8192) nt = (int) (n / 8192) + 1;
-  if (nt <= 1) { fn((int64_t) 0, n); return; }
-  std::vector<std::thread> pool;
-  const int64_t step = (n + nt - 1) / nt;
-  for (int k = 0; k < nt; ++k) {
-    const int64_t a = k * step, b = a + step < n ? a + step : n;
-    if (a >= b) break;
-    pool.emplace_back([=, &fn]() { fn(a, b); });
-  }
-  for (auto& th : pool) th.join();
-}
-}  // namespace
 
 // Running cluster ids, group order and group table of one labelled chunk of frames.
 //   local_labels, by_cluster [m]  outputs of ctk_cluster_frames for the chunk (chunk-local rows)
@@ -541,6 +584,40 @@ extern "C" int ctk_group_chunk(const int64_t* local_labels, const int64_t* by_cl
   return 0;
 }
 
+// Group table of a chunk from the per-frame tables of ctk_cluster_pack_frames.
+//   group_offset_out [total groups + 1] int32, group_frame_out [total groups] int32
+extern "C" int ctk_concat_groups(const int64_t* starts, const int64_t* stops,
+                                 const int32_t* group_count, const int32_t* group_start,
+                                 int64_t n_frames, int32_t frame_base, int32_t* group_offset_out,
+                                 int32_t* group_frame_out, int64_t* n_groups_out) {
+  if (n_frames < 0 || !n_groups_out) return CTK_E_INVALID;
+  int64_t g = 0;
+  for (int64_t f = 0; f < n_frames; ++f) {
+    const int32_t* src = group_start + starts[f];
+    for (int32_t k = 0; k < group_count[f]; ++k) {
+      group_offset_out[g] = src[k];
+      group_frame_out[g] = frame_base + (int32_t) f;
+      ++g;
+    }
+  }
+  group_offset_out[g] = n_frames ? (int32_t) stops[n_frames - 1] : 0;
+  *n_groups_out = g;
+  return 0;
+}
+
+// cluster_out[i] = local[i] + offset of row i's frame (find.py:127-128), on host threads
+extern "C" int ctk_apply_label_offsets(const int64_t* local, const int64_t* starts,
+                                       const int64_t* stops, const int64_t* frame_offset,
+                                       int64_t n_frames, int32_t n_threads, int64_t* cluster_out) {
+  if (n_frames < 0 || (n_frames > 0 && (!local || !starts || !stops || !frame_offset || !cluster_out)))
+    return CTK_E_INVALID;
+  parallel_ranges(n_frames, n_threads, [=](int64_t fa, int64_t fb) {
+    for (int64_t f = fa; f < fb; ++f)
+      for (int64_t i = starts[f]; i < stops[f]; ++i) cluster_out[i] = local[i] + frame_offset[f];
+  });
+  return 0;
+}
+
 // out[r, j] = columns[j] ? columns[j][rows[r]] : scalars[j]
 extern "C" int ctk_gather_rows(const double* const* columns, const double* scalars,
                                const int64_t* rows, int64_t n, int32_t n_cols, double* out,
@@ -560,7 +637,7 @@ extern "C" int ctk_gather_rows(const double* const* columns, const double* scala
 // status 0, the untouched input (params_in) for failed ones; cost_out[rows[r]] = the cluster's cost
 // or NaN.  Returns the number of failed clusters in *n_failed_out.
 extern "C" int ctk_scatter_rows(const double* params, const double* params_in, const int64_t* rows,
-                                int64_t n, int32_t n_cols, const int32_t* group_offset,
+                                int64_t row_base, int64_t n, int32_t n_cols, const int32_t* group_offset,
                                 const double* group_cost, const int32_t* group_status,
                                 int64_t n_groups, double* const* columns, double* cost_out,
                                 int32_t n_threads, int64_t* n_failed_out) {
@@ -575,7 +652,7 @@ extern "C" int ctk_scatter_rows(const double* params, const double* params_in, c
       const double* src = ok ? params : params_in;
       bad += ok ? 0 : 1;
       for (int64_t r = group_offset[g]; r < group_offset[g + 1]; ++r) {
-        const int64_t row = rows[r];
+        const int64_t row = row_base + rows[r];
         for (int j = 0; j < n_cols; ++j) columns[j][row] = src[r * n_cols + j];
         cost_out[row] = cost;
       }

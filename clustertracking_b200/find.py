@@ -280,15 +280,18 @@ class _LabelJob(object):
 
 class ChunkLabeller(object):
     """Labels a frame-sorted video chunk by chunk on a background thread, so that the caller can
-    pack and launch chunk k while chunk k+1 is being labelled.  ``frame_cuts`` = frame indices at
-    which the chunks begin and end (len K+1).  ``get(k)`` waits for chunk k and returns, for its
-    rows, (labels local to each frame, cluster sizes, permutation that lists the chunk's rows by
-    (frame, label) as indices into the chunk, per-frame label spans).
+    launch chunk k while chunk k+1 is being labelled.  ``frame_cuts`` = frame indices at which the
+    chunks begin and end (len K+1).  While a frame's rows are hot in a worker's cache the worker
+    also gathers the packed parameter rows of the frame (``sources`` -> ``params_out``, in
+    (cluster, row) order) and writes the frame's group table.  ``get(k)`` waits for chunk k and
+    returns, for its rows, (labels local to each frame, cluster sizes, permutation that lists the
+    chunk's rows by (frame, label) as indices into the chunk, per-frame label spans, group offsets
+    int32 [g + 1], frame index of every group int32 [g]).
 
     Without the verified native labelling (see ``_native_is_exact``) everything is one chunk
-    labelled through scipy."""
+    labelled through scipy and packed with numpy."""
 
-    def __init__(self, pos, starts, stops, frame_cuts, separation):
+    def __init__(self, pos, starts, stops, frame_cuts, separation, sources, params_out):
         import threading
         self.native = os.environ.get('CTK_FIND_NATIVE', '1') != '0' and _native_is_exact()
         self.starts, self.stops = np.asarray(starts, np.int64), np.asarray(stops, np.int64)
@@ -299,7 +302,17 @@ class ChunkLabeller(object):
         if not self.native:
             job = _LabelJob(pos, starts, stops, separation)
             job.result()
-            self.results[0] = (job.cluster, job.size, job.by_cluster, np.asarray(job.spans, np.int64))
+            rows = job.by_cluster
+            for j, src in enumerate(sources):
+                params_out[:, j] = src[rows] if isinstance(src, np.ndarray) else src
+            labels = job.cluster[rows]
+            frame_of_row = np.repeat(np.arange(len(starts), dtype=np.int32), self.stops - self.starts)
+            new_group = np.concatenate(([True], (labels[1:] != labels[:-1]) |
+                                        (frame_of_row[rows][1:] != frame_of_row[rows][:-1])))
+            g_starts = np.flatnonzero(new_group)
+            self.results[0] = (job.cluster, job.size, rows, np.asarray(job.spans, np.int64),
+                               np.concatenate((g_starts, [len(rows)])).astype(np.int32),
+                               frame_of_row[rows[g_starts]])
             self.events[0].set()
             return
         workers = max(1, _pool_workers())
@@ -309,8 +322,11 @@ class ChunkLabeller(object):
                 for k, (fa, fb) in enumerate(zip(self.frame_cuts[:-1], self.frame_cuts[1:])):
                     a = int(self.starts[fa]) if fb > fa else 0
                     b = int(self.stops[fb - 1]) if fb > fa else 0
-                    self.results[k] = _lib.cluster_frames(pos[a:b], self.starts[fa:fb] - a,
-                                                          self.stops[fa:fb] - a, separation, workers)
+                    st, sp = self.starts[fa:fb] - a, self.stops[fa:fb] - a
+                    local, size, by_cluster, spans, gcount, gstart = _lib.cluster_pack_frames(
+                        pos[a:b], st, sp, separation, workers, sources, a, params_out[a:b])
+                    goff, gframe = _lib.concat_groups(st, sp, gcount, gstart, fa)
+                    self.results[k] = (local, size, by_cluster, spans, goff, gframe)
                     self.events[k].set()
             except Exception as exc:
                 self.error = exc

@@ -907,9 +907,6 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
     frame_cuts = np.unique(np.searchsorted(starts, np.linspace(0, n, k_chunks + 1)[1:-1]))
     frame_cuts = [0] + [int(c) for c in frame_cuts if 0 < c < n_frames] + [n_frames]
     separation = np.asarray(validate_tuple(pre.separation, pre.ndim), dtype=np.float64)
-    labeller = ChunkLabeller(pos, starts, stops, frame_cuts, separation)
-    frame_cuts = labeller.frame_cuts
-    t1 = time.perf_counter()
 
     # ---- parameter columns: from the table, from param_val, or the model's defaults ---------------
     sources = []                                   # per column: 1-D float64 array or a scalar
@@ -921,6 +918,10 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
         else:
             sources.append(float(ff.default[col]))
     params_in = _pinned_array("params_in", (n, P), np.float64)     # packed, group order
+    # labelling, packing and the group tables run on host threads from here on
+    labeller = ChunkLabeller(pos, starts, stops, frame_cuts, separation, sources, params_in)
+    frame_cuts = labeller.frame_cuts
+    t1 = time.perf_counter()
     out_params = _pinned_array("params", (n, P), np.float64)
     out_cost = _pinned_array("cost", (n,), np.float64)             # one entry per cluster (<= n)
     out_status = _pinned_array("status", (n,), np.int32)
@@ -928,59 +929,59 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
     cost = np.empty(n, dtype=np.float64)
     cluster = np.empty(n, dtype=np.int64)
     csize = np.empty(n, dtype=np.int64)
-    chunks = []                                    # (a, b, order_c, plan, pending, c0)
+    threads = max(1, min(8, (os.cpu_count() or 2) // 2))
+    local_all = np.empty(n, dtype=np.int64)        # labels local to each frame
+    frame_offset = np.zeros(n_frames, dtype=np.int64)                 # find.py:127-128
+    chunks = []                                    # (a, b, rows by group (chunk-local), plan, pending, c0)
     totals = dict(h2d=0, d2h=0, launches=0, failed=0)
     next_id, c0 = 0, 0
-
-    threads = max(1, min(8, (os.cpu_count() or 2) // 2))
+    failures = []
 
     def finish(chunk):
-        a, b, order_c, plan, pending, _ = chunk
+        a, b, rows_c, plan, pending, _ = chunk
         res = pending.result()
-        n_failed = _lib.scatter_rows(res.params_out, plan.params_in, order_c, plan.cluster_offset,
-                                     res.cost, res.status, block, cost, threads)
+        n_failed = _lib.scatter_rows(res.params_out, plan.params_in, rows_c, plan.cluster_offset,
+                                     res.cost, res.status, block, cost, threads, row_base=a)
         if n_failed:
             failed = np.flatnonzero(res.status != 0)
-            for c in failed[:max(0, 20 - totals['failed'])]:
-                logger.warning("RefineException: cluster %d: %s",
-                               int(cluster[order_c[plan.cluster_offset[c]]]),
-                               _lib.STATUS_NAMES.get(int(res.status[c]), "status %d" % res.status[c]))
+            failures.extend((a + int(rows_c[plan.cluster_offset[c]]), int(res.status[c]))
+                            for c in failed[:max(0, 20 - totals['failed'])])
             totals['failed'] += n_failed
         session = res.session
         totals['h2d'] += session.h2d_bytes
         totals['d2h'] += session.d2h_bytes
         totals['launches'] += session.launches
 
-    lap = dict(label_wait=0., index=0., gather=0., launch=0., finish=0.)
+    lap = dict(label_wait=0., index=0., launch=0., finish=0.)
     for k, (fa, fb) in enumerate(zip(frame_cuts[:-1], frame_cuts[1:])):
         a, b = int(starts[fa]), int(stops[fb - 1])
         _ta = time.perf_counter()
-        local, size, by_cluster, spans = labeller.get(k)
+        local, size, by_cluster, spans, g_offset, g_frame = labeller.get(k)
         _tb = time.perf_counter()
         csize[a:b] = size
-        # running ids (find.py:127-128), rows by (frame, cluster) and the group table (refine.py:336)
-        order_c, g_offset, g_frame, next_id = _lib.group_chunk(
-            local, by_cluster, starts[fa:fb] - a, stops[fa:fb] - a, np.asarray(spans, np.int64),
-            next_id, a, fa, cluster[a:b])
-        chunk_in = params_in[a:b]
+        local_all[a:b] = local
+        frame_offset[fa:fb] = next_id + np.concatenate(([0], np.cumsum(spans)[:-1]))
+        next_id += int(np.sum(spans))
         _tc = time.perf_counter()
-        _lib.gather_rows(sources, order_c, chunk_in, threads)
-        _td = time.perf_counter()
-        plan = _plan_for(pre, order_c, g_offset, g_frame, chunk_in)
+        plan = _plan_for(pre, by_cluster, g_offset, g_frame, params_in[a:b])
         n_c = len(g_frame)
         pending = launch_cuda(plan, frameset, out_params[a:b], out_cost[c0:c0 + n_c],
                               out_status[c0:c0 + n_c])
-        chunks.append((a, b, order_c, plan, pending, c0))
+        chunks.append((a, b, by_cluster, plan, pending, c0))
         c0 += n_c
         _te = time.perf_counter()
         if k > 0:
             finish(chunks[k - 1])                  # while the device works on chunk k
         _tf = time.perf_counter()
-        for name, dt in (("label_wait", _tb - _ta), ("index", _tc - _tb), ("gather", _td - _tc),
-                         ("launch", _te - _td), ("finish", _tf - _te)):
+        for name, dt in (("label_wait", _tb - _ta), ("index", _tc - _tb), ("launch", _te - _tc),
+                         ("finish", _tf - _te)):
             lap[name] += 1e3 * dt
     t2 = time.perf_counter()
     finish(chunks[-1])
+    _lib.apply_label_offsets(local_all, starts, stops, frame_offset, threads, cluster)
+    for row, status in failures:
+        logger.warning("RefineException: cluster %d: %s", int(cluster[row]),
+                       _lib.STATUS_NAMES.get(status, "status %d" % status))
     if totals['failed'] > 20:
         logger.warning("RefineException: ... and %d more clusters failed", totals['failed'] - 20)
     t3 = time.perf_counter()

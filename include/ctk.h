@@ -257,13 +257,26 @@ int ctk_group_chunk(const int64_t* local_labels, const int64_t* by_cluster, cons
                     int64_t row_base, int32_t frame_base, int64_t* cluster_out, int64_t* order_out,
                     int32_t* group_offset_out, int32_t* group_frame_out, int64_t* n_groups_out,
                     int64_t* next_id_out);
+int ctk_cluster_pack_frames(const double* pos, int64_t n, int32_t ndim, const int64_t* starts,
+                            const int64_t* stops, int64_t n_frames, const double* separation,
+                            int32_t n_threads, int64_t* cluster_out, int64_t* size_out,
+                            int64_t* by_cluster_out, int64_t* span_out,
+                            const double* const* columns, const double* scalars, int32_t n_cols,
+                            int64_t row_base, double* params_out, int32_t* group_count_out,
+                            int32_t* group_start_out);
+int ctk_concat_groups(const int64_t* starts, const int64_t* stops, const int32_t* group_count,
+                      const int32_t* group_start, int64_t n_frames, int32_t frame_base,
+                      int32_t* group_offset_out, int32_t* group_frame_out, int64_t* n_groups_out);
+int ctk_apply_label_offsets(const int64_t* local, const int64_t* starts, const int64_t* stops,
+                            const int64_t* frame_offset, int64_t n_frames, int32_t n_threads,
+                            int64_t* cluster_out);
 int ctk_schedule(const int32_t* cluster_offset, int64_t n_clusters, const int32_t* caps,
                  int32_t n_caps, const int32_t* class_target, int32_t* work_ids_out,
                  int64_t* class_count_out, int32_t* not_run_out, int64_t* n_not_run_out);
 int ctk_gather_rows(const double* const* columns, const double* scalars, const int64_t* rows,
                     int64_t n, int32_t n_cols, double* out, int32_t n_threads);
-int ctk_scatter_rows(const double* params, const double* params_in, const int64_t* rows, int64_t n,
-                     int32_t n_cols, const int32_t* group_offset, const double* group_cost,
+int ctk_scatter_rows(const double* params, const double* params_in, const int64_t* rows,
+                     int64_t row_base, int64_t n, int32_t n_cols, const int32_t* group_offset, const double* group_cost,
                      const int32_t* group_status, int64_t n_groups, double* const* columns,
                      double* cost_out, int32_t n_threads, int64_t* n_failed_out);
 
