@@ -301,3 +301,34 @@ def test_query_pairs_within_is_the_scipy_set():
         want = cKDTree(data, 30).query_pairs(r, output_type='ndarray')
         got = _lib.query_pairs(data, r)
         assert set(map(tuple, got.tolist())) == set(map(tuple, want.tolist()))
+
+
+def test_pipelined_path_failures_and_tiny_inputs(monkeypatch, caplog):
+    """Failure bookkeeping of the pipelined path (refine.py:408-418 semantics: cost NaN, parameters
+    untouched, a warning) and inputs of one or two rows."""
+    import logging
+    import torch
+    monkeypatch.setattr(refine, "FrameSet", _NoFrames)
+    monkeypatch.setattr(refine, "_pinned_buffer",
+                        lambda torch_, key, nbytes: torch.empty(max(nbytes, 1), dtype=torch.uint8))
+    monkeypatch.setattr(refine, "launch_cuda", _emulated_launch)
+    img = np.zeros((40, 40), np.uint8)
+    img[18:23, 18:23] = 100
+    f = pd.DataFrame(dict(y=[20., 500., 20.], x=[20., 500., 32.], signal=[100., 100., np.nan], size=2.))
+    with caplog.at_level(logging.WARNING, logger="clustertracking_b200.refine"):
+        out = refine.refine_leastsq(f.copy(), img, 9, separation=4)
+    assert np.isfinite(out['cost'].values[0]) and np.isnan(out['cost'].values[1:]).all()
+    assert out['y'].values[1] == 500. and np.isnan(out['signal'].values[2])
+    assert sum("RefineException" in r.message for r in caplog.records) == 2
+    assert list(out['cluster']) == [0, 1, 2] and list(out['cluster_size']) == [1, 1, 1]
+    one = refine.refine_leastsq(f.iloc[:1].copy(), img, 9)
+    assert len(one) == 1 and np.isfinite(one['cost'].values[0])
+    two_frames = pd.DataFrame(dict(y=[20., 20.], x=[20., 20.], signal=100., size=2., frame=[7, 3]))
+
+    class Reader(dict):
+        frame_shape = (40, 40)
+
+    out2 = refine.refine_leastsq(two_frames, Reader({3: img, 7: img}), 9)
+    assert list(out2['frame']) == [3, 7] and list(out2.index) == [1, 0]
+    assert list(out2['cluster']) == [0, 1]
+    assert out2['y'].values[0] == out2['y'].values[1]
