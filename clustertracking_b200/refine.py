@@ -667,6 +667,8 @@ class DeviceSession(object):
             _FITS_CACHE[key] = (fits, retry_fits, merged)
         # classes whose typical-case capacities can overflow, and whether the rigorous ones fit
         fits, self.retry_fits, merged = _FITS_CACHE[key]
+        if os.environ.get('CTK_THREAD_MERGE') == '0':       # measurement knob: one launch per class
+            merged = 0
         first_big = int(np.flatnonzero(~small)[0])
         self.big_fallback = int(caps[first_big]) if fits[first_big] else None
         # class a cluster of class k runs in: k, the first large class when k's arrays do not fit
