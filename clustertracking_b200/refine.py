@@ -10,13 +10,12 @@ There is no CPU fallback: options the CUDA solver does not carry raise ``NotImpl
 """
 import logging
 import os
-import warnings
 
 import numpy as np
 
 from . import _lib
 from . import constraints as _constraints
-from .find import ChunkLabeller, cluster_table, find_clusters
+from .find import ChunkLabeller, cluster_table
 from .fitfunc import FitFunctions
 from .utils import guess_pos_columns, is_isotropic, validate_tuple
 
