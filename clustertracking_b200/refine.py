@@ -506,6 +506,7 @@ class FrameSet(object):
         self.launches = 0
         self.h2d_bytes = 0
         self.tensors = []                 # keeps the uploaded batches alive
+        self.batch_ready, self.batch_last = [], []       # per upload batch: event, last frame
         with torch.cuda.device(self.dev):
             self.d_ptrs = torch.zeros(self.n_frames, dtype=torch.int64, device=self.dev)
             self.d_fmax = torch.empty(self.n_frames, dtype=torch.float64, device=self.dev)
@@ -535,21 +536,33 @@ class FrameSet(object):
         self.d_ptrs[f0:f0 + n] = self.torch.from_numpy(ptrs).to(self.dev)
         self.tensors.append(d_frames)
 
-    def launch_frame_max(self, f0, n, events=None):
+    def launch_frame_max(self, f0, n, events=None, stream=None):
         if events is not None:
             start, stop = (self.torch.cuda.Event(enable_timing=True) for _ in range(2))
             start.record()
+        stream_ptr = (self.stream_ptr() if stream is None
+                      else _lib.ctypes.c_void_p(stream.cuda_stream))
         _lib.check(self.lib.ctk_frame_max(self.d_ptrs.data_ptr() + 8 * f0, n, self.n_pixels,
                                           self.pixel_code, self.d_fmax.data_ptr() + 8 * f0,
-                                          self.stream_ptr()), "ctk_frame_max")
+                                          stream_ptr), "ctk_frame_max")
         self.launches += 1
         if events is not None:
             stop.record()
             events.append(("frame_max", start, stop))
 
+    def wait_for_frames(self, last_frame):
+        """Make the current stream wait until frames 0 .. last_frame are resident and their maxima
+        computed (a launch that touches only the first frames need not wait for the whole video)."""
+        if not self.batch_ready:
+            return
+        k = int(np.searchsorted(self.batch_last, last_frame))
+        k = min(k, len(self.batch_ready) - 1)
+        self.torch.cuda.current_stream(self.dev).wait_event(self.batch_ready[k])
+
     def upload_async(self):
         """Allocate the device frames, upload the pointer table once (the only host-synchronous
-        step, done while the device is idle), then enqueue copy -> frame max per batch."""
+        step, done while the device is idle), then enqueue copy -> frame max per batch on a copy
+        stream; ``wait_for_frames`` orders later launches behind the batches they read."""
         torch = self.torch
         per_batch = max(1, min(self.n_frames, _FRAME_BATCH_BYTES // max(self.frame_bytes, 1)))
         cuts = list(range(0, self.n_frames, per_batch)) + [self.n_frames]
@@ -582,13 +595,15 @@ class FrameSet(object):
                     src = torch.from_numpy(view)
                 with torch.cuda.stream(copy_stream):
                     d_frames.copy_(src, non_blocking=True)
+                    self.launch_frame_max(f0, n, stream=copy_stream)
                     done = torch.cuda.Event()
                     done.record(copy_stream)
                 self.h2d_bytes += n * self.frame_bytes
-                compute.wait_event(done)
-                self.launch_frame_max(f0, n)
+                self.batch_ready.append(done)
+                self.batch_last.append(f1 - 1)
             if staging is not None:
                 copy_stream.synchronize()
+            self.copy_stream = copy_stream
         return self
 
 
@@ -726,6 +741,10 @@ class DeviceSession(object):
         return self.big_workspaces[cap]
 
     def run(self, slices, events=None):
+        self.frames.wait_for_frames(int(self.plan.cluster_frame.max()) if self.plan.n_clusters else 0)
+        self._run(slices, events)
+
+    def _run(self, slices, events=None):
         """One refine launch per size class; behind it, for the classes provisioned for the typical
         case, the relaunch of the clusters that overflowed (device-side list, usually empty or a
         percent of the class): with rigorous capacities if those fit the shared memory, else in the
@@ -822,9 +841,18 @@ class Pending(object):
         return res
 
 
-def launch_cuda(plan, frames, out_params, out_cost, out_status):
+def launch_cuda(plan, frames, out_params, out_cost, out_status, stream=None):
     """Enqueue one plan on the current CUDA device (uploads, one launch per size class, result
-    copies into the given pinned host arrays) and return a :class:`Pending` without waiting."""
+    copies into the given pinned host arrays) and return a :class:`Pending` without waiting.
+    ``stream``: torch stream to enqueue on (default: the current one)."""
+    import contextlib
+    import torch
+    scope = torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+    with scope:
+        return _launch_cuda(plan, frames, out_params, out_cost, out_status)
+
+
+def _launch_cuda(plan, frames, out_params, out_cost, out_status):
     session = DeviceSession(plan, frames=frames)
     torch = session.torch
     with torch.cuda.device(session.dev):
@@ -841,6 +869,19 @@ def launch_cuda(plan, frames, out_params, out_cost, out_status):
     result.params_out, result.cost, result.status = out_params, out_cost, out_status
     result.session = session
     return Pending(session, result, event)
+
+
+def _chunk_streams(frameset, count):
+    """Streams for the chunk launches; all of them are ordered behind the current stream (which
+    holds the pointer-table upload) -- or [None] (current stream) when there is no device."""
+    torch = getattr(frameset, 'torch', None)
+    if torch is None or count < 2:
+        return [None]
+    current = torch.cuda.current_stream(frameset.dev)
+    streams = [torch.cuda.Stream(device=frameset.dev) for _ in range(count)]
+    for st in streams:
+        st.wait_stream(current)
+    return streams
 
 
 _CHUNK_ROWS = int(os.environ.get('CTK_CHUNK_ROWS', 1 << 18))   # features per pipeline chunk
@@ -953,6 +994,10 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
         totals['d2h'] += session.d2h_bytes
         totals['launches'] += session.launches
 
+    # CTK_CHUNK_STREAMS > 1 sends consecutive chunks to alternating streams.  Measured on B200: the
+    # per-stream pools of torch's caching allocator make every chunk pay device allocations
+    # (74 ms -> 190-240 ms per call), so one stream is the default.
+    streams = _chunk_streams(frameset, int(os.environ.get('CTK_CHUNK_STREAMS', 1)))
     lap = dict(label_wait=0., index=0., launch=0., finish=0.)
     for k, (fa, fb) in enumerate(zip(frame_cuts[:-1], frame_cuts[1:])):
         a, b = int(starts[fa]), int(stops[fb - 1])
@@ -967,7 +1012,7 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
         plan = _plan_for(pre, by_cluster, g_offset, g_frame, params_in[a:b])
         n_c = len(g_frame)
         pending = launch_cuda(plan, frameset, out_params[a:b], out_cost[c0:c0 + n_c],
-                              out_status[c0:c0 + n_c])
+                              out_status[c0:c0 + n_c], stream=streams[k % len(streams)])
         chunks.append((a, b, by_cluster, plan, pending, c0))
         c0 += n_c
         _te = time.perf_counter()

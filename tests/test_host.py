@@ -219,7 +219,7 @@ class _Done(object):
         return self._result
 
 
-def _emulated_launch(plan, frames, out_params, out_cost, out_status):
+def _emulated_launch(plan, frames, out_params, out_cost, out_status, stream=None):
     import emul_backend
     result = emul_backend.execute(plan)
     out_params[...], out_cost[...], out_status[...] = result.params_out, result.cost, result.status

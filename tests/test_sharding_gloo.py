@@ -70,7 +70,7 @@ class _Done(object):
         return self._result
 
 
-def _emulated_launch(plan, frames, out_params, out_cost, out_status):
+def _emulated_launch(plan, frames, out_params, out_cost, out_status, stream=None):
     """Stand-in for ``refine.launch_cuda``: the one-lane host build of the device solver."""
     import emul_backend
     result = emul_backend.execute(plan)
