@@ -662,7 +662,8 @@ class DeviceSession(object):
         caps = np.asarray(_BINS)
         self.rigorous = rigorous_problem(self.plan.problem)
         small = caps <= _lib.CTK_MAX_CLUSTER_FEATURES
-        key = bytes(self.plan.problem) + os.environ.get('CTK_THREAD_KERNEL', '0').encode()
+        key = (bytes(self.plan.problem) + os.environ.get('CTK_THREAD_KERNEL', '0').encode()
+               + os.environ.get('CTK_MERGE_CLASSES', '0').encode())
         if key not in _FITS_CACHE:                 # the capacity queries only depend on the problem
             prob = _lib.ctypes.byref(self.plan.problem)
             rig = _lib.ctypes.byref(self.rigorous)
@@ -676,6 +677,16 @@ class DeviceSession(object):
             # it handles every size up to that in ONE launch, so those classes are merged
             merged = max([int(c) for c in caps[small]
                           if self.lib.ctk_refine_thread_kernel(prob, int(c))] + [0])
+            # CTK_MERGE_CLASSES=1 (measurement knob): the warp kernel's occupancy is bound by
+            # registers (16 warps per SM) as long as a cluster's slice stays below 227 KB / 16, so
+            # every class up to the largest such one could run in ONE launch with that class's
+            # layout.  Measured on config 2: 12.3 ms against 11.6 ms with one launch per class
+            # (the small clusters pay for the large layout), so it is off.
+            if not merged and os.environ.get('CTK_MERGE_CLASSES', '0') == '1':
+                roomy = [int(c) for c in caps[small]
+                         if 0 < self.lib.ctk_refine_shared_bytes(prob, int(c)) <= (227 * 1024) // 16
+                         and self.lib.ctk_refine_shared_bytes(rig, int(c)) > 0]
+                merged = max(roomy + [0])
             if len(_FITS_CACHE) > 64:
                 _FITS_CACHE.clear()
             _FITS_CACHE[key] = (fits, retry_fits, merged)
