@@ -1,6 +1,6 @@
 """Build ``libctk.so`` in-tree for sm_100a (``python -m clustertracking_b200.build``).
 
-One nvcc invocation per (arithmetic, model family) instance file plus the API and host files, run
+One nvcc invocation per (arithmetic, model family, flavour) instance file plus the API and host files, run
 in parallel, then one link.  Objects are cached under ``csrc/_build`` keyed by a hash of the sources
 and flags, so repeated calls are cheap.
 """
@@ -48,8 +48,10 @@ def _jobs():
             ("find", "ctk_find.cu", [])]
     for real in ("float", "double"):
         for fam in (0, 1, 2):
-            jobs.append(("inst_%s_%d" % (real, fam), "ctk_inst.cu",
-                         ["-DCTK_INST_REAL=%s" % real, "-DCTK_INST_FAM=%d" % fam]))
+            for extra in (0, 1):       # lean / full flavour of every instance (ctk_solver.cuh)
+                jobs.append(("inst_%s_%d_%d" % (real, fam, extra), "ctk_inst.cu",
+                             ["-DCTK_INST_REAL=%s" % real, "-DCTK_INST_FAM=%d" % fam,
+                              "-DCTK_INST_EXTRA=%d" % extra]))
     return jobs
 
 

@@ -228,13 +228,15 @@ inline bool dispatch_config(const ctk_problem_t& p, Fn&& fn, bool big = false) {
     return false;
   }
   const int ns = p.isotropic ? 1 : nd;
+  const bool extra = p.constraint_mask != 0 || p.lowpass != 0;   // else: the lean instances
   bool size_free = false;
   for (int k = 0; k < ns; ++k) size_free |= p.modes[2 + nd + k] != CTK_MODE_CONST;
   const bool extra_free = p.family != CTK_FAMILY_GAUSS && p.modes[2 + nd + ns] != CTK_MODE_CONST;
 #define CTK_CASE(ND, ISO, FAM, SZ, EX)                                                       \
   if (nd == ND && (p.isotropic != 0) == ISO && p.family == FAM && size_free == SZ &&         \
       extra_free == EX) {                                                                    \
-    fn.template operator()<Config<Real, ND, ISO, FAM, SZ, EX> >();                           \
+    if (extra) fn.template operator()<Config<Real, ND, ISO, FAM, SZ, EX, false, true> >();   \
+    else fn.template operator()<Config<Real, ND, ISO, FAM, SZ, EX, false, false> >();        \
     return true;                                                                             \
   }
 #define CTK_CASES_GEOM(FAM, SZ, EX)                                                          \
