@@ -957,7 +957,10 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
     n_frames = len(starts)
     # chunks of whole frames with about _CHUNK_ROWS features each
     k_chunks = int(max(1, min(_MAX_CHUNKS, n // max(1, _CHUNK_ROWS), n_frames)))
-    frame_cuts = np.unique(np.searchsorted(starts, np.linspace(0, n, k_chunks + 1)[1:-1]))
+    # equal chunks, except that the last one is split in two: what is left to do after the
+    # labelling has finished (launch, kernels, write-back of the final chunk) is on the critical path
+    weights = np.ones(k_chunks) if k_chunks < 4 else np.array([1.] * (k_chunks - 1) + [.6, .4])
+    frame_cuts = np.unique(np.searchsorted(starts, np.cumsum(weights)[:-1] / weights.sum() * n))
     frame_cuts = [0] + [int(c) for c in frame_cuts if 0 < c < n_frames] + [n_frames]
     separation = np.asarray(validate_tuple(pre.separation, pre.ndim), dtype=np.float64)
 

@@ -2,8 +2,8 @@
 run in the build container):  python profiles/tools/static_code.py [mangled-name-substring]"""
 import bisect, collections, os, re, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-want = sys.argv[1] if len(sys.argv) > 1 else "ConfigIfLi2ELb1ELi0ELb0ELb0ELb0E"
-obj = os.path.join(ROOT, "clustertracking_b200/csrc/_build/inst_float_0.o")
+want = sys.argv[1] if len(sys.argv) > 1 else "ConfigIfLi2ELb1ELi0ELb0ELb0ELb0ELb0E"
+obj = os.path.join(ROOT, "clustertracking_b200/csrc/_build/inst_float_0_0.o")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", obj], cwd=tmp, check=True, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
