@@ -80,6 +80,8 @@ _PROTOTYPES = {
                                         _vp, _i32, _vp]),
     "ctk_cluster_pack_frames": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp, _vp,
                                                _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
+    "ctk_cluster_pack_columns": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp,
+                                                _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "ctk_concat_groups": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "ctk_apply_label_offsets": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "ctk_find_workspace_bytes": (_sz, [_i32, _i64, _i32]),
@@ -261,10 +263,19 @@ def column_pointers(sources):
 
 
 def cluster_pack_frames(pos, starts, stops, separation, n_threads, sources, row_base, params_out):
-    """``ctk_cluster_pack_frames`` -> (labels local to each frame, sizes, by_cluster, spans,
-    group counts per frame, group starts); ``params_out`` [n, P] receives the packed rows."""
-    pos = np.ascontiguousarray(pos, dtype=np.float64)
-    n, ndim = pos.shape
+    """``ctk_cluster_pack_columns`` -> (labels local to each frame, sizes, by_cluster, spans,
+    group counts per frame, group starts); ``params_out`` [n, P] receives the packed rows.
+    ``pos``: [n, ndim] array of this call's rows, or a list of ndim table-order float64 columns
+    (then this call's rows are rows ``row_base .. row_base + len(params_out)`` of the table)."""
+    pos_cols = None
+    if isinstance(pos, (list, tuple)):
+        ndim, n = len(pos), len(params_out)
+        pos_cols, _ = column_pointers(list(pos))
+        pos_ptr = None
+    else:
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        n, ndim = pos.shape
+        pos_ptr = pos.ctypes.data
     starts = np.ascontiguousarray(starts, dtype=np.int64)
     stops = np.ascontiguousarray(stops, dtype=np.int64)
     separation = np.ascontiguousarray(separation, dtype=np.float64)
@@ -276,11 +287,11 @@ def cluster_pack_frames(pos, starts, stops, separation, n_threads, sources, row_
     gstart = np.empty(max(n, 1), dtype=np.int32)
     ptrs, scalars = column_pointers(sources)
     assert params_out.flags.c_contiguous and params_out.dtype == np.float64
-    check(load().ctk_cluster_pack_frames(
-        pos.ctypes.data, n, ndim, starts.ctypes.data, stops.ctypes.data, len(starts),
+    check(load().ctk_cluster_pack_columns(
+        pos_ptr, pos_cols, n, ndim, starts.ctypes.data, stops.ctypes.data, len(starts),
         separation.ctypes.data, int(n_threads), cluster.ctypes.data, size.ctypes.data,
         by_cluster.ctypes.data, spans.ctypes.data, ptrs, scalars, len(sources), int(row_base),
-        params_out.ctypes.data, gcount.ctypes.data, gstart.ctypes.data), "ctk_cluster_pack_frames")
+        params_out.ctypes.data, gcount.ctypes.data, gstart.ctypes.data), "ctk_cluster_pack_columns")
     return cluster, size, by_cluster, spans, gcount, gstart
 
 

@@ -148,15 +148,20 @@ struct KdTree {
   std::vector<KdNode> nodes;
   double mins[3], maxes[3];
 
-  // data [n, m]; every coordinate is divided by scale[k] (numpy's pos / separation)
-  void init(const double* data, int n_, int m_, const double* scale) {
+  // data [n, m] (or, when `cols` is given, m column arrays read from row `row0` on); every
+  // coordinate is divided by scale[k] (numpy's pos / separation)
+  void init(const double* data, int n_, int m_, const double* scale,
+            const double* const* cols = nullptr, int64_t row0 = 0) {
     n = n_; m = m_;
     pts.resize(n);
     for (int i = 0; i < n; ++i) {
       KdPoint& p = pts[i];
       p.idx = i;
-      for (int k = 0; k < 3; ++k)
-        p.c[k] = k < m ? (scale ? data[(int64_t) i * m + k] / scale[k] : data[(int64_t) i * m + k]) : 0.;
+      for (int k = 0; k < 3; ++k) {
+        if (k >= m) { p.c[k] = 0.; continue; }
+        const double v = cols ? cols[k][row0 + i] : data[(int64_t) i * m + k];
+        p.c[k] = scale ? v / scale[k] : v;
+      }
     }
     nodes.clear();
     nodes.reserve(n / 4 + 8);
@@ -459,11 +464,28 @@ extern "C" int ctk_cluster_pack_frames(const double* pos, int64_t n, int32_t ndi
                                        const double* const* columns, const double* scalars,
                                        int32_t n_cols, int64_t row_base, double* params_out,
                                        int32_t* group_count_out, int32_t* group_start_out) {
+  return ctk_cluster_pack_columns(pos, nullptr, n, ndim, starts, stops, n_frames, separation,
+                                  n_threads, cluster_out, size_out, by_cluster_out, span_out, columns,
+                                  scalars, n_cols, row_base, params_out, group_count_out,
+                                  group_start_out);
+}
+
+// The same with the positions given as `ndim` table-order column arrays (pos_cols[k][row_base + i]
+// is coordinate k of this call's row i) instead of one packed [n, ndim] array.
+extern "C" int ctk_cluster_pack_columns(const double* pos, const double* const* pos_cols, int64_t n,
+                                        int32_t ndim, const int64_t* starts, const int64_t* stops,
+                                        int64_t n_frames, const double* separation,
+                                        int32_t n_threads, int64_t* cluster_out, int64_t* size_out,
+                                        int64_t* by_cluster_out, int64_t* span_out,
+                                        const double* const* columns, const double* scalars,
+                                        int32_t n_cols, int64_t row_base, double* params_out,
+                                        int32_t* group_count_out, int32_t* group_start_out) {
   if (n < 0 || n_frames < 0 || ndim < 1 || ndim > 3 || !separation) return CTK_E_INVALID;
   if (columns && (n_cols < 1 || !scalars || !params_out)) return CTK_E_INVALID;
   if ((group_count_out == nullptr) != (group_start_out == nullptr)) return CTK_E_INVALID;
   if (n_frames == 0) return 0;
-  if (!pos || !starts || !stops || !cluster_out || !size_out || !by_cluster_out || !span_out)
+  if ((!pos && !pos_cols) || !starts || !stops || !cluster_out || !size_out || !by_cluster_out ||
+      !span_out)
     return CTK_E_INVALID;
   for (int64_t f = 0; f < n_frames; ++f)
     if (starts[f] < 0 || stops[f] < starts[f] || stops[f] > n || stops[f] - starts[f] > (1 << 30))
@@ -482,7 +504,7 @@ extern "C" int ctk_cluster_pack_frames(const double* pos, int64_t n, int32_t ndi
         if (group_count_out) group_count_out[f] = 0;
         continue;
       }
-      s.tree.init(pos + a * ndim, cnt, ndim, separation);
+      s.tree.init(pos ? pos + a * ndim : nullptr, cnt, ndim, separation, pos_cols, row_base + a);
       s.pairs.clear();
       s.query.t = &s.tree;
       s.query.out = &s.pairs;

@@ -300,6 +300,8 @@ class ChunkLabeller(object):
         self.events = [threading.Event() for _ in self.results]
         self.error = None
         if not self.native:
+            if isinstance(pos, (list, tuple)):
+                pos = np.stack(pos, axis=1)
             job = _LabelJob(pos, starts, stops, separation)
             job.result()
             rows = job.by_cluster
@@ -323,8 +325,9 @@ class ChunkLabeller(object):
                     a = int(self.starts[fa]) if fb > fa else 0
                     b = int(self.stops[fb - 1]) if fb > fa else 0
                     st, sp = self.starts[fa:fb] - a, self.stops[fa:fb] - a
+                    chunk_pos = pos if isinstance(pos, (list, tuple)) else pos[a:b]
                     local, size, by_cluster, spans, gcount, gstart = _lib.cluster_pack_frames(
-                        pos[a:b], st, sp, separation, workers, sources, a, params_out[a:b])
+                        chunk_pos, st, sp, separation, workers, sources, a, params_out[a:b])
                     goff, gframe = _lib.concat_groups(st, sp, gcount, gstart, fa)
                     self.results[k] = (local, size, by_cluster, spans, goff, gframe)
                     self.events[k].set()

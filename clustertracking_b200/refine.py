@@ -952,7 +952,8 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
     else:
         order0, base = None, f
         starts = info.run_starts if info.run_starts is not None else np.zeros(1, dtype=np.int64)
-    pos = np.ascontiguousarray(base[pre.pos_columns].values, dtype=np.float64)
+    # positions as table-order columns: the labelling workers read them in place
+    pos = [np.ascontiguousarray(base[col].values, dtype=np.float64) for col in pre.pos_columns]
     stops = np.concatenate((starts[1:], [n])).astype(np.int64)
     n_frames = len(starts)
     # chunks of whole frames with about _CHUNK_ROWS features each

@@ -264,6 +264,13 @@ int ctk_cluster_pack_frames(const double* pos, int64_t n, int32_t ndim, const in
                             const double* const* columns, const double* scalars, int32_t n_cols,
                             int64_t row_base, double* params_out, int32_t* group_count_out,
                             int32_t* group_start_out);
+int ctk_cluster_pack_columns(const double* pos, const double* const* pos_cols, int64_t n,
+                             int32_t ndim, const int64_t* starts, const int64_t* stops,
+                             int64_t n_frames, const double* separation, int32_t n_threads,
+                             int64_t* cluster_out, int64_t* size_out, int64_t* by_cluster_out,
+                             int64_t* span_out, const double* const* columns, const double* scalars,
+                             int32_t n_cols, int64_t row_base, double* params_out,
+                             int32_t* group_count_out, int32_t* group_start_out);
 int ctk_concat_groups(const int64_t* starts, const int64_t* stops, const int32_t* group_count,
                       const int32_t* group_start, int64_t n_frames, int32_t frame_base,
                       int32_t* group_offset_out, int32_t* group_frame_out, int64_t* n_groups_out);
