@@ -114,6 +114,8 @@ def load():
 
 
 def check(code, what):
+    if code == -5:                          # CTK_E_NONFINITE: what scipy's cKDTree raises
+        raise ValueError("data must be finite, check for nan or inf values")
     if code != 0:
         msg = load().ctk_last_error()
         raise RuntimeError("%s failed (%d): %s" % (what, code, msg.decode() if msg else "?"))

@@ -129,6 +129,10 @@ extern "C" int ctk_pairs_set_order(const int64_t* pairs, int64_t n_pairs, int64_
 
 namespace {
 
+// max of two finite doubles (std::fmax is an out-of-line libm call; the inputs here are never NaN:
+// ctk_cluster_pack_columns rejects non-finite positions like scipy does)
+static inline double dmax2(double x, double y) { return x > y ? x : y; }
+
 struct KdNode {
   int split_dim;          // -1: leaf
   double split;
@@ -144,6 +148,7 @@ struct KdPoint { double c[3]; int64_t idx; };
 
 struct KdTree {
   int n, m;
+  bool finite;                     // scipy refuses non-finite data; so do the callers of this tree
   std::vector<KdPoint> pts;
   std::vector<KdNode> nodes;
   double mins[3], maxes[3];
@@ -153,6 +158,7 @@ struct KdTree {
   void init(const double* data, int n_, int m_, const double* scale,
             const double* const* cols = nullptr, int64_t row0 = 0) {
     n = n_; m = m_;
+    finite = true;
     pts.resize(n);
     for (int i = 0; i < n; ++i) {
       KdPoint& p = pts[i];
@@ -161,6 +167,7 @@ struct KdTree {
         if (k >= m) { p.c[k] = 0.; continue; }
         const double v = cols ? cols[k][row0 + i] : data[(int64_t) i * m + k];
         p.c[k] = scale ? v / scale[k] : v;
+        finite = finite && std::isfinite(p.c[k]);
       }
     }
     nodes.clear();
@@ -172,7 +179,7 @@ struct KdTree {
         maxes[k] = maxes[k] > v ? maxes[k] : v;
         mins[k] = mins[k] < v ? mins[k] : v;
       }
-    if (n > 0) build(0, n);
+    if (n > 0 && finite) build(0, n);
   }
 
   int build(int start, int end) {
@@ -225,11 +232,12 @@ struct RectTracker {
   double r1mn[3], r1mx[3], r2mn[3], r2mx[3];
   double min_d, max_d, upper, limit;
   struct Item { int which, dim; double min_d, max_d, mn, mx; };
-  std::vector<Item> stack;
+  Item stack[256];                 // two pushes per level of two trees of depth <= ~40
+  int depth;
 
   void interval(int k, double* mn, double* mx) const {
-    *mn = std::fmax(0., std::fmax(r1mn[k] - r2mx[k], r2mn[k] - r1mx[k]));
-    *mx = std::fmax(r1mx[k] - r2mn[k], r2mx[k] - r1mn[k]);
+    *mn = dmax2(0., dmax2(r1mn[k] - r2mx[k], r2mn[k] - r1mx[k]));
+    *mx = dmax2(r1mx[k] - r2mn[k], r2mx[k] - r1mn[k]);
   }
   void rect_rect(double* mn, double* mx) const {
     *mn = 0.; *mx = 0.;
@@ -249,12 +257,12 @@ struct RectTracker {
     upper = r * r;
     rect_rect(&min_d, &max_d);
     limit = max_d;
-    stack.clear();
+    depth = 0;
   }
   void push(int which, bool less, int dim, double split) {
     double* mn = which == 1 ? r1mn : r2mn;
     double* mx = which == 1 ? r1mx : r2mx;
-    stack.push_back(Item{which, dim, min_d, max_d, mn[dim], mx[dim]});
+    stack[depth++] = Item{which, dim, min_d, max_d, mn[dim], mx[dim]};
     double min1, max1, min2, max2;
     interval(dim, &min1, &max1);
     min1 *= min1; max1 *= max1;
@@ -268,8 +276,7 @@ struct RectTracker {
     else { min_d += (min2 - min1); max_d += (max2 - max1); }
   }
   void pop() {
-    const Item it = stack.back();
-    stack.pop_back();
+    const Item it = stack[--depth];
     min_d = it.min_d; max_d = it.max_d;
     if (it.which == 1) { r1mn[it.dim] = it.mn; r1mx[it.dim] = it.mx; }
     else { r2mn[it.dim] = it.mn; r2mx[it.dim] = it.mx; }
@@ -319,7 +326,7 @@ struct PairQuery {
     if (n1 != n2) {
       double s = 0.;
       for (int k = 0; k < m; ++k) {
-        const double g = std::fmax(0., std::fmax(a.lo[k] - b.hi[k], b.lo[k] - a.hi[k]));
+        const double g = dmax2(0., dmax2(a.lo[k] - b.hi[k], b.lo[k] - a.hi[k]));
         s += g * g;
       }
       if (s > upper) return;
@@ -330,7 +337,7 @@ struct PairQuery {
       if (n1 != n2) {
         double s = 0.;
         for (int k = 0; k < m; ++k) {
-          const double g = std::fmax(0., std::fmax(u.c[k] - b.hi[k], b.lo[k] - u.c[k]));
+          const double g = dmax2(0., dmax2(u.c[k] - b.hi[k], b.lo[k] - u.c[k]));
           s += g * g;
         }
         if (s > upper) continue;
@@ -426,6 +433,7 @@ extern "C" int ctk_query_pairs_within(const double* data, int64_t n, int32_t ndi
   if (n < 0 || ndim < 1 || ndim > 3 || (n > 0 && !data) || !n_pairs_out || !(r >= 0.)) return CTK_E_INVALID;
   KdTree tree;
   tree.init(data, (int) n, ndim, nullptr);
+  if (!tree.finite) return CTK_E_NONFINITE;
   std::vector<int64_t> pairs;
   PairQuery q;
   q.t = &tree;
@@ -505,6 +513,7 @@ extern "C" int ctk_cluster_pack_columns(const double* pos, const double* const* 
         continue;
       }
       s.tree.init(pos ? pos + a * ndim : nullptr, cnt, ndim, separation, pos_cols, row_base + a);
+      if (!s.tree.finite) { failed = 2; continue; }
       s.pairs.clear();
       s.query.t = &s.tree;
       s.query.out = &s.pairs;
@@ -560,7 +569,7 @@ extern "C" int ctk_cluster_pack_columns(const double* pos, const double* const* 
     for (int k = 0; k < nt; ++k) pool.emplace_back(worker);
     for (auto& th : pool) th.join();
   }
-  return failed ? CTK_E_INVALID : 0;
+  return failed == 2 ? CTK_E_NONFINITE : (failed ? CTK_E_INVALID : 0);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -78,7 +78,8 @@ enum {
   CTK_E_INVALID = -1,         /* bad argument */
   CTK_E_UNSUPPORTED = -2,     /* combination not built into the library */
   CTK_E_CUDA = -3,            /* a CUDA runtime call failed */
-  CTK_E_CAPACITY = -4         /* requested capacity does not fit the device's shared memory */
+  CTK_E_CAPACITY = -4,        /* requested capacity does not fit the device's shared memory */
+  CTK_E_NONFINITE = -5        /* host helpers: non-finite coordinates (scipy's kd-tree refuses them too) */
 };
 
 /* Problem description, host memory, plain old data.  Mirrors the keyword arguments of
