@@ -81,9 +81,68 @@ def measure(name, reader, f0, diameter, oracle_constraints=None, **kwargs):
     print(json.dumps(line), flush=True)
 
 
+def config1():
+    """single 512x512 frame, 200 isolated gaussian features: a latency measurement"""
+    frame, f0, truth = artificial.isolated_frame((512, 512), count=200, seed=0)
+    for _ in range(3):
+        out = ctb.refine_leastsq(f0, frame, 11)
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(10):
+        t = time.perf_counter()
+        out = ctb.refine_leastsq(f0, frame, 11)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t)
+    t = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = cluster_oracle.refine_leastsq(f0.copy(), frame, 11)
+    cpu_s = time.perf_counter() - t
+    print(json.dumps(dict(config="config1: one 512x512 frame, 200 isolated gauss features", features=len(f0),
+                          e2e_ms_per_call=1e3 * float(np.median(times)), e2e_features_per_s=len(f0) / float(np.median(times)),
+                          cpu_1core_features_per_s=len(f0) / cpu_s,
+                          max_abs_dpos_px=float(np.abs(out[['y', 'x']].values - want[['y', 'x']].values).max()),
+                          rms_error_vs_truth_px=float(np.sqrt(np.mean((out[['y', 'x']].values - truth) ** 2))))), flush=True)
+
+
+def config5(n_frames):
+    """find + refine on one GPU (the linking step of find_link is sequential host code of the reference
+    and out of scope): grey_dilation on every frame, then refine_leastsq from the integer maxima"""
+    from clustertracking_b200 import find
+    sys.path.insert(0, ROOT)
+    import bench
+    pos, frame, signal, start = bench.video_geometry(n_frames, seed=7)
+    d_stack = bench.render_video_torch(pos, frame, signal, n_frames, torch.device("cuda", 0), seed=100)
+    stack = d_stack.cpu().numpy()
+    reader = artificial.FrameStack(stack)
+    best = None
+    for rep in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        found = find.grey_dilation_batch(list(stack), 5, percentile=95, margin=6)
+        t1 = time.perf_counter()
+        f0 = pd.DataFrame(dict(y=np.concatenate([p[:, 0] for p in found]).astype(float),
+                               x=np.concatenate([p[:, 1] for p in found]).astype(float),
+                               frame=np.repeat(np.arange(n_frames), [len(p) for p in found]),
+                               signal=120., size=2.75))
+        t2 = time.perf_counter()
+        out = ctb.refine_leastsq(f0, reader, 11)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        if best is None or t3 - t0 < best[0]:
+            best = (t3 - t0, t1 - t0, t2 - t1, t3 - t2, len(f0), int(np.isnan(out['cost']).sum()))
+    total, t_find, t_frame, t_refine, n_feat, n_fail = best
+    print(json.dumps(dict(config="config5 (find + refine, no linking): %d frames 1024x1024" % n_frames,
+                          features_found=n_feat, true_features=len(pos), failed_features=n_fail,
+                          frames_per_s=n_frames / total, features_per_s=n_feat / total,
+                          find_ms=1e3 * t_find, dataframe_ms=1e3 * t_frame, refine_ms=1e3 * t_refine)), flush=True)
+
+
 def main():
     n3 = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     n4 = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    config1()
+    config5(int(sys.argv[3]) if len(sys.argv) > 3 else 100)
 
     def positions3(rng):
         # rigid templates like artificial.py:144-185: dimers (two features one bond apart) and
