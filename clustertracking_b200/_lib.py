@@ -88,6 +88,7 @@ _PROTOTYPES = {
     "ctk_find_maxima": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_i64), _i32, _i32, _vp, ctypes.c_double,
                                        _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "ctk_find_last_error": (ctypes.c_char_p, []),
+    "ctk_drop_close_frames": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp]),
     "ctk_query_pairs_within": (ctypes.c_int, [_vp, _i64, _i32, ctypes.c_double, _vp, _i64, _vp]),
     "ctk_query_pairs": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i64, _vp]),
     "ctk_cluster_frames": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp,
@@ -316,3 +317,19 @@ def apply_label_offsets(local, starts, stops, frame_offset, n_threads, out):
     check(load().ctk_apply_label_offsets(local.ctypes.data, starts.ctypes.data, stops.ctypes.data,
                                          frame_offset.ctypes.data, len(starts), int(n_threads),
                                          out.ctypes.data), "ctk_apply_label_offsets")
+
+
+def drop_close_frames(coords, values, counts, separation, n_threads):
+    """``ctk_drop_close_frames`` -> keep flags [n_frames, capacity] (bool) for the maxima arrays of
+    ``ctk_find_maxima`` (coords int32 [n_frames, capacity, ndim], values int32, counts int32)."""
+    n_frames, capacity, ndim = coords.shape
+    for arr in (coords, values, counts):
+        assert arr.flags.c_contiguous and arr.dtype == np.int32
+    separation = np.ascontiguousarray(separation, dtype=np.float64)
+    keep = np.zeros((n_frames, capacity), dtype=np.uint8)
+    kept = np.zeros(n_frames, dtype=np.int32)
+    check(load().ctk_drop_close_frames(coords.ctypes.data, values.ctypes.data, counts.ctypes.data,
+                                       n_frames, capacity, ndim, separation.ctypes.data,
+                                       int(n_threads), keep.ctypes.data, kept.ctypes.data),
+          "ctk_drop_close_frames")
+    return keep.view(np.bool_)

@@ -730,3 +730,78 @@ extern "C" int ctk_schedule(const int32_t* cluster_offset, int64_t n_clusters, c
   *n_not_run_out = not_run;
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// drop_close for a batch of frames on host threads (find.py:166-207): of every pair of maxima
+// closer than `separation` (scaled distance <= 1 - 1e-7) the dimmer one is dropped, ties by the
+// smaller sum of scaled coordinates; all pairs are judged at once (a feature goes if it loses ANY
+// pair), so the order of the pairs does not matter.
+//   coords [n_frames, capacity, ndim] int32 and values [n_frames, capacity] int32 as written by
+//   ctk_find_maxima; counts [n_frames]; keep_out [n_frames, capacity] uint8 (1 = kept);
+//   kept_out [n_frames] number kept
+// ------------------------------------------------------------------------------------------------
+extern "C" int ctk_drop_close_frames(const int32_t* coords, const int32_t* values,
+                                     const int32_t* counts, int64_t n_frames, int32_t capacity,
+                                     int32_t ndim, const double* separation, int32_t n_threads,
+                                     uint8_t* keep_out, int32_t* kept_out) {
+  if (n_frames < 0 || capacity < 1 || ndim < 1 || ndim > 3 || !separation) return CTK_E_INVALID;
+  if (n_frames == 0) return 0;
+  if (!coords || !values || !counts || !keep_out || !kept_out) return CTK_E_INVALID;
+  bool no_op = false;
+  for (int k = 0; k < ndim; ++k) no_op = no_op || separation[k] == 0.;     // find.py:176-177
+  std::atomic<int64_t> next(0);
+  auto worker = [&]() {
+    std::vector<double> scaled, total;
+    std::vector<int64_t> pairs;
+    KdTree tree;
+    PairQuery query;
+    for (;;) {
+      const int64_t f = next.fetch_add(1);
+      if (f >= n_frames) break;
+      const int cnt = counts[f] < capacity ? counts[f] : capacity;
+      uint8_t* keep = keep_out + (size_t) f * capacity;
+      for (int i = 0; i < cnt; ++i) keep[i] = 1;
+      kept_out[f] = cnt;
+      if (cnt < 2 || no_op) continue;
+      const int32_t* c = coords + (size_t) f * capacity * ndim;
+      const int32_t* v = values + (size_t) f * capacity;
+      scaled.resize((size_t) cnt * ndim);
+      total.resize(cnt);
+      for (int i = 0; i < cnt; ++i) {
+        double s = 0.;
+        for (int k = 0; k < ndim; ++k) {
+          const double q = (double) c[(size_t) i * ndim + k] / separation[k];
+          scaled[(size_t) i * ndim + k] = q;
+          s = k == 0 ? q : s + q;
+        }
+        total[i] = s;
+      }
+      tree.init(scaled.data(), cnt, ndim, nullptr);
+      pairs.clear();
+      query.t = &tree;
+      query.out = &pairs;
+      query.tr.init(tree, 1 - 1e-7);
+      query.checking(0, 0);
+      for (size_t k = 0; k + 1 < pairs.size(); k += 2) {
+        const int64_t i0 = pairs[k], i1 = pairs[k + 1];           // i0 < i1
+        int64_t drop;
+        if (v[i0] != v[i1]) drop = v[i0] > v[i1] ? i1 : i0;
+        else drop = total[i0] > total[i1] ? i1 : i0;
+        keep[drop] = 0;
+      }
+      int kept = 0;
+      for (int i = 0; i < cnt; ++i) kept += keep[i];
+      kept_out[f] = kept;
+    }
+  };
+  int nt = n_threads < 1 ? 1 : n_threads;
+  if (nt > n_frames) nt = (int) n_frames;
+  if (nt == 1) {
+    worker();
+  } else {
+    std::vector<std::thread> pool;
+    for (int k = 0; k < nt; ++k) pool.emplace_back(worker);
+    for (auto& th : pool) th.join();
+  }
+  return 0;
+}

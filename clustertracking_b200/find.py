@@ -433,30 +433,31 @@ def drop_close(pos, separation, intensity=None):
 
 
 def _maxima_on_device(frames, size, percentile, margin):
-    """Maxima of a list of equally shaped integer frames on the current CUDA device through
-    ``ctk_find_maxima`` -> list of (positions int64 [k, ndim], pixel values int64 [k], threshold)."""
+    """Maxima of equally shaped integer frames (a list of arrays or one stacked array) on the current
+    CUDA device through ``ctk_find_maxima`` -> (coords int32 [n_frames, capacity, ndim], values
+    int32 [n_frames, capacity], counts int32 [n_frames], thresholds float64 [n_frames])."""
     import torch
     lib = _lib.load()
     if not torch.cuda.is_available():
         raise RuntimeError("clustertracking_b200 needs a CUDA device (B200, sm_100a); "
                            "there is no CPU fallback")
-    first = np.asarray(frames[0])
-    if first.dtype not in (np.dtype(np.uint8), np.dtype(np.uint16)):
+    if isinstance(frames, np.ndarray):
+        stack = np.ascontiguousarray(frames)                 # already [n_frames, *shape]: no copy
+    else:
+        stack = np.ascontiguousarray(np.stack([np.asarray(fr) for fr in frames]))
+    if stack.dtype not in (np.dtype(np.uint8), np.dtype(np.uint16)):
         raise NotImplementedError("grey_dilation on the GPU takes uint8 or uint16 frames, got %s"
-                                  % first.dtype)
-    ndim, shape = first.ndim, first.shape
+                                  % stack.dtype)
+    shape = stack.shape[1:]
+    ndim = len(shape)
     if ndim not in (2, 3):
         raise ValueError("only 2D and 3D images are supported")
     dev = torch.device('cuda', torch.cuda.current_device())
-    stack = np.ascontiguousarray(np.stack([np.asarray(fr) for fr in frames]))
-    if stack.shape[1:] != shape:
-        raise ValueError("frames must have equal shapes")
-    tdtype = torch.uint8 if first.dtype == np.uint8 else torch.uint16
     d_stack = torch.from_numpy(stack).to(dev)
     n_frames, n_pixels = len(stack), int(np.prod(shape))
     ptrs = d_stack.data_ptr() + stack[0].nbytes * np.arange(n_frames, dtype=np.int64)
     d_ptrs = torch.from_numpy(ptrs).to(dev)
-    code = _lib.PIXEL_CODES[first.dtype]
+    code = _lib.PIXEL_CODES[stack.dtype]
     d_ws = torch.empty(int(lib.ctk_find_workspace_bytes(n_frames, n_pixels, code)), dtype=torch.uint8,
                        device=dev)
     shape_arr = (_lib.ctypes.c_int64 * 3)(*(list(shape) + [1] * (3 - ndim)))
@@ -480,17 +481,19 @@ def _maxima_on_device(frames, size, percentile, margin):
         if counts.max(initial=0) <= capacity:
             break
         capacity = int(counts.max())
-    coords, values, thr = d_coords.cpu().numpy(), d_values.cpu().numpy(), d_thr.cpu().numpy()
-    del tdtype
-    return [(coords[k, :counts[k]].astype(np.int64), values[k, :counts[k]].astype(np.int64), thr[k])
-            for k in range(n_frames)]
+    used = max(1, int(counts.max(initial=0)))
+    coords = np.ascontiguousarray(d_coords[:, :used].cpu().numpy())
+    values = np.ascontiguousarray(d_values[:, :used].cpu().numpy())
+    return coords, values, counts, d_thr.cpu().numpy()
 
 
 def grey_dilation_batch(frames, separation, percentile=64, margin=None, precise=True):
-    """``grey_dilation`` for a sequence of equally shaped frames, image work on the GPU in one
-    batch -> list of position arrays."""
-    frames = list(frames)
-    if not frames:
+    """``grey_dilation`` for equally shaped frames (a sequence of arrays or one stacked array
+    [n_frames, *shape]): the image work on the GPU in one batch, ``drop_close`` for all frames on
+    host threads inside libctk -> list of position arrays."""
+    if not isinstance(frames, np.ndarray):
+        frames = list(frames)
+    if len(frames) == 0:
         return []
     ndim = np.asarray(frames[0]).ndim
     separation = validate_tuple(separation, ndim)
@@ -498,14 +501,18 @@ def grey_dilation_batch(frames, separation, percentile=64, margin=None, precise=
         margin = tuple([int(s / 2) for s in separation])                     # find.py:246-247
     margin = validate_tuple(margin, ndim)
     size = [int(2 * s / np.sqrt(ndim)) for s in separation]                   # find.py:255
+    coords, values, counts, thresholds = _maxima_on_device(frames, size, percentile, margin)
+    if precise:                                                               # find.py:275-276
+        keep = _lib.drop_close_frames(coords, values, counts, separation, max(1, _pool_workers()))
     out = []
-    for pos, values, threshold in _maxima_on_device(frames, size, percentile, margin):
-        if np.isnan(threshold) or len(pos) == 0:
+    for k in range(len(counts)):
+        if np.isnan(thresholds[k]) or counts[k] == 0:
             out.append(np.empty((0, ndim)))                                   # find.py:251-252, 262
             continue
+        pos = coords[k, :counts[k]]
         if precise:
-            pos = drop_close(pos, separation, values)                         # find.py:275-276
-        out.append(pos)
+            pos = pos[keep[k, :counts[k]]]
+        out.append(pos.astype(np.int64))
     return out
 
 

@@ -313,6 +313,12 @@ int ctk_find_maxima(const void* const* d_frames, int32_t n_frames, const int64_t
                     void* d_workspace, int32_t frames_aligned, void* stream);
 const char* ctk_find_last_error(void);
 
+/* drop_close (find.py:166-207) for the maxima of a batch of frames as written by ctk_find_maxima, on
+ * host threads: keep_out [n_frames, capacity] uint8 flags, kept_out [n_frames] counts. */
+int ctk_drop_close_frames(const int32_t* coords, const int32_t* values, const int32_t* counts,
+                          int64_t n_frames, int32_t capacity, int32_t ndim, const double* separation,
+                          int32_t n_threads, uint8_t* keep_out, int32_t* kept_out);
+
 /* ctk_query_pairs with a radius: pairs closer than `r` (the SET scipy's
  * cKDTree(data, leafsize).query_pairs(r) reports for any leafsize; used by where_close,
  * find.py:166-199, whose result does not depend on the order of the pairs). */

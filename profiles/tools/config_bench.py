@@ -119,7 +119,7 @@ def config5(n_frames):
     for rep in range(3):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        found = find.grey_dilation_batch(list(stack), 5, percentile=95, margin=6)
+        found = find.grey_dilation_batch(stack, 5, percentile=95, margin=6)
         t1 = time.perf_counter()
         f0 = pd.DataFrame(dict(y=np.concatenate([p[:, 0] for p in found]).astype(float),
                                x=np.concatenate([p[:, 1] for p in found]).astype(float),

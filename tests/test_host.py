@@ -332,3 +332,20 @@ def test_pipelined_path_failures_and_tiny_inputs(monkeypatch, caplog):
     assert list(out2['frame']) == [3, 7] and list(out2.index) == [1, 0]
     assert list(out2['cluster']) == [0, 1]
     assert out2['y'].values[0] == out2['y'].values[1]
+
+
+def test_drop_close_frames_matches_oracle():
+    from oracle import find_oracle
+    rng = np.random.RandomState(5)
+    for ndim, sep in ((2, (9., 9.)), (2, (8., 12.)), (3, (5., 9., 9.))):
+        n_frames, cap = 5, 250
+        counts = rng.randint(0, cap, n_frames).astype(np.int32)
+        counts[0], counts[1] = 0, 1
+        coords = rng.randint(0, 100, (n_frames, cap, ndim)).astype(np.int32)
+        values = rng.randint(50, 58, (n_frames, cap)).astype(np.int32)       # many ties
+        keep = _lib.drop_close_frames(coords, values, counts, sep, 3)
+        for f in range(n_frames):
+            pos = coords[f, :counts[f]].astype(np.int64)
+            want = np.ones(counts[f], bool)
+            want[list(find_oracle.where_close(pos, sep, values[f, :counts[f]]))] = False
+            assert_array_equal(keep[f, :counts[f]], want)
