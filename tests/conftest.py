@@ -11,6 +11,14 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a fresh checkout has no libctk.so yet (built artefacts are not in the history): build it when
+    # nvcc is available, as __graft_entry__.build() does; on a GPU box the shipped library is used
+    lib = os.path.join(ROOT, "clustertracking_b200", "libctk.so")
+    if not os.path.exists(lib):
+        import shutil
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            from clustertracking_b200 import build
+            build.build(verbose=False)
 
 
 @pytest.fixture(scope="session")
