@@ -133,14 +133,15 @@ __global__ void __launch_bounds__(256) maxfilter4_kernel(const void* const* src_
                                                          int d1, int d2, int axis, int before,
                                                          int after) {
   const int w2 = d2 >> 2;                                   // words per row
-  const int64_t n_words = (int64_t) d0 * d1 * w2;
-  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_words = d0 * d1 * w2;                         // < 2^29 (checked by the caller)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // 32-bit index arithmetic throughout
   if (i >= n_words) return;
-  const int64_t n_pixels = (int64_t) d0 * d1 * d2;
+  const size_t n_pixels = (size_t) n_words * 4;
   const uint8_t* src8 = src_ptrs ? reinterpret_cast<const uint8_t*>(src_ptrs[blockIdx.y])
                                  : src_flat + (size_t) blockIdx.y * n_pixels;
   const unsigned* src = reinterpret_cast<const unsigned*>(src8);
-  const int xw = (int) (i % w2), y = (int) ((i / w2) % d1), z = (int) (i / ((int64_t) d1 * w2));
+  const int row_id = i / w2;                                // z * d1 + y
+  const int xw = i - row_id * w2, z = row_id / d1, y = row_id - z * d1;
   unsigned best = 0u;                                       // zero padding / smallest value
   if (axis == 2) {
     const unsigned* row = src + (i - xw);
@@ -153,11 +154,11 @@ __global__ void __launch_bounds__(256) maxfilter4_kernel(const void* const* src_
     }
   } else {
     const int pos = axis == 0 ? z : y, len = axis == 0 ? d0 : d1;
-    const int64_t step = axis == 0 ? (int64_t) d1 * w2 : w2;
+    const int step = axis == 0 ? d1 * w2 : w2;
     int lo = pos - before, hi = pos + after;
     if (lo < 0) lo = 0;
     if (hi >= len) hi = len - 1;
-    const unsigned* p = src + i + (int64_t) (lo - pos) * step;
+    const unsigned* p = src + i + (lo - pos) * step;
     for (int k = lo; k <= hi; ++k, p += step) best = __vmaxu4(best, __ldg(p));
   }
   reinterpret_cast<unsigned*>(dst + (size_t) blockIdx.y * n_pixels)[i] = best;
@@ -189,14 +190,15 @@ __global__ void __launch_bounds__(SEG) count_kernel(const void* const* frames, c
 
 // ---- packed uint8 variants: one thread tests 4 neighbouring pixels (one 32-bit word) ---------------
 // 4-bit mask of the maxima among pixels 4 i .. 4 i + 3 (a row is a whole number of words)
-__device__ __forceinline__ unsigned maxima4(const unsigned* img, const unsigned* dil, int64_t i,
+__device__ __forceinline__ unsigned maxima4(const unsigned* img, const unsigned* dil, int i,
                                             double thr, int d0, int d1, int d2, int m0, int m1, int m2) {
   if (!(thr == thr)) return 0u;                              // all-black frame
   const unsigned v = __ldg(img + i), d = __ldg(dil + i);
   unsigned eq = __vcmpeq4(v, d);                             // 0xff per equal byte
   if (!eq) return 0u;
   const int w2 = d2 >> 2;
-  const int xw = (int) (i % w2), y = (int) ((i / w2) % d1), z = (int) (i / ((int64_t) d1 * w2));
+  const int row_id = i / w2;
+  const int xw = i - row_id * w2, z = row_id / d1, y = row_id - z * d1;
   if (y < m1 || y > d1 - m1 - 1 || z < m0 || z > d0 - m0 - 1) return 0u;
   const int cut = (int) floor(thr);                          // integer v: v > thr  <=>  v > floor(thr)
   unsigned mask = 0u;
@@ -212,8 +214,9 @@ __device__ __forceinline__ unsigned maxima4(const unsigned* img, const unsigned*
 __global__ void __launch_bounds__(SEG / 4) count4_kernel(const void* const* frames, const uint8_t* dil,
                                                          const double* threshold, int d0, int d1, int d2,
                                                          int m0, int m1, int m2, int* seg_count) {
-  const int64_t n_pixels = (int64_t) d0 * d1 * d2, n_words = n_pixels >> 2;
-  const int64_t i = (int64_t) blockIdx.x * (SEG / 4) + threadIdx.x;
+  const int64_t n_pixels = (int64_t) d0 * d1 * d2;
+  const int n_words = (int) (n_pixels >> 2);
+  const int i = blockIdx.x * (SEG / 4) + threadIdx.x;
   unsigned mask = 0u;
   if (i < n_words)
     mask = maxima4(reinterpret_cast<const unsigned*>(frames[blockIdx.y]),
@@ -238,8 +241,9 @@ __global__ void __launch_bounds__(SEG / 4) write4_kernel(const void* const* fram
                                                          int m0, int m1, int m2, const int* seg_offset,
                                                          int ndim, int capacity, int32_t* coords,
                                                          int32_t* values) {
-  const int64_t n_pixels = (int64_t) d0 * d1 * d2, n_words = n_pixels >> 2;
-  const int64_t i = (int64_t) blockIdx.x * (SEG / 4) + threadIdx.x;
+  const int64_t n_pixels = (int64_t) d0 * d1 * d2;
+  const int n_words = (int) (n_pixels >> 2);
+  const int i = blockIdx.x * (SEG / 4) + threadIdx.x;
   const unsigned* img = reinterpret_cast<const unsigned*>(frames[blockIdx.y]);
   unsigned mask = 0u;
   if (i < n_words)
@@ -260,7 +264,8 @@ __global__ void __launch_bounds__(SEG / 4) write4_kernel(const void* const* fram
   int rank = seg_offset[(size_t) blockIdx.y * gridDim.x + blockIdx.x] + incl - mine;
   for (int w = 0; w < warp; ++w) rank += warp_total[w];
   const int w2 = d2 >> 2;
-  const int xw = (int) (i % w2), y = (int) ((i / w2) % d1), z = (int) (i / ((int64_t) d1 * w2));
+  const int row_id = i / w2;
+  const int xw = i - row_id * w2, z = row_id / d1, y = row_id - z * d1;
   const unsigned v = __ldg(img + i);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
