@@ -239,3 +239,43 @@ def test_pixel_types_agree():
         out = ctb.refine_leastsq(f0, frame.astype(dtype), 11)
         assert np.abs(out[['y', 'x', 'signal', 'cost']].values
                       - ref[['y', 'x', 'signal', 'cost']].values).max() < 1e-6
+
+
+@pytest.mark.gpu
+def test_video_chunking_and_sharding_invariance(monkeypatch):
+    """Config-2 video (120 frames, 250 k features) through the pipelined public API: the result does
+    not depend on how the frames are cut into pipeline chunks, and refining two halves separately
+    (what frame sharding over GPUs does) gives exactly the same table once the cluster ids of the
+    second half are shifted (find.py:120-129).  Every cluster converges."""
+    import os
+    import sys
+    import torch
+    import clustertracking_b200 as ctb
+    from clustertracking_b200 import artificial, parallel, refine
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    n_frames = 120
+    pos, frame, signal, start = bench.video_geometry(n_frames, seed=11)
+    d_stack = bench.render_video_torch(pos, frame, signal, n_frames, torch.device("cuda", 0), seed=12)
+    stack = d_stack.cpu().numpy()
+    reader = artificial.FrameStack(stack)
+    f0 = bench.start_dataframe(start, frame)
+    whole = ctb.refine_leastsq(f0, reader, 11)
+    assert refine.LAST_CALL["chunks"] == 1
+    assert not np.isnan(whole['cost'].values).any()
+    monkeypatch.setattr(refine, "_CHUNK_ROWS", 30000)
+    chunked = ctb.refine_leastsq(f0, reader, 11)
+    assert refine.LAST_CALL["chunks"] >= 8
+    for col in whole.columns:
+        assert np.array_equal(whole[col].values, chunked[col].values), col
+    half = n_frames // 2
+    parts = [ctb.refine_leastsq(f0[f0['frame'] < half], reader, 11),
+             ctb.refine_leastsq(f0[f0['frame'] >= half], reader, 11)]
+    merged = parallel.merge_shards(parts)
+    assert np.array_equal(merged.index.values, whole.index.values)
+    for col in whole.columns:
+        assert np.array_equal(whole[col].values, merged[col].values), col
+    # positions improve on the start coordinates (rms against the rendered truth)
+    err0 = np.sqrt(np.mean((f0[['y', 'x']].values - pos) ** 2))
+    err1 = np.sqrt(np.mean((whole[['y', 'x']].values - pos) ** 2))
+    assert err1 < 0.12 and err1 < 0.5 * err0
