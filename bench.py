@@ -175,13 +175,15 @@ class ClockSampler(object):
 # --------------------------------------------------------------------------------------------------
 # accounting (DESIGN.md "Measurement"): algorithmic bytes and flops of the refine kernel
 # --------------------------------------------------------------------------------------------------
-def refine_accounting(plan, stats):
+def refine_accounting(plan, stats, ids=None):
     """-> (HBM bytes, FP32 flops) one pass of the refine launches has to move / execute, from the
     per-cluster device counters.  Bytes: every masked pixel once per outer iteration, the parameter
     and bounds rows, the outputs.  Flops: per objective evaluation E*F_VAL + 2M, per
     normal-equation accumulation E*F_DER + 2*(v^2 (E+2Q)/2 + 2.5 v E + 2 M), with E pixel-feature
     pairs, Q shared pixel pairs, M union pixels, v free parameters per feature."""
     n = plan.cluster_sizes().astype(np.float64)
+    if ids is not None:                       # accounting of one launch: its clusters only
+        n, stats = n[ids], stats[ids]
     P = plan.problem.n_params
     px = np.dtype(plan.pixel_dtype).itemsize
     evals, accums, outer = stats[:, 0], stats[:, 1], np.maximum(stats[:, 2], 1)
@@ -371,10 +373,51 @@ def run_ours(args):
     peaks = measured_peaks()
     sms = torch.cuda.get_device_properties(device).multi_processor_count
     fp32_peak = sms * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
-    roofline = dict(bound="hbm", kernel="refine_kernel (all size bins of one step)",
-                    achieved=nbytes / (refine_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
-                    traffic=None, peak_source=peaks["source"], ms_per_step=refine_ms,
-                    algorithmic_bytes_per_feature=nbytes / n_features)
+    # the dominant launch: the size class with the longest launch.  Launch order inside a step
+    # (DeviceSession.run): per class its main launch, then (classes below 32) its overflow relaunch.
+    refine_events = [(a, b) for kind, a, b in kernel_events if kind == "refine"]
+    per_step = len(refine_events) // args.steps
+    order = []
+    for cap, start_, count in slices:
+        order.append((cap, start_, count, True))
+        if cap in session.overflow_at and cap < 32:
+            order.append((cap, start_, count, False))
+    dominant = None
+    if len(order) == per_step:
+        durations = np.zeros(per_step)
+        for k, (a, b) in enumerate(refine_events):
+            durations[k % per_step] += a.elapsed_time(b) / args.steps
+        k_dom = int(np.argmax(durations))
+        cap, start_, count, _ = order[k_dom]
+        ids = session.d_work[start_:start_ + count].cpu().numpy()
+        sub_bytes, _ = refine_accounting(plan, stats, ids)
+        dominant = dict(cap=int(cap), clusters=int(count), ms=float(durations[k_dom]), nbytes=sub_bytes)
+    traffic, traffic_source = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if dominant is not None and os.path.exists(tpath):
+        with open(tpath) as fh:
+            t = json.load(fh)
+        if (t.get("frames_per_gpu") == n_frames and t.get("max_cluster_features") == dominant["cap"]
+                and t.get("precision") == args.precision):
+            traffic = int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+            traffic_source = "profiles/r01_traffic.json (ncu --set full capture of this launch)"
+    if dominant is not None:
+        roofline = dict(bound="hbm",
+                        kernel="refine_kernel, launch of the size class up to %d features (%d clusters, "
+                               "%.0f %% of the step)" % (dominant["cap"], dominant["clusters"],
+                                                         100. * dominant["ms"] / (refine_ms + fmax_ms)),
+                        achieved=dominant["nbytes"] / (dominant["ms"] * 1e-3) / 1e9, peak=peaks["hbm_gbs"],
+                        unit="GB/s", traffic=traffic, traffic_source=traffic_source,
+                        peak_source=peaks["source"], ms_per_launch=dominant["ms"],
+                        algorithmic_bytes_per_launch=dominant["nbytes"],
+                        all_refine_launches=dict(ms_per_step=refine_ms,
+                                                 achieved=nbytes / (refine_ms * 1e-3) / 1e9,
+                                                 algorithmic_bytes_per_feature=nbytes / n_features))
+    else:
+        roofline = dict(bound="hbm", kernel="refine_kernel (all size bins of one step)",
+                        achieved=nbytes / (refine_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
+                        traffic=None, peak_source=peaks["source"], ms_per_step=refine_ms,
+                        algorithmic_bytes_per_feature=nbytes / n_features)
     roofline["frac"] = roofline["achieved"] / roofline["peak"]
     roofline_fp32 = dict(bound="fp32", kernel="refine_kernel", achieved=flops / (refine_ms * 1e-3) / 1e12,
                          peak=fp32_peak, unit="TFLOP/s",
