@@ -43,10 +43,14 @@
 #else
 #define CTK_DEV __device__ __forceinline__
 #define CTK_DEV_BIG __device__ __forceinline__  // large phases: each has exactly ONE call site
-#ifdef CTK_COLD_INLINE
-#define CTK_COLD static __device__ __forceinline__
+// Rarely executed helpers (bounds from the tables, distance constraints).  They used to be out of
+// line; since the kernels without constraints no longer contain them (Config::EXTRA), inlining them
+// is what pays: an out-of-line call gives the whole kernel a stack frame (368 bytes) and costs the
+// constrained fits 29 % (config 3: 8.6e6 -> 1.1e7 features/s).  -DCTK_COLD_NOINLINE restores calls.
+#ifdef CTK_COLD_NOINLINE
+#define CTK_COLD static __device__ __noinline__
 #else
-#define CTK_COLD static __device__ __noinline__ // rarely executed: keep it out of the hot loop's footprint
+#define CTK_COLD static __device__ __forceinline__
 #endif
 #define CTK_WARP 32
 #endif
