@@ -29,6 +29,9 @@ def _build():
     out = os.path.join(BUILD, "libctk_emul_%s.so" % tag)
     if not os.path.exists(out):
         os.makedirs(BUILD, exist_ok=True)
+        for stale in os.listdir(BUILD):                     # one build at a time: they travel with the repo
+            if stale.startswith("libctk_emul_") and stale.endswith(".so"):
+                os.remove(os.path.join(BUILD, stale))
         opt = os.environ.get("CTK_EMUL_OPT", "-O1")
         subprocess.check_call(["g++", opt, "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
                                "-I", os.path.join(ROOT, "include"),
