@@ -48,6 +48,8 @@ class Problem(ctypes.Structure):
         ("lowpass", ctypes.c_int32), ("lowpass_half", ctypes.c_int32 * 3),
         ("lowpass_threshold", ctypes.c_double),
         ("lowpass_sigma", ctypes.c_double * 3),
+        ("probe_step", ctypes.c_double), ("probe_sweeps", ctypes.c_int32),
+        ("reserved_", ctypes.c_int32),
     ]
 
 

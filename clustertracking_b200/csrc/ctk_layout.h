@@ -131,6 +131,7 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
   lay->o_x0 = take(v_max * 8);
   lay->o_lo = take(v_max * 8);
   lay->o_hi = take(v_max * 8);
+  lay->o_xb = take(p.family != CTK_FAMILY_GAUSS ? v_max * 8 : 0);
   lay->o_cs = take((v_max + 1) * 4);
   lay->o_rc = take(v_max * (v_max + 1) / 2 * (big ? 4 : 2));
   lay->o_cv = take(n_max * p.n_params * 4);

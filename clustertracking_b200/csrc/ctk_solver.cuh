@@ -146,6 +146,7 @@ struct Layout {
   int real_bytes;  // 4 | 8
   // byte offsets into the cluster's slice
   int o_x, o_xt, o_x0, o_lo, o_hi, o_rhs, o_rhsf, o_d, o_dg, o_act;
+  int o_xb;                // best point of the basin search (ring / disc only)
   int o_H, o_L;            // normal matrix / its damped factor, packed lower, COLUMN-major
   int o_idg;               // inverse diagonal of the factor
   int o_cs;                // [v_max + 1] start of each packed column
@@ -412,6 +413,7 @@ struct ClusterSolver {
   CTK_DEV double* X() const { return dvec(a.lay.o_x); }
   CTK_DEV double* XT() const { return dvec(a.lay.o_xt); }
   CTK_DEV double* X0() const { return dvec(a.lay.o_x0); }
+  CTK_DEV double* XB() const { return dvec(a.lay.o_xb); }
   CTK_DEV double* LO() const { return dvec(a.lay.o_lo); }
   CTK_DEV double* HI() const { return dvec(a.lay.o_hi); }
   CTK_DEV double* RHS() const { return dvec(a.lay.o_rhs); }
@@ -1546,6 +1548,151 @@ struct ClusterSolver {
     return last_step <= 1e-3 ? CTK_OK : CTK_FAIL_NO_CONVERGENCE;
   }
 
+  // ---- basin search (ring / disc) ---------------------------------------------------------------
+  // The ring and disc objectives jump whenever a "safe" pixel (closer than one pixel to a centre,
+  // fitfunc.py:20-26) enters or leaves the sums, and the disc objective jumps at disc_size = 0
+  // (fitfunc.py:121-131: gauss branch, safe pixels dropped instead of forced to 1).  They are
+  // piecewise smooth with many shallow basins; SLSQP's line search hops between them, a damped
+  // Gauss-Newton iteration stays in the basin it starts in.  So that the fit never ends ABOVE the
+  // reference's minimum, the neighbouring basins are probed: from the minimum found, every centre is
+  // displaced along every axis (and the disc is switched to its gauss branch), the minimiser runs
+  // again, and a lower end point replaces the current one; repeated while a sweep improves.
+  // The smooth gauss objective has no such structure: one run.
+  // Probe list: [axis shifts +-step | axis shifts +-step/5 | safe-pixel crossings | shape parameter]
+  enum { N_NEIGH = ND == 2 ? 9 : 27 };
+  CTK_DEV int extra_count() const {
+    if (!(C::EX && C::NE)) return 0;
+    const int m = mode(2 + ND + NS);
+    return m == CTK_MODE_VAR ? n : (m == CTK_MODE_CLUSTER ? 1 : 0);
+  }
+  CTK_DEV int probe_count() const {
+    if (C::FAM == CTK_FAMILY_GAUSS) return 0;
+    return (4 * ND + N_NEIGH) * n + (C::FAM == CTK_FAMILY_DISC ? 3 : 2) * extra_count();
+  }
+  // X() = XB() + probe q; false when the probe does not apply (constant column, bound in the way,
+  // no pixel near the unit sphere in that direction)
+  CTK_DEV bool apply_probe(int q) {
+    double *x = X();
+    const double *xb = XB(), *lo = LO(), *hi = HI();
+#pragma unroll 1
+    for (int v = lane; v < V; v += CTK_WARP) x[v] = xb[v];
+    warp_sync();
+    bool ok = false;
+    if (q < 4 * ND * n) {
+      // centres: +-probe_step along every axis, then +-probe_step / 5
+      const double step = q < 2 * ND * n ? a.prob.probe_step : 0.2 * a.prob.probe_step;
+      if (q >= 2 * ND * n) q -= 2 * ND * n;
+      const int i = q / (2 * ND), k = (q >> 1) % ND;
+      const int v = var_of(2 + k, i);
+      if (v >= 0 && mode(2 + k) == CTK_MODE_VAR) {
+        const double t = fmin(fmax(xb[v] + ((q & 1) ? step : -step), lo[v]), hi[v]);
+        ok = t != xb[v];
+        warp_sync();
+        if (lane == 0) x[v] = t;
+      }
+      warp_sync();
+      return ok;
+    }
+    q -= 4 * ND * n;
+    if (q < N_NEIGH * n) {
+      // safe-pixel crossings: a pixel whose distance to the centre is close to 1 enters or leaves
+      // the sums when the centre moves a little (fitfunc.py:20-26); put the centre just on the
+      // other side of that unit sphere, moving along the line through the pixel
+      const int i = q / N_NEIGH;
+      int o = q - i * N_NEIGH;
+      double c[3] = {0., 0., 0.}, dlt[3] = {0., 0., 0.};
+      double d2 = 0.;
+      bool free_pos = true;
+#pragma unroll
+      for (int k = ND - 1; k >= 0; --k) {
+        c[k] = value_of(xb, 2 + k, i);
+        const double pix = rint(c[k]) + (double) (o % 3 - 1);
+        o /= 3;
+        dlt[k] = c[k] - pix;
+        d2 += dlt[k] * dlt[k];
+        free_pos = free_pos && mode(2 + k) == CTK_MODE_VAR;
+      }
+      const double dist = sqrt(d2);
+      if (free_pos && dist > 0.75 && dist < 1.25) {
+        const double target = dist >= 1. ? 1. - 1e-3 : 1. + 1e-3;
+        ok = true;
+#pragma unroll
+        for (int k = 0; k < ND; ++k) {
+          const int v = var_of(2 + k, i);
+          const double t = c[k] + dlt[k] * (target / dist - 1.);
+          ok = ok && t >= lo[v] && t <= hi[v];
+        }
+        warp_sync();
+        if (ok && lane == 0) {
+#pragma unroll
+          for (int k = 0; k < ND; ++k) x[var_of(2 + k, i)] = c[k] + dlt[k] * (target / dist - 1.);
+        }
+      }
+      warp_sync();
+      return ok;
+    }
+    q -= N_NEIGH * n;
+    {
+      // the shape parameter (thickness / disc_size) of one feature: x 0.75, x 1.33, and for the disc
+      // its gauss branch disc_size <= 0 (flat in disc_size, safe pixels dropped, fitfunc.py:121-131)
+      const int per = C::FAM == CTK_FAMILY_DISC ? 3 : 2;
+      const int j = q / per, kind = q - j * per;
+      const int v = var_of(2 + ND + NS, 0) + j;
+      double t;
+      if (kind == 2) t = fmin(xb[v], -0.25);
+      else t = xb[v] * (kind ? 4. / 3. : 0.75);
+      t = fmin(fmax(t, lo[v]), hi[v]);
+      ok = kind == 2 ? (t <= 0. && xb[v] > 0.) : (t != xb[v]);
+      warp_sync();
+      if (ok && lane == 0) x[v] = t;
+    }
+    warp_sync();
+    return ok;
+  }
+
+  CTK_DEV_BIG int search(double* f_data) {
+    const int n_probe = (a.prob.probe_step > 0. && a.prob.probe_sweeps > 0 &&
+                         n <= CTK_PROBE_MAX_FEATURES) ? probe_count() : 0;
+    const int total = 1 + a.prob.probe_sweeps * n_probe;
+    double best = INFINITY;
+    bool improved = false;
+    int status = CTK_OK;
+    for (int k = 0; k < total; ++k) {
+      bool go = true;
+      if (k == 0) {
+#pragma unroll 1
+        for (int v = lane; v < V; v += CTK_WARP) X()[v] = X0()[v];
+        warp_sync();
+      } else {
+        go = apply_probe((k - 1) % n_probe);
+      }
+      if (go) {
+        double fd = 0.;
+        const int st = minimise(&fd);
+        if (k == 0) {
+          status = st;
+          if (st != CTK_OK || n_probe == 0) { *f_data = fd; return st; }
+        }
+        if (st == CTK_OK && (k == 0 || fd < best * (1. - 1e-9))) {
+          best = fd;
+          improved = k > 0;
+#pragma unroll 1
+          for (int v = lane; v < V; v += CTK_WARP) XB()[v] = X()[v];
+          warp_sync();
+        }
+      }
+      if (k > 0 && (k - 1) % n_probe == n_probe - 1) {     // end of a sweep
+        if (!improved) break;
+        improved = false;
+      }
+    }
+#pragma unroll 1
+    for (int v = lane; v < V; v += CTK_WARP) X()[v] = XB()[v];
+    warp_sync();
+    *f_data = best;
+    return status;
+  }
+
   // ---- whole cluster (refine.py:343-430) -------------------------------------------------------
   CTK_DEV void run(int cluster) {
     feat0 = a.cluster_offset[cluster];
@@ -1600,10 +1747,7 @@ struct ClusterSolver {
         ++outers;
         status = build_pixels();
         if (status != CTK_OK) break;
-#pragma unroll 1
-        for (int v = lane; v < V; v += CTK_WARP) X()[v] = X0()[v];   // restart, refine.py:361-365
-        warp_sync();
-        status = minimise(&fd);
+        status = search(&fd);                  // restarts from X0, refine.py:361-365
         if (status != CTK_OK) break;
         // accept when every feature stayed within max_shift of its mask centre, refine.py:383-385
         bool moved = false;

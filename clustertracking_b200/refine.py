@@ -27,6 +27,9 @@ _FRAME_BATCH_BYTES = 128 << 20        # frames per upload batch (uploads overlap
 # scaled step below which the factorised normal matrix is reused (chord iterations)
 _CHORD_TOL = float(os.environ.get('CTK_CHORD_TOL', 0.02))
 _BIG_WORKSPACE_LIMIT = 8 << 30         # device scratch a large-cluster launch may take
+# basin search of the ring / disc families (ctk.h: probe_step, probe_sweeps)
+_PROBE_STEP = float(os.environ.get('CTK_PROBE_STEP', 0.25))
+_PROBE_SWEEPS = int(os.environ.get('CTK_PROBE_SWEEPS', 2))
 
 
 _THREADS = None
@@ -130,7 +133,8 @@ def _solver_options(kwargs, compute_default):
     The CUDA solver honours ``options['maxiter']``; ``tol`` only matters to SLSQP and is accepted
     and ignored (the device solver always converges tighter than SLSQP's default).  Extra keys:
     ``precision`` ('float32' | 'float64' pixel arithmetic), ``xtol`` (step tolerance) and
-    ``chord_tol`` (scaled step size below which the factorised normal matrix is reused)."""
+    ``chord_tol`` (scaled step size below which the factorised normal matrix is reused),
+    ``probe_step`` / ``probe_sweeps`` (basin search of the ring / disc families, see ctk.h)."""
     kwargs = dict(kwargs)
     method = kwargs.pop('method', 'SLSQP')
     if method != 'SLSQP':
@@ -142,12 +146,13 @@ def _solver_options(kwargs, compute_default):
     precision = kwargs.pop('precision', compute_default)
     xtol = float(kwargs.pop('xtol', 0.))
     chord_tol = float(kwargs.pop('chord_tol', _CHORD_TOL))
+    probe = (float(kwargs.pop('probe_step', _PROBE_STEP)), int(kwargs.pop('probe_sweeps', _PROBE_SWEEPS)))
     if kwargs or options:
         raise TypeError("unsupported keyword arguments: %r" % sorted(list(kwargs) + list(options)))
     if precision not in ('float32', 'float64'):
         raise ValueError("precision must be 'float32' or 'float64'")
     return (lm_max_iter, (_lib.COMPUTE_F64 if precision == 'float64' else _lib.COMPUTE_F32), xtol,
-            chord_tol)
+            chord_tol, probe)
 
 
 class Prepared(object):
@@ -163,7 +168,7 @@ def prepare_common(f, reader, diameter, separation=None, fit_function='gauss', p
     """Argument handling of refine.py:242-315 (no clustering, no GPU work) -> :class:`Prepared`.
     ``frames_hook`` is called with the :class:`FrameInfo` as soon as the frames of the call are
     known: ``refine_leastsq`` uses it to start the uploads while the host is still busy."""
-    lm_max_iter, compute_dtype, xtol, chord_tol = _solver_options(kwargs, 'float32')
+    lm_max_iter, compute_dtype, xtol, chord_tol, probe = _solver_options(kwargs, 'float32')
     if pos_columns is None:
         pos_columns = guess_pos_columns(f)
     if compute_error:
@@ -212,6 +217,7 @@ def prepare_common(f, reader, diameter, separation=None, fit_function='gauss', p
     prob.max_iter, prob.lm_max_iter = int(max_iter), lm_max_iter
     prob.max_shift, prob.max_rms_dev = float(max_shift), float(max_rms_dev)
     prob.residual_factor, prob.xtol, prob.chord_tol = float(residual_factor), xtol, chord_tol
+    prob.probe_step, prob.probe_sweeps = probe
     mask = 0
     if cons['dimer'] is not None:
         mask |= _lib.CONSTRAINT_DIMER

@@ -34,6 +34,8 @@ extern "C" {
                                          arrays in a global-memory workspace, see ctk_refine_batch) */
 #define CTK_MAX_RADIUS 30        /* mask radius per axis (pixel offsets are packed in 6 bits) */
 #define CTK_MAX_TAPS 33          /* taps of the lowpass kernel per axis: half width <= 16 */
+#define CTK_PROBE_MAX_FEATURES 8 /* ring / disc: clusters of up to this many features get the basin
+                                    search (ctk_problem_t.probe_step); larger ones one minimisation */
 
 /* parameter modes, same codes as fitfunc.py:9-11 (2 = 'global' is out of scope) */
 enum { CTK_MODE_CONST = 0, CTK_MODE_VAR = 1, CTK_MODE_CLUSTER = 3 };
@@ -124,6 +126,15 @@ typedef struct {
   double  lowpass_sigma[3];     /* noise_size per axis; the device builds the taps of
                                    trackpy.masks.gaussian_kernel(sigma, 4): exp(-x^2 / (2 sigma^2)),
                                    x = -lw .. lw, normalised to sum 1 */
+  /* Basin search of the ring / disc families (piecewise-smooth objectives, fitfunc.py:20-26,
+   * 121-131): after the first minimisation every centre is displaced by +-probe_step pixels along
+   * every axis (and a disc with a free disc_size is switched to its gauss branch), the minimiser
+   * runs again and a lower end point replaces the current one; at most probe_sweeps sweeps, stopping
+   * when a sweep brings no improvement.  probe_step <= 0 or probe_sweeps <= 0: one minimisation only
+   * (always the case for the smooth gauss family). */
+  double  probe_step;
+  int32_t probe_sweeps;
+  int32_t reserved_;
 } ctk_problem_t;
 
 int ctk_version(void);

@@ -548,6 +548,10 @@ def _frame_lookup(f, reader, pos_columns, t_column):
     return {0: reader}, ndim
 
 
+# cluster id -> (outer iterations used, settled) of the most recent refine_leastsq call
+OUTER_LOOP = {}
+
+
 def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', param_mode=None,
                    param_val=None, constraints=None, bounds=None, pos_columns=None,
                    t_column='frame', noise_size=None, threshold=None, max_iter=10, max_shift=1,
@@ -555,6 +559,7 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
     """Cluster-level ``refine_leastsq`` (refine.py:82-452; global branch 319-332 out of scope)."""
     solver = dict(method='SLSQP', tol=1E-6, options=dict(maxiter=100, disp=False))   # :242-244
     solver.update(kwargs)
+    OUTER_LOOP.clear()
     if compute_error:
         raise NotImplementedError("compute_error is out of scope (SURVEY.md section 2 row 13)")
     if pos_columns is None:
@@ -593,7 +598,8 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
             x0 = pack_vector(params, spec.modes, np.mean)               # refine.py:361
             cons = bind_constraints(constraints, params, spec.modes)    # refine.py:363
             box = spec.cluster_bounds(tables, params)                   # refine.py:364
-            for _ in range(max_iter):                                   # refine.py:365
+            settled = False
+            for n_outer in range(1, max_iter + 1):                      # refine.py:365
                 values, mesh, masks = cluster_pixels(coords, np.asarray(frame), radius,
                                                      noise_size, threshold)
                 fun, grad = spec.objective(values, mesh, masks, params, norm)
@@ -604,6 +610,7 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
                 params = unpack_vector(res['x'], params, spec.modes)
                 moved = params[:, 2:2 + ndim]
                 if np.all(np.sum((moved - coords) ** 2, 1) < max_shift ** 2):    # :383-385
+                    settled = True
                     break
                 coords = moved                                          # refine.py:388
             if rms_dev > max_rms_dev:                                   # refine.py:391-394
@@ -615,4 +622,7 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
         else:                                                           # refine.py:426-427
             f.loc[group.index, spec.params] = params
             f.loc[group.index, 'cost'] = rms_dev
+            # diagnostics (not part of the reference's output): did the re-mask loop settle, or was
+            # the last of max_iter results taken while the mask was still moving (refine.py:365-388)?
+            OUTER_LOOP[int(group['cluster'].values[0])] = (n_outer, settled)
     return f

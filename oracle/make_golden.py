@@ -14,6 +14,8 @@ clusters_*  ``find_clusters`` labels (find.py:132-163)
 refine_*    ``refine_leastsq`` end to end (refine.py:82-452), default ``tol`` and ``tol=1e-12``
 lowpass_*   ``prepare_subimage`` with ``noise_size`` (refine.py:36-40, preprocessing.py:12-49)
 find_*      ``grey_dilation`` local maxima (find.py:166-277)
+refine_ring* / refine_disc*  ring and disc in 2D / 3D, isotropic / anisotropic, shape parameter free
+fuzz_*      fixed-seed subset of the randomised option sweep (tests/fuzz_cases.py)
 """
 import json
 import os
@@ -168,18 +170,29 @@ def _grow_clusters(rng, centres, sizes_k, bond, ndim):
     return np.array(pos), np.array(member_of)
 
 
-def _refine_case(ct, name, image, f0, diameter, call_kwargs, frames=None, constraint=None):
+def _refine_case(ct, name, image, f0, diameter, call_kwargs, frames=None, constraint=None,
+                 watch_loop=False):
     """Run the reference with default tol and tol=1e-12 and store everything.
-    ``constraint`` = (kind, dist) describes ``call_kwargs['constraints']`` for the fixture."""
+    ``constraint`` = (kind, dist) describes ``call_kwargs['constraints']`` for the fixture.
+    ``watch_loop``: also store the clusters whose re-mask loop did not settle (_OuterLoopSpy)."""
+    import clustertracking.refine as ref_refine
     reader = image if frames is None else frames
-    outs = {}
+    outs, unsettled = {}, set()
+    cols = [c for c in ('z', 'y', 'x') if c in f0.columns]
     for tag, extra in (("ref_", {}), ("tight_", dict(tol=1e-12, options=dict(maxiter=1000)))):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            res = ct.refine_leastsq(f0.copy(), reader, diameter, **dict(call_kwargs, **extra))
+            if watch_loop:
+                with _OuterLoopSpy(ref_refine) as spy:
+                    res = ct.refine_leastsq(f0.copy(), reader, diameter, **dict(call_kwargs, **extra))
+                unsettled.update(spy.unsettled(f0, res, cols))
+            else:
+                res = ct.refine_leastsq(f0.copy(), reader, diameter, **dict(call_kwargs, **extra))
         outs.update(frame_to_arrays(tag, res))
     meta = dict(diameter=diameter, constraint=constraint,
                 kwargs={k: v for k, v in call_kwargs.items() if k != 'constraints'})
+    if watch_loop:
+        meta['unsettled'] = sorted(unsettled)
     save(name, image=np.asarray(image), meta=np.array(json.dumps(meta)),
          **frame_to_arrays("in_", f0), **outs)
 
@@ -476,9 +489,132 @@ def golden_find(ct):
              pos=np.asarray(pos, dtype=np.int64).reshape(-1, image.ndim))
 
 
+def golden_ringdisc(ct):
+    """Ring and disc in the geometries the reference's own suite runs them in
+    (tests/test_refine.py:768-881: 2D, 2D anisotropic, 3D, 3D anisotropic), with the default modes
+    and with the shape parameter (``thickness`` / ``disc_size``) free.  refine_ring2d /
+    refine_ring2d_sizevar / refine_disc2d (golden_refine) hold the 2D isotropic default cases."""
+    from clustertracking.artificial import feat_ring, feat_disc
+    rng = np.random.RandomState(2468)
+
+    def grid_positions(shape, pitch, margin, jitter):
+        axes = [np.arange(margin, s - margin + 1e-9, pitch) for s in shape]
+        pos = np.array([g.ravel() for g in np.meshgrid(*axes, indexing='ij')], float).T
+        return pos + rng.uniform(-jitter, jitter, pos.shape)
+
+    geometries = [
+        ("2d", (120, 120), 32, 18, 4., 16, ['y', 'x']),
+        ("2d_aniso", (140, 110), 36, 20, (5., 3.), (20, 12), ['y', 'x']),
+        ("3d", (28, 60, 60), 28, 14, 2.5, 10, ['z', 'y', 'x']),
+        ("3d_aniso", (30, 72, 72), 34, 15, (2.25, 3.25, 3.25), (9, 13, 13), ['z', 'y', 'x']),
+    ]
+    for family, feat, extra in (("ring", feat_ring, dict(thickness=0.25)),
+                                ("disc", feat_disc, dict(disc_size=0.5))):
+        for tag, shape, pitch, margin, size, diameter, cols in geometries:
+            pos = grid_positions(shape, pitch, margin, 2)
+            image = _draw(shape, pos, size, rng.uniform(120, 180, len(pos)), feat, 4, rng, **extra)
+            f0 = pd.DataFrame(pos + rng.uniform(-0.5, 0.5, pos.shape), columns=cols)
+            f0['signal'] = 150.
+            f0['background'] = 2.
+            if np.isscalar(size):
+                f0['size'] = size
+            else:
+                for c, sz in zip(cols, size):
+                    f0['size_' + c] = sz
+            free = dict(param_mode={list(extra)[0]: 'var'})
+            if not (tag == "2d"):
+                _refine_case(ct, "refine_%s%s" % (family, tag), image, f0, diameter,
+                             dict(fit_function=family, param_val=extra), watch_loop=True)
+            _refine_case(ct, "refine_%s%s_free" % (family, tag), image, f0, diameter,
+                         dict(fit_function=family, param_val=extra, **free), watch_loop=True)
+
+
+# (seed, case) of the randomised sweep (tests/fuzz_cases.py, seeds 1-4 of
+# profiles/tools/fuzz_parity.py) kept as fixtures: every ring / disc case with a free shape
+# parameter or with ``noise_size``, plus every case in which the two solvers end further than
+# 1e-3 px apart or the reference's re-mask loop cycles.
+FUZZ_SUBSET = [
+    (1, 2), (1, 3), (1, 5), (1, 10), (1, 31), (1, 33), (1, 35), (2, 6), (2, 10), (2, 22), (2, 45),
+    (2, 50), (2, 52), (2, 57), (3, 6), (3, 16), (3, 17), (3, 18), (3, 19), (3, 20), (3, 22), (3, 24),
+    (3, 26), (3, 27), (3, 29), (3, 41), (3, 48), (3, 51), (3, 54), (4, 9), (4, 10), (4, 17), (4, 22),
+    (4, 27), (4, 34), (4, 37), (4, 40), (4, 42), (4, 43), (4, 45), (4, 47), (4, 56)]
+
+
+class _OuterLoopSpy(object):
+    """Observes (does not alter) the reference's re-mask loop: records the mask centres handed to
+    ``prepare_subimages`` (refine.py:366), from which ``unsettled`` derives the clusters whose loop
+    ran out of ``max_iter`` while the mask was still moving (refine.py:383-388)."""
+
+    def __init__(self, module):
+        self.module, self.inner, self.calls = module, module.prepare_subimages, []
+
+    def __enter__(self):
+        def spy(coords, *args, **kwargs):
+            self.calls.append(np.array(coords, dtype=float))
+            return self.inner(coords, *args, **kwargs)
+        self.module.prepare_subimages = spy
+        return self
+
+    def __exit__(self, *exc):
+        self.module.prepare_subimages = self.inner
+
+    def unsettled(self, f0, res, cols, max_shift=1.):
+        """Cluster ids whose final positions are further than max_shift from the last mask centre."""
+        groups = [(int(cid), group) for (_, cid), group in res.groupby(['frame', 'cluster'])]
+        starts = [f0.loc[group.index, cols].values.astype(float) for _, group in groups]
+        out, at = [], 0
+        for k, (cid, group) in enumerate(groups):
+            assert at < len(self.calls) and np.array_equal(self.calls[at], starts[k]), "spy lost track"
+            last = at
+            at += 1
+            # later calls of this cluster: until the next cluster's start vector shows up
+            while at < len(self.calls) and not (k + 1 < len(groups) and
+                                                np.array_equal(self.calls[at], starts[k + 1])):
+                last = at
+                at += 1
+            if np.isnan(group['cost'].values).any():
+                continue
+            moved = np.sum((group[cols].values - self.calls[last]) ** 2, axis=1)
+            if not np.all(moved < max_shift ** 2):
+                out.append(cid)
+        assert at == len(self.calls), "spy lost track"
+        return out
+
+
+def golden_fuzz(ct):
+    """The fixed-seed subset of the randomised option sweep, answered by the unmodified reference at
+    its default tolerance and at tol=1e-12, plus the clusters whose re-mask loop did not settle."""
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tests"))
+    sys.path.insert(0, os.path.dirname(HERE))
+    import fuzz_cases
+    import clustertracking.refine as ref_refine
+    by_seed = {}
+    for seed, case in FUZZ_SUBSET:
+        by_seed.setdefault(seed, []).append(case)
+    for seed, wanted in sorted(by_seed.items()):
+        for case in fuzz_cases.cases(seed, max(wanted) + 1, only=wanted):
+            kwargs = fuzz_cases.bind(case, ct.constraints)
+            f0, cols = case['f0'], case['cols']
+            outs, unsettled = {}, set()
+            for tag, extra in (("ref_", {}), ("tight_", dict(tol=1e-12, options=dict(maxiter=1000)))):
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    with _OuterLoopSpy(ref_refine) as spy:
+                        res = ct.refine_leastsq(f0.copy(), case['frame'], case['diameter'],
+                                                **dict(kwargs, **extra))
+                unsettled.update(spy.unsettled(f0, res, cols))
+                outs.update(frame_to_arrays(tag, res))
+            meta = dict(diameter=case['diameter'], constraint=case['constraint'], seed=seed,
+                        case=case['case'], kwargs=case['kwargs'], unsettled=sorted(unsettled),
+                        **case['meta'])
+            save("fuzz_%d_%02d" % (seed, case['case']), image=case['frame'],
+                 meta=np.array(json.dumps(meta)), **frame_to_arrays("in_", f0), **outs)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ct = ref_loader.load()
-    only = sys.argv[1:] or ["fitfunc", "pixels", "clusters", "refine", "tetramer", "lowpass", "find"]
+    only = sys.argv[1:] or ["fitfunc", "pixels", "clusters", "refine", "tetramer", "lowpass", "find",
+                            "ringdisc", "fuzz"]
     for part in only:
         globals()["golden_" + part](ct)

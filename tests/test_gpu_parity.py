@@ -48,7 +48,29 @@ def _compare(got, want, pos_tol, rel_tol):
 # The 2D tetramer constraint is built on a sort of the six pair distances (constraints.py:102-114),
 # which SLSQP differentiates numerically; the reference stops at slightly sub-optimal points there
 # (and fails two of four clusters at tol=1e-12), so that fixture gets its own test below.
-STRICT = [n for n in golden_io.names("refine_") if n != "refine_tetramer2d_constrained"]
+# Ring and disc have piecewise-smooth objectives with many shallow basins (the "safe" pixels of
+# fitfunc.py:20-26 enter and leave the sums; the disc switches branch at disc_size = 0); outside the
+# reference's default modes in 2D the two solvers need not end in the same basin.  Those fixtures
+# are judged basin-aware (check_basins below); everything else must meet the strict tolerances.
+BASIN = [n for n in golden_io.names("refine_ring") + golden_io.names("refine_disc")
+         if n not in ("refine_ring2d", "refine_ring2d_sizevar", "refine_disc2d")]
+STRICT = [n for n in golden_io.names("refine_")
+          if n != "refine_tetramer2d_constrained" and n not in BASIN]
+
+
+def check_basins(got, d):
+    """Every cluster is within 1e-3 px of the reference at its default tolerance, or ends at a cost
+    not above the reference's at BOTH tolerances (tests/fuzz_cases.judge).  Clusters whose re-mask
+    loop cycles in the reference (meta['unsettled']) are no target."""
+    import fuzz_cases
+    ref, tight = golden_io.frame(d, "ref_"), golden_io.frame(d, "tight_")
+    assert_array_equal(got.index.values, ref.index.values)
+    assert_array_equal(got['cluster_size'].values, ref['cluster_size'].values)
+    assert not np.isnan(got['cost'].values).any()
+    cols = [c for c in ('z', 'y', 'x') if c in ref.columns]
+    verdict = fuzz_cases.judge(got, ref, tight, cols, unsettled=golden_io.meta(d).get('unsettled', ()))
+    assert verdict['ok'], verdict
+    return verdict
 
 
 def check_tetramer2d(got, d):
@@ -84,6 +106,20 @@ def test_cuda_matches_reference_golden(name, precision):
         got = ctb.refine_leastsq(f0, reader, diameter, precision=precision, **kwargs)
     _compare(got, golden_io.frame(d, "ref_"), POS_TOL, REL_TOL)
     _compare(got, golden_io.frame(d, "tight_"), POS_TOL_TIGHT, REL_TOL_TIGHT)
+
+
+@pytest.mark.parametrize("precision", ["float32", "float64"])
+@pytest.mark.parametrize("name", BASIN)
+def test_cuda_ring_disc_basins(name, precision):
+    """Ring / disc x {2D anisotropic, 3D, 3D anisotropic} x {default modes, shape parameter free}: the
+    combinations the reference's own suite runs (tests/test_refine.py:768-881)."""
+    import clustertracking_b200 as ctb
+    d = golden_io.load(name)
+    f0, reader, diameter, kwargs = golden_io.refine_inputs(d, ctb.constraints)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = ctb.refine_leastsq(f0, reader, diameter, precision=precision, **kwargs)
+    check_basins(got, d)
 
 
 THREAD_CASES = ["refine_gauss2d_isolated", "refine_gauss2d_clusters", "refine_gauss2d_integer_start",

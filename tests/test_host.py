@@ -30,9 +30,21 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().ctk_version() >= 100
 
 
-def test_problem_struct_matches_header_size():
-    # ctk_problem_t: 4 + 12 + 3 + 4 int32, 5 doubles, 2 int32, 9 doubles, 3 x 2 x 12 doubles
-    assert ctypes.sizeof(_lib.Problem) == (4 + 12 + 3 + 4) * 4 + 4 + 5 * 8 + 2 * 4 + 9 * 8 + 72 * 8 + 4 * 4 + 8 + 3 * 8
+def test_problem_struct_matches_header(tmp_path):
+    """The ctypes mirror of ctk_problem_t has the size and the field offsets the C compiler gives
+    the struct of include/ctk.h."""
+    import subprocess
+    names = [name for name, _ in _lib.Problem._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ctk.h"\nint main(void) {\n'
+                   '  printf("%zu\\n", sizeof(ctk_problem_t));\n'
+                   + "".join('  printf("%%zu\\n", offsetof(ctk_problem_t, %s));\n' % n for n in names)
+                   + '  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == ctypes.sizeof(_lib.Problem)
+    assert out[1:] == [getattr(_lib.Problem, n).offset for n in names]
 
 
 def test_shared_bytes_query_needs_no_gpu():

@@ -12,8 +12,8 @@ from numpy.testing import assert_allclose, assert_array_equal
 import golden_io
 import emul_backend
 import clustertracking_b200 as ctb
-from test_gpu_parity import (_compare, check_tetramer2d, POS_TOL, REL_TOL, POS_TOL_TIGHT,
-                             REL_TOL_TIGHT, STRICT)
+from test_gpu_parity import (_compare, check_tetramer2d, check_basins, POS_TOL, REL_TOL, POS_TOL_TIGHT,
+                             REL_TOL_TIGHT, STRICT, BASIN)
 
 CASES = STRICT
 
@@ -38,6 +38,28 @@ def test_emulated_solver_float64(name):
         warnings.simplefilter("ignore")
         got, _ = emul_backend.refine_leastsq(f0, reader, diameter, precision='float64', **kwargs)
     _compare(got, golden_io.frame(d, "tight_"), 1e-6, 1e-6)
+
+
+@pytest.mark.parametrize("name", [n for n in BASIN if "3d" not in n])
+def test_emulated_ring_disc_basins(name):
+    d = golden_io.load(name)
+    f0, reader, diameter, kwargs = golden_io.refine_inputs(d, ctb.constraints)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got, _ = emul_backend.refine_leastsq(f0, reader, diameter, **kwargs)
+    check_basins(got, d)
+
+
+# a few 2D cases of the randomised sweep (the full fixed-seed subset runs on the GPU,
+# tests/test_gpu_fuzz.py; the one-lane build is slow on 3D)
+@pytest.mark.parametrize("name", ["fuzz_1_35", "fuzz_2_22", "fuzz_3_17", "fuzz_3_24", "fuzz_4_40"])
+def test_emulated_fuzz_subset(name):
+    d = golden_io.load(name)
+    f0, reader, diameter, kwargs = golden_io.refine_inputs(d, ctb.constraints)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got, _ = emul_backend.refine_leastsq(f0, reader, diameter, **kwargs)
+    check_basins(got, d)
 
 
 def test_emulated_tetramer2d():
