@@ -367,15 +367,15 @@ def run_ours(args):
     value = total_features * args.steps / (resident_ms * 1e-3)
 
     # kernel-level durations of the refine launches (same timed region, same stream)
-    refine_ms = sum(a.elapsed_time(b) for kind, a, b in kernel_events if kind == "refine") / args.steps
-    fmax_ms = sum(a.elapsed_time(b) for kind, a, b in kernel_events if kind == "frame_max") / args.steps
+    refine_ms = sum(a.elapsed_time(b) for kind, a, b, _ in kernel_events if kind == "refine") / args.steps
+    fmax_ms = sum(a.elapsed_time(b) for kind, a, b, _ in kernel_events if kind == "frame_max") / args.steps
     nbytes, flops = refine_accounting(plan, stats)
     peaks = measured_peaks()
     sms = torch.cuda.get_device_properties(device).multi_processor_count
     fp32_peak = sms * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
     # the dominant launch: the size class with the longest launch.  Launch order inside a step
     # (DeviceSession.run): per class its main launch, then (classes below 32) its overflow relaunch.
-    refine_events = [(a, b) for kind, a, b in kernel_events if kind == "refine"]
+    refine_events = [(a, b) for kind, a, b, _ in kernel_events if kind == "refine"]
     per_step = len(refine_events) // args.steps
     order = []
     for cap, start_, count in slices:

@@ -20,6 +20,7 @@ PIXEL_CODES = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float3
                np.dtype(np.float64): 3, np.dtype(np.int16): 4, np.dtype(np.int32): 5}
 COMPUTE_F32, COMPUTE_F64 = 0, 1
 CONSTRAINT_DIMER, CONSTRAINT_TRIMER, CONSTRAINT_TETRAMER = 1, 2, 4
+LAUNCH_APPEND_OVERFLOW = 1        # ctk_refine_batch_ex flags
 
 STATUS_NAMES = {0: 'ok', 1: 'non-finite initial parameters', 2: 'cluster outside of the image',
                 3: 'solver did not converge', 4: 'rms deviation above max_rms_dev',
@@ -60,18 +61,21 @@ _lib = None
 _vp, _i32, _i64, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
 _PROTOTYPES = {
     "ctk_version": (ctypes.c_int, []),
+    "ctk_problem_bytes": (ctypes.c_size_t, []),
     "ctk_last_error": (ctypes.c_char_p, []),
     "ctk_frame_max": (ctypes.c_int, [_vp, _i32, _i64, _i32, _vp, _vp]),
     "ctk_refine_workspace_bytes": (_sz, []),
     "ctk_refine_shared_bytes": (_sz, [ctypes.POINTER(Problem), _i32]),
     "ctk_refine_workspace_bytes_for": (_sz, [ctypes.POINTER(Problem), _i32]),
-    "ctk_refine_thread_kernel": (ctypes.c_int, [ctypes.POINTER(Problem), _i32]),
     "ctk_refine_batch": (ctypes.c_int, [ctypes.POINTER(Problem), _vp, ctypes.POINTER(_i64), _vp,
                                         _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp]),
     "ctk_refine_batch_chained": (ctypes.c_int, [ctypes.POINTER(Problem), _vp, ctypes.POINTER(_i64),
                                                 _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                                 _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "ctk_refine_batch_ex": (ctypes.c_int, [ctypes.POINTER(Problem), _vp, ctypes.POINTER(_i64),
+                                           _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                           _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "ctk_label_clusters": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "ctk_pairs_set_order": (ctypes.c_int, [_vp, _i64, _vp]),
     "ctk_group_chunk": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp,
@@ -112,6 +116,10 @@ def load():
         fn = getattr(lib, name)                 # AttributeError if the symbol is missing
         fn.restype = restype
         fn.argtypes = argtypes
+    if lib.ctk_problem_bytes() != ctypes.sizeof(Problem):
+        raise ImportError("clustertracking_b200: %s was built from a different include/ctk.h "
+                          "(ctk_problem_t is %d bytes there, %d here); rebuild it"
+                          % (LIB_PATH, lib.ctk_problem_bytes(), ctypes.sizeof(Problem)))
     _lib = lib
     return lib
 

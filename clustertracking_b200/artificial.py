@@ -193,3 +193,57 @@ def clustered_video(n_frames, shape=(1024, 1024), pitch=44, size=2.75, noise=8, 
         f0['frame'] = t
         rows.append(f0)
     return FrameStack(stack), pd.concat(rows, ignore_index=True)
+
+
+def _video(n_frames, shape, make_positions, draw_size, noise, columns, seed, signal_range=(100., 180.),
+           **const):
+    """``n_frames`` independent frames: positions from ``make_positions(rng)``, start coordinates
+    within +-0.5 px of the truth.  -> (FrameStack, start DataFrame with a 'frame' column)."""
+    rng = np.random.default_rng(seed)
+    stack, rows = [], []
+    for t in range(n_frames):
+        pos = make_positions(rng)
+        signal = rng.uniform(*signal_range, len(pos))
+        stack.append(draw_features(shape, pos, draw_size, signal, noise=noise, rng=rng))
+        f0 = _start_frame(pos, rng, 0.5, columns, **const)
+        f0['frame'] = t
+        rows.append(f0)
+    return FrameStack(np.ascontiguousarray(np.array(stack))), pd.concat(rows, ignore_index=True)
+
+
+def dimer_trimer_video(n_frames, shape=(512, 512), size=4.0, bond=8.0, n_dimers=60, n_trimers=40,
+                       noise=6, seed=3):
+    """BASELINE config 3: rigid dimers (two features one bond apart) and equilateral trimers at
+    random angles, like the templates of artificial.py:144-185 -- the shapes ``constraints.dimer`` /
+    ``constraints.trimer`` describe.  Fit with diameter 16."""
+    def positions(rng):
+        centres = jittered_grid(shape, 48, 30, 4, rng)
+        centres = centres[rng.permutation(len(centres))[:n_dimers + n_trimers]]
+        pos = []
+        for k, c in enumerate(centres):
+            theta = rng.uniform(0, 2 * np.pi)
+            if k < n_dimers:
+                offs = [(bond / 2., theta), (bond / 2., theta + np.pi)]
+            else:
+                offs = [(bond / np.sqrt(3.), theta + 2 * np.pi * m / 3) for m in range(3)]
+            pos.extend([c + r * np.array([np.sin(a), np.cos(a)]) for r, a in offs])
+        return np.array(pos)
+
+    return _video(n_frames, shape, positions, size, noise, ['y', 'x'], seed,
+                  signal=150., size=size, background=noise / 2.)
+
+
+def confocal_video(n_stacks, shape=(64, 256, 256), size=(2.25, 3.25, 3.25), n_clusters=60,
+                   noise=4, seed=4):
+    """BASELINE config 4: anisotropic 3D stacks with clusters of 1-4 features at a bond of two
+    sizes per axis.  Fit with diameter (9, 13, 13) and ``param_mode=dict(size='var')``."""
+    bond = tuple(2 * s for s in size)
+
+    def positions(rng):
+        centres = jittered_grid(shape, 30, 16, 3, rng)
+        centres = centres[rng.permutation(len(centres))[:n_clusters]]
+        counts = rng.integers(1, 5, len(centres))
+        return grow_clusters(rng, centres, counts, bond, max_reach=None)[0]
+
+    return _video(n_stacks, shape, positions, size, noise, ['z', 'y', 'x'], seed, signal=150.,
+                  size_z=size[0], size_y=size[1], size_x=size[2], background=noise / 2.)

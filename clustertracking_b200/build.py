@@ -29,22 +29,41 @@ def _nvcc():
     return exe
 
 
-def _source_hash(extra):
+_INCLUDE = None
+
+
+def _deps(path, seen=None):
+    """The file and every quoted include reachable from it (csrc/ and include/)."""
+    import re
+    global _INCLUDE
+    if _INCLUDE is None:
+        _INCLUDE = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+    seen = set() if seen is None else seen
+    if path in seen or not os.path.isfile(path):
+        return seen
+    seen.add(path)
+    with open(path) as fh:
+        text = fh.read()
+    for name in _INCLUDE.findall(text):
+        for base in (os.path.dirname(path), CSRC, os.path.join(ROOT, "include")):
+            _deps(os.path.join(base, name), seen)
+    return seen
+
+
+def _job_hash(job):
+    """Hash of one translation unit: its source, the headers it includes, its flags."""
+    name, src, defs = job
     h = hashlib.sha256()
-    for name in sorted(os.listdir(CSRC)):
-        path = os.path.join(CSRC, name)
-        if os.path.isfile(path):
-            h.update(name.encode())
-            with open(path, "rb") as fh:
-                h.update(fh.read())
-    with open(os.path.join(ROOT, "include", "ctk.h"), "rb") as fh:
-        h.update(fh.read())
-    h.update(repr(extra).encode())
+    for path in sorted(_deps(os.path.join(CSRC, src))):
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    h.update(repr((ARCH, [c for c in COMMON if ROOT not in c], defs)).encode())
     return h.hexdigest()[:16]
 
 
 def _jobs():
-    jobs = [("api", "ctk_api.cu", []), ("host", "ctk_host.cpp", []), ("thread", "ctk_thread.cu", []),
+    jobs = [("api", "ctk_api.cu", []), ("host", "ctk_host.cpp", []),
             ("find", "ctk_find.cu", [])]
     for real in ("float", "double"):
         for fam in (0, 1, 2):
@@ -56,13 +75,22 @@ def _jobs():
 
 
 def _compile(job):
+    """Compile one translation unit unless its cached object is current (per-object stamp)."""
     name, src, defs = job
     obj = os.path.join(BUILD, name + ".o")
+    stamp = obj + ".hash"
+    want = _job_hash(job)
+    if os.path.exists(obj) and os.path.exists(stamp):
+        with open(stamp) as fh:
+            if fh.read().strip() == want:
+                return obj, False
     cmd = [_nvcc()] + ARCH + COMMON + defs + ["-c", os.path.join(CSRC, src), "-o", obj]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (name, " ".join(cmd), proc.stderr))
-    return obj
+    with open(stamp, "w") as fh:
+        fh.write(want)
+    return obj, True
 
 
 def build_variant(out, defines, only=None):
@@ -87,21 +115,27 @@ def build_variant(out, defines, only=None):
 
 
 def build(force=False, verbose=True):
-    """Compile and link ``libctk.so``; returns its path."""
+    """Compile (only the translation units whose sources changed) and link ``libctk.so``."""
+    os.makedirs(BUILD, exist_ok=True)
+    jobs = _jobs()
+    if force:
+        for name, _, _ in jobs:
+            path = os.path.join(BUILD, name + ".o.hash")
+            if os.path.exists(path):
+                os.remove(path)
     stamp = os.path.join(BUILD, "stamp")
-    want = _source_hash((ARCH, [c for c in COMMON if ROOT not in c]))
+    want = hashlib.sha256("".join(_job_hash(j) for j in jobs).encode()).hexdigest()[:16]
     if not force and os.path.exists(OUT) and os.path.exists(stamp):
         with open(stamp) as fh:
             if fh.read().strip() == want:
                 return OUT
-    os.makedirs(BUILD, exist_ok=True)
-    jobs = _jobs()
-    if verbose:
-        print("building libctk.so: %d translation units for sm_100a ..." % len(jobs), flush=True)
     workers = max(1, min(len(jobs), os.cpu_count() or 1))
     with concurrent.futures.ThreadPoolExecutor(workers) as pool:
-        objs = list(pool.map(_compile, jobs))
-    cmd = [_nvcc()] + ARCH + ["-shared", "-cudart", "static", "-o", OUT] + objs
+        done = list(pool.map(_compile, jobs))
+    if verbose:
+        print("libctk.so: compiled %d of %d translation units for sm_100a"
+              % (sum(1 for _, fresh in done if fresh), len(jobs)), flush=True)
+    cmd = [_nvcc()] + ARCH + ["-shared", "-cudart", "static", "-o", OUT] + [obj for obj, _ in done]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (" ".join(cmd), proc.stderr))

@@ -6,11 +6,6 @@
 #include <stdlib.h>
 
 #include "ctk_launch.h"
-#include "ctk_thread.cuh"
-
-namespace ctk {
-int launch_refine_threads(const BatchArgs& args, cudaStream_t stream, char* err, size_t err_len);
-}
 
 namespace {
 
@@ -81,6 +76,7 @@ __global__ void __launch_bounds__(1024) frame_max_kernel(const void* const* fram
 extern "C" {
 
 int ctk_version(void) { return CTK_VERSION; }
+size_t ctk_problem_bytes(void) { return sizeof(ctk_problem_t); }
 
 const char* ctk_last_error(void) { return g_error; }
 
@@ -128,18 +124,6 @@ size_t ctk_refine_shared_bytes(const ctk_problem_t* prob, int32_t max_cluster_fe
   return lay.total <= 227 * 1024 ? (size_t) lay.total : 0;
 }
 
-int ctk_refine_thread_kernel(const ctk_problem_t* prob, int32_t max_cluster_features) {
-  // Opt-in (CTK_THREAD_KERNEL=1): the thread-per-cluster kernel executes 2.4x fewer warp
-  // instructions per cluster than the warp-per-cluster kernel but its per-thread working set
-  // (entry lists, normal matrix and factor in local memory, ~8 KB touched per thread) overflows
-  // L1 and L2 at full occupancy, and it ends up 6 % slower on config 2.
-  const char* env = getenv("CTK_THREAD_KERNEL");
-  const bool on = env && env[0] == '1';
-  return prob && on && !ctk::validate_problem(*prob) &&
-                 ctk::thread_eligible(*prob, max_cluster_features)
-             ? 1 : 0;
-}
-
 int ctk_refine_batch(const ctk_problem_t* prob, const void* const* d_frames,
                      const int64_t* frame_shape, const double* d_frame_max, int32_t n_work,
                      const int32_t* d_work_ids, int32_t max_cluster_features,
@@ -162,6 +146,22 @@ int ctk_refine_batch_chained(const ctk_problem_t* prob, const void* const* d_fra
                              int32_t* d_status_out, int32_t* d_stats_out, void* d_workspace,
                              const int32_t* d_n_work, int32_t* d_overflow,
                              int32_t overflow_capacity, void* stream) {
+  return ctk_refine_batch_ex(prob, d_frames, frame_shape, d_frame_max, n_work, d_work_ids,
+                             max_cluster_features, d_cluster_frame, d_cluster_offset, d_params_in,
+                             d_bounds_lo, d_bounds_hi, d_params_out, d_cost_out, d_status_out,
+                             d_stats_out, d_workspace, d_n_work, d_overflow, overflow_capacity, 0,
+                             stream);
+}
+
+int ctk_refine_batch_ex(const ctk_problem_t* prob, const void* const* d_frames,
+                             const int64_t* frame_shape, const double* d_frame_max, int32_t n_work,
+                             const int32_t* d_work_ids, int32_t max_cluster_features,
+                             const int32_t* d_cluster_frame, const int32_t* d_cluster_offset,
+                             const double* d_params_in, const double* d_bounds_lo,
+                             const double* d_bounds_hi, double* d_params_out, double* d_cost_out,
+                             int32_t* d_status_out, int32_t* d_stats_out, void* d_workspace,
+                             const int32_t* d_n_work, int32_t* d_overflow,
+                             int32_t overflow_capacity, int32_t flags, void* stream) {
   if (!prob) return fail(CTK_E_INVALID, "ctk_refine_batch: prob is NULL");
   if (const char* why = ctk::validate_problem(*prob)) return fail(CTK_E_INVALID, "ctk_refine_batch: %s", why);
   if (n_work < 0) return fail(CTK_E_INVALID, "ctk_refine_batch: n_work < 0");
@@ -206,10 +206,8 @@ int ctk_refine_batch_chained(const ctk_problem_t* prob, const void* const* d_fra
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CTK_CUDA(cudaMemsetAsync(d_workspace, 0, sizeof(int32_t), st));
-  if (a.overflow) CTK_CUDA(cudaMemsetAsync(a.overflow, 0, sizeof(int32_t), st));
-  // small clusters of the default 2D gauss model: one thread per cluster (ctk_thread.cuh)
-  if (!big && ctk_refine_thread_kernel(prob, max_cluster_features))
-    return ctk::launch_refine_threads(a, st, g_error, sizeof(g_error));
+  if (a.overflow && !(flags & CTK_LAUNCH_APPEND_OVERFLOW))
+    CTK_CUDA(cudaMemsetAsync(a.overflow, 0, sizeof(int32_t), st));
   Launcher launcher{&a, st, 0};
   bool found = prob->compute_dtype == CTK_COMPUTE_F64
                    ? ctk::dispatch_config<double>(*prob, launcher, big)

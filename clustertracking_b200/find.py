@@ -318,10 +318,13 @@ class ChunkLabeller(object):
             self.events[0].set()
             return
         workers = max(1, _pool_workers())
+        self.cancelled = False
 
         def work():
             try:
                 for k, (fa, fb) in enumerate(zip(self.frame_cuts[:-1], self.frame_cuts[1:])):
+                    if self.cancelled:
+                        raise RuntimeError("labelling cancelled")
                     a = int(self.starts[fa]) if fb > fa else 0
                     b = int(self.stops[fb - 1]) if fb > fa else 0
                     st, sp = self.starts[fa:fb] - a, self.stops[fa:fb] - a
@@ -341,6 +344,15 @@ class ChunkLabeller(object):
 
     def __len__(self):
         return len(self.results)
+
+    def close(self):
+        """Stop after the chunk in flight and wait for the thread: it writes into the caller's
+        (cached, pinned) ``params_out``, which must not be reused while it runs."""
+        thread = getattr(self, 'thread', None)
+        if thread is not None:
+            self.cancelled = True
+            thread.join()
+            self.thread = None
 
     def get(self, k):
         self.events[k].wait()

@@ -384,15 +384,24 @@ def bin_clusters(sizes, cluster_ids):
 
 def run_bins(sizes, cluster_ids, status, launch):
     """Launch every bin; clusters that overflowed their bin's typical-case capacity (status
-    TOO_LARGE) are relaunched once with rigorous capacities.  ``launch(capacity, ids, rigorous)``
-    must fill ``status[ids]``."""
+    TOO_LARGE) are relaunched once with rigorous capacities, and what even those cannot hold (dense
+    clusters with more overlapping pairs than 4 n) once more in the first large-cluster class --
+    the host-driven mirror of ``DeviceSession._run`` (used by the emulated backend of the tests).
+    ``launch(capacity, ids, rigorous)`` must fill ``status[ids]``."""
     too_big = cluster_ids[sizes[cluster_ids] > _BINS[-1]]
     status[too_big] = _lib.STATUS_TOO_LARGE
+    first_big = min(c for c in _BINS if c > _lib.CTK_MAX_CLUSTER_FEATURES)
+    leftover = []
     for cap, ids in bin_clusters(sizes, cluster_ids):
         launch(cap, ids, False)
         retry = ids[status[ids] == _lib.STATUS_TOO_LARGE]
         if len(retry) and cap < _lib.CTK_MAX_CLUSTER_FEATURES:
             launch(cap, retry, True)              # same class, rigorous capacities
+            retry = retry[status[retry] == _lib.STATUS_TOO_LARGE]
+        if len(retry) and cap <= _lib.CTK_MAX_CLUSTER_FEATURES:
+            leftover.append(retry)
+    if leftover:
+        launch(first_big, np.concatenate(leftover), False)
 
 
 def finalize(plan, result):
@@ -512,6 +521,7 @@ class FrameSet(object):
         self.launches = 0
         self.h2d_bytes = 0
         self.tensors = []                 # keeps the uploaded batches alive
+        self.big_workspaces = {}          # large-cluster scratch, shared by the chunks of the call
         self.batch_ready, self.batch_last = [], []       # per upload batch: event, last frame
         with torch.cuda.device(self.dev):
             self.d_ptrs = torch.zeros(self.n_frames, dtype=torch.int64, device=self.dev)
@@ -554,7 +564,7 @@ class FrameSet(object):
         self.launches += 1
         if events is not None:
             stop.record()
-            events.append(("frame_max", start, stop))
+            events.append(("frame_max", start, stop, None))
 
     def wait_for_frames(self, last_frame):
         """Make the current stream wait until frames 0 .. last_frame are resident and their maxima
@@ -635,7 +645,6 @@ class DeviceSession(object):
         self.launches = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
-        self.big_workspaces = {}
         with torch.cuda.device(self.dev):
             dev = self.dev
             self.workspace = torch.empty(int(self.lib.ctk_refine_workspace_bytes()),
@@ -668,8 +677,7 @@ class DeviceSession(object):
         caps = np.asarray(_BINS)
         self.rigorous = rigorous_problem(self.plan.problem)
         small = caps <= _lib.CTK_MAX_CLUSTER_FEATURES
-        key = (bytes(self.plan.problem) + os.environ.get('CTK_THREAD_KERNEL', '0').encode()
-               + os.environ.get('CTK_MERGE_CLASSES', '0').encode())
+        key = bytes(self.plan.problem)
         if key not in _FITS_CACHE:                 # the capacity queries only depend on the problem
             prob = _lib.ctypes.byref(self.plan.problem)
             rig = _lib.ctypes.byref(self.rigorous)
@@ -679,35 +687,17 @@ class DeviceSession(object):
                              for c in caps] + [False])
             retry_fits = {int(c): self.lib.ctk_refine_shared_bytes(rig, int(c)) > 0
                           for c in caps[small]}
-            # largest capacity the thread-per-cluster kernel takes (0: the problem does not qualify);
-            # it handles every size up to that in ONE launch, so those classes are merged
-            merged = max([int(c) for c in caps[small]
-                          if self.lib.ctk_refine_thread_kernel(prob, int(c))] + [0])
-            # CTK_MERGE_CLASSES=1 (measurement knob): the warp kernel's occupancy is bound by
-            # registers (16 warps per SM) as long as a cluster's slice stays below 227 KB / 16, so
-            # every class up to the largest such one could run in ONE launch with that class's
-            # layout.  Measured on config 2: 12.3 ms against 11.6 ms with one launch per class
-            # (the small clusters pay for the large layout), so it is off.
-            if not merged and os.environ.get('CTK_MERGE_CLASSES', '0') == '1':
-                roomy = [int(c) for c in caps[small]
-                         if 0 < self.lib.ctk_refine_shared_bytes(prob, int(c)) <= (227 * 1024) // 16
-                         and self.lib.ctk_refine_shared_bytes(rig, int(c)) > 0]
-                merged = max(roomy + [0])
             if len(_FITS_CACHE) > 64:
                 _FITS_CACHE.clear()
-            _FITS_CACHE[key] = (fits, retry_fits, merged)
+            _FITS_CACHE[key] = (fits, retry_fits)
         # classes whose typical-case capacities can overflow, and whether the rigorous ones fit
-        fits, self.retry_fits, merged = _FITS_CACHE[key]
-        if os.environ.get('CTK_THREAD_MERGE') == '0':       # measurement knob: one launch per class
-            merged = 0
+        fits, self.retry_fits = _FITS_CACHE[key]
         first_big = int(np.flatnonzero(~small)[0])
         self.big_fallback = int(caps[first_big]) if fits[first_big] else None
         # class a cluster of class k runs in: k, the first large class when k's arrays do not fit
         # the shared memory, or -1
         target = np.where(fits[:len(caps)], np.arange(len(caps)),
                           np.where(small & bool(self.big_fallback), first_big, -1)).astype(np.int32)
-        if merged:
-            target[caps <= merged] = int(np.flatnonzero(caps == merged)[0])
         ids, counts, self.never_run = _lib.schedule(self.plan.cluster_offset, caps, target)
         self.d_work = self._up(ids)
         slices, at = [], 0
@@ -723,15 +713,22 @@ class DeviceSession(object):
             if cap <= _lib.CTK_MAX_CLUSTER_FEATURES:
                 self.overflow_at[cap] = (words, count)
                 words += 1 + count
+        # the FINAL list [count, ids...]: clusters that are still too large for the rigorous
+        # capacities of their class (dense clusters: more overlapping pairs than 4 n, a box wider
+        # than 1023 pixels) or for the largest shared-memory class; one large-cluster launch
+        # (global-memory workspace) behind all classes consumes it
+        self.final_at = (words, sum(count for cap, _, count in slices
+                                    if cap <= _lib.CTK_MAX_CLUSTER_FEATURES))
+        words += 1 + self.final_at[1]
         self.d_overflow = self.torch.zeros(max(words, 1), dtype=self.torch.int32, device=self.dev)
         return slices
 
     def launch_refine(self, cap, work_ptr, count, events=None, problem=None, n_work_ptr=None,
-                      overflow_ptr=None, overflow_cap=0):
+                      overflow_ptr=None, overflow_cap=0, flags=0, label=None):
         if events is not None:
             start, stop = (self.torch.cuda.Event(enable_timing=True) for _ in range(2))
             start.record()
-        _lib.check(self.lib.ctk_refine_batch_chained(
+        _lib.check(self.lib.ctk_refine_batch_ex(
             _lib.ctypes.byref(problem if problem is not None else self.plan.problem),
             self.frames.d_ptrs.data_ptr(), self.shape_arr,
             self.frames.d_fmax.data_ptr(), count, work_ptr, int(cap), self.d_cframe.data_ptr(),
@@ -740,22 +737,24 @@ class DeviceSession(object):
             self.d_hi.data_ptr() if self.d_hi is not None else None, self.d_out.data_ptr(),
             self.d_cost.data_ptr(), self.d_status.data_ptr(), self.d_stats.data_ptr(),
             self._workspace_for(cap).data_ptr(), n_work_ptr, overflow_ptr, int(overflow_cap),
-            self.stream_ptr()), "ctk_refine_batch_chained")
+            int(flags), self.stream_ptr()), "ctk_refine_batch_ex")
         self.launches += 1
         if events is not None:
             stop.record()
-            events.append(("refine", start, stop))
+            events.append(("refine", start, stop, label if label is not None else (cap, "main")))
 
     def _workspace_for(self, cap):
         """Small classes share one scratch word; a large-cluster class gets its own workspace."""
         if cap <= _lib.CTK_MAX_CLUSTER_FEATURES:
             return self.workspace
-        if cap not in self.big_workspaces:
+        # one workspace per class and CALL (kept by the FrameSet): the chunks of a call run on one
+        # stream, so their large-cluster launches can share it
+        pool = self.frames.big_workspaces
+        if cap not in pool:
             nbytes = int(self.lib.ctk_refine_workspace_bytes_for(
                 _lib.ctypes.byref(self.plan.problem), int(cap)))
-            self.big_workspaces[cap] = self.torch.empty(nbytes, dtype=self.torch.uint8,
-                                                        device=self.dev)
-        return self.big_workspaces[cap]
+            pool[cap] = self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.dev)
+        return pool[cap]
 
     def run(self, slices, events=None):
         self.frames.wait_for_frames(int(self.plan.cluster_frame.max()) if self.plan.n_clusters else 0)
@@ -765,22 +764,47 @@ class DeviceSession(object):
         """One refine launch per size class; behind it, for the classes provisioned for the typical
         case, the relaunch of the clusters that overflowed (device-side list, usually empty or a
         percent of the class): with rigorous capacities if those fit the shared memory, else in the
-        first large-cluster class."""
+        first large-cluster class.  What even the rigorous capacities cannot hold (dense clusters
+        with more than 4 n overlapping pairs, boxes wider than 1023 pixels) is appended to the final
+        list, which ONE large-cluster launch at the end consumes -- still no host round trip."""
         base = self.d_overflow.data_ptr()
+        final = base + 4 * self.final_at[0]
+        final_cap = self.final_at[1] if self.big_fallback is not None else 0
+        used_final = False
+
+        def to_final():
+            """Overflow arguments of a launch that feeds the final list: the first such launch of
+            a pass resets the list's count, the later ones append."""
+            nonlocal used_final
+            if not final_cap:
+                return dict()
+            flags = _lib.LAUNCH_APPEND_OVERFLOW if used_final else 0
+            used_final = True
+            return dict(overflow_ptr=final, overflow_cap=final_cap, flags=flags)
+
         for cap, start, count in slices:
             at = self.overflow_at.get(cap)
             if at is None:
                 self.launch_refine(cap, self.d_work.data_ptr() + 4 * start, count, events)
                 continue
             lst = base + 4 * at[0]
-            self.launch_refine(cap, self.d_work.data_ptr() + 4 * start, count, events,
-                               overflow_ptr=lst, overflow_cap=count)
-            if self.retry_fits.get(cap):
-                if cap < _lib.CTK_MAX_CLUSTER_FEATURES:       # the largest class is rigorous already
-                    self.launch_refine(cap, lst + 4, count, events, problem=self.rigorous,
-                                       n_work_ptr=lst)
-            elif self.big_fallback is not None:
-                self.launch_refine(self.big_fallback, lst + 4, count, events, n_work_ptr=lst)
+            if self.retry_fits.get(cap) and cap < _lib.CTK_MAX_CLUSTER_FEATURES:
+                self.launch_refine(cap, self.d_work.data_ptr() + 4 * start, count, events,
+                                   overflow_ptr=lst, overflow_cap=count)
+                self.launch_refine(cap, lst + 4, count, events, problem=self.rigorous,
+                                   n_work_ptr=lst, label=(cap, "rigorous"), **to_final())
+            elif self.retry_fits.get(cap):               # the largest class is rigorous already
+                self.launch_refine(cap, self.d_work.data_ptr() + 4 * start, count, events,
+                                   **to_final())
+            else:
+                self.launch_refine(cap, self.d_work.data_ptr() + 4 * start, count, events,
+                                   overflow_ptr=lst, overflow_cap=count)
+                if self.big_fallback is not None:
+                    self.launch_refine(self.big_fallback, lst + 4, count, events, n_work_ptr=lst,
+                                       label=(cap, "large"))
+        if used_final:
+            self.launch_refine(self.big_fallback, final + 4, final_cap, events, n_work_ptr=final,
+                               label=(0, "final"))
 
     def download(self, want_stats=True):
         """Results through cached pinned buffers.  The arrays of the returned Result are views of
@@ -911,10 +935,33 @@ def _pinned_array(key, shape, dtype):
     return _pinned_buffer(torch, key, nbytes)[:nbytes].numpy().view(dtype).reshape(shape)
 
 
+_CALL_LOCK = __import__('threading').Lock()
+_LABELLERS = []       # the running call's labelling thread(s), closed when the call ends
+
+
 def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', param_mode=None,
                    param_val=None, constraints=None, bounds=None, pos_columns=None,
                    t_column='frame', noise_size=None, threshold=None, max_iter=10, max_shift=1,
                    max_rms_dev=1., residual_factor=100000., compute_error=False, **kwargs):
+    """Refine cluster coordinates by least-squares fitting of radial model functions, on the GPU.
+    See :func:`_refine_leastsq` for the parameters.  The cached pinned staging buffers are
+    process-wide, so concurrent calls are serialised here; whatever happens inside, the labelling
+    thread has stopped writing into them before the call returns or raises."""
+    with _CALL_LOCK:
+        try:
+            return _refine_leastsq(f, reader, diameter, separation, fit_function, param_mode,
+                                   param_val, constraints, bounds, pos_columns, t_column,
+                                   noise_size, threshold, max_iter, max_shift, max_rms_dev,
+                                   residual_factor, compute_error, **kwargs)
+        finally:
+            while _LABELLERS:
+                _LABELLERS.pop().close()
+
+
+def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', param_mode=None,
+                    param_val=None, constraints=None, bounds=None, pos_columns=None,
+                    t_column='frame', noise_size=None, threshold=None, max_iter=10, max_shift=1,
+                    max_rms_dev=1., residual_factor=100000., compute_error=False, **kwargs):
     """Refine cluster coordinates by least-squares fitting of radial model functions, on the GPU.
 
     Same signature, same returned columns and the same failure convention as the reference
@@ -983,6 +1030,7 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
     params_in = _pinned_array("params_in", (n, P), np.float64)     # packed, group order
     # labelling, packing and the group tables run on host threads from here on
     labeller = ChunkLabeller(pos, starts, stops, frame_cuts, separation, sources, params_in)
+    _LABELLERS.append(labeller)
     frame_cuts = labeller.frame_cuts
     t1 = time.perf_counter()
     out_params = _pinned_array("params", (n, P), np.float64)
@@ -1082,6 +1130,9 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
                                     last_chunk=1e3 * (t3 - t2), table=1e3 * (t4 - t3), **lap))
     return out
 
+
+refine_leastsq.__doc__ = _refine_leastsq.__doc__ + """
+    Concurrent calls are serialised (the pinned staging buffers are process-wide)."""
 
 # diagnostics of the most recent refine_leastsq call (bytes copied, kernel launches, host phases)
 LAST_CALL = {}

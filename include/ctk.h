@@ -44,7 +44,10 @@ enum { CTK_FAMILY_GAUSS = 0, CTK_FAMILY_RING = 1, CTK_FAMILY_DISC = 2 };
 /* pixel types of the frames */
 enum { CTK_PIXEL_U8 = 0, CTK_PIXEL_U16 = 1, CTK_PIXEL_F32 = 2, CTK_PIXEL_F64 = 3,
        CTK_PIXEL_I16 = 4, CTK_PIXEL_I32 = 5 };
-/* arithmetic of the pixel pass (normal equations, factorisation and parameters are always f64) */
+/* arithmetic of the pixel pass.  Parameters, bounds, the gradient (J^T r) and the objective are
+ * float64 in both modes; the normal matrix J^T J, its Cholesky factor and the model values follow
+ * the pixel arithmetic (float32 in CTK_COMPUTE_F32, float64 in CTK_COMPUTE_F64): the step only has
+ * to be a descent direction, the fixed point is decided by the float64 gradient. */
 enum { CTK_COMPUTE_F32 = 0, CTK_COMPUTE_F64 = 1 };
 /* equality constraints, constraints.py:59-137; applied to clusters of exactly that size */
 enum { CTK_CONSTRAINT_DIMER = 1, CTK_CONSTRAINT_TRIMER = 2, CTK_CONSTRAINT_TETRAMER = 4 };
@@ -138,6 +141,8 @@ typedef struct {
 } ctk_problem_t;
 
 int ctk_version(void);
+/* sizeof(ctk_problem_t) as compiled into the library: lets a binding check its struct mirror */
+size_t ctk_problem_bytes(void);
 const char* ctk_last_error(void);
 
 /* Maximum pixel value of each frame, as float64 (replaces `frame.max()` at refine.py:354, which the
@@ -160,15 +165,6 @@ size_t ctk_refine_workspace_bytes_for(const ctk_problem_t* prob, int32_t max_clu
 /* Shared memory (bytes per cluster) a launch with this capacity would use, or 0 when it does not
  * fit the device limit (227 KB on sm_100a).  Lets the caller bin clusters by size. */
 size_t ctk_refine_shared_bytes(const ctk_problem_t* prob, int32_t max_cluster_features);
-
-/* 1 when a launch with this problem and capacity runs the thread-per-cluster kernel (the
- * reference's default model -- 2D isotropic gauss, signal and position free, constant size, no
- * constraints, no lowpass -- and at most 8 features per cluster): such a launch takes clusters of
- * ANY size up to max_cluster_features at full efficiency, so a caller should hand it all of them
- * in one launch instead of one launch per size class.  0: the warp-per-cluster kernel runs.
- * The thread-per-cluster kernel is opt-in (environment variable CTK_THREAD_KERNEL=1): on B200 its
- * per-thread working set does not fit the caches and it is slightly slower than the warp kernel. */
-int ctk_refine_thread_kernel(const ctk_problem_t* prob, int32_t max_cluster_features);
 
 /* Refine a batch of clusters: the body of the reference's loop over (frame, cluster) groups
  * (refine.py:343-430) including the pixel-set construction (refine.py:28-58, masks.py:30-68), the
@@ -225,6 +221,22 @@ int ctk_refine_batch_chained(const ctk_problem_t* prob,
                      int32_t* d_stats_out, void* d_workspace,
                      const int32_t* d_n_work, int32_t* d_overflow, int32_t overflow_capacity,
                      void* stream);
+
+/* ctk_refine_batch_chained with launch flags:
+ *   CTK_LAUNCH_APPEND_OVERFLOW  do not reset word 0 of d_overflow: the clusters this launch cannot
+ *                   hold are APPENDED to a list earlier launches on the stream started.  Lets every
+ *                   size class hand its hardest clusters to ONE final large-cluster launch. */
+enum { CTK_LAUNCH_APPEND_OVERFLOW = 1 };
+int ctk_refine_batch_ex(const ctk_problem_t* prob,
+                     const void* const* d_frames, const int64_t* frame_shape,
+                     const double* d_frame_max,
+                     int32_t n_work, const int32_t* d_work_ids, int32_t max_cluster_features,
+                     const int32_t* d_cluster_frame, const int32_t* d_cluster_offset,
+                     const double* d_params_in, const double* d_bounds_lo, const double* d_bounds_hi,
+                     double* d_params_out, double* d_cost_out, int32_t* d_status_out,
+                     int32_t* d_stats_out, void* d_workspace,
+                     const int32_t* d_n_work, int32_t* d_overflow, int32_t overflow_capacity,
+                     int32_t flags, void* stream);
 
 /* Host helper (no GPU): cluster labels of one frame from the close pairs, visiting the pairs in the
  * given order with the reference's "the label of a's cluster survives" rule (find.py:41-48, 84-93).

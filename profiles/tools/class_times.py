@@ -1,5 +1,5 @@
-"""Per size class: duration of the refine launch with the warp-per-cluster and with the
-thread-per-cluster kernel (config 2, inputs resident).  python profiles/tools/class_times.py [frames]"""
+"""Per size class: duration of the refine launches (config 2, inputs resident).
+python profiles/tools/class_times.py [frames]"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -13,22 +13,19 @@ pos, frame, signal, start = bench.video_geometry(n_frames, seed=7)
 d_stack = bench.render_video_torch(pos, frame, signal, n_frames, dev, seed=100)
 reader = artificial.FrameStack(d_stack.cpu().numpy())
 f0 = bench.start_dataframe(start, frame)
-os.environ['CTK_THREAD_MERGE'] = '0'
-for mode in ('0', '1'):
-    os.environ['CTK_THREAD_KERNEL'] = mode
-    plan = refine.prepare(f0.copy(), reader, bench.DIAMETER)
-    session = refine.DeviceSession(plan, dev)
-    session.frames.register(d_stack, 0)
-    session.frames.launch_frame_max(0, n_frames)
-    slices = session.schedule()
-    for _ in range(2):
-        session.run(slices)
-    torch.cuda.synchronize()
-    events = []
-    session.run(slices, events)
-    torch.cuda.synchronize()
-    times = [a.elapsed_time(b) for kind, a, b in events if kind == "refine"]
-    # launches come in pairs (class, its overflow relaunch)
-    print("thread kernel" if mode == '1' else "warp kernel  ", " ".join(
-        "cap%d:%d clusters %.2f+%.2f ms" % (cap, count, times[2 * k], times[2 * k + 1])
-        for k, (cap, start_, count) in enumerate(slices)), "| total %.2f ms" % sum(times), flush=True)
+plan = refine.prepare(f0.copy(), reader, bench.DIAMETER)
+session = refine.DeviceSession(plan, dev)
+session.frames.register(d_stack, 0)
+session.frames.launch_frame_max(0, n_frames)
+slices = session.schedule()
+for _ in range(2):
+    session.run(slices)
+torch.cuda.synchronize()
+events = []
+session.run(slices, events)
+torch.cuda.synchronize()
+counts = {cap: count for cap, _, count in slices}
+for kind, a, b, label in events:
+    if kind == "refine":
+        print("class %3d %-8s %7d clusters %8.3f ms" % (label[0], label[1], counts.get(label[0], 0), a.elapsed_time(b)))
+print("total %.2f ms" % sum(a.elapsed_time(b) for kind, a, b, _ in events if kind == "refine"))

@@ -21,6 +21,17 @@ def pytest_configure(config):
             build.build(verbose=False)
 
 
+def pytest_collection_modifyitems(config, items):
+    """Tests marked ``gpu`` are skipped (not failed) where there is no CUDA device."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (run with -m gpu on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN

@@ -13,7 +13,6 @@
 using std::min;
 using std::max;
 #include "ctk_layout.h"
-#include "ctk_thread.cuh"
 
 namespace {
 struct RunAll {
@@ -58,22 +57,6 @@ extern "C" int ctk_emul_refine_batch(const ctk_problem_t* prob, const void* cons
   a.status_out = status_out;
   a.stats_out = iters_out;
   if (!ctk::compute_layout(*prob, max_cluster_features, &a.lay)) return CTK_E_CAPACITY;
-  if (ctk::thread_eligible(*prob, max_cluster_features) && !getenv("CTK_EMUL_WARP_ONLY")) {
-    // the thread-per-cluster solver is scalar code: it runs here unchanged
-    for (int w = 0; w < n_work; ++w) {
-      const int cluster = work_ids ? work_ids[w] : w;
-      if (prob->compute_dtype == CTK_COMPUTE_F64) {
-        ctk::ThreadSolver<double>* s = new ctk::ThreadSolver<double>(a);
-        s->run(cluster);
-        delete s;
-      } else {
-        ctk::ThreadSolver<float>* s = new ctk::ThreadSolver<float>(a);
-        s->run(cluster);
-        delete s;
-      }
-    }
-    return 0;
-  }
   RunAll run{&a};
   const bool big = max_cluster_features > CTK_MAX_CLUSTER_FEATURES;
   bool ok = prob->compute_dtype == CTK_COMPUTE_F64 ? ctk::dispatch_config<double>(*prob, run, big)

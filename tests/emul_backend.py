@@ -21,7 +21,6 @@ def _build():
     h = hashlib.sha256()
     for path in (SRC, os.path.join(ROOT, "include", "ctk.h"),
                  os.path.join(ROOT, "clustertracking_b200", "csrc", "ctk_solver.cuh"),
-                 os.path.join(ROOT, "clustertracking_b200", "csrc", "ctk_thread.cuh"),
                  os.path.join(ROOT, "clustertracking_b200", "csrc", "ctk_layout.h")):
         with open(path, "rb") as fh:
             h.update(fh.read())

@@ -73,9 +73,14 @@ def check_basins(got, d):
     return verdict
 
 
-def check_tetramer2d(got, d):
-    """Constraint met to 1e-6, cost not above the reference's, positions within 2e-2 px (that
-    residue is the reference's: its cost is higher by up to 3e-4 relative on these clusters)."""
+def check_tetramer2d(got, d, f0, image, pos_tol):
+    """The 2D tetramer constraint (four shortest pair distances = bond: a rhombus) is a sorted,
+    non-smooth function that SLSQP differentiates numerically; the reference stops 2e-3 .. 1e-2 px
+    short of the minimum.  Proof, not assertion: an independent minimiser on the exactly
+    parametrised feasible set (tests/tetramer_check.py) lands on the DEVICE answer to ``pos_tol``
+    and at the device's cost, and the reference's cost is not lower.  The 2e-2 px left against the
+    reference's stored answer is therefore the reference's residue."""
+    import tetramer_check
     want = golden_io.frame(d, "ref_")
     assert_array_equal(got['cluster'].values, want['cluster'].values)
     assert not np.isnan(got['cost'].values).any()
@@ -85,6 +90,7 @@ def check_tetramer2d(got, d):
         p = g[['y', 'x']].values
         d2 = sorted(np.sum(((p[a] - p[b]) / 8.) ** 2) for a in range(4) for b in range(a + 1, 4))
         assert max(abs(1 - x) for x in d2[:4]) < 1e-6
+    return tetramer_check.check_against_independent_minimum(got, d, f0, image, pos_tol)
 
 
 @pytest.mark.parametrize("precision", ["float32", "float64"])
@@ -92,7 +98,8 @@ def test_cuda_tetramer2d(precision):
     import clustertracking_b200 as ctb
     d = golden_io.load("refine_tetramer2d_constrained")
     f0, reader, diameter, kwargs = golden_io.refine_inputs(d, ctb.constraints)
-    check_tetramer2d(ctb.refine_leastsq(f0, reader, diameter, precision=precision, **kwargs), d)
+    got = ctb.refine_leastsq(f0.copy(), reader, diameter, precision=precision, **kwargs)
+    check_tetramer2d(got, d, f0, np.asarray(reader), 1e-6 if precision == 'float64' else 2e-5)
 
 
 @pytest.mark.parametrize("precision", ["float32", "float64"])
@@ -120,29 +127,3 @@ def test_cuda_ring_disc_basins(name, precision):
         warnings.simplefilter("ignore")
         got = ctb.refine_leastsq(f0, reader, diameter, precision=precision, **kwargs)
     check_basins(got, d)
-
-
-THREAD_CASES = ["refine_gauss2d_isolated", "refine_gauss2d_clusters", "refine_gauss2d_integer_start",
-                "refine_gauss2d_overlap_7px", "refine_gauss2d_video", "refine_failure_rms",
-                "refine_dimer2d_free", "refine_trimer2d_free"]
-
-
-@pytest.mark.parametrize("precision", ["float32", "float64"])
-@pytest.mark.parametrize("name", THREAD_CASES)
-def test_thread_per_cluster_kernel_matches_reference_golden(name, precision, monkeypatch):
-    """The opt-in thread-per-cluster kernel (csrc/ctk_thread.cuh, CTK_THREAD_KERNEL=1) on the cases
-    it takes: default 2D gauss model, clusters of up to 8 features; larger ones overflow to the warp
-    kernel through the device-side list."""
-    import clustertracking_b200 as ctb
-    from clustertracking_b200 import _lib
-    monkeypatch.setenv("CTK_THREAD_KERNEL", "1")
-    d = golden_io.load(name)
-    f0, reader, diameter, kwargs = golden_io.refine_inputs(d, ctb.constraints)
-    from clustertracking_b200 import refine as ctb_refine
-    plan = ctb_refine.prepare(f0.copy(), reader, diameter, precision=precision, **kwargs)
-    assert _lib.load().ctk_refine_thread_kernel(_lib.ctypes.byref(plan.problem), 8) == 1
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        got = ctb.refine_leastsq(f0, reader, diameter, precision=precision, **kwargs)
-    _compare(got, golden_io.frame(d, "ref_"), POS_TOL, REL_TOL)
-    _compare(got, golden_io.frame(d, "tight_"), POS_TOL_TIGHT, REL_TOL_TIGHT)

@@ -62,11 +62,12 @@ def test_emulated_fuzz_subset(name):
     check_basins(got, d)
 
 
-def test_emulated_tetramer2d():
+@pytest.mark.parametrize("precision", ["float32", "float64"])
+def test_emulated_tetramer2d(precision):
     d = golden_io.load("refine_tetramer2d_constrained")
     f0, reader, diameter, kwargs = golden_io.refine_inputs(d, ctb.constraints)
-    got, _ = emul_backend.refine_leastsq(f0, reader, diameter, **kwargs)
-    check_tetramer2d(got, d)
+    got, _ = emul_backend.refine_leastsq(f0.copy(), reader, diameter, precision=precision, **kwargs)
+    check_tetramer2d(got, d, f0, np.asarray(reader), 1e-6 if precision == 'float64' else 2e-5)
 
 
 def test_constraints_are_satisfied():
@@ -149,3 +150,36 @@ def test_edge_clipped_and_overlapping_masks():
     assert_array_equal(got['cluster'].values, want['cluster'].values)
     assert_allclose(got[['y', 'x']].values, want[['y', 'x']].values, atol=1e-5)
     assert_allclose(got['cost'].values, want['cost'].values, rtol=1e-6)
+
+
+def dense_cluster_case(ny, nx, pitch=4.0, seed=3):
+    """A lattice of ny x nx narrow features ``pitch`` apart, fitted with diameter 11: every mask
+    overlaps many others (more overlapping pairs than the 4 n lists the shared-memory classes
+    provision even with rigorous capacities)."""
+    import pandas as pd
+    from clustertracking_b200 import artificial
+    rng = np.random.default_rng(seed)
+    gy, gx = np.meshgrid(np.arange(ny) * pitch, np.arange(nx) * pitch, indexing='ij')
+    pos = np.stack([gy.ravel(), gx.ravel()], axis=1) + 20. + rng.uniform(-0.3, 0.3, (ny * nx, 2))
+    shape = (int(pos[:, 0].max()) + 21, int(pos[:, 1].max()) + 21)
+    image = artificial.draw_features(shape, pos, 1.5, 180., noise=2, rng=rng)
+    f0 = pd.DataFrame(pos + rng.uniform(-0.2, 0.2, pos.shape), columns=['y', 'x'])
+    f0['signal'] = 150.
+    f0['size'] = 1.5
+    return image, f0, pos
+
+
+@pytest.mark.parametrize("ny,nx", [(3, 4), (4, 4), (4, 5), (4, 7), (5, 6)])
+def test_dense_cluster_is_fitted_not_dropped(ny, nx):
+    """12-30 features with more than 4 n overlapping pairs overflowed even the rigorous
+    capacities and came back with cost = NaN where the reference fits them; they now take the
+    large-cluster path."""
+    from clustertracking_b200 import _lib, refine
+    image, f0, pos = dense_cluster_case(ny, nx)
+    plan = refine.prepare(f0.copy(), image, 11, precision='float64')
+    assert plan.n_clusters == 1 and plan.cluster_sizes()[0] == ny * nx
+    result = emul_backend.execute(plan)
+    assert result.status[0] == 0, _lib.STATUS_NAMES.get(int(result.status[0]))
+    got = refine.finalize(plan, result)
+    assert np.isfinite(got['cost'].values).all()
+    assert np.abs(got[['y', 'x']].values - pos).max() < 0.1
