@@ -4,15 +4,18 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
 
 One step = one pass of the hot path (``refine_leastsq``: cluster-level least-squares refinement) over
-one video of ``--frames`` frames of 1024x1024 uint8 with ~2100 features per frame in clusters of
-2-6 (SURVEY.md section 8d, config 2).  Weak scaling: every rank refines its own video of that size;
-frames are independent, so there is no collective on the data path (only the timing reduction).
+one video of ``--gpus x --frames`` frames of 1024x1024 uint8 with ~2100 features per frame in
+clusters of 2-6.  Weak scaling: rank r owns frames
+[r * frames, (r + 1) * frames) of that ONE video; frames are independent, so there is no collective
+on the data path.
 
   value   whole-job features/s with all inputs resident in HBM (frames, packed parameters, bounds):
           the C-ABI launches only (ctk_frame_max + ctk_refine_batch per size bin), CUDA-event timed;
-  e2e     the same metric through the public API ``clustertracking_b200.refine_leastsq(f, reader, 11)``
-          with HOST frames and a pandas DataFrame: clustering, packing, pinned staging, H2D, kernels,
-          D2H and DataFrame write-back all inside the timed region.
+  e2e     the same metric through the public API with HOST frames and a pandas DataFrame: clustering,
+          packing, pinned staging, H2D, kernels, D2H and DataFrame write-back inside the timed
+          region.  N = 1: ``clustertracking_b200.refine_leastsq(f, reader, 11)``; N > 1: the sharded
+          product path ``parallel.refine_leastsq_sharded`` on the one video (every rank passes only
+          its own rows, the merged table is gathered on rank 0 -- inside the timed region).
 
 Prints ONE JSON line on rank 0.
 """
@@ -188,7 +191,9 @@ def refine_accounting(plan, stats, ids=None):
     px = np.dtype(plan.pixel_dtype).itemsize
     evals, accums, outer = stats[:, 0], stats[:, 1], np.maximum(stats[:, 2], 1)
     M, E, Q = stats[:, 3].astype(np.float64), stats[:, 4].astype(np.float64), stats[:, 5].astype(np.float64)
-    nbytes = (M * px * outer + n * P * 8 * 4 + 8 + 4 + 32 + 8 + 4).sum()
+    # per cluster: masked pixels, parameter rows in + out (bounds come from the problem's tables,
+    # they are never materialised), offsets / frame index / counters / cost / status
+    nbytes = (M * px * outer + n * P * 8 * 2 + 8 + 4 + 32 + 8 + 4).sum()
     v = sum(1 for m in list(plan.problem.modes)[1:P] if m != 0)       # free parameters per feature
     f_val, f_der = 10., 6.
     flops = (evals * (E * f_val + 2 * M)
@@ -289,7 +294,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import clustertracking_b200 as ctb
-    from clustertracking_b200 import artificial, refine as ctb_refine
+    from clustertracking_b200 import artificial, parallel, refine as ctb_refine
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -322,49 +327,65 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # ---- inputs: rendered on the device, host copy for the end-to-end leg -------------------------
+    # ---- inputs: ONE video of world * frames frames; rank r owns frames [r * frames, (r + 1) * frames)
+    # (rendered on its device; no rank ever holds the whole video or the whole table) ----------------
     n_frames = args.frames
+    first = rank * n_frames
     pos, frame, signal, start = video_geometry(n_frames, seed=7 + rank)
     d_stack = render_video_torch(pos, frame, signal, n_frames, device, seed=100 + rank)
     torch.cuda.synchronize()
     host_stack = torch.empty(d_stack.shape, dtype=torch.uint8, pin_memory=True)
     host_stack.copy_(d_stack)
     torch.cuda.synchronize()
-    reader = artificial.FrameStack(host_stack.numpy())
-    f0 = start_dataframe(start, frame)
+    reader = artificial.FrameStack(host_stack.numpy(), first_frame=first)
+    f0 = start_dataframe(start, frame + first)
+    f0.index = f0.index + int(sum_before(len(f0), rank, world, dist, device))
     n_features = len(f0)
 
     # ---- value: everything resident in HBM, C-ABI launches only ----------------------------------
-    plan = ctb_refine.prepare(f0.copy(), reader, DIAMETER, precision=args.precision)
-    session = ctb_refine.DeviceSession(plan, device)
-    session.frames.register(d_stack, 0)                 # frames are already resident
-    slices = session.schedule()                         # every size class once
+    def resident(precision, steps, warmup):
+        plan = ctb_refine.prepare(f0.copy(), reader, DIAMETER, precision=precision)
+        session = ctb_refine.DeviceSession(plan, device)
+        session.frames.register(d_stack, 0)                 # frames are already resident
+        slices = session.schedule()                         # every size class once
 
-    def one_step(events=None):
-        session.frames.launch_frame_max(0, n_frames, events)
-        session.run(slices, events)
+        def one_step(events=None):
+            session.frames.launch_frame_max(0, n_frames, events)
+            session.run(slices, events)
 
-    for _ in range(max(3, args.warmup)):
-        one_step()
-    torch.cuda.synchronize()
-    stats = session.d_stats.cpu().numpy()
-    status = session.d_status.cpu().numpy()
+        for _ in range(max(3, warmup)):
+            one_step()
+        torch.cuda.synchronize()
+        stats = session.d_stats.cpu().numpy()
+        status = session.d_status.cpu().numpy()
+        launches0 = session.launches + session.frames.launches
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        events = []
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            one_step(events)
+        ev1.record()
+        barrier()
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
+        launches = session.launches + session.frames.launches - launches0
+        return dict(plan=plan, session=session, slices=slices, stats=stats, status=status, ms=ms,
+                    events=events, launches=launches, steps=steps)
+
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = session.launches + session.frames.launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_events = []
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        one_step(kernel_events)
-    ev1.record()
-    barrier()
-    resident_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    run = resident(args.precision, args.steps, args.warmup)
     clocks = sampler.stop()
-    gpu_launches = session.launches + session.frames.launches - launches0
+    plan, session, slices, stats, status = (run[k] for k in ("plan", "session", "slices", "stats", "status"))
+    resident_ms, kernel_events, gpu_launches = run["ms"], run["events"], run["launches"]
     total_features = sum_over_ranks(n_features)
     value = total_features * args.steps / (resident_ms * 1e-3)
+
+    # the reference's own arithmetic (everything float64) beside the float32 headline
+    other = "float64" if args.precision == "float32" else "float32"
+    run2 = resident(other, max(1, min(args.steps, 3)), 3)
+    value_other = total_features * run2["steps"] / (run2["ms"] * 1e-3)
+    del run2["session"]
 
     # kernel-level durations of the refine launches (same timed region, same stream)
     refine_ms = sum(a.elapsed_time(b) for kind, a, b, _ in kernel_events if kind == "refine") / args.steps
@@ -373,82 +394,129 @@ def run_ours(args):
     peaks = measured_peaks()
     sms = torch.cuda.get_device_properties(device).multi_processor_count
     fp32_peak = sms * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
-    # the dominant launch: the size class with the longest launch.  Launch order inside a step
-    # (DeviceSession.run): per class its main launch, then (classes below 32) its overflow relaunch.
-    refine_events = [(a, b) for kind, a, b, _ in kernel_events if kind == "refine"]
-    per_step = len(refine_events) // args.steps
-    order = []
-    for cap, start_, count in slices:
-        order.append((cap, start_, count, True))
-        if cap in session.overflow_at and cap < 32:
-            order.append((cap, start_, count, False))
+    # the dominant launch: the (size class, kind) whose launches take the longest per step
+    by_label = {}
+    for kind, a, b, label in kernel_events:
+        if kind == "refine":
+            by_label[label] = by_label.get(label, 0.) + a.elapsed_time(b) / args.steps
+    dom_label = max(by_label, key=by_label.get)
     dominant = None
-    if len(order) == per_step:
-        durations = np.zeros(per_step)
-        for k, (a, b) in enumerate(refine_events):
-            durations[k % per_step] += a.elapsed_time(b) / args.steps
-        k_dom = int(np.argmax(durations))
-        cap, start_, count, _ = order[k_dom]
+    if dom_label[1] == "main":
+        cap, start_, count = next(s for s in slices if s[0] == dom_label[0])
         ids = session.d_work[start_:start_ + count].cpu().numpy()
-        sub_bytes, _ = refine_accounting(plan, stats, ids)
-        dominant = dict(cap=int(cap), clusters=int(count), ms=float(durations[k_dom]), nbytes=sub_bytes)
+        sub_bytes, sub_flops = refine_accounting(plan, stats, ids)
+        dominant = dict(cap=int(cap), clusters=int(count), ms=float(by_label[dom_label]),
+                        nbytes=sub_bytes, flops=sub_flops)
     traffic, traffic_source = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if dominant is not None and os.path.exists(tpath):
-        with open(tpath) as fh:
+    for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
+        if dominant is None or not (name.startswith("r0") and name.endswith("_traffic.json")):
+            continue
+        with open(os.path.join(ROOT, "profiles", name)) as fh:
             t = json.load(fh)
         if (t.get("frames_per_gpu") == n_frames and t.get("max_cluster_features") == dominant["cap"]
                 and t.get("precision") == args.precision):
             traffic = int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
-            traffic_source = "profiles/r01_traffic.json (ncu --set full capture of this launch)"
+            traffic_source = "profiles/%s (ncu --set full capture of this launch)" % name
+            break
+    peak_fp32_source = ("%d SMs x 128 lanes x 2 x %.0f MHz (sm_max_mhz, %s; MEASURED_PEAKS.json has no "
+                        "FP32 figure)" % (sms, peaks["sm_max_mhz"], peaks["source"]))
     if dominant is not None:
-        roofline = dict(bound="hbm",
-                        kernel="refine_kernel, launch of the size class up to %d features (%d clusters, "
-                               "%.0f %% of the step)" % (dominant["cap"], dominant["clusters"],
-                                                         100. * dominant["ms"] / (refine_ms + fmax_ms)),
-                        achieved=dominant["nbytes"] / (dominant["ms"] * 1e-3) / 1e9, peak=peaks["hbm_gbs"],
-                        unit="GB/s", traffic=traffic, traffic_source=traffic_source,
-                        peak_source=peaks["source"], ms_per_launch=dominant["ms"],
-                        algorithmic_bytes_per_launch=dominant["nbytes"],
+        share = 100. * dominant["ms"] / (refine_ms + fmax_ms)
+        kernel = ("refine_kernel, launch of the size class up to %d features (%d clusters, %.0f %% of "
+                  "the step)" % (dominant["cap"], dominant["clusters"], share))
+        # the BINDING bound of this kernel is FP32 issue, not HBM (arithmetic intensity ~1e2 flop/B)
+        roofline = dict(bound="fp32", kernel=kernel,
+                        achieved=dominant["flops"] / (dominant["ms"] * 1e-3) / 1e12, peak=fp32_peak,
+                        unit="TFLOP/s", peak_source=peak_fp32_source, ms_per_launch=dominant["ms"],
+                        algorithmic_flops_per_launch=dominant["flops"],
+                        traffic=traffic, traffic_source=traffic_source,
                         all_refine_launches=dict(ms_per_step=refine_ms,
-                                                 achieved=nbytes / (refine_ms * 1e-3) / 1e9,
-                                                 algorithmic_bytes_per_feature=nbytes / n_features))
+                                                 achieved=flops / (refine_ms * 1e-3) / 1e12,
+                                                 algorithmic_flops_per_feature=flops / n_features))
+        roofline_hbm = dict(bound="hbm", kernel=kernel,
+                            achieved=dominant["nbytes"] / (dominant["ms"] * 1e-3) / 1e9,
+                            peak=peaks["hbm_gbs"], unit="GB/s", traffic=traffic,
+                            traffic_source=traffic_source, peak_source=peaks["source"],
+                            ms_per_launch=dominant["ms"],
+                            algorithmic_bytes_per_launch=dominant["nbytes"],
+                            all_refine_launches=dict(ms_per_step=refine_ms,
+                                                     achieved=nbytes / (refine_ms * 1e-3) / 1e9,
+                                                     algorithmic_bytes_per_feature=nbytes / n_features))
     else:
-        roofline = dict(bound="hbm", kernel="refine_kernel (all size bins of one step)",
-                        achieved=nbytes / (refine_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
-                        traffic=None, peak_source=peaks["source"], ms_per_step=refine_ms,
-                        algorithmic_bytes_per_feature=nbytes / n_features)
+        kernel = "refine_kernel (all size classes of one step)"
+        roofline = dict(bound="fp32", kernel=kernel, achieved=flops / (refine_ms * 1e-3) / 1e12,
+                        peak=fp32_peak, unit="TFLOP/s", peak_source=peak_fp32_source,
+                        ms_per_step=refine_ms, traffic=None,
+                        algorithmic_flops_per_feature=flops / n_features)
+        roofline_hbm = dict(bound="hbm", kernel=kernel, achieved=nbytes / (refine_ms * 1e-3) / 1e9,
+                            peak=peaks["hbm_gbs"], unit="GB/s", traffic=None,
+                            peak_source=peaks["source"], ms_per_step=refine_ms,
+                            algorithmic_bytes_per_feature=nbytes / n_features)
     roofline["frac"] = roofline["achieved"] / roofline["peak"]
-    roofline_fp32 = dict(bound="fp32", kernel="refine_kernel", achieved=flops / (refine_ms * 1e-3) / 1e12,
-                         peak=fp32_peak, unit="TFLOP/s",
-                         peak_source="%d SMs x 128 lanes x 2 x %.0f MHz (sm_max_mhz, %s)"
-                                     % (sms, peaks["sm_max_mhz"], peaks["source"]),
-                         algorithmic_flops_per_feature=flops / n_features)
-    roofline_fp32["frac"] = roofline_fp32["achieved"] / roofline_fp32["peak"]
+    roofline_hbm["frac"] = roofline_hbm["achieved"] / roofline_hbm["peak"]
     frame_bytes = float(d_stack.numel())
     roofline_fmax = dict(bound="hbm", kernel="frame_max_kernel", achieved=frame_bytes / (fmax_ms * 1e-3) / 1e9,
                          peak=peaks["hbm_gbs"], unit="GB/s", ms_per_step=fmax_ms)
     roofline_fmax["frac"] = roofline_fmax["achieved"] / roofline_fmax["peak"]
+    del run["session"], session
 
     # ---- e2e: public API, host frames and DataFrame, copies inside the timed region -----------------
-    e2e_times = []
-    out = None
-    for step in range(args.warmup + args.steps):
-        barrier()
-        t0 = time.perf_counter()
-        out = ctb.refine_leastsq(f0, reader, DIAMETER, precision=args.precision)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        dt = max_over_ranks(dt)
-        if step >= args.warmup:
-            e2e_times.append(dt)
-    e2e_s = sum(e2e_times)
-    info = ctb_refine.LAST_CALL
+    def call_api(table, rd):
+        """One end-to-end pass.  N = 1: refine_leastsq.  N > 1: the product's sharded path on ONE
+        video -- every rank passes only ITS frames, the merged table is gathered on rank 0."""
+        if world == 1:
+            return ctb.refine_leastsq(table, rd, DIAMETER, precision=args.precision)
+        return parallel.refine_leastsq_sharded(table, rd, DIAMETER, presharded=True, gather='root',
+                                               precision=args.precision)
+
+    def time_api(table, rd, steps, warmup):
+        times, out = [], None
+        for step in range(warmup + steps):
+            out = None
+            barrier()
+            t0 = time.perf_counter()
+            out = call_api(table, rd)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            if step >= warmup:
+                times.append(dt)
+        return sum(times), out
+
+    e2e_s, out = time_api(f0, reader, args.steps, args.warmup)
+    info = dict(ctb_refine.LAST_CALL)
+    h2d, d2h = sum_over_ranks(info["h2d_bytes"]), sum_over_ranks(info["d2h_bytes"])
+    api = ("clustertracking_b200.refine_leastsq(DataFrame, FrameStack(pinned host uint8), 11)" if world == 1 else
+           "clustertracking_b200.parallel.refine_leastsq_sharded(this rank's rows of ONE %d-frame video, "
+           "FrameStack(pinned host uint8), 11, presharded=True, gather='root'): frames sharded over %d "
+           "ranks, merged DataFrame on rank 0, gather inside the timed region"
+           % (n_frames * world, world))
     e2e = dict(value=total_features * args.steps / e2e_s, unit="features/s",
-               h2d_bytes_per_step=int(info["h2d_bytes"]), d2h_bytes_per_step=int(info["d2h_bytes"]),
-               ms_per_step=1e3 * e2e_s / args.steps,
-               api="clustertracking_b200.refine_leastsq(DataFrame, FrameStack(host uint8), 11)",
-               host_ms=info.get("phases_ms"))
+               h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+               ms_per_step=1e3 * e2e_s / args.steps, api=api, host_ms=info.get("phases_ms"))
+    if world > 1 and rank == 0:
+        assert out is not None and len(out) == int(total_features)
+        assert np.all(np.diff(out['frame'].values) >= 0)
+    out_first = out if world == 1 else None
+    if world > 1:
+        # strong scaling: ONE video of `frames` frames over all ranks (frames / N each)
+        share = max(1, n_frames // world)
+        sel = f0['frame'].values < first + share
+        f_strong = f0[sel]
+        strong_s, _ = time_api(f_strong, reader, max(2, args.steps // 2), 2)
+        strong_features = sum_over_ranks(int(sel.sum()))
+        e2e["strong"] = dict(value=strong_features * max(2, args.steps // 2) / strong_s, unit="features/s",
+                             ms_per_step=1e3 * strong_s / max(2, args.steps // 2),
+                             frames_total=share * world,
+                             what="the same call on ONE video of %d frames, %d per rank"
+                                  % (share * world, share))
+    else:
+        # the same call from a PAGEABLE numpy stack (what a user who never heard of pinned memory has)
+        pageable = artificial.FrameStack(np.array(host_stack.numpy(), copy=True), first_frame=first)
+        page_s, _ = time_api(f0, pageable, max(2, args.steps // 2), 2)
+        e2e["pageable"] = dict(value=total_features * max(2, args.steps // 2) / page_s, unit="features/s",
+                               ms_per_step=1e3 * page_s / max(2, args.steps // 2),
+                               what="the same call with the frames in pageable host memory")
+        del pageable
 
     # ---- cpu_baseline (rank 0, N=1 only) and parity on the same sample ------------------------------
     cpu_baseline, parity = None, None
@@ -466,41 +534,67 @@ def run_ours(args):
         cpu_baseline = dict(value=len(sub) / dt, unit="features/s", cores=1, kind="port",
                             sample="first %d frames of the same video (%d features), oracle port "
                                    "(scipy SLSQP) on 1 thread, %.1f s" % (k, len(sub), dt))
-        got = out[out['frame'].values < k]
-        assert np.array_equal(got.index.values, want.index.values)
-        both = ~np.isnan(got['cost'].values) & ~np.isnan(want['cost'].values)
-        parity = dict(
-            sample_features=int(len(sub)),
-            cluster_membership_identical=bool(np.array_equal(got['cluster'].values, want['cluster'].values)),
-            failures_ours=int(np.isnan(got['cost'].values).sum()),
-            failures_oracle=int(np.isnan(want['cost'].values).sum()),
-            max_abs_dpos_px=float(np.abs(got[['y', 'x']].values[both] - want[['y', 'x']].values[both]).max()),
-            max_rel_dsignal=float(np.abs(got['signal'].values[both] / want['signal'].values[both] - 1).max()),
-            max_abs_dcost=float(np.abs(got['cost'].values[both] - want['cost'].values[both]).max()))
+
+        def compare(got):
+            assert np.array_equal(got.index.values, want.index.values)
+            both = ~np.isnan(got['cost'].values) & ~np.isnan(want['cost'].values)
+            return dict(
+                sample_features=int(len(sub)),
+                cluster_membership_identical=bool(np.array_equal(got['cluster'].values, want['cluster'].values)),
+                failures_ours=int(np.isnan(got['cost'].values).sum()),
+                failures_oracle=int(np.isnan(want['cost'].values).sum()),
+                max_abs_dpos_px=float(np.abs(got[['y', 'x']].values[both] - want[['y', 'x']].values[both]).max()),
+                max_rel_dsignal=float(np.abs(got['signal'].values[both] / want['signal'].values[both] - 1).max()),
+                max_abs_dcost=float(np.abs(got['cost'].values[both] - want['cost'].values[both]).max()))
+
+        parity = {args.precision: compare(out_first[out_first['frame'].values < k])}
+        parity[other] = compare(ctb.refine_leastsq(sub.copy(), sub_reader, DIAMETER, precision=other))
 
     if rank == 0:
         ok = status == 0
+        f32 = args.precision == "float32"
         line = dict(
             metric="features_refined_per_sec", value=value, unit="features/s", n_gpus=args.gpus,
             steps=args.steps, warmup=max(3, args.warmup), ms_per_step=resident_ms / args.steps,
             higher_is_better=True, scaling="weak", vs_baseline=None,
-            dtype="f32" if args.precision == "float32" else "f64", data="synthetic",
+            dtype="f32" if f32 else "f64", data="synthetic",
             config=dict(workload=WORKLOAD % n_frames, frames_per_gpu=n_frames,
+                        video="one video of %d frames, %d per GPU" % (n_frames * world, n_frames),
                         features_per_gpu=int(n_features), clusters_per_gpu=int(plan.n_clusters),
                         l2="inputs larger than L2: %.2f GB of frames per GPU vs 126 MB"
                            % (frame_bytes / 1e9) if frame_bytes > 2.6e8 else
                            "WARNING: inputs (%.0f MB) not larger than L2" % (frame_bytes / 1e6),
-                        pixel_arithmetic=args.precision, normal_equations="float64",
+                        pixel_arithmetic=args.precision,
+                        normal_equations=("J^T J, its Cholesky factor and the model values float32; "
+                                          "J^T r, parameters, bounds and the objective float64" if f32
+                                          else "float64 throughout"),
                         converged_clusters=int(ok.sum()), failed_clusters=int((~ok).sum()),
                         mean_evaluations_per_cluster=float(stats[:, 0].mean()),
                         mean_outer_iterations=float(stats[:, 2].mean()),
                         mean_union_pixels=float(stats[:, 3].mean())),
             clocks=clocks, e2e=e2e, gpu_launches=int(gpu_launches),
-            roofline=roofline, roofline_fp32=roofline_fp32, roofline_frame_max=roofline_fmax,
+            roofline=roofline, roofline_hbm=roofline_hbm, roofline_frame_max=roofline_fmax,
             cpu_baseline=cpu_baseline, parity_vs_oracle=parity)
+        line["value_" + ("f64" if f32 else "f32")] = dict(
+            value=value_other, unit="features/s", ms_per_step=run2["ms"] / run2["steps"],
+            steps=run2["steps"], pixel_arithmetic=other,
+            failed_clusters=int((run2["status"] != 0).sum()),
+            mean_evaluations_per_cluster=float(run2["stats"][:, 0].mean()),
+            what="the same resident measurement with precision=%r" % other)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sum_before(n, rank, world, dist, device):
+    """Number of rows held by the ranks before this one (so that index labels run on)."""
+    if world == 1:
+        return 0
+    import torch
+    mine = torch.tensor([n], dtype=torch.int64, device=device)
+    counts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(counts, mine)
+    return int(sum(int(c.item()) for c in counts[:rank]))
 
 
 def main():

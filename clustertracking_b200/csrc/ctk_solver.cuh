@@ -59,6 +59,8 @@
 // and lowpass paths compiled out.  They are rarely used, but inside the one big inlined kernel they
 // cost every launch instruction-cache space and registers: the lean flavour is 22 % faster on
 // config 2.  Inside ClusterSolver, CTK_NCON / CTK_LOWPASS read as compile-time zeros when lean.
+// loop of a lane over "its" unknowns: v = lane, lane + 32, ...
+#define CTK_FOR_V(v) _Pragma("unroll 1") for (int v = lane; v < V; v += CTK_WARP)
 #define CTK_NCON (C::EXTRA ? n_con : 0)
 #define CTK_LOWPASS (C::EXTRA && a.prob.lowpass)
 
@@ -463,9 +465,6 @@ struct ClusterSolver {
   }
 
   // pixel values are staged in shared memory in their native width
-  template <class T> CTK_DEV static void copy_px(const void* src, int64_t i, void* dst, int p) {
-    reinterpret_cast<T*>(dst)[p] = reinterpret_cast<const T*>(src)[i];
-  }
   // type of the staged values: the frame's own, or the arithmetic type when they are filtered
   CTK_DEV int staged_dtype() const {
     return CTK_LOWPASS ? (sizeof(Real) == 4 ? CTK_PIXEL_F32 : CTK_PIXEL_F64) : a.prob.pixel_dtype;
@@ -509,17 +508,29 @@ struct ClusterSolver {
     }
     return acc2 > a.prob.lowpass_threshold ? acc2 : 0.;
   }
-  CTK_DEV void stage_pixel(int64_t idx, int p, const int (&c)[3]) const {
+  // The pixel of a box position is FETCHED at the top of the box walk (bits of its native width in
+  // a 64-bit register) and STORED after the coverage tests, so that the global-memory latency hides
+  // behind them instead of stalling the warp once per 32 box pixels (7 % of all stall samples).
+  CTK_DEV uint64_t fetch_pixel(int64_t idx) const {
+    if (CTK_LOWPASS) return 0;
+    switch (a.prob.pixel_dtype) {
+      case CTK_PIXEL_U8: return reinterpret_cast<const uint8_t*>(frame)[idx];
+      case CTK_PIXEL_U16: case CTK_PIXEL_I16: return reinterpret_cast<const uint16_t*>(frame)[idx];
+      case CTK_PIXEL_F64: return reinterpret_cast<const uint64_t*>(frame)[idx];
+      default: return reinterpret_cast<const uint32_t*>(frame)[idx];
+    }
+  }
+  CTK_DEV void stage_pixel(uint64_t raw, int p, const int (&c)[3]) const {
     void* dst = slice() + a.lay.o_pval;
     if (CTK_LOWPASS) {
       reinterpret_cast<Real*>(dst)[p] = (Real) lowpass_value(c);
       return;
     }
     switch (a.prob.pixel_dtype) {
-      case CTK_PIXEL_U8: copy_px<uint8_t>(frame, idx, dst, p); break;
-      case CTK_PIXEL_U16: case CTK_PIXEL_I16: copy_px<uint16_t>(frame, idx, dst, p); break;
-      case CTK_PIXEL_F64: copy_px<double>(frame, idx, dst, p); break;
-      default: copy_px<uint32_t>(frame, idx, dst, p); break;
+      case CTK_PIXEL_U8: reinterpret_cast<uint8_t*>(dst)[p] = (uint8_t) raw; break;
+      case CTK_PIXEL_U16: case CTK_PIXEL_I16: reinterpret_cast<uint16_t*>(dst)[p] = (uint16_t) raw; break;
+      case CTK_PIXEL_F64: reinterpret_cast<uint64_t*>(dst)[p] = raw; break;
+      default: reinterpret_cast<uint32_t*>(dst)[p] = (uint32_t) raw; break;
     }
   }
   CTK_DEV Real pixel_value(int p) const {
@@ -631,8 +642,7 @@ struct ClusterSolver {
     }
     warp_sync();
     bad = false;
-#pragma unroll 1
-    for (int v2 = lane; v2 < V; v2 += CTK_WARP) {
+    CTK_FOR_V(v2) {
       bad |= !(lo[v2] <= hi[v2]);
       x0[v2] = fmin(fmax(x0[v2], lo[v2]), hi[v2]);     // scipy clips the start into the box
     }
@@ -781,10 +791,15 @@ struct ClusterSolver {
       int q = q0 + lane;
       uint32_t bits = 0u;            // the mask itself (one word), or "any word set" (BIG)
       int c[3] = {0, 0, 0};
+      uint64_t raw = 0;
       if (q < itotal) {
         int rem = q;
 #pragma unroll
         for (int k = ND - 1; k >= 0; --k) { c[k] = rem % bdim[k]; rem /= bdim[k]; }
+        int64_t gi = 0;
+#pragma unroll
+        for (int k = 0; k < ND; ++k) gi = gi * a.shape[k] + (blo[k] + c[k]);
+        raw = fetch_pixel(gi);
         if (!C::BIG) {
           for (int i = 0; i < n; ++i)
             if (covers(i, c, fi, tab)) bits |= (1u << i);
@@ -803,10 +818,7 @@ struct ClusterSolver {
       if (bits != 0u) {
         int pos = count + popc(ball & lanemask_lt());
         if (pos < a.lay.m_cap) {
-          int64_t gi = 0;
-#pragma unroll
-          for (int k = 0; k < ND; ++k) gi = gi * a.shape[k] + (blo[k] + c[k]);
-          stage_pixel(gi, pos, c);
+          stage_pixel(raw, pos, c);
           if (!C::BIG) {
             pbits[pos] = bits;
             pcrd[pos] = (uint32_t) c[0] | ((uint32_t) c[1] << 10) | ((uint32_t) c[2] << 20);
@@ -821,21 +833,29 @@ struct ClusterSolver {
     M = count;
     if (M > a.lay.m_cap || M == 0) return M == 0 ? CTK_FAIL_OUT_OF_IMAGE : CTK_FAIL_TOO_LARGE;
     warp_sync();
-    // per-feature pixel lists, in union order
+    // Per-feature pixel lists, in union order, and -- feature by feature -- the lists of the pixels
+    // a feature shares with every earlier one: entries (t_i | t_j << 16) grouped per pair.  While
+    // feature j's list is written, the position t_j of every pixel in it goes to a per-pixel rank
+    // array (in the model-value cache, unused until the first evaluate()), so that a shared pixel
+    // found through feature i's list gets its t_j by one load instead of a binary search.
     Entry* flist = FLIST();
-    bool overflow = false;
-    for (int i = 0; i < n; ++i) {
-      const int* f = fi + i * FI_STRIDE;
+    uint16_t* rank = reinterpret_cast<uint16_t*>(FE());
+    uint32_t* pairs = PAIRS();
+    int* phdr = PHDR();
+    int np = 0, ptotal = 0;
+    for (int j = 0; j < n; ++j) {
+      const int* f_j = fi + j * FI_STRIDE;
       int oc[3];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) oc[k] = (k < ND) ? f[FI_CI + k] - blo[k] : 0;
-      int cnt = 0;
+      for (int k = 0; k < 3; ++k) oc[k] = (k < ND) ? f_j[FI_CI + k] - blo[k] : 0;
+      int cnt_j = 0;
       for (int p0 = 0; p0 < M; p0 += CTK_WARP) {
         int p = p0 + lane;
-        bool has = (p < M) && covered(pbits, p, i, nw);
+        bool has = (p < M) && covered(pbits, p, j, nw);
         uint32_t ball = ballot(has);
         if (has) {
-          int t = cnt + popc(ball & lanemask_lt());
+          int t = cnt_j + popc(ball & lanemask_lt());
+          rank[p] = (uint16_t) t;
           if (t < a.lay.f_cap) {
             uint32_t crd = pcrd[p];
             int o[3] = {0, 0, 0};
@@ -847,51 +867,36 @@ struct ClusterSolver {
 #pragma unroll
               for (int k = ND - 1; k >= 0; --k) { o[k] = rem % bdim[k]; rem /= bdim[k]; }
             }
-            store_entry(flist + (size_t) i * a.lay.f_cap + t, p, o[0] - oc[0],
+            store_entry(flist + (size_t) j * a.lay.f_cap + t, p, o[0] - oc[0],
                         ND > 1 ? o[1] - oc[1] : 0, ND > 2 ? o[2] - oc[2] : 0);
           }
         }
-        cnt += popc(ball);
+        cnt_j += popc(ball);
       }
-      if (lane == 0) fi[i * FI_STRIDE + FI_CNT] = cnt;
-      overflow |= cnt > a.lay.f_cap;
-    }
-    if (overflow) return CTK_FAIL_TOO_LARGE;
-    warp_sync();
-    // pixels shared by two features: entries (t_i | t_j << 16) grouped per pair
-    uint32_t* pairs = PAIRS();
-    int* phdr = PHDR();
-    int np = 0, ptotal = 0;
-    for (int i = 0; i < n - 1; ++i) {
-      const int* f_i = fi + i * FI_STRIDE;
-      const int cnt_i = f_i[FI_CNT];
-      for (int j = i + 1; j < n; ++j) {
-        const int* f_j = fi + j * FI_STRIDE;
+      if (lane == 0) fi[j * FI_STRIDE + FI_CNT] = cnt_j;
+      if (cnt_j > a.lay.f_cap) return CTK_FAIL_TOO_LARGE;
+      warp_sync();
+      for (int i = 0; i < j; ++i) {
+        const int* f_i = fi + i * FI_STRIDE;
         bool apart = false;
 #pragma unroll
         for (int k = 0; k < ND; ++k)
           apart |= abs(f_i[FI_CI + k] - f_j[FI_CI + k]) > 2 * a.prob.radius[k] + 2;
         if (apart) continue;
-        const int cnt_j = f_j[FI_CNT];
-        const Entry* fl_j = flist + j * a.lay.f_cap;
+        const int cnt_i = f_i[FI_CNT];
         int cnt = 0;
         for (int t0 = 0; t0 < cnt_i; t0 += CTK_WARP) {
           int t = t0 + lane;
-          int p = -1;
+          int p = 0;
           bool has = false;
           if (t < cnt_i) {
-            p = entry_pixel(flist[i * a.lay.f_cap + t]);
+            p = entry_pixel(flist[(size_t) i * a.lay.f_cap + t]);
             has = covered(pbits, p, j, nw);
           }
           uint32_t ball = ballot(has);
           if (has) {
-            int lo_ = 0, hi_ = cnt_j;            // lower bound of p in feature j's (sorted) list
-            while (lo_ < hi_) {
-              int mid = (lo_ + hi_) >> 1;
-              if (entry_pixel(fl_j[mid]) < p) lo_ = mid + 1; else hi_ = mid;
-            }
             int pos = ptotal + cnt + popc(ball & lanemask_lt());
-            if (pos < a.lay.pair_cap) pairs[pos] = (uint32_t) t | ((uint32_t) lo_ << 16);
+            if (pos < a.lay.pair_cap) pairs[pos] = (uint32_t) t | ((uint32_t) rank[p] << 16);
           }
           cnt += popc(ball);
         }
@@ -905,6 +910,7 @@ struct ClusterSolver {
           ptotal += cnt;
         }
       }
+      warp_sync();                       // the rank array is rewritten by the next feature
     }
     npairs = np;
     n_pair_entries = ptotal;
@@ -1171,8 +1177,7 @@ struct ClusterSolver {
     double* rhs = RHS();
     const int nt = CS()[V];
     if (!grad_only) for (int t = lane; t < nt; t += CTK_WARP) H[t] = 0;
-#pragma unroll 1
-    for (int v = lane; v < V; v += CTK_WARP) rhs[v] = 0.;
+    CTK_FOR_V(v) rhs[v] = 0.;
     warp_sync();
     const int* cv = CV();
     const int vb = cv[0];
@@ -1416,8 +1421,7 @@ struct ClusterSolver {
       const int r = rc_row(rc[t]), c = rc_col(rc[t]);
       acc -= (r == c ? 0.5 : 1.) * (double) H[t] * s[r] * s[c];
     }
-#pragma unroll 1
-    for (int u = lane; u < V; u += CTK_WARP) acc += s[u] * rhs_full[u];
+    CTK_FOR_V(u) acc += s[u] * rhs_full[u];
     acc = warp_sum(acc);
     // constraint rows: the gradient part is already in rhs_full; add -0.5 w (A s)^2
     if (CTK_NCON > 0) acc += con_quadratic(con_view(X()), s);
@@ -1448,8 +1452,7 @@ struct ClusterSolver {
     double* rhs_full = dvec(a.lay.o_rhsf);            // rhs incl. constraint terms, before freezing
     double lambda = 1e-3, nu = 2.;
     if (lane == 0) for (int j = 0; j < 6; ++j) CON()[j] = 0.;
-#pragma unroll 1
-    for (int v = lane; v < V; v += CTK_WARP) xt[v] = x[v];
+    CTK_FOR_V(v) xt[v] = x[v];
     warp_sync();
     pen_w = 0.;
     double pen_w0 = 0.;
@@ -1469,6 +1472,12 @@ struct ClusterSolver {
     newton = false;
     bool newton_allowed = C::FAM == CTK_FAMILY_GAUSS;
     for (int it = 0; it <= a.prob.lm_max_iter; ++it) {
+#ifndef CTK_EMUL
+      // keep the flag opaque: knowing its value on the back edges, the compiler threads those
+      // jumps and duplicates the whole tail of the loop (solve, predicted) -- 30 KB of code in a
+      // kernel that is bound by instruction fetch
+      { int flag = need_eval ? 1 : 0; asm volatile("" : "+r"(flag)); need_eval = flag != 0; }
+#endif
       if (need_eval) {
         const double fdt = evaluate(xt);
         const double fat = fdt + (first ? 0. : penalty(xt));
@@ -1507,8 +1516,7 @@ struct ClusterSolver {
             if (chord_next) {
               // the step from the stale matrix failed: rebuild everything at x (the caches hold the
               // rejected point, so x is evaluated again)
-#pragma unroll 1
-              for (int v = lane; v < V; v += CTK_WARP) xt[v] = x[v];
+              CTK_FOR_V(v) xt[v] = x[v];
               warp_sync();
               force = true;
               chord_next = false;
@@ -1517,8 +1525,7 @@ struct ClusterSolver {
           }
         }
         if (accept) {
-#pragma unroll 1
-          for (int v = lane; v < V; v += CTK_WARP) x[v] = xt[v];
+          CTK_FOR_V(v) x[v] = xt[v];
           warp_sync();
           fd = fdt;
           fa = fat;
@@ -1529,8 +1536,7 @@ struct ClusterSolver {
           if (first && CTK_NCON > 0) {
             // penalty weight relative to the curvature of the data term in the position variables
             double hmax = 0.;
-#pragma unroll 1
-            for (int v = lane; v < V; v += CTK_WARP)
+            CTK_FOR_V(v)
               if (is_pos_var(v)) hmax = fmax(hmax, (double) Hm()[CS()[v]]);
             hmax = warp_max_d(hmax);
             double a2 = 0.;
@@ -1549,8 +1555,7 @@ struct ClusterSolver {
           // the corrected matrix is not positive definite here: back to Gauss-Newton at x
           newton = false;
           newton_allowed = false;
-#pragma unroll 1
-          for (int v = lane; v < V; v += CTK_WARP) xt[v] = x[v];
+          CTK_FOR_V(v) xt[v] = x[v];
           warp_sync();
           force = true;
           chord_next = false;
@@ -1563,8 +1568,7 @@ struct ClusterSolver {
       }
       // trial point, projected on the box
       worst = 0.;
-#pragma unroll 1
-      for (int v = lane; v < V; v += CTK_WARP) {
+      CTK_FOR_V(v) {
         const double t = fmin(fmax(x[v] + d[v], LO()[v]), HI()[v]);
         xt[v] = t;
         const double s = t - x[v];
@@ -1586,8 +1590,7 @@ struct ClusterSolver {
         if (CTK_NCON == 0) { *f_data = fd; return CTK_OK; }
         // take the (sub-tolerance) step: it carries the Newton correction towards c(x) = 0; the
         // data term is flat at this scale, so its caches stay valid
-#pragma unroll 1
-        for (int v = lane; v < V; v += CTK_WARP) x[v] = xt[v];
+        CTK_FOR_V(v) x[v] = xt[v];
         warp_sync();
         const double cv = con_violation(x);
         if (cv <= ctol || al_rounds >= 40 || (al_rounds > 2 && cv >= 0.5 * c_prev && cv <= 1e-6)) {
@@ -1642,8 +1645,7 @@ struct ClusterSolver {
   CTK_DEV bool apply_probe(int q) {
     double *x = X();
     const double *xb = XB(), *lo = LO(), *hi = HI();
-#pragma unroll 1
-    for (int v = lane; v < V; v += CTK_WARP) x[v] = xb[v];
+    CTK_FOR_V(v) x[v] = xb[v];
     warp_sync();
     bool ok = false;
     if (q < 4 * ND * n) {
@@ -1728,8 +1730,7 @@ struct ClusterSolver {
     for (int k = 0; k < total; ++k) {
       bool go = true;
       if (k == 0) {
-#pragma unroll 1
-        for (int v = lane; v < V; v += CTK_WARP) X()[v] = X0()[v];
+        CTK_FOR_V(v) X()[v] = X0()[v];
         warp_sync();
       } else {
         go = apply_probe((k - 1) % n_probe);
@@ -1744,8 +1745,7 @@ struct ClusterSolver {
         if (st == CTK_OK && (k == 0 || fd < best * (1. - 1e-9))) {
           best = fd;
           improved = k > 0;
-#pragma unroll 1
-          for (int v = lane; v < V; v += CTK_WARP) XB()[v] = X()[v];
+          CTK_FOR_V(v) XB()[v] = X()[v];
           warp_sync();
         }
       }
@@ -1754,8 +1754,7 @@ struct ClusterSolver {
         improved = false;
       }
     }
-#pragma unroll 1
-    for (int v = lane; v < V; v += CTK_WARP) X()[v] = XB()[v];
+    CTK_FOR_V(v) X()[v] = XB()[v];
     warp_sync();
     *f_data = best;
     return status;
@@ -1815,7 +1814,13 @@ struct ClusterSolver {
         ++outers;
         status = build_pixels();
         if (status != CTK_OK) break;
-        status = search(&fd);                  // restarts from X0, refine.py:361-365
+        if (C::FAM == CTK_FAMILY_GAUSS) {      // smooth objective: one minimisation, no basin search
+          CTK_FOR_V(v) X()[v] = X0()[v];       // restarts from X0, refine.py:361-365
+          warp_sync();
+          status = minimise(&fd);
+        } else {
+          status = search(&fd);
+        }
         if (status != CTK_OK) break;
         // accept when every feature stayed within max_shift of its mask centre, refine.py:383-385
         bool moved = false;

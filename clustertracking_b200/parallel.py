@@ -2,10 +2,22 @@
 
 At cluster level every (frame, cluster) group of the reference's loop is an independent problem
 (refine.py:333-343), so the path shards by frames with NO collective on the data path: each rank
-refines a contiguous block of frames on its own GPU.  Only the small result tables are gathered on
-the host at the end (``all_gather_object``), and the per-shard cluster ids are shifted so that they
-equal the running ids the reference assigns over the whole video (find.py:120-129).
+refines a contiguous block of frames on its own GPU.  What remains is the reference's "one table
+out" (find.py:157-158 concatenates the per-frame tables):
+
+* the running cluster ids (find.py:120-129) need one number per rank -- how many ids the ranks
+  before it used -- which travels in a 2-element ``all_gather``;
+* the result tables are gathered WITHOUT pickling: on one host (the case this repository is built
+  for: 8 GPUs of one box) every rank writes its columns straight into its slice of one shared-memory
+  block (``/dev/shm``) and the receiving rank(s) build the DataFrame over that block without a copy;
+  across hosts the same packed blocks (one float64 and one int64 matrix) go through
+  ``dist.gather`` / ``dist.all_gather`` as tensors.  Tables with non-numeric columns or a
+  non-integer index fall back to ``all_gather_object``.
 """
+import os
+import socket
+import uuid
+
 import numpy as np
 import pandas as pd
 
@@ -45,19 +57,213 @@ def merge_shards(parts):
     return pd.concat(out) if out else None
 
 
-def refine_leastsq_sharded(f, reader, diameter, t_column='frame', group=None, **kwargs):
-    """``refine_leastsq`` over the ranks of a ``torch.distributed`` process group: every rank passes
-    the same ``f`` and ``reader``, refines its own block of frames on its current CUDA device and
-    returns the merged DataFrame (identical on all ranks, identical to a single-GPU call)."""
+# --------------------------------------------------------------------------------------------------
+# packed gather
+# --------------------------------------------------------------------------------------------------
+def _layout(part):
+    """Column split of a result table: -> (float columns, int columns) or None when the table
+    cannot travel as two numeric blocks."""
+    if not (isinstance(part.index, pd.RangeIndex) or part.index.dtype.kind in 'iu'):
+        return None
+    floats, ints = [], []
+    for col in part.columns:
+        kind = part[col].dtype.kind
+        if kind == 'f':
+            floats.append(col)
+        elif kind in 'iub':
+            ints.append(col)
+        else:
+            return None
+    return floats, ints
+
+
+def _dist_device(dist, group):
+    """Tensors of a collective must live where the backend works: CUDA for NCCL, host for gloo."""
+    import torch
+    if dist.get_backend(group) == 'nccl':
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device('cpu')
+
+
+def _all_gather_ints(values, group):
+    """Small all_gather of a few int64 per rank -> array [world, len(values)]."""
+    import torch
+    import torch.distributed as dist
+    dev = _dist_device(dist, group)
+    mine = torch.tensor([int(v) for v in values], dtype=torch.int64, device=dev)
+    out = [torch.empty_like(mine) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(out, mine, group=group)
+    return np.stack([t.cpu().numpy() for t in out])
+
+
+class _SharedBlock(object):
+    """One file in /dev/shm holding the merged table: float block [n_f, N], int block [n_i, N]
+    (the last int row is the index).  Created by rank 0, written by every rank into its row range,
+    unlinked as soon as every reader has mapped it (the mappings keep the memory alive)."""
+
+    def __init__(self, path, n_f, n_i, total, create):
+        self.path, self.n_f, self.n_i, self.total = path, n_f, n_i, total
+        nbytes = max(8, 8 * total * (n_f + n_i))
+        if create:
+            with open(path, 'wb') as fh:
+                fh.truncate(nbytes)
+        self.nbytes = nbytes
+
+    def arrays(self, mode):
+        raw = np.memmap(self.path, dtype=np.uint8, mode=mode, shape=(self.nbytes,))
+        split = 8 * self.total * self.n_f
+        fblock = raw[:split].view(np.float64).reshape(self.n_f, self.total)
+        iblock = raw[split:split + 8 * self.total * self.n_i].view(np.int64).reshape(self.n_i, self.total)
+        return fblock, iblock
+
+
+def _table_from_blocks(fblock, iblock, floats, ints, columns, dtypes):
+    data = {}
+    for col in columns:
+        if col in floats:
+            values = np.asarray(fblock[floats.index(col)])
+        else:
+            values = np.asarray(iblock[ints.index(col)])
+        data[col] = values.astype(dtypes[col], copy=False)          # e.g. float32 / bool columns
+    return pd.DataFrame(data, index=np.asarray(iblock[len(ints)]), copy=False)[list(columns)]
+
+
+def _same_host(group):
+    import torch.distributed as dist
+    if os.environ.get('CTK_GATHER', '') == 'tensors' or not os.path.isdir('/dev/shm'):
+        mine = "no-shm-%s" % uuid.uuid4().hex
+    else:
+        try:
+            with open('/proc/sys/kernel/random/boot_id') as fh:
+                boot = fh.read().strip()
+        except OSError:
+            boot = ''
+        mine = socket.gethostname() + boot
+    names = [None] * dist.get_world_size(group)
+    dist.all_gather_object(names, mine, group=group)
+    return all(name == names[0] for name in names)
+
+
+def gather_tables(part, group=None, gather='all'):
+    """Merge the per-rank result tables (rank order = frame order) with running cluster ids.
+    ``gather``: 'all' -> every rank returns the merged table; 'root' -> rank 0 does, the others
+    return None; 'none' -> every rank returns its own part (ids already running on)."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_rows = 0 if part is None else len(part)
+    n_ids = 0 if n_rows == 0 else int(part['cluster'].values.max()) + 1
+    layout = _layout(part) if n_rows else ([], [])
+    counts = _all_gather_ints([n_rows, n_ids, 0 if layout is None else 1], group)
+    row_off = np.concatenate(([0], np.cumsum(counts[:, 0])))
+    id_off = np.concatenate(([0], np.cumsum(counts[:, 1])))
+    total = int(row_off[-1])
+    if total == 0:
+        return None
+    if n_rows:
+        part['cluster'] = part['cluster'].values + int(id_off[rank])     # find.py:127-128
+    if gather == 'none':
+        return part
+    if not counts[:, 2].all():
+        # non-numeric columns or labels: the general (pickling) path
+        parts = [None] * world
+        dist.all_gather_object(parts, part, group=group)
+        parts = [p for p in parts if p is not None and len(p)]
+        return pd.concat(parts) if (gather == 'all' or rank == 0) else None
+
+    # column order and split: taken from the first non-empty rank (all ranks ran the same call)
+    meta = [None] * world
+    dist.all_gather_object(meta, None if n_rows == 0 else
+                           (list(part.columns), layout, {c: str(part[c].dtype) for c in part.columns}),
+                           group=group)
+    columns, (floats, ints), dtypes = next(m for m in meta if m is not None)
+    n_f, n_i = len(floats), len(ints) + 1                     # + the index
+    a, b = int(row_off[rank]), int(row_off[rank + 1])
+
+    def fill(fblock, iblock, lo, hi):
+        """This rank's columns -> rows lo..hi of the blocks."""
+        jobs = [(fblock[j], part[col].values) for j, col in enumerate(floats)]
+        jobs += [(iblock[j], part[col].values) for j, col in enumerate(ints)]
+        jobs.append((iblock[len(ints)], part.index.values))
+
+        def copy(job):
+            job[0][lo:hi] = job[1]
+        _refine._parallel(copy, jobs)
+
+    if _same_host(group):
+        name = [None]
+        if rank == 0:
+            name[0] = os.path.join('/dev/shm', 'ctk_%s' % uuid.uuid4().hex)
+            block = _SharedBlock(name[0], n_f, n_i, total, create=True)
+        dist.broadcast_object_list(name, src=0, group=group)
+        if rank != 0:
+            block = _SharedBlock(name[0], n_f, n_i, total, create=False)
+        out = None
+        try:
+            if n_rows:
+                fblock, iblock = block.arrays('r+')
+                fill(fblock, iblock, a, b)
+                del fblock, iblock
+            dist.barrier(group=group)                          # every slice is written
+            if gather == 'all' or rank == 0:
+                # rank 0 owns the block; other readers map it copy-on-write (private tables)
+                fblock, iblock = block.arrays('r+' if rank == 0 else 'c')
+                out = _table_from_blocks(fblock, iblock, floats, ints, columns, dtypes)
+            dist.barrier(group=group)                          # every reader has mapped it
+        finally:
+            if rank == 0 and os.path.exists(name[0]):
+                os.unlink(name[0])
+        return out
+
+    # across hosts: the packed blocks as tensors
+    dev = _dist_device(dist, group)
+    fmine = torch.empty((n_f, n_rows), dtype=torch.float64)
+    imine = torch.empty((n_i, n_rows), dtype=torch.int64)
+    if n_rows:
+        fill(fmine.numpy(), imine.numpy(), 0, n_rows)
+    out = None
+    blocks = []
+    for mine, dtype in ((fmine, torch.float64), (imine, torch.int64)):
+        rows = mine.shape[0]
+        # equal-sized pieces (padded to the largest shard): what gather / all_gather need
+        width = int(counts[:, 0].max())
+        padded = torch.zeros((rows, width), dtype=dtype, device=dev)
+        padded[:, :n_rows] = mine.to(dev)
+        if gather == 'all':
+            pieces = [torch.empty_like(padded) for _ in range(world)]
+            dist.all_gather(pieces, padded, group=group)
+        else:
+            pieces = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
+            dist.gather(padded, pieces, dst=0, group=group)
+        if pieces is not None:
+            blocks.append(torch.cat([p[:, :int(counts[r, 0])] for r, p in enumerate(pieces)],
+                                    dim=1).cpu().numpy())
+    if blocks:
+        out = _table_from_blocks(blocks[0], blocks[1], floats, ints, columns, dtypes)
+    return out
+
+
+def refine_leastsq_sharded(f, reader, diameter, t_column='frame', group=None, presharded=False,
+                           gather='all', **kwargs):
+    """``refine_leastsq`` over the ranks of a ``torch.distributed`` process group.  Every rank
+    refines a contiguous block of frames on its current CUDA device; the result equals a single-GPU
+    call on the whole table (rows, order, cluster ids, numbers).
+
+    ``presharded=False``: every rank passes the same whole table ``f`` and takes its block of the
+    sorted unique frames.  ``presharded=True``: ``f`` holds THIS rank's frames only; rank order must
+    be frame order (rank 0 the earliest frames) -- no rank ever holds the whole input.
+    ``gather``: 'all' (default) every rank returns the merged DataFrame; 'root' only rank 0 does (the
+    others return None); 'none' every rank returns its own part.  ``reader`` must serve the frames
+    of this rank's rows."""
     import torch.distributed as dist
     if t_column not in f:
         raise ValueError("sharding needs a %r column" % t_column)
+    if gather not in ('all', 'root', 'none'):
+        raise ValueError("gather must be 'all', 'root' or 'none'")
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    mine = frame_shard(f, rank, world, t_column)
+    mine = f if presharded else frame_shard(f, rank, world, t_column)
     part = None
     if len(mine):
         part = _refine.refine_leastsq(mine, reader, diameter, t_column=t_column, **kwargs)
-    parts = [None] * world
-    dist.all_gather_object(parts, part, group=group)
-    return merge_shards(parts)
+    return gather_tables(part, group, gather)

@@ -39,8 +39,7 @@ PHASES = [
     ("setup_variables", r"CTK_DEV_BIG int setup_variables"),
     ("build: box / tables", r"CTK_DEV_BIG int build_pixels"),
     ("build: walk box, compact union", r"// walk the box in C order"),
-    ("build: per-feature lists", r"// per-feature pixel lists"),
-    ("build: shared-pixel lists", r"// pixels shared by two features"),
+    ("build: per-feature and shared-pixel lists", r"// Per-feature pixel lists"),
     ("load_features / feat", r"CTK_DEV void load_features"),
     ("geometry / model value / derivatives", r"CTK_DEV Geo geometry"),
     ("evaluate", r"CTK_DEV_BIG double evaluate"),

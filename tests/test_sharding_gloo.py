@@ -43,8 +43,27 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank,
                             world_size=world)
     reader, f0 = _video()
+    # (1) every rank passes the whole table, every rank gets the merged result (shared-memory gather)
     out = parallel.refine_leastsq_sharded(f0, reader, 11)
     out.to_pickle(os.path.join(out_dir, "rank%d.pkl" % rank))
+    # (2) the same through the tensor gather (what runs across hosts)
+    os.environ['CTK_GATHER'] = 'tensors'
+    out = parallel.refine_leastsq_sharded(f0, reader, 11)
+    out.to_pickle(os.path.join(out_dir, "tensors%d.pkl" % rank))
+    del os.environ['CTK_GATHER']
+    # (3) every rank passes only ITS frames; the merged table goes to rank 0 alone
+    mine = parallel.frame_shard(f0, rank, world)
+    for mode in ('shm', 'tensors'):
+        if mode == 'tensors':
+            os.environ['CTK_GATHER'] = 'tensors'
+        out = parallel.refine_leastsq_sharded(mine, reader, 11, presharded=True, gather='root')
+        assert (out is None) == (rank != 0)
+        if out is not None:
+            out.to_pickle(os.path.join(out_dir, "root_%s.pkl" % mode))
+    os.environ.pop('CTK_GATHER', None)
+    # (4) no gather: every rank keeps its part, cluster ids already running on across ranks
+    out = parallel.refine_leastsq_sharded(mine, reader, 11, presharded=True, gather='none')
+    out.to_pickle(os.path.join(out_dir, "part%d.pkl" % rank))
     dist.destroy_process_group()
 
 
@@ -87,13 +106,17 @@ def test_two_rank_sharding_matches_single_process(tmp_path):
     emul_backend.lib()                           # build once, before the workers start
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    parts = [pd.read_pickle(os.path.join(str(tmp_path), "rank%d.pkl" % r)) for r in range(2)]
+    read = lambda name: pd.read_pickle(os.path.join(str(tmp_path), name))
+    parts = [read("rank%d.pkl" % r) for r in range(2)] + [read("tensors%d.pkl" % r) for r in range(2)]
+    parts += [read("root_shm.pkl"), read("root_tensors.pkl"),
+              pd.concat([read("part%d.pkl" % r) for r in range(2)])]
     reader, f0 = _video()
     single, _ = emul_backend.refine_leastsq(f0, reader, 11)
-    for part in parts:                           # every rank holds the full, identical result
+    for part in parts:                           # every variant: the full, identical result
         assert list(part.columns) == list(single.columns)
         assert np.array_equal(part.index.values, single.index.values)
         for col in single.columns:
+            assert part[col].dtype == single[col].dtype, col
             assert np.array_equal(part[col].values, single[col].values, equal_nan=True), col
 
 
