@@ -108,8 +108,8 @@ def _pool_workers():
     if env is not None:
         return max(0, int(env))
     # one process per GPU shares the host: split the cores between the local ranks
-    local_ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1') or 1))
-    return min(16, max(1, (os.cpu_count() or 1) // local_ranks))
+    from .utils import host_threads
+    return host_threads(16)
 
 
 class _WorkerPool(object):

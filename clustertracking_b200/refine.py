@@ -17,7 +17,7 @@ from . import _lib
 from . import constraints as _constraints
 from .find import ChunkLabeller, cluster_table
 from .fitfunc import FitFunctions
-from .utils import guess_pos_columns, is_isotropic, validate_tuple
+from .utils import guess_pos_columns, host_threads, is_isotropic, validate_tuple
 
 logger = logging.getLogger(__name__)
 
@@ -45,7 +45,7 @@ def _parallel(fn, items):
         return
     if _THREADS is None:
         from concurrent.futures import ThreadPoolExecutor
-        _THREADS = ThreadPoolExecutor(min(8, os.cpu_count() or 1))
+        _THREADS = ThreadPoolExecutor(host_threads(8))
     list(_THREADS.map(fn, items))
 
 
@@ -523,6 +523,7 @@ class FrameSet(object):
         self.tensors = []                 # keeps the uploaded batches alive
         self.big_workspaces = {}          # large-cluster scratch, shared by the chunks of the call
         self.batch_ready, self.batch_last = [], []       # per upload batch: event, last frame
+        self.recorded, self.thread, self.upload_error = None, None, None   # background staging
         with torch.cuda.device(self.dev):
             self.d_ptrs = torch.zeros(self.n_frames, dtype=torch.int64, device=self.dev)
             self.d_fmax = torch.empty(self.n_frames, dtype=torch.float64, device=self.dev)
@@ -569,20 +570,49 @@ class FrameSet(object):
     def wait_for_frames(self, last_frame):
         """Make the current stream wait until frames 0 .. last_frame are resident and their maxima
         computed (a launch that touches only the first frames need not wait for the whole video)."""
-        if not self.batch_ready:
+        if not self.batch_last:
             return
         k = int(np.searchsorted(self.batch_last, last_frame))
-        k = min(k, len(self.batch_ready) - 1)
+        k = min(k, len(self.batch_last) - 1)
+        if self.recorded is not None:
+            # staged upload on a background thread: the event exists once that thread has enqueued
+            # the batch (waiting on an event that was never recorded would be a no-op)
+            self.recorded[k].wait()
+            if self.upload_error is not None:
+                raise self.upload_error
         self.torch.cuda.current_stream(self.dev).wait_event(self.batch_ready[k])
+
+    def close(self):
+        """Join the staging thread (if any) before the pinned ring can be reused."""
+        thread, self.thread = self.thread, None
+        if thread is not None:
+            thread.join()
+        if self.upload_error is not None:
+            error, self.upload_error = self.upload_error, None
+            raise error
 
     def upload_async(self):
         """Allocate the device frames, upload the pointer table once (the only host-synchronous
         step, done while the device is idle), then enqueue copy -> frame max per batch on a copy
-        stream; ``wait_for_frames`` orders later launches behind the batches they read."""
+        stream; ``wait_for_frames`` orders later launches behind the batches they read.
+
+        Frames that already sit in pinned host memory go to the device by DMA straight from the
+        caller's array.  Anything else (a pageable numpy stack, a reader that produces frames one
+        by one) is staged on a BACKGROUND thread through a ring of two pinned buffers: while batch
+        k travels to the device, batch k + 1 is copied (or read) into the other buffer, and the
+        caller goes on with the cluster labelling meanwhile.  (A pageable ``copy_`` would block the
+        host for the whole upload at ~2-6 GB/s: config 4 lost 6.5x to that.)"""
         torch = self.torch
         per_batch = max(1, min(self.n_frames, _FRAME_BATCH_BYTES // max(self.frame_bytes, 1)))
         cuts = list(range(0, self.n_frames, per_batch)) + [self.n_frames]
+        self.recorded, self.thread, self.upload_error = None, None, None
         with torch.cuda.device(self.dev):
+            free, _ = torch.cuda.mem_get_info(self.dev)
+            need = self.n_frames * self.frame_bytes
+            if need > free + torch.cuda.memory_reserved(self.dev) - torch.cuda.memory_allocated(self.dev):
+                raise MemoryError("the %d frames of this call need %.1f GB of device memory, %.1f GB "
+                                  "are free: refine the video in blocks of frames"
+                                  % (self.n_frames, need / 1e9, free / 1e9))
             compute = torch.cuda.current_stream(self.dev)
             copy_stream = torch.cuda.Stream(device=self.dev)
             batches, ptrs = [], np.empty(self.n_frames, dtype=np.int64)
@@ -594,33 +624,69 @@ class FrameSet(object):
             self.d_ptrs.copy_(torch.from_numpy(ptrs))
             self.tensors.extend(batches)
             copy_stream.wait_stream(compute)
-            staging = None
-            for d_frames, f0, f1 in zip(batches, cuts[:-1], cuts[1:]):
-                n = f1 - f0
-                view = self._direct_view(f0, f1)
-                if view is None:
-                    if staging is None:
-                        staging = torch.empty((per_batch,) + tuple(self.info.shape),
-                                              dtype=self.torch_dtype, pin_memory=True)
-                    host = staging.numpy()
-                    copy_stream.synchronize()        # the previous batch has left the staging buffer
-                    for k in range(f0, f1):
-                        host[k - f0] = load_frame(self.info, self.info.numbers[k])
-                    src = staging[:n]
-                else:
-                    src = torch.from_numpy(view)
-                with torch.cuda.stream(copy_stream):
-                    d_frames.copy_(src, non_blocking=True)
-                    self.launch_frame_max(f0, n, stream=copy_stream)
-                    done = torch.cuda.Event()
-                    done.record(copy_stream)
-                self.h2d_bytes += n * self.frame_bytes
-                self.batch_ready.append(done)
-                self.batch_last.append(f1 - 1)
-            if staging is not None:
-                copy_stream.synchronize()
             self.copy_stream = copy_stream
+            self.batch_last = [f1 - 1 for f1 in cuts[1:]]
+            self.batch_ready = [torch.cuda.Event() for _ in batches]
+            views = [self._direct_view(f0, f1) for f0, f1 in zip(cuts[:-1], cuts[1:])]
+            pinned = all(v is not None and torch.from_numpy(v).is_pinned() for v in views)
+
+            def enqueue(k, src):
+                n = cuts[k + 1] - cuts[k]
+                with torch.cuda.stream(copy_stream):
+                    batches[k].copy_(src, non_blocking=True)
+                    self.launch_frame_max(cuts[k], n, stream=copy_stream)
+                    self.batch_ready[k].record(copy_stream)
+                self.h2d_bytes += n * self.frame_bytes
+
+            if pinned:
+                for k, view in enumerate(views):
+                    enqueue(k, torch.from_numpy(view))
+                return self
+
+            import threading
+            ring = [_pinned_buffer(torch, "frames%d" % j, per_batch * self.frame_bytes)
+                    for j in range(2)]
+            self.recorded = [threading.Event() for _ in batches]
+
+            def stage():
+                try:
+                    torch.cuda.set_device(self.dev)
+                    for k, view in enumerate(views):
+                        n = cuts[k + 1] - cuts[k]
+                        if k >= 2:
+                            self.batch_ready[k - 2].synchronize()    # its ring slot is free again
+                        slot = ring[k % 2][:n * self.frame_bytes].view(self.torch_dtype)
+                        slot = slot.reshape((n,) + tuple(self.info.shape))
+                        host = slot.numpy()
+                        if view is not None:
+                            _copy_frames(host, view)
+                        else:
+                            for j in range(n):
+                                host[j] = load_frame(self.info, self.info.numbers[cuts[k] + j])
+                        enqueue(k, slot)
+                        self.recorded[k].set()
+                except BaseException as exc:                  # surface it in the calling thread
+                    self.upload_error = exc
+                    for flag in self.recorded:
+                        flag.set()
+
+            self.thread = threading.Thread(target=stage, daemon=True)
+            self.thread.start()
         return self
+
+
+def _copy_frames(dst, src):
+    """dst[...] = src on a few threads (numpy's copy releases the GIL; one thread moves ~10 GB/s)."""
+    n = len(src)
+    k = max(1, min(n, host_threads(4)))
+    if k == 1 or src.nbytes < (8 << 20):
+        dst[...] = src
+        return
+    cuts = np.linspace(0, n, k + 1).astype(int)
+
+    def one(span):
+        dst[span[0]:span[1]] = src[span[0]:span[1]]
+    _parallel(one, list(zip(cuts[:-1], cuts[1:])))
 
 
 class DeviceSession(object):
@@ -854,6 +920,7 @@ def execute_cuda(plan, device=None, want_stats=True, frames=None):
         _t2 = _time.perf_counter()
         _t3 = _t2
         result = session.download(want_stats)
+    frames.close()
     session.launches += frames.launches
     session.h2d_bytes += frames.h2d_bytes
     result.session = session
@@ -937,6 +1004,7 @@ def _pinned_array(key, shape, dtype):
 
 _CALL_LOCK = __import__('threading').Lock()
 _LABELLERS = []       # the running call's labelling thread(s), closed when the call ends
+_FRAMESETS = []       # ... and its frame uploads (staging thread)
 
 
 def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', param_mode=None,
@@ -956,6 +1024,13 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
         finally:
             while _LABELLERS:
                 _LABELLERS.pop().close()
+            while _FRAMESETS:
+                _FRAMESETS.pop().close()
+
+
+def _track(frameset):
+    _FRAMESETS.append(frameset)
+    return frameset
 
 
 def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', param_mode=None,
@@ -987,7 +1062,7 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
     pre = prepare_common(f, reader, diameter, separation, fit_function, param_mode, param_val,
                          constraints, bounds, pos_columns, t_column, noise_size, threshold,
                          max_iter, max_shift, max_rms_dev, residual_factor, compute_error,
-                         frames_hook=lambda info: started.append(FrameSet(info).upload_async()),
+                         frames_hook=lambda info: started.append(_track(FrameSet(info)).upload_async()),
                          **kwargs)
     ff, info = pre.ff, pre.info
     frameset = started[0]
@@ -1040,7 +1115,7 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
     cost = np.empty(n, dtype=np.float64)
     cluster = np.empty(n, dtype=np.int64)
     csize = np.empty(n, dtype=np.int64)
-    threads = max(1, min(8, (os.cpu_count() or 2) // 2))
+    threads = host_threads(8)
     local_all = np.empty(n, dtype=np.int64)        # labels local to each frame
     frame_offset = np.zeros(n_frames, dtype=np.int64)                 # find.py:127-128
     chunks = []                                    # (a, b, rows by group (chunk-local), plan, pending, c0)

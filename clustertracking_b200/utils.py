@@ -39,3 +39,15 @@ def is_isotropic(value):
         value = np.asarray(value)
         return bool(np.all(value[1:] == value[:-1]))
     return True
+
+
+def host_threads(cap=16):
+    """Host threads one process may use: the cores this process can run on, split between the
+    ranks that share the box (one process per GPU, ``LOCAL_WORLD_SIZE`` set by torchrun)."""
+    import os
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 1
+    local_ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1') or 1))
+    return int(min(cap, max(1, cores // local_ranks)))

@@ -58,6 +58,9 @@ def main(name, out_path):
     exec(compile(second, "INTEGRATION.md:refine.py", "exec"), ns)
     assert not any(m.startswith("clustertracking_b200") for m in sys.modules), "stub must stand alone"
     f = ns['f']
+    status = ns['status'].cpu().numpy()
+    if (status != 0).any():
+        print("cluster status codes:", status.tolist(), "sizes:", ns['sizes'].tolist(), file=sys.stderr)
     np.savez(out_path, index=f.index.values, columns=np.array(list(f.columns)),
              **{"col_" + c: f[c].values for c in f.columns})
 

@@ -30,7 +30,7 @@ def test_integration_stub_verbatim(name, tmp_path):
     assert_array_equal(got["index"], want.index.values)
     assert_array_equal(got["col_cluster"], want["cluster"].values)
     assert_array_equal(got["col_cluster_size"], want["cluster_size"].values)
-    assert not np.isnan(got["col_cost"]).any() and not np.isnan(want["cost"].values).any()
+    assert not np.isnan(got["col_cost"]).any() and not np.isnan(want["cost"].values).any(), proc.stderr[-2000:]
     for col in ("y", "x"):
         assert_allclose(got["col_" + col], want[col].values, rtol=0, atol=1e-3, err_msg=col)
     assert_allclose(got["col_signal"], want["signal"].values, rtol=1e-3)

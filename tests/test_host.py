@@ -222,6 +222,9 @@ class _NoFrames(object):
     def upload_async(self):
         return self
 
+    def close(self):
+        pass
+
 
 class _Done(object):
     def __init__(self, result):

@@ -76,6 +76,9 @@ class _NoFrames(object):
     def upload_async(self):
         return self
 
+    def close(self):
+        pass
+
 
 class _Session(object):
     h2d_bytes = d2h_bytes = launches = 0
