@@ -228,10 +228,10 @@ def scatter_rows(params, params_in, rows, group_offset, group_cost, group_status
                  n_threads, row_base=0):
     """``ctk_scatter_rows``: write one chunk back into the table-order column block [P, N] and the
     cost column (table row = row_base + rows[r]); returns the number of failed clusters."""
-    n_cols = block.shape[0]
+    n_cols = len(block)                       # [P, N] array or a list of P column arrays
     ptrs = (ctypes.c_void_p * n_cols)(*[block[j].ctypes.data for j in range(n_cols)])
     failed = ctypes.c_int64(0)
-    for arr in (params, params_in, rows, group_offset, group_cost, group_status, block, cost_out):
+    for arr in [params, params_in, rows, group_offset, group_cost, group_status, cost_out] + list(block):
         assert arr.flags.c_contiguous
     check(load().ctk_scatter_rows(params.ctypes.data, params_in.ctypes.data, rows.ctypes.data,
                                   int(row_base), len(rows), n_cols, group_offset.ctypes.data,

@@ -144,7 +144,7 @@ def _same_host(group):
     return all(name == names[0] for name in names)
 
 
-def gather_tables(part, group=None, gather='all'):
+def gather_tables(part, group=None, gather='all', ids_done=False):
     """Merge the per-rank result tables (rank order = frame order) with running cluster ids.
     ``gather``: 'all' -> every rank returns the merged table; 'root' -> rank 0 does, the others
     return None; 'none' -> every rank returns its own part (ids already running on)."""
@@ -160,7 +160,7 @@ def gather_tables(part, group=None, gather='all'):
     total = int(row_off[-1])
     if total == 0:
         return None
-    if n_rows:
+    if n_rows and not ids_done:
         part['cluster'] = part['cluster'].values + int(id_off[rank])     # find.py:127-128
     if gather == 'none':
         return part
@@ -243,6 +243,98 @@ def gather_tables(part, group=None, gather='all'):
     return out
 
 
+class _SharedColumns(object):
+    """A [n_slots, total] matrix of 8-byte cells in /dev/shm that all ranks of the host map: column
+    k of the merged result table is row k, and a rank's rows are cells row_off[rank] ..
+    row_off[rank + 1].  ``refine_leastsq`` writes its result columns straight into these cells
+    (its ``_alloc`` hook), so that "gathering" the table costs no copy at all."""
+
+    def __init__(self, path, n_slots, total, a, b, create):
+        self.path, self.n_slots, self.total, self.a, self.b = path, n_slots, total, a, b
+        self.nbytes = max(8, 8 * n_slots * total)
+        if create:
+            with open(path, 'wb') as fh:
+                fh.truncate(self.nbytes)
+        self.cells = np.memmap(path, dtype=np.int64, mode='r+', shape=(n_slots, total))
+        self.columns = []                          # (name, dtype) in allocation order
+        self.spilled = False                       # a column did not fit the 8-byte cells
+
+    def alloc(self, name, dtype):
+        dtype = np.dtype(dtype)
+        k = len(self.columns)
+        if dtype.itemsize != 8 or dtype.kind not in 'fiu' or k >= self.n_slots - 1:
+            self.spilled = True
+            return np.empty(self.b - self.a, dtype=dtype)
+        self.columns.append((name, dtype.str))
+        return np.asarray(self.cells[k, self.a:self.b]).view(dtype)
+
+    def table(self, columns, private):
+        cells = self.cells if not private else np.memmap(self.path, dtype=np.int64, mode='c',
+                                                         shape=(self.n_slots, self.total))
+        data = {name: np.asarray(cells[k]).view(np.dtype(dt)) for k, (name, dt) in enumerate(columns)}
+        index = np.asarray(cells[self.n_slots - 1])
+        return pd.DataFrame(data, index=index, copy=False)
+
+
+def _refine_into_shared(mine, reader, diameter, t_column, group, gather, kwargs):
+    """The one-host path: result columns allocated in a shared block, no copy at gather time.
+    -> (done, result); done = False: fall back to gather_tables (inputs this scheme cannot hold)."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    index_ok = isinstance(mine.index, pd.RangeIndex) or mine.index.dtype.kind in 'iu'
+    numeric = all(mine[c].dtype.kind in 'fiu' and mine[c].dtype.itemsize == 8 for c in mine.columns)
+    counts = _all_gather_ints([len(mine), 1 if (index_ok and numeric) else 0, len(mine.columns)], group)
+    host_ok = _same_host(group)
+    if not (host_ok and counts[:, 1].all()) or counts[:, 0].sum() == 0:
+        return False, None
+    row_off = np.concatenate(([0], np.cumsum(counts[:, 0])))
+    total, a, b = int(row_off[-1]), int(row_off[rank]), int(row_off[rank + 1])
+    n_slots = int(counts[:, 2].max()) + 24               # input columns + model columns + index
+    name = [None]
+    if rank == 0:
+        name[0] = os.path.join('/dev/shm', 'ctk_%s' % uuid.uuid4().hex)
+        shared = _SharedColumns(name[0], n_slots, total, a, b, create=True)
+    dist.broadcast_object_list(name, src=0, group=group)
+    if rank != 0:
+        shared = _SharedColumns(name[0], n_slots, total, a, b, create=False)
+    try:
+        part = None
+        if b > a:
+            part = _refine.refine_leastsq(mine, reader, diameter, t_column=t_column,
+                                          _alloc=shared.alloc, **kwargs)
+            complete = (not shared.spilled and [c for c, _ in shared.columns] != [] and
+                        set(part.columns) == set(c for c, _ in shared.columns))
+            shared.cells[n_slots - 1, a:b] = part.index.values
+        else:
+            complete = True
+        n_ids = 0 if part is None else int(part['cluster'].values.max()) + 1
+        ids = _all_gather_ints([n_ids, 1 if complete else 0], group)
+        id_off = int(ids[:rank, 0].sum())
+        if part is not None and id_off:                            # find.py:127-128
+            if complete:                                           # the column IS a view of the cells
+                k = [c for c, _ in shared.columns].index('cluster')
+                shared.cells[k, a:b] += id_off
+            else:
+                part['cluster'] = part['cluster'].values + id_off
+        if not ids[:, 1].all():
+            return True, gather_tables(part, group, gather, ids_done=True)
+        if gather == 'none':
+            dist.barrier(group=group)
+            return True, part
+        meta = [None] * world
+        dist.all_gather_object(meta, None if part is None else (shared.columns, list(part.columns)),
+                               group=group)                        # doubles as "all slices written"
+        columns, order = next(m for m in meta if m is not None)
+        out = None
+        if gather == 'all' or rank == 0:
+            out = shared.table(columns, private=rank != 0)[order]
+        dist.barrier(group=group)                                  # every reader has mapped it
+        return True, out
+    finally:
+        if rank == 0 and os.path.exists(name[0]):
+            os.unlink(name[0])
+
+
 def refine_leastsq_sharded(f, reader, diameter, t_column='frame', group=None, presharded=False,
                            gather='all', **kwargs):
     """``refine_leastsq`` over the ranks of a ``torch.distributed`` process group.  Every rank
@@ -263,6 +355,10 @@ def refine_leastsq_sharded(f, reader, diameter, t_column='frame', group=None, pr
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     mine = f if presharded else frame_shard(f, rank, world, t_column)
+    if os.environ.get('CTK_GATHER', '') not in ('tensors', 'copy'):
+        done, out = _refine_into_shared(mine, reader, diameter, t_column, group, gather, kwargs)
+        if done:
+            return out
     part = None
     if len(mine):
         part = _refine.refine_leastsq(mine, reader, diameter, t_column=t_column, **kwargs)

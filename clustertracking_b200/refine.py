@@ -1015,12 +1015,13 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
     See :func:`_refine_leastsq` for the parameters.  The cached pinned staging buffers are
     process-wide, so concurrent calls are serialised here; whatever happens inside, the labelling
     thread has stopped writing into them before the call returns or raises."""
+    alloc = kwargs.pop('_alloc', None)       # internal: where the result columns live (parallel.py)
     with _CALL_LOCK:
         try:
             return _refine_leastsq(f, reader, diameter, separation, fit_function, param_mode,
                                    param_val, constraints, bounds, pos_columns, t_column,
                                    noise_size, threshold, max_iter, max_shift, max_rms_dev,
-                                   residual_factor, compute_error, **kwargs)
+                                   residual_factor, compute_error, _alloc=alloc, **kwargs)
         finally:
             while _LABELLERS:
                 _LABELLERS.pop().close()
@@ -1036,7 +1037,8 @@ def _track(frameset):
 def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', param_mode=None,
                     param_val=None, constraints=None, bounds=None, pos_columns=None,
                     t_column='frame', noise_size=None, threshold=None, max_iter=10, max_shift=1,
-                    max_rms_dev=1., residual_factor=100000., compute_error=False, **kwargs):
+                    max_rms_dev=1., residual_factor=100000., compute_error=False, _alloc=None,
+                    **kwargs):
     """Refine cluster coordinates by least-squares fitting of radial model functions, on the GPU.
 
     Same signature, same returned columns and the same failure convention as the reference
@@ -1111,10 +1113,13 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
     out_params = _pinned_array("params", (n, P), np.float64)
     out_cost = _pinned_array("cost", (n,), np.float64)             # one entry per cluster (<= n)
     out_status = _pinned_array("status", (n,), np.int32)
-    block = np.empty((P, n), dtype=np.float64)                     # fitted columns, table order
-    cost = np.empty(n, dtype=np.float64)
-    cluster = np.empty(n, dtype=np.int64)
-    csize = np.empty(n, dtype=np.int64)
+    # The result columns.  ``_alloc(name, dtype)`` lets the sharded path place them in a block all
+    # ranks share, so that the final gather copies nothing (parallel.py).
+    alloc = _alloc if _alloc is not None else (lambda name, dtype: np.empty(n, dtype=dtype))
+    block = [alloc(col, np.float64) for col in ff.params]          # fitted columns, table order
+    cost = alloc('cost', np.float64)
+    cluster = alloc('cluster', np.int64)
+    csize = alloc('cluster_size', np.int64)
     threads = host_threads(8)
     local_all = np.empty(n, dtype=np.int64)        # labels local to each frame
     frame_offset = np.zeros(n_frames, dtype=np.int64)                 # find.py:127-128
@@ -1179,19 +1184,27 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
     # ---- the result table: a frame-sorted copy of f with the new columns (refine.py:296-305) -------
     data = {}
     fitted = {col: block[j] for j, col in enumerate(ff.params)}
+
+    def filled(col, values):
+        """A result column holding ``values`` (array or scalar): an independent copy, like f.copy()."""
+        values = np.asarray(values)
+        dst = alloc(col, values.dtype)
+        dst[...] = values
+        return dst
+
     for col in base.columns:
         if col in fitted:
             data[col] = fitted[col]
         elif param_val is not None and col in param_val:
-            data[col] = np.full(n, param_val[col])
+            data[col] = filled(col, param_val[col])
         else:
-            data[col] = np.array(base[col].values)          # an independent copy, like f.copy()
+            data[col] = filled(col, base[col].values)
     data['cluster'] = cluster
     data['cluster_size'] = csize
     if param_val is not None:
         for col in param_val:
             if col not in data:
-                data[col] = fitted[col] if col in fitted else np.full(n, param_val[col])
+                data[col] = fitted[col] if col in fitted else filled(col, param_val[col])
     for col in ff.params:
         if col not in data:
             data[col] = fitted[col]

@@ -53,9 +53,9 @@ def _worker(rank, world, port, out_dir):
     del os.environ['CTK_GATHER']
     # (3) every rank passes only ITS frames; the merged table goes to rank 0 alone
     mine = parallel.frame_shard(f0, rank, world)
-    for mode in ('shm', 'tensors'):
-        if mode == 'tensors':
-            os.environ['CTK_GATHER'] = 'tensors'
+    for mode in ('shm', 'copy', 'tensors'):     # zero-copy shared block | copy into one | tensors
+        if mode != 'shm':
+            os.environ['CTK_GATHER'] = mode
         out = parallel.refine_leastsq_sharded(mine, reader, 11, presharded=True, gather='root')
         assert (out is None) == (rank != 0)
         if out is not None:
@@ -111,7 +111,7 @@ def test_two_rank_sharding_matches_single_process(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     read = lambda name: pd.read_pickle(os.path.join(str(tmp_path), name))
     parts = [read("rank%d.pkl" % r) for r in range(2)] + [read("tensors%d.pkl" % r) for r in range(2)]
-    parts += [read("root_shm.pkl"), read("root_tensors.pkl"),
+    parts += [read("root_shm.pkl"), read("root_copy.pkl"), read("root_tensors.pkl"),
               pd.concat([read("part%d.pkl" % r) for r in range(2)])]
     reader, f0 = _video()
     single, _ = emul_backend.refine_leastsq(f0, reader, 11)
