@@ -258,6 +258,38 @@ class _SharedColumns(object):
         self.cells = np.memmap(path, dtype=np.int64, mode='r+', shape=(n_slots, total))
         self.columns = []                          # (name, dtype) in allocation order
         self.spilled = False                       # a column did not fit the 8-byte cells
+        self.thread = None
+        if b > a:
+            # Fresh tmpfs pages fault one 4 KB page at a time (no transparent huge pages): ~30 ms
+            # per rank for a 2 M-row table if the faults happen where the columns are first written.
+            # A background thread populates this rank's cells while the host labels clusters and
+            # the device works.
+            import threading
+            self.thread = threading.Thread(target=self._populate, daemon=True)
+            self.thread.start()
+
+    def _populate(self):
+        import mmap
+        page = mmap.PAGESIZE
+        handle = getattr(self.cells, '_mmap', None)
+        populate_write = 23                        # MADV_POPULATE_WRITE (Linux 5.14+)
+        for k in range(self.n_slots):
+            start = 8 * (k * self.total + self.a)
+            stop = 8 * (k * self.total + self.b)
+            lo, hi = start // page * page, min(self.nbytes, -(-stop // page) * page)
+            try:
+                if handle is None:
+                    raise OSError
+                handle.madvise(populate_write, lo, hi - lo)
+            except (OSError, ValueError, AttributeError):
+                # fallback: READ one word per page (allocates and zeroes the page; a write here
+                # could land after refine_leastsq has filled the column)
+                int(np.asarray(self.cells[k, self.a:self.b:page // 8]).sum())
+
+    def ready(self):
+        thread, self.thread = self.thread, None
+        if thread is not None:
+            thread.join()
 
     def alloc(self, name, dtype):
         dtype = np.dtype(dtype)
@@ -302,6 +334,7 @@ def _refine_into_shared(mine, reader, diameter, t_column, group, gather, kwargs)
         if b > a:
             part = _refine.refine_leastsq(mine, reader, diameter, t_column=t_column,
                                           _alloc=shared.alloc, **kwargs)
+            shared.ready()
             complete = (not shared.spilled and [c for c, _ in shared.columns] != [] and
                         set(part.columns) == set(c for c, _ in shared.columns))
             shared.cells[n_slots - 1, a:b] = part.index.values
