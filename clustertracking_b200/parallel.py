@@ -258,30 +258,36 @@ class _SharedColumns(object):
         self.cells = np.memmap(path, dtype=np.int64, mode='r+', shape=(n_slots, total))
         self.columns = []                          # (name, dtype) in allocation order
         self.spilled = False                       # a column did not fit the 8-byte cells
-        self.thread = None
-        if b > a:
-            # Fresh tmpfs pages fault one 4 KB page at a time (no transparent huge pages): ~30 ms
-            # per rank for a 2 M-row table if the faults happen where the columns are first written.
-            # A background thread populates this rank's cells while the host labels clusters and
-            # the device works.
-            import threading
-            self.thread = threading.Thread(target=self._populate, daemon=True)
-            self.thread.start()
+        # Fresh tmpfs pages fault one 4 KB page at a time (no transparent huge pages): ~30 ms per
+        # rank for a 2 M-row table if the faults happen where the columns are first written.  A
+        # background thread populates the cells of every column as soon as it is allocated, while
+        # the host labels clusters and the device works (libc's madvise through ctypes: the call
+        # releases the GIL).
+        import queue
+        import threading
+        self.todo = queue.Queue()
+        self.thread = threading.Thread(target=self._populate, daemon=True)
+        self.thread.start()
 
     def _populate(self):
+        import ctypes
         import mmap
         page = mmap.PAGESIZE
-        handle = getattr(self.cells, '_mmap', None)
         populate_write = 23                        # MADV_POPULATE_WRITE (Linux 5.14+)
-        for k in range(self.n_slots):
+        try:
+            libc = ctypes.CDLL(None, use_errno=True)
+            libc.madvise.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        except (OSError, AttributeError):
+            libc = None
+        base = self.cells.ctypes.data
+        while True:
+            k = self.todo.get()
+            if k is None:
+                return
             start = 8 * (k * self.total + self.a)
             stop = 8 * (k * self.total + self.b)
             lo, hi = start // page * page, min(self.nbytes, -(-stop // page) * page)
-            try:
-                if handle is None:
-                    raise OSError
-                handle.madvise(populate_write, lo, hi - lo)
-            except (OSError, ValueError, AttributeError):
+            if libc is None or libc.madvise(base + lo, hi - lo, populate_write) != 0:
                 # fallback: READ one word per page (allocates and zeroes the page; a write here
                 # could land after refine_leastsq has filled the column)
                 int(np.asarray(self.cells[k, self.a:self.b:page // 8]).sum())
@@ -289,6 +295,7 @@ class _SharedColumns(object):
     def ready(self):
         thread, self.thread = self.thread, None
         if thread is not None:
+            self.todo.put(None)
             thread.join()
 
     def alloc(self, name, dtype):
@@ -298,6 +305,7 @@ class _SharedColumns(object):
             self.spilled = True
             return np.empty(self.b - self.a, dtype=dtype)
         self.columns.append((name, dtype.str))
+        self.todo.put(k)
         return np.asarray(self.cells[k, self.a:self.b]).view(dtype)
 
     def table(self, columns, private):
@@ -340,6 +348,7 @@ def _refine_into_shared(mine, reader, diameter, t_column, group, gather, kwargs)
             shared.cells[n_slots - 1, a:b] = part.index.values
         else:
             complete = True
+            shared.ready()
         n_ids = 0 if part is None else int(part['cluster'].values.max()) + 1
         ids = _all_gather_ints([n_ids, 1 if complete else 0], group)
         id_off = int(ids[:rank, 0].sum())
