@@ -15,10 +15,11 @@ CTK_MAX_BIG_FEATURES = 256
 CTK_MAX_RADIUS = 30
 CTK_MAX_TAPS = 33
 
-MODE_CONST, MODE_VAR, MODE_CLUSTER = 0, 1, 3
 PIXEL_CODES = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2,
                np.dtype(np.float64): 3, np.dtype(np.int16): 4, np.dtype(np.int32): 5}
 COMPUTE_F32, COMPUTE_F64 = 0, 1
+MODE_CONST, MODE_VAR, MODE_GLOBAL, MODE_CLUSTER = 0, 1, 2, 3
+FAMILY_GAUSS, FAMILY_RING, FAMILY_DISC = 0, 1, 2
 CONSTRAINT_DIMER, CONSTRAINT_TRIMER, CONSTRAINT_TETRAMER = 1, 2, 4
 LAUNCH_APPEND_OVERFLOW = 1        # ctk_refine_batch_ex flags
 
@@ -76,6 +77,9 @@ _PROTOTYPES = {
     "ctk_refine_batch_ex": (ctypes.c_int, [ctypes.POINTER(Problem), _vp, ctypes.POINTER(_i64),
                                            _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                            _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "ctk_global_pass": (ctypes.c_int, [ctypes.POINTER(Problem), _vp, ctypes.POINTER(_i64),
+                                       ctypes.c_double, _i32, _i32, _vp, _vp, _vp, _vp, _i32,
+                                       ctypes.c_double, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ctk_label_clusters": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "ctk_pairs_set_order": (ctypes.c_int, [_vp, _i64, _vp]),
     "ctk_group_chunk": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp,

@@ -26,6 +26,18 @@ int fail(int code, const char* fmt, ...) {
       return fail(CTK_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_));                      \
   } while (0)
 
+struct GlobalLauncher {
+  const ctk::BatchArgs* args;
+  cudaStream_t stream;
+  int result;
+  template <class C> void operator()() {
+    if constexpr (C::EXTRA && !C::BIG)
+      result = ctk::launch_global<C>(*args, stream, g_error, sizeof(g_error));
+    else
+      result = CTK_E_UNSUPPORTED;
+  }
+};
+
 struct Launcher {
   const ctk::BatchArgs* args;
   cudaStream_t stream;
@@ -213,6 +225,62 @@ int ctk_refine_batch_ex(const ctk_problem_t* prob, const void* const* d_frames,
                    ? ctk::dispatch_config<double>(*prob, launcher, big)
                    : ctk::dispatch_config<float>(*prob, launcher, big);
   if (!found) return fail(CTK_E_UNSUPPORTED, "ctk_refine_batch: no kernel instance for this problem");
+  return launcher.result;
+}
+
+int ctk_global_pass(const ctk_problem_t* prob, const void* const* d_frames,
+                    const int64_t* frame_shape, double norm, int32_t n_clusters,
+                    int32_t max_cluster_features, const int32_t* d_cluster_frame,
+                    const int32_t* d_cluster_offset, const double* d_params_in,
+                    const double* d_mask_centres, int32_t phase, double lambda, int32_t use_newton,
+                    const double* d_global_step, double* d_params_out, double* d_accum,
+                    double* d_cost_out, int32_t* d_status_out, void* d_workspace, void* stream) {
+  if (!prob) return fail(CTK_E_INVALID, "ctk_global_pass: prob is NULL");
+  if (const char* why = ctk::validate_problem(*prob, true)) return fail(CTK_E_INVALID, "ctk_global_pass: %s", why);
+  if (prob->constraint_mask) return fail(CTK_E_UNSUPPORTED, "ctk_global_pass: constraints are not supported");
+  if (n_clusters <= 0) return 0;
+  if (!d_frames || !frame_shape || !d_cluster_frame || !d_cluster_offset || !d_params_in ||
+      !d_params_out || !d_accum || !d_cost_out || !d_status_out || !d_workspace ||
+      (phase != 1 && phase != 2) || (phase == 2 && !d_global_step) || !(norm > 0.) ||
+      max_cluster_features > CTK_MAX_CLUSTER_FEATURES)
+    return fail(CTK_E_INVALID, "ctk_global_pass: bad argument");
+  ctk::BatchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.prob = *prob;
+  a.frames = d_frames;
+  for (int k = 0; k < prob->ndim; ++k) {
+    if (frame_shape[k] <= 0 || frame_shape[k] > (1 << 30))
+      return fail(CTK_E_INVALID, "ctk_global_pass: bad frame shape");
+    a.shape[k] = frame_shape[k];
+  }
+  a.n_work = n_clusters;
+  a.cluster_frame = d_cluster_frame;
+  a.cluster_offset = d_cluster_offset;
+  a.params_in = d_params_in;
+  a.params_out = d_params_out;
+  a.cost_out = d_cost_out;
+  a.status_out = d_status_out;
+  a.counter = static_cast<int32_t*>(d_workspace);
+  a.mask_centres = d_mask_centres;
+  a.global_step = d_global_step;
+  a.global_accum = d_accum;
+  a.global_norm = norm;
+  a.global_lambda = lambda;
+  a.global_phase = phase;
+  a.use_newton = use_newton;
+  ctk_problem_t rigorous = *prob;
+  rigorous.capacity_mode = 1;                      // no relaunch logic here: worst-case capacities
+  if (!ctk::compute_layout(rigorous, max_cluster_features, &a.lay))
+    return fail(CTK_E_CAPACITY, "ctk_global_pass: max_cluster_features %d out of range", max_cluster_features);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CTK_CUDA(cudaMemsetAsync(d_workspace, 0, sizeof(int32_t), st));
+  // the full-flavour instances carry the pass; select them like a problem with constraints would
+  ctk_problem_t select = *prob;
+  select.constraint_mask = CTK_CONSTRAINT_DIMER;
+  GlobalLauncher launcher{&a, st, 0};
+  bool found = prob->compute_dtype == CTK_COMPUTE_F64 ? ctk::dispatch_config<double>(select, launcher, false)
+                                                      : ctk::dispatch_config<float>(select, launcher, false);
+  if (!found) return fail(CTK_E_UNSUPPORTED, "ctk_global_pass: no kernel instance for this problem");
   return launcher.result;
 }
 

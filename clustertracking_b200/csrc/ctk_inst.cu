@@ -8,10 +8,18 @@
 #endif
 
 namespace ctk {
+#if CTK_INST_EXTRA
+// the full flavour also carries the global-level pass (ctk_global_pass)
 #define CTK_INST(ND, ISO, SZ, EX)                                                             \
   template int launch_refine<Config<CTK_INST_REAL, ND, ISO, CTK_INST_FAM, SZ, EX, false,      \
-                                    CTK_INST_EXTRA != 0> >(                                   \
-      const BatchArgs&, cudaStream_t, char*, size_t);
+                                    true> >(const BatchArgs&, cudaStream_t, char*, size_t);   \
+  template int launch_global<Config<CTK_INST_REAL, ND, ISO, CTK_INST_FAM, SZ, EX, false,      \
+                                    true> >(const BatchArgs&, cudaStream_t, char*, size_t);
+#else
+#define CTK_INST(ND, ISO, SZ, EX)                                                             \
+  template int launch_refine<Config<CTK_INST_REAL, ND, ISO, CTK_INST_FAM, SZ, EX, false,      \
+                                    false> >(const BatchArgs&, cudaStream_t, char*, size_t);
+#endif
 #define CTK_INST_GEOM(SZ, EX)                                                                 \
   CTK_INST(2, true, SZ, EX) CTK_INST(2, false, SZ, EX) CTK_INST(3, true, SZ, EX)              \
   CTK_INST(3, false, SZ, EX)

@@ -8,4 +8,7 @@
 namespace ctk {
 template <class C>
 int launch_refine(const BatchArgs& args, cudaStream_t stream, char* err, size_t err_len);
+// one pass of a global-level fit (ctk_global_pass); instantiated for the full flavour only
+template <class C>
+int launch_global(const BatchArgs& args, cudaStream_t stream, char* err, size_t err_len);
 }

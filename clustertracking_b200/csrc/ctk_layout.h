@@ -75,7 +75,7 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
   int v_max = 0;
   for (int c = 0; c < p.n_params; ++c) {
     if (p.modes[c] == CTK_MODE_VAR) v_max += n_max;
-    else if (p.modes[c] == CTK_MODE_CLUSTER) v_max += 1;
+    else if (p.modes[c] == CTK_MODE_CLUSTER || p.modes[c] == CTK_MODE_GLOBAL) v_max += 1;
   }
   if (v_max < 1) v_max = 1;
   if (v_max > (big ? 65535 : 255)) return false;        // packed (row, column) fields
@@ -177,15 +177,16 @@ inline bool compute_layout(const ctk_problem_t& p, int n_max, Layout* lay) {
   return true;
 }
 
-inline const char* validate_problem(const ctk_problem_t& p) {
+inline const char* validate_problem(const ctk_problem_t& p, bool allow_global = false) {
   if (p.ndim != 2 && p.ndim != 3) return "ndim must be 2 or 3";
   if (p.family < CTK_FAMILY_GAUSS || p.family > CTK_FAMILY_DISC) return "unknown family";
   const int ns = p.isotropic ? 1 : p.ndim;
   const int ne = p.family == CTK_FAMILY_GAUSS ? 0 : 1;
   if (p.n_params != 2 + p.ndim + ns + ne) return "n_params does not match ndim/isotropic/family";
   for (int c = 0; c < p.n_params; ++c)
-    if (p.modes[c] != CTK_MODE_CONST && p.modes[c] != CTK_MODE_VAR && p.modes[c] != CTK_MODE_CLUSTER)
-      return "parameter modes must be const, var or cluster (global is out of scope)";
+    if (p.modes[c] != CTK_MODE_CONST && p.modes[c] != CTK_MODE_VAR && p.modes[c] != CTK_MODE_CLUSTER &&
+        !(allow_global && p.modes[c] == CTK_MODE_GLOBAL))
+      return "parameter modes must be const, var or cluster (global: ctk_global_pass only)";
   if (p.modes[0] == CTK_MODE_VAR) return "background cannot vary per feature (fitfunc.py:389-392)";
   for (int k = 0; k < p.ndim; ++k)
     if (p.radius[k] < 1 || p.radius[k] > CTK_MAX_RADIUS) return "radius out of range [1, 30]";

@@ -84,6 +84,8 @@ CTK_DEV double dmul(double a, double b) { return a * b; }
 CTK_DEV double dadd(double a, double b) { return a + b; }
 CTK_DEV float fast_exp(float x) { return expf(x); }
 CTK_DEV int atomic_next(int32_t* c) { return (*c)++; }
+CTK_DEV void atomic_add_d(double* p, double v) { *p += v; }
+CTK_DEV void atomic_max_nonneg_d(double* p, double v) { if (v > *p) *p = v; }
 #else
 CTK_DEV int lane_id() { return threadIdx.x & 31; }
 CTK_DEV void warp_sync() { __syncwarp(); }
@@ -100,6 +102,11 @@ CTK_DEV double dmul(double a, double b) { return __dmul_rn(a, b); }
 CTK_DEV double dadd(double a, double b) { return __dadd_rn(a, b); }
 CTK_DEV float fast_exp(float x) { return __expf(x); }
 CTK_DEV int atomic_next(int32_t* c) { return atomicAdd(c, 1); }
+CTK_DEV void atomic_add_d(double* p, double v) { atomicAdd(p, v); }
+// maximum of non-negative doubles: their bit patterns order like unsigned integers
+CTK_DEV void atomic_max_nonneg_d(double* p, double v) {
+  atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long) __double_as_longlong(v));
+}
 #endif
 CTK_DEV double fast_exp(double x) { return exp(x); }
 #ifdef CTK_EMUL
@@ -225,6 +232,12 @@ struct BatchArgs {
   const int32_t* n_work_dev; // optional device-side work count (<= n_work)
   char* big_workspace;       // BIG kernels: one slice of lay.total bytes per block
   int big_blocks;            // number of slices
+  // global-level fits (ctk_global_pass): see ClusterSolver::run_global
+  const double* mask_centres;  // optional [n_features, ndim]: centres of the pixel sets
+  const double* global_step;   // phase 2: step of the global unknowns [G]
+  double* global_accum;        // [CTK_GLOBAL_HEADER + G + G (G + 1) / 2] sums over the clusters
+  double global_norm, global_lambda;
+  int global_phase, use_newton;
   Layout lay;
 };
 
@@ -389,7 +402,7 @@ struct ClusterSolver {
 #endif
 
   // cluster
-  int n, feat0, V, M, npairs;
+  int n, feat0, V, V_loc, M, npairs;   // V_loc: unknowns private to the cluster (globals come last)
   int blo[3], bdim[3];
   int cached_V;                  // V the packed-index tables were built for (-1 = none)
   int shared_columns;            // parameter columns (besides background) shared within the cluster
@@ -585,7 +598,8 @@ struct ClusterSolver {
     }
     shared_columns = 0;
 #pragma unroll
-    for (int c = 1; c < P; ++c) shared_columns += mode(c) == CTK_MODE_CLUSTER ? 1 : 0;
+    for (int c = 1; c < P; ++c)
+      shared_columns += (mode(c) == CTK_MODE_CLUSTER || mode(c) == CTK_MODE_GLOBAL) ? 1 : 0;
     warp_sync();
   }
 
@@ -598,8 +612,17 @@ struct ClusterSolver {
     int v = 0;
     for (int c = 0; c < P; ++c) {
       const int m = cmode[c];
+      if (m == CTK_MODE_GLOBAL) continue;
       if (lane == 0) cbase[c] = v;
       v += m == CTK_MODE_VAR ? n : (m == CTK_MODE_CLUSTER ? 1 : 0);
+    }
+    V_loc = v;
+    // columns shared by ALL features of the table ('global', refine.py:319-332): one unknown each,
+    // numbered after the cluster's own so that eliminating the first V_loc leaves their Schur block
+    for (int c = 0; c < P; ++c) {
+      if (cmode[c] != CTK_MODE_GLOBAL) continue;
+      if (lane == 0) cbase[c] = v;
+      v += 1;
     }
     V = v;
     if (V > a.lay.v_max || V > (C::BIG ? 65535 : 255)) return CTK_FAIL_TOO_LARGE;
@@ -616,7 +639,8 @@ struct ClusterSolver {
       const int m = cmode[c];
       const double p = pin[t];
       bad |= !finite_d(p);
-      cv[t] = m == CTK_MODE_VAR ? cbase[c] + i : (m == CTK_MODE_CLUSTER ? cbase[c] : -1);
+      cv[t] = m == CTK_MODE_VAR ? cbase[c] + i
+                                : ((m == CTK_MODE_CLUSTER || m == CTK_MODE_GLOBAL) ? cbase[c] : -1);
       if (m == CTK_MODE_VAR) {
         const int vi = cbase[c] + i;
         const double* tb = ctab + c * 6;
@@ -628,8 +652,8 @@ struct ClusterSolver {
     if (warp_any(bad)) return CTK_FAIL_NONFINITE;
 #pragma unroll 1
     for (int c = lane; c < P; c += CTK_WARP) {
-      if (cmode[c] != CTK_MODE_CLUSTER) continue;       // shared entry: mean start, widest bound
-      const double* tb = ctab + c * 6;
+      if (cmode[c] != CTK_MODE_CLUSTER && cmode[c] != CTK_MODE_GLOBAL) continue;
+      const double* tb = ctab + c * 6;                  // shared entry: mean start, widest bound
       double s = 0., l = INFINITY, h = -INFINITY;
       for (int i = 0; i < n; ++i) {
         const double p = pin[i * P + c];
@@ -639,6 +663,7 @@ struct ClusterSolver {
       }
       const int vi = cbase[c];
       x0[vi] = s / n; lo[vi] = l; hi[vi] = h;
+      if (cmode[c] == CTK_MODE_GLOBAL) { lo[vi] = -INFINITY; hi[vi] = INFINITY; }   // the host's job
     }
     warp_sync();
     bad = false;
@@ -1304,7 +1329,11 @@ struct ClusterSolver {
   // trailing block) with the forward substitution folded in, then back-substitutes.  On return D()
   // holds the step.  Returns false on breakdown.
   // reuse: keep the factor of the previous call (same active set required, else refactorise).
-  CTK_DEV_BIG bool solve(double lambda, double* rhs_full, bool reuse) {
+  // n_elim >= 0 (global-level fits): eliminate only the first n_elim unknowns -- the cluster's own
+  // -- and return: the trailing block of the factor then holds the (scaled) Schur complement of
+  // the shared unknowns and the tail of D() their reduced right-hand side.  Those unknowns get no
+  // damping here (the host damps the summed block).
+  CTK_DEV_BIG bool solve(double lambda, double* rhs_full, bool reuse, int n_elim = -1) {
     const Real* H = Hm();
     Real* Kf = Lm();
     double* d = D();
@@ -1370,12 +1399,13 @@ struct ClusterSolver {
         const int r = rc_row(rc[t]), c = rc_col(rc[t]);
         Real v;
         if (act[r] || act[c]) v = (r == c) ? (Real) 1 : (Real) 0;
-        else if (r == c) v = lam1;
+        else if (r == c) v = (n_elim >= 0 && r >= n_elim) ? (Real) 1 : lam1;
         else v = Kf[t] * (Real) (sc[r] * sc[c]);
         Kf[t] = v;
       }
       warp_sync();
-      for (int j = 0; j < V; ++j) {
+      const int n_cols = n_elim >= 0 ? n_elim : V;
+      for (int j = 0; j < n_cols; ++j) {
         const int cj = cs[j];
         const Real piv = Kf[cj];
         if (!(piv > (Real) 1e-7)) return false;              // also catches NaN
@@ -1396,6 +1426,7 @@ struct ClusterSolver {
         warp_sync();
       }
     }
+    if (n_elim >= 0) return true;
     for (int j = V - 1; j >= 0; --j) {                     // back substitution with L^T
       const double zj = d[j] * (double) idg[j];
       warp_sync();
@@ -1758,6 +1789,133 @@ struct ClusterSolver {
     warp_sync();
     *f_data = best;
     return status;
+  }
+
+  // ---- global-level fits (refine.py:319-332): one pass over one cluster ---------------------------
+  // Some columns are shared by ALL features of the table, so the whole table is ONE problem:
+  //   F = sum_c w_c f_c(x_c, g),  f_c = 0.5 sum r^2 of cluster c, w_c = 2 / (M_c norm)
+  // (fitfunc.py:436-450 divides every cluster's sum by its own pixel count).  Its normal matrix is
+  // a block arrow: per-cluster blocks A_c, couplings B_c to the shared unknowns g, and sum_c C_c.
+  // The host iterates; every iteration launches two passes over all clusters:
+  //   phase 1  at the current point: pixel set, residuals, normal equations (as in the per-cluster
+  //            fit), elimination of the cluster's own unknowns, and w_c (C_c - B_c^T A_c^-1 B_c),
+  //            w_c (g_g - B_c^T A_c^-1 g_c), w_c f_c added to the global accumulators -- the only
+  //            reduction across clusters (an all-reduce when frames are sharded over ranks);
+  //   phase 2  with the step of the shared unknowns (the host solved the small summed system): the
+  //            cluster's own step by back substitution, the trial point projected on the box, its
+  //            objective, the predicted decrease and the step size, and the trial parameters.
+  enum { GLOBAL_F = 0, GLOBAL_FT = 1, GLOBAL_PRED = 2, GLOBAL_STEP = 3, GLOBAL_FAILED = 4,
+         GLOBAL_SINGULAR = 5, GLOBAL_HEADER = CTK_GLOBAL_HEADER };
+  CTK_DEV void run_global(int cluster) {
+    feat0 = a.cluster_offset[cluster];
+    n = a.cluster_offset[cluster + 1] - feat0;
+    const int fidx = a.cluster_frame[cluster];
+    frame = a.frames[fidx];
+    fmax_ = 0.;
+    evals = accums = grad_accums = outers = n_entries = n_pair_entries = 0;
+    M = 0; V = 0; n_con = 0; pen_w = 0.;
+    double* acc = a.global_accum;
+    int status = (n <= 0 || n > a.lay.n_max) ? CTK_FAIL_TOO_LARGE : CTK_OK;
+    if (status == CTK_OK) status = setup_variables();
+    if (status == CTK_OK) {
+      double* mc = MC();
+#pragma unroll 1
+      for (int i = lane; i < n; i += CTK_WARP) {
+#pragma unroll
+        for (int k = 0; k < ND; ++k)
+          mc[i * 3 + k] = a.mask_centres ? a.mask_centres[(int64_t) (feat0 + i) * ND + k]
+                                         : a.params_in[(int64_t) (feat0 + i) * P + 2 + k];
+      }
+      warp_sync();
+      status = build_pixels();
+    }
+    double fd = 0.;
+    if (status == CTK_OK) {
+      CTK_FOR_V(v) { X()[v] = X0()[v]; XT()[v] = X0()[v]; }
+      warp_sync();
+      fd = evaluate(X());
+      if (!finite_d(fd)) status = CTK_FAIL_NUMERIC;
+    }
+    if (status != CTK_OK) {
+      if (lane == 0) { atomic_add_d(acc + GLOBAL_FAILED, 1.); a.status_out[cluster] = status; }
+      warp_sync();
+      return;
+    }
+    const double w = 2. / ((double) M * a.global_norm);
+    const int G = V - V_loc;
+    newton = C::FAM == CTK_FAMILY_GAUSS && a.use_newton != 0;
+    accumulate(false);
+    double* rhs_full = dvec(a.lay.o_rhsf);
+    if (!solve(a.global_lambda, rhs_full, false, V_loc)) {
+      if (lane == 0) { atomic_add_d(acc + GLOBAL_SINGULAR, 1.); a.status_out[cluster] = CTK_OK; }
+      warp_sync();
+      return;
+    }
+    double* d = D();
+    const double* sc = DG();
+    const Real* Kf = Lm();
+    const int* cs = CS();
+    if (a.global_phase == 1) {
+      if (lane == 0) atomic_add_d(acc + GLOBAL_F, w * fd);
+#pragma unroll 1
+      for (int t = lane; t < G * (G + 3) / 2; t += CTK_WARP) {
+        if (t < G) {                                   // reduced right-hand side, unscaled
+          atomic_add_d(acc + GLOBAL_HEADER + t, w * d[V_loc + t] / sc[V_loc + t]);
+        } else {                                       // Schur block entry (u, v), u >= v
+          int u = 0, rem = t - G;
+          while (rem > u) { rem -= u + 1; ++u; }
+          const int ru = V_loc + u, rv = V_loc + rem;
+          atomic_add_d(acc + GLOBAL_HEADER + t, w * (double) Kf[cs[rv] + ru - rv] / (sc[ru] * sc[rv]));
+        }
+      }
+    } else {
+      // step of the cluster's own unknowns with the shared part fixed: L_ll^T y_l = d_l - L_gl^T y_g
+      warp_sync();
+      for (int j = V - 1; j >= 0; --j) {
+        const double zj = j >= V_loc ? a.global_step[j - V_loc] / sc[j] : d[j] * (double) IDG()[j];
+        warp_sync();
+        if (lane == 0) d[j] = zj;
+        const int top = j < V_loc ? j : V_loc;
+#pragma unroll 1
+        for (int r = lane; r < top; r += CTK_WARP) d[r] -= (double) Kf[cs[r] + j - r] * zj;
+        warp_sync();
+      }
+      CTK_FOR_V(v) d[v] *= sc[v];
+      warp_sync();
+      double worst = 0.;
+      double *x = X(), *xt = XT();
+      CTK_FOR_V(v) {
+        const double t = fmin(fmax(x[v] + d[v], LO()[v]), HI()[v]);
+        xt[v] = t;
+        const double st = t - x[v];
+        d[v] = st;
+        if (v < V_loc) {
+          const double scale = is_pos_var(v) ? 1. : fmax(1., fabs(x[v]));
+          worst = fmax(worst, fabs(st) / scale);
+        }
+      }
+      worst = warp_max_d(worst);
+      warp_sync();
+      const double pred = predicted(d, rhs_full);
+      const double ft = evaluate(xt);
+      if (lane == 0) {
+        atomic_add_d(acc + GLOBAL_FT, finite_d(ft) ? w * ft : INFINITY);
+        atomic_add_d(acc + GLOBAL_PRED, w * pred);
+        if (finite_d(worst)) atomic_max_nonneg_d(acc + GLOBAL_STEP, worst);
+        else atomic_add_d(acc + GLOBAL_FT, INFINITY);
+      }
+      double* pout = a.params_out + (int64_t) feat0 * P;
+#pragma unroll 1
+      for (int t = lane; t < n * P; t += CTK_WARP) {
+        const int i = t / P, c = t - i * P;
+        pout[t] = value_of(xt, c, i);
+      }
+    }
+    if (lane == 0) {
+      a.status_out[cluster] = CTK_OK;
+      a.cost_out[cluster] = w * fd;
+    }
+    warp_sync();
   }
 
   // ---- whole cluster (refine.py:343-430) -------------------------------------------------------

@@ -243,6 +243,9 @@ def gather_tables(part, group=None, gather='all', ids_done=False):
     return out
 
 
+LAST_GATHER = {}      # diagnostics of the most recent shared-block call (host phases, this rank)
+
+
 class _SharedColumns(object):
     """A [n_slots, total] matrix of 8-byte cells in /dev/shm that all ranks of the host map: column
     k of the merged result table is row k, and a rank's rows are cells row_off[rank] ..
@@ -319,7 +322,9 @@ class _SharedColumns(object):
 def _refine_into_shared(mine, reader, diameter, t_column, group, gather, kwargs):
     """The one-host path: result columns allocated in a shared block, no copy at gather time.
     -> (done, result); done = False: fall back to gather_tables (inputs this scheme cannot hold)."""
+    import time
     import torch.distributed as dist
+    lap = [time.perf_counter()]
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     index_ok = isinstance(mine.index, pd.RangeIndex) or mine.index.dtype.kind in 'iu'
     numeric = all(mine[c].dtype.kind in 'fiu' and mine[c].dtype.itemsize == 8 for c in mine.columns)
@@ -339,9 +344,11 @@ def _refine_into_shared(mine, reader, diameter, t_column, group, gather, kwargs)
         shared = _SharedColumns(name[0], n_slots, total, a, b, create=False)
     try:
         part = None
+        lap.append(time.perf_counter())
         if b > a:
             part = _refine.refine_leastsq(mine, reader, diameter, t_column=t_column,
                                           _alloc=shared.alloc, **kwargs)
+            lap.append(time.perf_counter())
             shared.ready()
             complete = (not shared.spilled and [c for c, _ in shared.columns] != [] and
                         set(part.columns) == set(c for c, _ in shared.columns))
@@ -368,9 +375,16 @@ def _refine_into_shared(mine, reader, diameter, t_column, group, gather, kwargs)
                                group=group)                        # doubles as "all slices written"
         columns, order = next(m for m in meta if m is not None)
         out = None
+        lap.append(time.perf_counter())
         if gather == 'all' or rank == 0:
             out = shared.table(columns, private=rank != 0)[order]
+        lap.append(time.perf_counter())
         dist.barrier(group=group)                                  # every reader has mapped it
+        lap.append(time.perf_counter())
+        LAST_GATHER.clear()
+        if len(lap) == 6:
+            LAST_GATHER.update(zip(("setup_ms", "refine_ms", "ids_and_wait_ms", "table_ms", "barrier_ms"),
+                                   (1e3 * (y - x) for x, y in zip(lap[:-1], lap[1:]))))
         return True, out
     finally:
         if rank == 0 and os.path.exists(name[0]):

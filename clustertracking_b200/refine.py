@@ -164,7 +164,7 @@ def prepare_common(f, reader, diameter, separation=None, fit_function='gauss', p
                    param_val=None, constraints=None, bounds=None, pos_columns=None,
                    t_column='frame', noise_size=None, threshold=None, max_iter=10, max_shift=1,
                    max_rms_dev=1., residual_factor=100000., compute_error=False, frames_hook=None,
-                   **kwargs):
+                   allow_global=False, **kwargs):
     """Argument handling of refine.py:242-315 (no clustering, no GPU work) -> :class:`Prepared`.
     ``frames_hook`` is called with the :class:`FrameInfo` as soon as the frames of the call are
     known: ``refine_leastsq`` uses it to start the uploads while the host is still busy."""
@@ -186,9 +186,10 @@ def prepare_common(f, reader, diameter, separation=None, fit_function='gauss', p
         separation = diameter
 
     ff = FitFunctions(fit_function, ndim, isotropic, param_mode)       # refine.py:291
-    if any(m == 2 for m in ff.modes):
+    if any(m == 2 for m in ff.modes) and not allow_global:
         raise NotImplementedError("param_mode 'global' couples all clusters into one problem "
-                                  "(refine.py:319-332) and is out of scope of the CUDA solver")
+                                  "(refine.py:319-332): call refine_leastsq, which runs it through "
+                                  "clustertracking_b200.global_fit")
     if any(m > 3 for m in ff.modes):
         raise NotImplementedError("param modes 'particle' and 'frame' are not implemented")
     if len(ff.params) > _lib.CTK_MAX_PARAMS:
@@ -275,13 +276,13 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
             param_val=None, constraints=None, bounds=None, pos_columns=None, t_column='frame',
             noise_size=None, threshold=None, max_iter=10, max_shift=1, max_rms_dev=1.,
             residual_factor=100000., compute_error=False, frames_hook=None, empty=np.empty,
-            **kwargs):
+            allow_global=False, **kwargs):
     """Host half of ``refine_leastsq`` for the whole table at once: returns a :class:`Plan` (no GPU
     work).  ``empty(shape, dtype)`` allocates the packed parameter table."""
     pre = prepare_common(f, reader, diameter, separation, fit_function, param_mode, param_val,
                          constraints, bounds, pos_columns, t_column, noise_size, threshold,
                          max_iter, max_shift, max_rms_dev, residual_factor, compute_error,
-                         frames_hook=frames_hook, **kwargs)
+                         frames_hook=frames_hook, allow_global=allow_global, **kwargs)
     ff, info = pre.ff, pre.info
     import time as _time
     _t0 = _time.perf_counter()
@@ -318,6 +319,8 @@ def prepare(f, reader, diameter, separation=None, fit_function='gauss', param_mo
                      np.searchsorted(info.sorted_numbers, frames_s[starts]).astype(np.int32),
                      params_in)
     plan.f = f
+    plan.solver = dict(max_iter=int(max_iter), max_shift=float(max_shift),
+                       max_rms_dev=float(max_rms_dev), residual_factor=float(residual_factor))
     plan.timing = dict(cluster_ms=1e3 * (_t1 - _t0), pack_ms=1e3 * (_time.perf_counter() - _t1))
     return plan
 
@@ -1029,6 +1032,38 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
                 _FRAMESETS.pop().close()
 
 
+def _has_global(fit_function, param_mode):
+    return bool(param_mode) and any(v == 'global' or v == 2 for v in param_mode.values())
+
+
+def _refine_global(f, reader, diameter, separation, fit_function, param_mode, param_val, constraints,
+                   bounds, pos_columns, t_column, noise_size, threshold, max_iter, max_shift,
+                   max_rms_dev, residual_factor, compute_error, passes_factory=None, **kwargs):
+    """``param_mode`` with a 'global' column: ONE problem over the whole table (refine.py:319-332),
+    solved as a block-arrow system -- see :mod:`clustertracking_b200.global_fit`."""
+    from . import global_fit
+    if constraints:
+        raise NotImplementedError("constraints on a global-level fit (constraints.dimer_global) are "
+                                  "not available in the CUDA solver")
+    lm_max_iter, _, xtol, _, _ = _solver_options(dict(kwargs), 'float32')
+    started = []
+    hook = None if passes_factory is not None else (
+        lambda info: started.append(_track(FrameSet(info)).upload_async()))
+    plan = prepare(f, reader, diameter, separation, fit_function, param_mode, param_val, None, bounds,
+                   pos_columns, t_column, noise_size, threshold, max_iter, max_shift, max_rms_dev,
+                   residual_factor, compute_error, frames_hook=hook, allow_global=True, **kwargs)
+    if plan.cluster_sizes().max() > _lib.CTK_MAX_CLUSTER_FEATURES:
+        raise NotImplementedError("global-level fits take clusters of up to %d features"
+                                  % _lib.CTK_MAX_CLUSTER_FEATURES)
+    passes = (passes_factory(plan) if passes_factory is not None
+              else global_fit.CudaPasses(plan, started[0]))
+    ok, params, rms_dev = global_fit.solve(plan, passes, plan.ff, int(max_iter), float(max_shift),
+                                           float(max_rms_dev), float(residual_factor), lm_max_iter, xtol)
+    LAST_CALL.clear()
+    LAST_CALL.update(launches=getattr(passes, 'launches', 0), chunks=1, h2d_bytes=0, d2h_bytes=0)
+    return global_fit.write_back(plan, ok, params, rms_dev)
+
+
 def _track(frameset):
     _FRAMESETS.append(frameset)
     return frameset
@@ -1060,6 +1095,11 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
     import pandas as pd
     t0 = time.perf_counter()
     _ARENA.reset()
+    if _has_global(fit_function, param_mode):
+        return _refine_global(f, reader, diameter, separation, fit_function, param_mode, param_val,
+                              constraints, bounds, pos_columns, t_column, noise_size, threshold,
+                              max_iter, max_shift, max_rms_dev, residual_factor, compute_error,
+                              **kwargs)
     started = []          # the uploads start as soon as the frames are known, before the clustering
     pre = prepare_common(f, reader, diameter, separation, fit_function, param_mode, param_val,
                          constraints, bounds, pos_columns, t_column, noise_size, threshold,

@@ -37,8 +37,10 @@ extern "C" {
 #define CTK_PROBE_MAX_FEATURES 8 /* ring / disc: clusters of up to this many features get the basin
                                     search (ctk_problem_t.probe_step); larger ones one minimisation */
 
-/* parameter modes, same codes as fitfunc.py:9-11 (2 = 'global' is out of scope) */
-enum { CTK_MODE_CONST = 0, CTK_MODE_VAR = 1, CTK_MODE_CLUSTER = 3 };
+/* parameter modes, same codes as fitfunc.py:9-11.  CTK_MODE_GLOBAL (one value for ALL features,
+ * refine.py:319-332) is only valid for ctk_global_pass. */
+enum { CTK_MODE_CONST = 0, CTK_MODE_VAR = 1, CTK_MODE_GLOBAL = 2, CTK_MODE_CLUSTER = 3 };
+#define CTK_GLOBAL_HEADER 8      /* leading entries of the ctk_global_pass accumulator */
 /* radial model families, fitfunc.py:112-146, 195-204 */
 enum { CTK_FAMILY_GAUSS = 0, CTK_FAMILY_RING = 1, CTK_FAMILY_DISC = 2 };
 /* pixel types of the frames */
@@ -237,6 +239,36 @@ int ctk_refine_batch_ex(const ctk_problem_t* prob,
                      int32_t* d_stats_out, void* d_workspace,
                      const int32_t* d_n_work, int32_t* d_overflow, int32_t overflow_capacity,
                      int32_t flags, void* stream);
+
+/* One pass of a GLOBAL-level fit (param_mode 'global': some columns are shared by all features, so
+ * the whole table is one problem; refine.py:319-332, 343-394 with level == 'global', objective
+ * fitfunc.py:421-489 with groups).  The host iterates a damped Newton / Gauss-Newton method on the
+ * block-arrow system; every iteration calls this twice over all clusters:
+ *   phase 1  at d_params_in: per cluster the pixel set, residuals, normal equations, elimination of
+ *            the cluster's own unknowns; adds to d_accum (which the caller zeroes):
+ *              [0] F = sum_c nansum(diff^2) / M_c / norm          (the reference's objective)
+ *              [4] clusters that failed (out of image, non-finite)   [5] singular eliminations
+ *              [8 .. 8+G)            reduced right-hand side of the G shared unknowns
+ *              [8+G .. 8+G+G(G+1)/2) their Schur complement, lower triangle row by row
+ *            -- the ONLY reduction across clusters: all-reduce d_accum when frames are sharded;
+ *   phase 2  given d_global_step [G] (the host solved the summed system): per cluster the step of
+ *            its own unknowns by back substitution, the trial point projected on its bounds,
+ *            written to d_params_out; adds [1] F at the trial point, [2] the decrease predicted by
+ *            the quadratic model, [3] (max) the largest scaled step of a per-cluster unknown.
+ * Shared unknowns are numbered in column order.  modes may contain CTK_MODE_GLOBAL; constraints
+ * are not supported.  lambda: Marquardt damping of the per-cluster blocks; use_newton: add the
+ * second-order term of the Hessian (gauss family).  d_mask_centres [n_features, ndim] or NULL
+ * (= the positions in d_params_in): centres of the pixel sets (refine.py:365-388 re-centres them
+ * between minimisations).  norm = max over frames of max()^2 / residual_factor (refine.py:325-331).
+ * max_cluster_features <= CTK_MAX_CLUSTER_FEATURES. */
+int ctk_global_pass(const ctk_problem_t* prob,
+                    const void* const* d_frames, const int64_t* frame_shape, double norm,
+                    int32_t n_clusters, int32_t max_cluster_features,
+                    const int32_t* d_cluster_frame, const int32_t* d_cluster_offset,
+                    const double* d_params_in, const double* d_mask_centres,
+                    int32_t phase, double lambda, int32_t use_newton,
+                    const double* d_global_step, double* d_params_out, double* d_accum,
+                    double* d_cost_out, int32_t* d_status_out, void* d_workspace, void* stream);
 
 /* Host helper (no GPU): cluster labels of one frame from the close pairs, visiting the pairs in the
  * given order with the reference's "the label of a's cluster survives" rule (find.py:41-48, 84-93).

@@ -454,6 +454,131 @@ class ModelSpec(object):
 
 
 # ----------------------------------------------------------------------------------------------
+# global level: one problem over the whole table                       refine.py:319-332
+# ----------------------------------------------------------------------------------------------
+def pack_vector_groups(params, modes, groups, reduce_op=None):
+    """fitfunc.py:207-263 WITH groups (the clusters): const skipped, var -> n entries, global -> one
+    entry over all rows, cluster -> one entry per group."""
+    chunks = []
+    for j, mode in enumerate(modes):
+        if mode == CONST:
+            continue
+        if mode == VAR:
+            chunks.append(params[:, j])
+        elif mode == GLOBAL:
+            chunks.append([params[0, j] if reduce_op is None else reduce_op(params[:, j])])
+        elif reduce_op is None:
+            chunks.append(params[[g[0] for g in groups], j])
+        else:
+            chunks.append([reduce_op(params[g, j]) for g in groups])
+    if not chunks:
+        return np.empty((0,))
+    return np.concatenate([np.asarray(c, dtype=np.float64) for c in chunks])
+
+
+def unpack_vector_groups(vect, params, modes, groups):
+    """fitfunc.py:266-315 WITH groups."""
+    n = params.shape[0]
+    out = params.copy()
+    at = 0
+    for j, mode in enumerate(modes):
+        if mode == CONST:
+            continue
+        if mode == VAR:
+            out[:, j] = vect[at:at + n]
+            at += n
+        elif mode == GLOBAL:
+            out[:, j] = vect[at]
+            at += 1
+        else:
+            for g, value in zip(groups, vect[at:at + len(groups)]):
+                out[g, j] = value
+            at += len(groups)
+    return out
+
+
+def _refine_global(f, frames, spec, tables, radius, ndim, t_column, noise_size, threshold,
+                   max_iter, max_shift, max_rms_dev, residual_factor, constraints, solver):
+    """refine.py:319-332 + 343-430 for level == 'global': ONE minimisation over all rows; the
+    objective is the sum of the per-cluster terms of fitfunc.py:436-450 (each divided by its own
+    pixel count), the norm comes from the brightest frame."""
+    if constraints:
+        raise NotImplementedError("constraints on a global fit (dimer_global) are out of scope")
+    params = f[spec.params].values.astype(np.float64)
+    # refine.py:349-350: groups = row positions per cluster, in the order of the cluster ids
+    groups = [np.asarray(g) for g in f.reset_index().groupby('cluster').indices.values()]
+    frame_nos = f[t_column].values
+    norm = max(float(np.asarray(frames[int(i)]).max()) for i in np.unique(frame_nos)) ** 2 / residual_factor
+    modes, n_cols, n_extra = spec.modes, params.shape[1], len(spec.extra)
+    iso, safe = spec.isotropic, spec.safe
+    try:
+        if not np.isfinite(params).all():
+            raise FitFailure("non-finite initial parameters")
+        coords = params[:, 2:2 + ndim]
+        x0 = pack_vector_groups(params, modes, groups, np.mean)              # refine.py:361
+        low, high = spec.feature_bounds(tables, params)
+        box = np.array([pack_vector_groups(low, modes, groups, np.min),
+                        pack_vector_groups(high, modes, groups, np.max)]).T  # fitfunc.py:552-558
+        for _ in range(max_iter):                                            # refine.py:365
+            pix = [cluster_pixels(coords[g], np.asarray(frames[int(frame_nos[g[0]])]), radius,
+                                  noise_size, threshold) for g in groups]    # refine.py:61-79
+
+            def fun(vect):                                                   # fitfunc.py:436-450
+                if np.any(np.isnan(vect)):
+                    raise FitFailure("non-finite parameter vector")
+                p = unpack_vector_groups(vect, params, modes, groups)
+                total = 0.
+                for g, (values, mesh, masks) in zip(groups, pix):
+                    diff = values - p[g[0], 0]
+                    for i, mask in zip(g, masks):
+                        r2 = _reduced_r2(mesh[:, mask], p[i], ndim, iso, safe)
+                        diff[mask] -= p[i, 1] * spec.value(r2, p[i, n_cols - n_extra:], ndim)
+                    total += np.nansum(diff ** 2) / len(values)
+                return total / norm
+
+            def grad(vect):                                                  # fitfunc.py:455-487
+                if np.any(np.isnan(vect)):
+                    raise FitFailure("non-finite parameter vector")
+                p = unpack_vector_groups(vect, params, modes, groups)
+                out = p.copy()
+                for g, (values, mesh, masks) in zip(groups, pix):
+                    diff = values - p[g[0], 0]
+                    derivs = np.zeros((len(g), n_cols - 1, len(values)))
+                    for k, (i, m) in enumerate(zip(g, masks)):
+                        r2 = _reduced_r2(mesh[:, m], p[i], ndim, iso, safe)
+                        dr2 = _reduced_r2_grad(mesh[:, m], p[i], ndim, iso)
+                        model, dmodel = spec.value_grad(r2, p[i, n_cols - n_extra:], ndim)
+                        diff[m] -= p[i, 1] * model
+                        derivs[k, 0, m] = model
+                        derivs[k, 1:1 + len(dr2), m] = p[i, 1] * (dmodel[0] * dr2).T
+                        if n_extra > 0:
+                            derivs[k, -n_extra:, m] = p[i, 1] * np.array(dmodel[1:]).T
+                    out[g, 1:] = np.nansum(-2 * diff * derivs, axis=2) / len(values)
+                    out[g, 0] = np.nansum(-2 * diff) / (len(g) * len(values))
+                return pack_vector_groups(out, modes, groups, np.sum) / norm
+
+            res = minimize(fun, x0, bounds=box, jac=grad if spec.value_grad is not None else None,
+                           **solver)
+            if not res['success']:
+                raise FitFailure(res['message'])
+            rms_dev = np.sqrt(res['fun'] / residual_factor)
+            params = unpack_vector_groups(res['x'], params, modes, groups)
+            moved = params[:, 2:2 + ndim]
+            if np.all(np.sum((moved - coords) ** 2, 1) < max_shift ** 2):
+                break
+            coords = moved
+        if rms_dev > max_rms_dev:
+            raise FitFailure("rms deviation %.4f above the maximum %.4f" % (rms_dev, max_rms_dev))
+    except FitFailure as exc:                                                # refine.py:409-411
+        f['cost'] = np.nan
+        logger.warning('RefineException: %s', exc.args[0] if exc.args else '')
+    else:                                                                    # refine.py:420-422
+        f[spec.params] = params
+        f['cost'] = rms_dev
+    return f
+
+
+# ----------------------------------------------------------------------------------------------
 # constraints                                                          constraints.py:17-137
 # ----------------------------------------------------------------------------------------------
 def _pair_defect(pos, a, b, dist):
@@ -574,8 +699,6 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
         separation = diameter
 
     spec = ModelSpec(fit_function, ndim, isotropic, param_mode)
-    if any(m == GLOBAL for m in spec.modes):
-        raise NotImplementedError("global parameter modes are out of scope")
     if any(m > CLUSTER for m in spec.modes):
         raise NotImplementedError("modes 'particle' and 'frame' are not implemented upstream")
 
@@ -586,6 +709,9 @@ def refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', p
     for col in [p for p in spec.params if p not in f.columns]:          # refine.py:303-305
         f[col] = spec.default[col]
     tables = spec.bounds_tables(bounds, radius)                         # refine.py:315
+    if any(m == GLOBAL for m in spec.modes):                            # refine.py:319-332
+        return _refine_global(f, frames, spec, tables, radius, ndim, t_column, noise_size, threshold,
+                              max_iter, max_shift, max_rms_dev, residual_factor, constraints, solver)
 
     for _, group in f.groupby(['frame', 'cluster']):                    # refine.py:336, 343
         params = group[spec.params].values.astype(np.float64)

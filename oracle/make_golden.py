@@ -171,7 +171,7 @@ def _grow_clusters(rng, centres, sizes_k, bond, ndim):
 
 
 def _refine_case(ct, name, image, f0, diameter, call_kwargs, frames=None, constraint=None,
-                 watch_loop=False):
+                 watch_loop=False, first_frame=0):
     """Run the reference with default tol and tol=1e-12 and store everything.
     ``constraint`` = (kind, dist) describes ``call_kwargs['constraints']`` for the fixture.
     ``watch_loop``: also store the clusters whose re-mask loop did not settle (_OuterLoopSpy)."""
@@ -191,6 +191,8 @@ def _refine_case(ct, name, image, f0, diameter, call_kwargs, frames=None, constr
         outs.update(frame_to_arrays(tag, res))
     meta = dict(diameter=diameter, constraint=constraint,
                 kwargs={k: v for k, v in call_kwargs.items() if k != 'constraints'})
+    if first_frame:
+        meta['first_frame'] = first_frame
     if watch_loop:
         meta['unsettled'] = sorted(unsettled)
     save(name, image=np.asarray(image), meta=np.array(json.dumps(meta)),
@@ -609,6 +611,76 @@ def golden_fuzz(ct):
                         **case['meta'])
             save("fuzz_%d_%02d" % (seed, case['case']), image=case['frame'],
                  meta=np.array(json.dumps(meta)), **frame_to_arrays("in_", f0), **outs)
+
+
+def golden_global(ct):
+    """Global-mode fits (refine.py:319-332): one problem over the whole table, some columns shared
+    by ALL features.  The combinations the reference's suite exercises (tests/test_refine.py:924-938:
+    ``signal='global'`` with free positions) plus a shared size, single- and multi-frame, 3D."""
+    rng = np.random.RandomState(97531)
+
+    def grid_positions(shape, pitch, margin, jitter):
+        axes = [np.arange(margin, s - margin + 1e-9, pitch) for s in shape]
+        pos = np.array([g.ravel() for g in np.meshgrid(*axes, indexing='ij')], float).T
+        return pos + rng.uniform(-jitter, jitter, pos.shape)
+
+    def start_frame(pos, err, cols, **const):
+        f0 = pd.DataFrame(pos + rng.uniform(-err, err, pos.shape), columns=cols)
+        for k, v in const.items():
+            f0[k] = v
+        return f0
+
+    shape = (128, 128)
+    centres = grid_positions(shape, 40, 24, 3)
+    pos, _ = _grow_clusters(rng, centres, rng.randint(1, 4, len(centres)), 5.5, 2)
+    image = _draw(shape, pos, 2.75, 160., 'gauss', 6, rng)
+    f0 = start_frame(pos, 0.4, ['y', 'x'], signal=130., size=2.75, background=3.)
+    _refine_case(ct, "refine_global_signal2d", image, f0, 11,
+                 dict(param_mode=dict(signal='global')))
+    f0 = start_frame(pos, 0.4, ['y', 'x'], signal=130., size=3.2, background=3.)
+    _refine_case(ct, "refine_global_size2d", image, f0, 11,
+                 dict(param_mode=dict(signal='var', size='global')))
+    # the train_leastsq pattern (refine.py:494-512): positions, signal, background fixed, shape global
+    f0 = start_frame(pos, 0.0, ['y', 'x'], signal=150., size=3.3, background=6.)
+    _refine_case(ct, "refine_global_train2d", image, f0, 11,
+                 dict(param_mode=dict(signal='const', background='const', pos='const', size='global'),
+                      bounds=dict(size_rel_diff=(0.9, 9))))
+    # three frames, signal and size global
+    stack, rows = [], []
+    for t in range(3):
+        c = grid_positions((96, 96), 44, 26, 3)
+        p, _ = _grow_clusters(rng, c, rng.randint(1, 3, len(c)), 5.5, 2)
+        stack.append(_draw((96, 96), p, 2.75, 150., 'gauss', 5, rng))
+        ft = start_frame(p, 0.4, ['y', 'x'], signal=120., size=3.0, background=2.)
+        ft['frame'] = t + 2
+        rows.append(ft)
+    f0 = pd.concat(rows, ignore_index=True)
+    frames = {t + 2: img for t, img in enumerate(stack)}
+    _refine_case(ct, "refine_global_video2d", np.array(stack), f0, 11,
+                 dict(param_mode=dict(signal='global', size='global')), frames=_VideoAt(np.array(stack), 2),
+                 first_frame=2)
+    shape = (32, 64, 64)
+    centres = grid_positions(shape, 30, 15, 2)
+    pos, _ = _grow_clusters(rng, centres, rng.randint(1, 3, len(centres)), (4.5, 6.5, 6.5), 3)
+    image = _draw(shape, pos, (2.25, 3.25, 3.25), 150., 'gauss', 4, rng)
+    f0 = start_frame(pos, 0.4, ['z', 'y', 'x'], signal=120., size_z=2.5, size_y=3.0, size_x=3.0,
+                     background=2.)
+    _refine_case(ct, "refine_global_size3d", image, f0, (9, 13, 13),
+                 dict(param_mode=dict(signal='var', size='global')))
+
+
+class _VideoAt(object):
+    """_Video whose first frame has a number other than 0."""
+
+    def __init__(self, stack, first):
+        self.stack, self.first = stack, first
+        self.frame_shape = stack.shape[1:]
+
+    def __getitem__(self, i):
+        return self.stack[int(i) - self.first]
+
+    def __len__(self):
+        return len(self.stack)
 
 
 if __name__ == "__main__":

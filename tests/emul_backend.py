@@ -44,6 +44,12 @@ def lib():
     if _handle is None:
         _handle = ctypes.CDLL(_build())
         _handle.ctk_emul_refine_batch.restype = ctypes.c_int
+        _handle.ctk_emul_global_pass.restype = ctypes.c_int
+        _handle.ctk_emul_global_pass.argtypes = (
+            [ctypes.POINTER(_lib.Problem), ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64),
+             ctypes.c_double, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_double, ctypes.c_int32]
+            + [ctypes.c_void_p] * 5)
         _handle.ctk_emul_refine_batch.argtypes = (
             [ctypes.POINTER(_lib.Problem), ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64),
              ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32] + [ctypes.c_void_p] * 9)
@@ -78,5 +84,47 @@ def execute(plan):
 
 
 def refine_leastsq(f, reader, diameter, **kwargs):
+    if _refine._has_global(kwargs.get('fit_function', 'gauss'), kwargs.get('param_mode')):
+        return refine_leastsq_global(f, reader, diameter, **kwargs), None
     plan = _refine.prepare(f, reader, diameter, **kwargs)
     return _refine.finalize(plan, execute(plan)), plan
+
+
+class GlobalPasses(object):
+    """Emulated counterpart of ``global_fit.CudaPasses`` (host arrays, ``ctk_emul_global_pass``)."""
+
+    def __init__(self, plan):
+        self.plan, self.handle = plan, lib()
+        self.frames = [_refine.load_frame(plan, no) for no in plan.frame_numbers]
+        self.ptrs = np.array([fr.ctypes.data for fr in self.frames], dtype=np.uint64)
+        self.shape = (ctypes.c_int64 * 3)(*(list(plan.frame_shape) + [1] * (3 - len(plan.frame_shape))))
+        P = plan.problem.n_params
+        self.G = sum(1 for m in list(plan.problem.modes)[:P] if m == _lib.MODE_GLOBAL)
+        self.cap = int(plan.cluster_sizes().max())
+        self.launches = 0
+
+    def frame_max(self):
+        return max(float(fr.max()) for fr in self.frames)
+
+    def run(self, phase, params, centres, norm, lam, newton, step=None):
+        plan = self.plan
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        centres = np.ascontiguousarray(centres, dtype=np.float64)
+        acc = np.zeros(8 + self.G + self.G * (self.G + 1) // 2)
+        out = np.empty_like(params)
+        cost = np.empty(plan.n_clusters)
+        status = np.zeros(plan.n_clusters, dtype=np.int32)
+        step = np.ascontiguousarray(step if step is not None else np.zeros(max(self.G, 1)), dtype=np.float64)
+        code = self.handle.ctk_emul_global_pass(
+            ctypes.byref(plan.problem), self.ptrs.ctypes.data, self.shape, float(norm), plan.n_clusters,
+            self.cap, plan.cluster_frame.ctypes.data, plan.cluster_offset.ctypes.data,
+            params.ctypes.data, centres.ctypes.data, int(phase), float(lam), int(bool(newton)),
+            step.ctypes.data, out.ctypes.data, acc.ctypes.data, cost.ctypes.data, status.ctypes.data)
+        assert code == 0, "emulated global pass failed: %d" % code
+        self.launches += 1
+        return acc, (out if phase == 2 else None)
+
+
+def refine_leastsq_global(f, reader, diameter, **kwargs):
+    """``clustertracking_b200.refine_leastsq`` for a global-level fit with the emulated passes."""
+    return _refine.refine_leastsq(f, reader, diameter, passes_factory=GlobalPasses, **kwargs)

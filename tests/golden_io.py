@@ -30,12 +30,13 @@ def meta(data):
 class Video(object):
     """Pre-rendered stack exposing what ``refine_leastsq`` needs from a pims reader."""
 
-    def __init__(self, stack):
+    def __init__(self, stack, first_frame=0):
         self.stack = stack
+        self.first_frame = first_frame
         self.frame_shape = stack.shape[1:]
 
     def __getitem__(self, i):
-        return self.stack[i]
+        return self.stack[int(i) - self.first_frame]
 
     def __len__(self):
         return len(self.stack)
@@ -55,5 +56,5 @@ def refine_inputs(data, constraints_module):
     image = data["image"]
     f0 = frame(data, "in_")
     ndim = 3 if "z" in f0.columns else 2
-    reader = Video(image) if image.ndim == ndim + 1 else image
+    reader = Video(image, int(m.get("first_frame", 0))) if image.ndim == ndim + 1 else image
     return f0, reader, diameter, kwargs
