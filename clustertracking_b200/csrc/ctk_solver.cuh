@@ -663,7 +663,9 @@ struct ClusterSolver {
       }
       const int vi = cbase[c];
       x0[vi] = s / n; lo[vi] = l; hi[vi] = h;
-      if (cmode[c] == CTK_MODE_GLOBAL) { lo[vi] = -INFINITY; hi[vi] = INFINITY; }   // the host's job
+      if (cmode[c] == CTK_MODE_GLOBAL) {               // one value for the whole table, bounds: the host's job
+        x0[vi] = pin[c]; lo[vi] = -INFINITY; hi[vi] = INFINITY;
+      }
     }
     warp_sync();
     bad = false;
@@ -1885,7 +1887,9 @@ struct ClusterSolver {
       double worst = 0.;
       double *x = X(), *xt = XT();
       CTK_FOR_V(v) {
-        const double t = fmin(fmax(x[v] + d[v], LO()[v]), HI()[v]);
+        // shared unknowns take the host's step exactly (every cluster must end with the same value)
+        const double t = v >= V_loc ? x[v] + a.global_step[v - V_loc]
+                                    : fmin(fmax(x[v] + d[v], LO()[v]), HI()[v]);
         xt[v] = t;
         const double st = t - x[v];
         d[v] = st;

@@ -31,12 +31,52 @@ HEADER = 8                      # CTK_GLOBAL_HEADER
 F0, FT, PRED, STEP, FAILED, SINGULAR = 0, 1, 2, 3, 4, 5
 
 
+class Reducer(object):
+    """Reductions over the ranks that share one global-level fit (frames sharded over GPUs): the
+    accumulator of ``ctk_global_pass`` -- a few dozen doubles -- is the only thing that crosses
+    ranks on this path.  Without a process group everything is the identity."""
+
+    def __init__(self, group=None, sharded=False):
+        self.group, self.sharded = group, sharded
+
+    def host(self, values, op):
+        """All-reduce a small host array (op: 'sum' | 'max' | 'min')."""
+        values = np.asarray(values, dtype=np.float64)
+        if not self.sharded:
+            return values
+        import torch
+        import torch.distributed as dist
+        dev = ('cuda' if dist.get_backend(self.group) == 'nccl' else 'cpu')
+        t = torch.from_numpy(values.copy()).to(dev)
+        dist.all_reduce(t, op=dict(sum=dist.ReduceOp.SUM, max=dist.ReduceOp.MAX,
+                                   min=dist.ReduceOp.MIN)[op], group=self.group)
+        dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if self.group else 0, group=self.group)
+        return t.cpu().numpy()
+
+    def accumulator(self, acc):
+        """All-reduce the pass accumulator (a torch tensor on the device or a host array): sums,
+        except the step-size slot, which is a maximum."""
+        if not self.sharded:
+            return acc
+        import torch
+        import torch.distributed as dist
+        t = acc if isinstance(acc, torch.Tensor) else torch.from_numpy(acc)
+        step = t[STEP:STEP + 1].clone()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(step, op=dist.ReduceOp.MAX, group=self.group)
+        t[STEP:STEP + 1] = step
+        # every rank must take the SAME accept / reject decisions: make the sums bit-identical
+        dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if self.group else 0, group=self.group)
+        return acc
+
+
 class CudaPasses(object):
     """Device side of the iteration: buffers as torch tensors, ``ctk_global_pass`` through ctypes."""
 
-    def __init__(self, plan, frames):
+    def __init__(self, plan, frames, reducer=None):
         import torch
         self.torch, self.plan, self.frames = torch, plan, frames
+        self.reducer = reducer or Reducer()
         self.lib = _lib.load()
         self.dev = frames.dev
         n, P = plan.params_in.shape
@@ -80,6 +120,7 @@ class CudaPasses(object):
                 self.d_acc.data_ptr(), self.d_cost.data_ptr(), self.d_status.data_ptr(),
                 self.workspace.data_ptr(), stream), "ctk_global_pass")
             self.launches += 1
+            self.reducer.accumulator(self.d_acc)
             acc = self.d_acc.cpu().numpy()
             trial = self.d_out.cpu().numpy() if phase == 2 else None
         return acc, trial
@@ -183,7 +224,8 @@ def solve(plan, passes, ff, max_iter, max_shift, max_rms_dev, residual_factor, l
     gcols = [c for c in range(P) if modes[c] == _lib.MODE_GLOBAL]
     f32 = prob.compute_dtype == _lib.COMPUTE_F32
     start = np.array(plan.params_in, dtype=np.float64, copy=True)
-    if not np.isfinite(start).all():                                   # refine.py:356-357
+    red0 = getattr(passes, 'reducer', None) or Reducer()
+    if red0.host([float(not np.isfinite(start).all())], 'max')[0] > 0.:    # refine.py:356-357
         return False, start, np.nan
     # bounds of the shared unknowns: as broad as possible over the rows (fitfunc.py:552-557)
     tables = [np.array([[t[side][j] for j in range(P)] for side in range(2)])
@@ -194,11 +236,15 @@ def solve(plan, passes, ff, max_iter, max_shift, max_rms_dev, residual_factor, l
         high = np.fmin(np.fmin(start + diff_t[1], start * (1 + rel_t[1])), abs_t[1])
     low[np.isnan(low)] = -np.inf
     high[np.isnan(high)] = np.inf
-    lo_g, hi_g = low[:, gcols].min(axis=0), high[:, gcols].max(axis=0)
-    for c in gcols:                                                    # refine.py:361: the mean
-        start[:, c] = start[:, c].mean()
+    red = getattr(passes, 'reducer', None) or Reducer()
+    lo_g = red.host(low[:, gcols].min(axis=0), 'min')
+    hi_g = red.host(high[:, gcols].max(axis=0), 'max')
+    sums = red.host(np.concatenate((start[:, gcols].sum(axis=0), [len(start)])), 'sum')
+    for k, c in enumerate(gcols):                                      # refine.py:361: the mean
+        start[:, c] = sums[k] / sums[-1]
     start[:, gcols] = np.clip(start[:, gcols], lo_g, hi_g)             # scipy clips x0 into the box
-    norm = passes.frame_max() ** 2 / residual_factor                   # refine.py:325-331
+    fmax = float(red.host([passes.frame_max()], 'max')[0])
+    norm = fmax ** 2 / residual_factor                                 # refine.py:325-331
     if not norm > 0.:
         return False, start, np.nan
     centres = start[:, 2:2 + ndim].copy()
@@ -210,7 +256,8 @@ def solve(plan, passes, ff, max_iter, max_shift, max_rms_dev, residual_factor, l
         if not ok:
             return False, start, np.nan
         moved = params[:, 2:2 + ndim]
-        if np.all(np.sum((moved - centres) ** 2, axis=1) < max_shift ** 2):    # refine.py:383-385
+        far = float(np.any(~(np.sum((moved - centres) ** 2, axis=1) < max_shift ** 2)))
+        if red.host([far], 'max')[0] == 0.:                            # refine.py:383-385
             break
         centres = moved.copy()                                         # refine.py:388
     rms_dev = float(np.sqrt(F / residual_factor))                      # refine.py:379

@@ -411,6 +411,15 @@ def refine_leastsq_sharded(f, reader, diameter, t_column='frame', group=None, pr
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     mine = f if presharded else frame_shard(f, rank, world, t_column)
+    if _refine._has_global(kwargs.get('fit_function', 'gauss'), kwargs.get('param_mode')):
+        # a global-level fit is ONE problem over all ranks: the accumulator of every pass is
+        # all-reduced (global_fit.Reducer) -- the only collective on a data path of this package
+        from . import global_fit
+        if world > 1 and len(mine) == 0:
+            raise ValueError("global-level fits need at least one frame per rank")
+        part = _refine.refine_leastsq(mine, reader, diameter, t_column=t_column,
+                                      reducer=global_fit.Reducer(group, sharded=world > 1), **kwargs)
+        return gather_tables(part, group, gather)
     if os.environ.get('CTK_GATHER', '') not in ('tensors', 'copy'):
         done, out = _refine_into_shared(mine, reader, diameter, t_column, group, gather, kwargs)
         if done:

@@ -1038,7 +1038,8 @@ def _has_global(fit_function, param_mode):
 
 def _refine_global(f, reader, diameter, separation, fit_function, param_mode, param_val, constraints,
                    bounds, pos_columns, t_column, noise_size, threshold, max_iter, max_shift,
-                   max_rms_dev, residual_factor, compute_error, passes_factory=None, **kwargs):
+                   max_rms_dev, residual_factor, compute_error, passes_factory=None, reducer=None,
+                   **kwargs):
     """``param_mode`` with a 'global' column: ONE problem over the whole table (refine.py:319-332),
     solved as a block-arrow system -- see :mod:`clustertracking_b200.global_fit`."""
     from . import global_fit
@@ -1056,7 +1057,9 @@ def _refine_global(f, reader, diameter, separation, fit_function, param_mode, pa
         raise NotImplementedError("global-level fits take clusters of up to %d features"
                                   % _lib.CTK_MAX_CLUSTER_FEATURES)
     passes = (passes_factory(plan) if passes_factory is not None
-              else global_fit.CudaPasses(plan, started[0]))
+              else global_fit.CudaPasses(plan, started[0], reducer))
+    if reducer is not None:
+        passes.reducer = reducer
     ok, params, rms_dev = global_fit.solve(plan, passes, plan.ff, int(max_iter), float(max_shift),
                                            float(max_rms_dev), float(residual_factor), lm_max_iter, xtol)
     LAST_CALL.clear()

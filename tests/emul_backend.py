@@ -122,6 +122,9 @@ class GlobalPasses(object):
             step.ctypes.data, out.ctypes.data, acc.ctypes.data, cost.ctypes.data, status.ctypes.data)
         assert code == 0, "emulated global pass failed: %d" % code
         self.launches += 1
+        reducer = getattr(self, 'reducer', None)
+        if reducer is not None:
+            reducer.accumulator(acc)
         return acc, (out if phase == 2 else None)
 
 

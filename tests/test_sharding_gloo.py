@@ -61,6 +61,12 @@ def _worker(rank, world, port, out_dir):
         if out is not None:
             out.to_pickle(os.path.join(out_dir, "root_%s.pkl" % mode))
     os.environ.pop('CTK_GATHER', None)
+    # (5) a global-level fit over both ranks: the accumulator of every pass is all-reduced
+    out = parallel.refine_leastsq_sharded(mine, reader, 11, presharded=True, gather='root',
+                                          param_mode=dict(signal='var', size='global'),
+                                          passes_factory=emul_backend.GlobalPasses)
+    if out is not None:
+        out.to_pickle(os.path.join(out_dir, "global.pkl"))
     # (4) no gather: every rank keeps its part, cluster ids already running on across ranks
     out = parallel.refine_leastsq_sharded(mine, reader, 11, presharded=True, gather='none')
     out.to_pickle(os.path.join(out_dir, "part%d.pkl" % rank))
@@ -121,6 +127,24 @@ def test_two_rank_sharding_matches_single_process(tmp_path):
         for col in single.columns:
             assert part[col].dtype == single[col].dtype, col
             assert np.array_equal(part[col].values, single[col].values, equal_nan=True), col
+
+
+def test_sharded_global_fit_matches_single_process(tmp_path):
+    """param_mode 'global' over two ranks (frames sharded, Schur accumulators all-reduced) gives
+    the single-process answer."""
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emul_backend
+    emul_backend.lib()
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    got = pd.read_pickle(os.path.join(str(tmp_path), "global.pkl"))
+    reader, f0 = _video()
+    single = emul_backend.refine_leastsq_global(f0, reader, 11, param_mode=dict(signal='var', size='global'))
+    assert np.array_equal(got.index.values, single.index.values)
+    assert np.array_equal(got['cluster'].values, single['cluster'].values)
+    assert np.ptp(got['size'].values) == 0.
+    for col in ('y', 'x', 'signal', 'size', 'background', 'cost'):
+        assert np.allclose(got[col].values, single[col].values, rtol=1e-7, atol=1e-7), col
 
 
 def test_shard_bounds_and_frame_shard():
