@@ -669,6 +669,44 @@ def golden_global(ct):
                  dict(param_mode=dict(signal='var', size='global')))
 
 
+def golden_preprocess(ct):
+    """The reference's ``preprocess`` (preprocessing.py:52-75) and ``characterize``
+    (find_link.py:44-79).  Both lean on trackpy functions that are absent here; the shim restates
+    those from the published algorithm (oracle/ref_shim/trackpy: PARITY UNPINNED against trackpy),
+    so these fixtures pin the reference's own arithmetic around them."""
+    from clustertracking.preprocessing import preprocess, lowpass
+    from clustertracking.find_link import characterize
+    rng = np.random.RandomState(2468)
+    img = (rng.poisson(12, (96, 128)) + 90 * np.exp(-((np.indices((96, 128)) - np.array([40, 70])[:, None, None]) ** 2).sum(0) / 18.)).astype(np.uint8)
+    cases = dict(u8_band=(img, dict(noise_size=1, smoothing_size=11)),
+                 u8_band_aniso=(img, dict(noise_size=(1, 1.5), smoothing_size=(9, 13), threshold=2)),
+                 u8_plain=(img, dict()),
+                 f64_plain=(img.astype(np.float64) / 7.3, dict()),
+                 u16_band=((img.astype(np.uint16) * 37), dict(noise_size=1.2, smoothing_size=9)))
+    vol = (rng.poisson(6, (24, 40, 40)) + 80 * np.exp(-((np.indices((24, 40, 40)) - np.array([12, 20, 22])[:, None, None, None]) ** 2 / np.array([8., 18., 18.])[:, None, None, None]).sum(0))).astype(np.uint8)
+    cases['u8_band_3d'] = (vol, dict(noise_size=1, smoothing_size=(5, 9, 9)))
+    for name, (image, kw) in cases.items():
+        out = preprocess(image, **kw)
+        save("preprocess_" + name, image=image, kwargs=np.array(json.dumps(kw)), out=np.asarray(out),
+             scale_factor=np.float64(out.metadata['scale_factor']))
+    lp = lowpass(img, (1, 1.5), threshold=3)
+    save("preprocess_lowpass", image=img, kwargs=np.array(json.dumps(dict(lshort=(1, 1.5), threshold=3))),
+         out=np.asarray(lp), scale_factor=np.float64(1.))
+    # characterize: features inside, at the edge (zero padding) and at half-integer coordinates
+    coords = np.array([[40.3, 70.2], [3.2, 5.7], [92.5, 120.5], [50.5, 64.0], [41.0, 69.5]])
+    pre = preprocess(img, noise_size=1, smoothing_size=11)
+    for name, image, radius, iso, cds in (
+            ("iso2d", pre, (5, 5), True, coords), ("aniso2d", pre, (4, 6), False, coords),
+            ("raw2d", img, (5, 5), True, coords),
+            ("aniso3d", vol, (3, 5, 5), False, np.array([[12.2, 20.4, 21.7], [1.5, 3.0, 36.5], [20.6, 30.1, 8.8]]))):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = characterize(cds, image, radius, isotropic=iso)
+        save("characterize_" + name, image=np.asarray(image), coords=cds, radius=np.array(radius),
+             isotropic=np.array(iso), scale_factor=np.float64(getattr(image, 'metadata', {}).get('scale_factor', 1.)),
+             **{"out_" + k: np.asarray(v) for k, v in res.items()})
+
+
 class _VideoAt(object):
     """_Video whose first frame has a number other than 0."""
 

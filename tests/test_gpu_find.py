@@ -89,3 +89,27 @@ def test_find_then_refine_matches_oracle():
     # clusters with a missed member are ill-posed fits with flat directions, where SLSQP's default
     # tolerance stops early: the bulk must agree to the contract, the tail to a tenth of a pixel
     assert np.percentile(dpos, 90) < 1e-3 and dpos.max() < 0.1, (np.percentile(dpos, 90), dpos.max())
+
+
+def test_find_features_equals_reference_steps():
+    """``find_features`` = the find half of find_link (find_link.py:954-969) frame by frame: the same
+    coordinates, mass, signal and size as the oracle / reference-pinned pieces give one frame at a
+    time, and a table ``refine_leastsq`` takes as it is."""
+    import clustertracking_b200 as ctb
+    from clustertracking_b200 import artificial, preprocessing
+    from oracle import find_oracle
+    reader, _ = artificial.clustered_video(3, shape=(256, 256), seed=40)
+    table = ctb.find_features(reader.stack, separation=9, diameter=11, minmass=200, noise_size=1)
+    assert list(table.columns) == ['y', 'x', 'mass', 'signal', 'size', 'frame']
+    for t in range(3):
+        raw = reader.stack[t]
+        proc = np.asarray(preprocessing.preprocess(raw, 1, (9, 9), None))
+        coords = find_oracle.grey_dilation(proc, (9, 9), 64, (5, 5), precise=True)
+        extra = preprocessing.characterize(coords, raw, (5, 5), True)
+        keep = extra['mass'] >= 200
+        part = table[table['frame'] == t]
+        assert_array_equal(part[['y', 'x']].values, coords[keep].astype(float))
+        for key in ('mass', 'signal', 'size'):
+            assert_array_equal(part[key].values, extra[key][keep])
+    out = ctb.refine_leastsq(table, reader, 11)
+    assert np.isfinite(out['cost'].values).mean() > 0.9
