@@ -42,21 +42,30 @@ def find_features(frames, separation, diameter=None, minmass=0, noise_size=1, sm
     if any(s <= 2 * m for s, m in zip(shape, margin)):                      # find_link.py:939-949
         raise ValueError('The feature finding margins are larger than the image shape. Please use '
                          'smaller radius, separation or smoothing_size.')
-    processed = [np.asarray(_pre.preprocess(np.asarray(fr), noise_size, smoothing_size, threshold))
-                 for fr in frames]
-    found = _find.grey_dilation_batch(processed, separation, percentile, margin, precise=True)
-    pos_columns = ['z', 'y', 'x'][-ndim:]
-    rows = []
-    for k, (coords, raw) in enumerate(zip(found, frames)):
-        if len(coords) == 0:
-            continue
-        extra = _pre.characterize(coords, np.asarray(raw), radius, isotropic)   # find_link.py:964
-        keep = extra['mass'] >= minmass
-        table = pd.DataFrame(np.asarray(coords, dtype=np.float64)[keep], columns=pos_columns)
-        for key, values in extra.items():
-            table[key] = values[keep]
-        table['frame'] = first_frame + k
-        rows.append(table)
+    # the per-frame host steps (scipy.ndimage / numpy release the GIL) run on a thread pool
+    from concurrent.futures import ThreadPoolExecutor
+    from .utils import host_threads
+    with ThreadPoolExecutor(host_threads(32)) as pool:
+        processed = list(pool.map(lambda fr: np.asarray(_pre.preprocess(np.asarray(fr), noise_size,
+                                                                        smoothing_size, threshold)),
+                                  frames))
+        found = _find.grey_dilation_batch(processed, separation, percentile, margin, precise=True)
+        del processed
+        pos_columns = ['z', 'y', 'x'][-ndim:]
+
+        def describe(k):
+            coords = found[k]
+            if len(coords) == 0:
+                return None
+            extra = _pre.characterize(coords, np.asarray(frames[k]), radius, isotropic)   # find_link.py:964
+            keep = extra['mass'] >= minmass
+            table = pd.DataFrame(np.asarray(coords, dtype=np.float64)[keep], columns=pos_columns)
+            for key, values in extra.items():
+                table[key] = values[keep]
+            table['frame'] = first_frame + k
+            return table
+
+        rows = [t for t in pool.map(describe, range(len(found))) if t is not None]
     if not rows:
         return pd.DataFrame(columns=pos_columns + ['mass', 'signal', 'frame'])
     return pd.concat(rows, ignore_index=True)
