@@ -492,7 +492,8 @@ def run_ours(args):
            % (n_frames * world, world))
     e2e = dict(value=total_features * args.steps / e2e_s, unit="features/s",
                h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-               ms_per_step=1e3 * e2e_s / args.steps, api=api, host_ms=info.get("phases_ms"))
+               ms_per_step=1e3 * e2e_s / args.steps, api=api, host_ms=info.get("phases_ms"),
+               labelling=info.get("labelling"))
     if world > 1:
         e2e["sharded_ms_rank0"] = dict(parallel.LAST_GATHER)
     if world > 1 and rank == 0:

@@ -92,6 +92,12 @@ _PROTOTYPES = {
                                                _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "ctk_cluster_pack_columns": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp,
                                                 _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
+    "ctk_cluster_pack_labelled": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp,
+                                                 _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp,
+                                                 _vp, _vp]),
+    "ctk_wait_flags": (ctypes.c_int, [_vp, _i64, _i64]),
+    "ctk_label_frames_scratch": (ctypes.c_int, [_i64, _i32, _i64, _vp]),
+    "ctk_label_frames": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     "ctk_concat_groups": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "ctk_apply_label_offsets": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "ctk_find_workspace_bytes": (_sz, [_i32, _i64, _i32]),
@@ -279,11 +285,34 @@ def column_pointers(sources):
     return ptrs, scalars
 
 
-def cluster_pack_frames(pos, starts, stops, separation, n_threads, sources, row_base, params_out):
+def label_frames_scratch_bytes(max_points, ndim, n_frames):
+    """``ctk_label_frames_scratch``: bytes of device scratch ``ctk_label_frames`` wants."""
+    out = ctypes.c_int64(0)
+    check(load().ctk_label_frames_scratch(int(max_points), int(ndim), int(n_frames), ctypes.byref(out)),
+          "ctk_label_frames_scratch")
+    return int(out.value)
+
+
+def label_frames_device(pos_ptrs, ndim, d_starts, d_stops, n_frames, max_points, separation, d_labels,
+                        d_flags, d_scratch, scratch_bytes, stream):
+    """``ctk_label_frames`` (asynchronous): device pointers as ints; ``pos_ptrs`` = ndim column pointers."""
+    cols = (ctypes.c_void_p * 3)(*([int(p) for p in pos_ptrs] + [None] * (3 - ndim)))
+    separation = np.ascontiguousarray(separation, dtype=np.float64)
+    check(load().ctk_label_frames(cols, int(ndim), int(d_starts), int(d_stops), int(n_frames),
+                                  int(max_points), separation.ctypes.data, int(d_labels),
+                                  int(d_flags), int(d_scratch),
+                                  int(scratch_bytes), int(stream) if stream else None),
+          "ctk_label_frames")
+
+
+def cluster_pack_frames(pos, starts, stops, separation, n_threads, sources, row_base, params_out,
+                        labels=None, flags=None, cluster_out=None, size_out=None):
     """``ctk_cluster_pack_columns`` -> (labels local to each frame, sizes, by_cluster, spans,
     group counts per frame, group starts); ``params_out`` [n, P] receives the packed rows.
     ``pos``: [n, ndim] array of this call's rows, or a list of ndim table-order float64 columns
-    (then this call's rows are rows ``row_base .. row_base + len(params_out)`` of the table)."""
+    (then this call's rows are rows ``row_base .. row_base + len(params_out)`` of the table).
+    ``labels`` (int32, this call's rows) and ``flags`` (int32 per frame): labels computed on the
+    device by ``ctk_label_frames``; frames with a non-zero flag are labelled here."""
     pos_cols = None
     if isinstance(pos, (list, tuple)):
         ndim, n = len(pos), len(params_out)
@@ -296,14 +325,26 @@ def cluster_pack_frames(pos, starts, stops, separation, n_threads, sources, row_
     starts = np.ascontiguousarray(starts, dtype=np.int64)
     stops = np.ascontiguousarray(stops, dtype=np.int64)
     separation = np.ascontiguousarray(separation, dtype=np.float64)
-    cluster = np.empty(n, dtype=np.int64)
-    size = np.empty(n, dtype=np.int64)
+    cluster = np.empty(n, dtype=np.int64) if cluster_out is None else cluster_out
+    size = np.empty(n, dtype=np.int64) if size_out is None else size_out
+    for arr in (cluster, size):                    # optional caller-owned outputs (views are fine)
+        assert arr.dtype == np.int64 and arr.flags.c_contiguous and len(arr) == n
     by_cluster = np.empty(n, dtype=np.int64)
     spans = np.zeros(len(starts), dtype=np.int64)
     gcount = np.zeros(len(starts), dtype=np.int32)
     gstart = np.empty(max(n, 1), dtype=np.int32)
     ptrs, scalars = column_pointers(sources)
     assert params_out.flags.c_contiguous and params_out.dtype == np.float64
+    if labels is not None:
+        assert labels.dtype == np.int32 and labels.flags.c_contiguous and len(labels) == n
+        assert flags.dtype == np.int32 and flags.flags.c_contiguous and len(flags) == len(starts)
+        check(load().ctk_cluster_pack_labelled(
+            pos_ptr, pos_cols, n, ndim, starts.ctypes.data, stops.ctypes.data, len(starts),
+            separation.ctypes.data, int(n_threads), cluster.ctypes.data, size.ctypes.data,
+            by_cluster.ctypes.data, spans.ctypes.data, ptrs, scalars, len(sources), int(row_base),
+            params_out.ctypes.data, gcount.ctypes.data, gstart.ctypes.data, labels.ctypes.data,
+            flags.ctypes.data), "ctk_cluster_pack_labelled")
+        return cluster, size, by_cluster, spans, gcount, gstart
     check(load().ctk_cluster_pack_columns(
         pos_ptr, pos_cols, n, ndim, starts.ctypes.data, stops.ctypes.data, len(starts),
         separation.ctypes.data, int(n_threads), cluster.ctypes.data, size.ctypes.data,

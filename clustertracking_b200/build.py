@@ -64,7 +64,7 @@ def _job_hash(job):
 
 def _jobs():
     jobs = [("api", "ctk_api.cu", []), ("host", "ctk_host.cpp", []),
-            ("find", "ctk_find.cu", [])]
+            ("find", "ctk_find.cu", []), ("label", "ctk_label.cu", [])]
     for real in ("float", "double"):
         for fam in (0, 1, 2):
             for extra in (0, 1):       # lean / full flavour of every instance (ctk_solver.cuh)
@@ -102,6 +102,8 @@ def build_variant(out, defines, only=None):
 
     def one(job):
         name, src, defs = job
+        if only is not None and name not in only:      # unchanged unit: the cached object of build()
+            return _compile(job)[0]
         obj = os.path.join(scratch, name + ".o")
         cmd = [_nvcc()] + ARCH + COMMON + defs + list(defines) + ["-c", os.path.join(CSRC, src), "-o", obj]
         subprocess.run(cmd, check=True, capture_output=True)

@@ -480,14 +480,19 @@ extern "C" int ctk_cluster_pack_frames(const double* pos, int64_t n, int32_t ndi
 
 // The same with the positions given as `ndim` table-order column arrays (pos_cols[k][row_base + i]
 // is coordinate k of this call's row i) instead of one packed [n, ndim] array.
-extern "C" int ctk_cluster_pack_columns(const double* pos, const double* const* pos_cols, int64_t n,
-                                        int32_t ndim, const int64_t* starts, const int64_t* stops,
-                                        int64_t n_frames, const double* separation,
-                                        int32_t n_threads, int64_t* cluster_out, int64_t* size_out,
-                                        int64_t* by_cluster_out, int64_t* span_out,
-                                        const double* const* columns, const double* scalars,
-                                        int32_t n_cols, int64_t row_base, double* params_out,
-                                        int32_t* group_count_out, int32_t* group_start_out) {
+//
+// ctk_cluster_pack_labelled: the same, with the labels of the frames already computed on the
+// device (ctk_label_frames): labels_in [n] int32 (this call's rows), frame_flags [n_frames]; a frame
+// whose flag is not 0 (scratch capacity exceeded on the device) is labelled here instead.
+static int cluster_pack_impl(const double* pos, const double* const* pos_cols, int64_t n,
+                             int32_t ndim, const int64_t* starts, const int64_t* stops,
+                             int64_t n_frames, const double* separation,
+                             int32_t n_threads, int64_t* cluster_out, int64_t* size_out,
+                             int64_t* by_cluster_out, int64_t* span_out,
+                             const double* const* columns, const double* scalars,
+                             int32_t n_cols, int64_t row_base, double* params_out,
+                             int32_t* group_count_out, int32_t* group_start_out,
+                             const int32_t* labels_in, const int32_t* frame_flags) {
   if (n < 0 || n_frames < 0 || ndim < 1 || ndim > 3 || !separation) return CTK_E_INVALID;
   if (columns && (n_cols < 1 || !scalars || !params_out)) return CTK_E_INVALID;
   if ((group_count_out == nullptr) != (group_start_out == nullptr)) return CTK_E_INVALID;
@@ -512,24 +517,39 @@ extern "C" int ctk_cluster_pack_columns(const double* pos, const double* const* 
         if (group_count_out) group_count_out[f] = 0;
         continue;
       }
-      s.tree.init(pos ? pos + a * ndim : nullptr, cnt, ndim, separation, pos_cols, row_base + a);
-      if (!s.tree.finite) { failed = 2; continue; }
-      s.pairs.clear();
-      s.query.t = &s.tree;
-      s.query.out = &s.pairs;
-      s.query.tr.init(s.tree, 1.0);
-      s.query.checking(0, 0);
-      const int64_t np = (int64_t) s.pairs.size() / 2;
-      s.order.resize(np);
-      s.ordered.resize(2 * np);
-      if (ctk_pairs_set_order(s.pairs.data(), np, s.order.data()) != 0) { failed = 1; continue; }
-      for (int64_t k = 0; k < np; ++k) {
-        s.ordered[2 * k] = s.pairs[2 * s.order[k]];
-        s.ordered[2 * k + 1] = s.pairs[2 * s.order[k] + 1];
-      }
-      if (ctk_label_clusters(s.ordered.data(), np, cnt, cluster_out + a, size_out + a) != 0) {
-        failed = 1;
-        continue;
+      if (labels_in && frame_flags[f] == 0) {
+        // labels from the device; sizes by counting
+        s.count.assign((size_t) cnt, 0);
+        bool ok = true;
+        for (int i = 0; i < cnt; ++i) {
+          const int32_t id = labels_in[a + i];
+          if (id < 0 || id >= cnt) { ok = false; break; }
+          cluster_out[a + i] = id;
+          ++s.count[id];
+        }
+        if (!ok) { failed = 1; continue; }
+        for (int i = 0; i < cnt; ++i) size_out[a + i] = s.count[cluster_out[a + i]];
+      } else {
+        if (labels_in && frame_flags[f] == 2) { failed = 2; continue; }
+        s.tree.init(pos ? pos + a * ndim : nullptr, cnt, ndim, separation, pos_cols, row_base + a);
+        if (!s.tree.finite) { failed = 2; continue; }
+        s.pairs.clear();
+        s.query.t = &s.tree;
+        s.query.out = &s.pairs;
+        s.query.tr.init(s.tree, 1.0);
+        s.query.checking(0, 0);
+        const int64_t np = (int64_t) s.pairs.size() / 2;
+        s.order.resize(np);
+        s.ordered.resize(2 * np);
+        if (ctk_pairs_set_order(s.pairs.data(), np, s.order.data()) != 0) { failed = 1; continue; }
+        for (int64_t k = 0; k < np; ++k) {
+          s.ordered[2 * k] = s.pairs[2 * s.order[k]];
+          s.ordered[2 * k + 1] = s.pairs[2 * s.order[k] + 1];
+        }
+        if (ctk_label_clusters(s.ordered.data(), np, cnt, cluster_out + a, size_out + a) != 0) {
+          failed = 1;
+          continue;
+        }
       }
       // stable argsort of the labels (counting sort: labels are point indices of the frame)
       s.count.assign((size_t) cnt + 1, 0);
@@ -570,6 +590,35 @@ extern "C" int ctk_cluster_pack_columns(const double* pos, const double* const* 
     for (auto& th : pool) th.join();
   }
   return failed == 2 ? CTK_E_NONFINITE : (failed ? CTK_E_INVALID : 0);
+}
+
+extern "C" int ctk_cluster_pack_columns(const double* pos, const double* const* pos_cols, int64_t n,
+                                        int32_t ndim, const int64_t* starts, const int64_t* stops,
+                                        int64_t n_frames, const double* separation,
+                                        int32_t n_threads, int64_t* cluster_out, int64_t* size_out,
+                                        int64_t* by_cluster_out, int64_t* span_out,
+                                        const double* const* columns, const double* scalars,
+                                        int32_t n_cols, int64_t row_base, double* params_out,
+                                        int32_t* group_count_out, int32_t* group_start_out) {
+  return cluster_pack_impl(pos, pos_cols, n, ndim, starts, stops, n_frames, separation, n_threads,
+                           cluster_out, size_out, by_cluster_out, span_out, columns, scalars, n_cols,
+                           row_base, params_out, group_count_out, group_start_out, nullptr, nullptr);
+}
+
+extern "C" int ctk_cluster_pack_labelled(const double* pos, const double* const* pos_cols, int64_t n,
+                                         int32_t ndim, const int64_t* starts, const int64_t* stops,
+                                         int64_t n_frames, const double* separation,
+                                         int32_t n_threads, int64_t* cluster_out, int64_t* size_out,
+                                         int64_t* by_cluster_out, int64_t* span_out,
+                                         const double* const* columns, const double* scalars,
+                                         int32_t n_cols, int64_t row_base, double* params_out,
+                                         int32_t* group_count_out, int32_t* group_start_out,
+                                         const int32_t* labels_in, const int32_t* frame_flags) {
+  if ((labels_in == nullptr) != (frame_flags == nullptr)) return CTK_E_INVALID;
+  return cluster_pack_impl(pos, pos_cols, n, ndim, starts, stops, n_frames, separation, n_threads,
+                           cluster_out, size_out, by_cluster_out, span_out, columns, scalars, n_cols,
+                           row_base, params_out, group_count_out, group_start_out, labels_in,
+                           frame_flags);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -804,4 +853,22 @@ extern "C" int ctk_drop_close_frames(const int32_t* coords, const int32_t* value
     for (auto& th : pool) th.join();
   }
   return 0;
+}
+
+// Wait (sleeping, without the interpreter lock: the caller is a ctypes call) until none of
+// flags[0 .. n-1] is negative -- the per-frame flags ctk_label_frames writes into mapped host memory
+// -- or until timeout_us have passed.  Returns 0 when all are set, 1 on timeout.
+#include <chrono>
+extern "C" int ctk_wait_flags(const int32_t* flags, int64_t n, int64_t timeout_us) {
+  if (n < 0 || (n > 0 && !flags)) return CTK_E_INVALID;
+  const volatile int32_t* f = flags;
+  const auto t0 = std::chrono::steady_clock::now();
+  int64_t done = 0;
+  for (;;) {
+    while (done < n && f[done] >= 0) ++done;
+    if (done >= n) return 0;
+    std::this_thread::sleep_for(std::chrono::microseconds(50));
+    if (std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() > timeout_us)
+      return 1;
+  }
 }

@@ -278,6 +278,96 @@ class _LabelJob(object):
         return cluster, self.size, self.by_cluster
 
 
+_PINNED = {}        # cached pinned staging buffers of the device labelling (one call at a time)
+_SCRATCH = {}       # cached device scratch per device
+
+
+def _pinned(torch, key, nbytes):
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        _PINNED[key] = buf
+    return buf[:nbytes]
+
+
+class DeviceLabels(object):
+    """Labels of all frames of a frame-sorted table from ``ctk_label_frames`` (one warp per frame on
+    the GPU, label values identical to the reference's).  Both directions go through MAPPED pinned
+    memory: the kernel reads the staged position columns and writes labels and per-frame flags
+    straight into host memory, so nothing queues behind the frame uploads on the copy engines and
+    a chunk of frames can be consumed as soon as ITS flags have arrived.
+
+    ``start()`` (on the labelling thread) stages the columns and launches; ``wait_frames(fa, fb)``
+    blocks until frames fa..fb-1 are labelled -> (labels int32 [n], flags int32 [n_frames]) views.
+    Frames whose flag is 1 exceeded a scratch capacity on the device and are labelled by the host
+    path."""
+
+    def __init__(self, pos, starts, stops, separation, device):
+        self.pos, self.starts, self.stops = pos, starts, stops
+        self.separation, self.device = separation, device
+        n, n_frames, ndim = len(pos[0]), len(starts), len(pos)
+        self.h2d_bytes = n * ndim * 8 + n_frames * 16
+        self.d2h_bytes = n * 4 + n_frames * 4
+        self.ms = {}
+
+    def start(self):
+        import time
+        import torch
+        from concurrent.futures import ThreadPoolExecutor
+        from .utils import host_threads
+        pos, device = self.pos, self.device
+        n, n_frames, ndim = len(pos[0]), len(self.starts), len(pos)
+        t0 = time.perf_counter()
+        max_points = int((self.stops - self.starts).max())
+        stage = _pinned(torch, "pos", (ndim * n + 2 * n_frames) * 8)
+        host = stage.numpy()
+        cols = host[:ndim * n * 8].view(np.float64).reshape(ndim, n)
+        pieces = [(k, a, min(n, a + (1 << 20))) for k in range(ndim) for a in range(0, n, 1 << 20)]
+        with ThreadPoolExecutor(max(1, min(4, host_threads(4), len(pieces)))) as pool:
+            list(pool.map(lambda p: np.copyto(cols[p[0], p[1]:p[2]], pos[p[0]][p[1]:p[2]]), pieces))
+        bounds = host[ndim * n * 8:].view(np.int64).reshape(2, n_frames)
+        bounds[0], bounds[1] = self.starts, self.stops
+        out = _pinned(torch, "labels", (n + n_frames) * 4)
+        result = out.numpy().view(np.int32)
+        self.labels, self.flags = result[:n], result[n:n + n_frames]
+        self.flags[:] = -1                                  # "not labelled yet"
+        t1 = time.perf_counter()
+        with torch.cuda.device(device):
+            self.stream = torch.cuda.Stream(device=device, priority=-1)
+            nbytes = _lib.label_frames_scratch_bytes(max_points, ndim, n_frames)
+            scratch = _SCRATCH.get(device)
+            if scratch is None or scratch.numel() < nbytes:
+                _SCRATCH.clear()
+                scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
+                _SCRATCH[device] = scratch
+                torch.cuda.current_stream(device).synchronize()
+            base, obase = stage.data_ptr(), out.data_ptr()       # pinned: the same address on the device
+            _lib.label_frames_device([base + k * n * 8 for k in range(ndim)], ndim,
+                                     base + ndim * n * 8, base + ndim * n * 8 + n_frames * 8,
+                                     n_frames, max_points, self.separation, obase, obase + n * 4,
+                                     scratch.data_ptr(), nbytes, self.stream.cuda_stream)
+        self.keep = (stage, out, scratch)
+        self.t_launch = time.perf_counter()
+        self.ms = dict(stage=1e3 * (t1 - t0), launch=1e3 * (self.t_launch - t1))
+
+    def wait_frames(self, fa, fb):
+        import time
+        flags = self.flags[fa:fb]
+        while len(flags) and _lib.load().ctk_wait_flags(flags.ctypes.data, len(flags), 20000) != 0:
+            if self.stream.query():                      # the kernel has ended (or failed)
+                self.stream.synchronize()
+                if flags.min() < 0:
+                    raise RuntimeError("ctk_label_frames finished without labelling frames %d..%d" % (fa, fb))
+        if fb == len(self.flags):
+            self.ms['all_frames_labelled'] = 1e3 * (time.perf_counter() - self.t_launch)
+        return self.labels, self.flags
+
+
+def device_labelling_enabled():
+    """CTK_LABEL_DEVICE=0 keeps the labelling on the host threads."""
+    return os.environ.get('CTK_LABEL_DEVICE', '1') != '0'
+
+
 class ChunkLabeller(object):
     """Labels a frame-sorted video chunk by chunk on a background thread, so that the caller can
     launch chunk k while chunk k+1 is being labelled.  ``frame_cuts`` = frame indices at which the
@@ -291,9 +381,12 @@ class ChunkLabeller(object):
     Without the verified native labelling (see ``_native_is_exact``) everything is one chunk
     labelled through scipy and packed with numpy."""
 
-    def __init__(self, pos, starts, stops, frame_cuts, separation, sources, params_out):
+    def __init__(self, pos, starts, stops, frame_cuts, separation, sources, params_out, device=None,
+                 size_out=None, label_out=None):
         import threading
         self.native = os.environ.get('CTK_FIND_NATIVE', '1') != '0' and _native_is_exact()
+        self.device_labels = None
+        self.flagged_frames = 0
         self.starts, self.stops = np.asarray(starts, np.int64), np.asarray(stops, np.int64)
         self.frame_cuts = list(frame_cuts) if self.native else [0, len(starts)]
         self.results = [None] * (len(self.frame_cuts) - 1)
@@ -319,18 +412,35 @@ class ChunkLabeller(object):
             return
         workers = max(1, _pool_workers())
         self.cancelled = False
+        if (device is not None and device_labelling_enabled() and isinstance(pos, (list, tuple))
+                and len(starts) > 0 and len(pos[0]) > 0):
+            # the labels themselves come from the GPU (one warp per frame); the host threads below
+            # only count, order and pack
+            self.device_labels = DeviceLabels(pos, self.starts, self.stops, separation, device)
 
         def work():
             try:
+                labels = flags = None
+                if self.device_labels is not None:
+                    self.device_labels.start()
                 for k, (fa, fb) in enumerate(zip(self.frame_cuts[:-1], self.frame_cuts[1:])):
                     if self.cancelled:
                         raise RuntimeError("labelling cancelled")
+                    if self.device_labels is not None:
+                        labels, flags = self.device_labels.wait_frames(fa, fb)
+                        self.flagged_frames += int(np.count_nonzero(flags[fa:fb]))
                     a = int(self.starts[fa]) if fb > fa else 0
                     b = int(self.stops[fb - 1]) if fb > fa else 0
                     st, sp = self.starts[fa:fb] - a, self.stops[fa:fb] - a
                     chunk_pos = pos if isinstance(pos, (list, tuple)) else pos[a:b]
                     local, size, by_cluster, spans, gcount, gstart = _lib.cluster_pack_frames(
-                        chunk_pos, st, sp, separation, workers, sources, a, params_out[a:b])
+                        chunk_pos, st, sp, separation, workers, sources, a, params_out[a:b],
+                        labels=None if labels is None else labels[a:b],
+                        flags=None if flags is None else flags[fa:fb],
+                        cluster_out=None if label_out is None else label_out[a:b],
+                        size_out=None if size_out is None else size_out[a:b])
+                    if size_out is not None:       # written in place: tell the caller not to copy
+                        size, local = size_out, label_out
                     goff, gframe = _lib.concat_groups(st, sp, gcount, gstart, fa)
                     self.results[k] = (local, size, by_cluster, spans, goff, gframe)
                     self.events[k].set()

@@ -1149,22 +1149,23 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
             sources.append(float(ff.default[col]))
     params_in = _pinned_array("params_in", (n, P), np.float64)     # packed, group order
     # labelling, packing and the group tables run on host threads from here on
-    labeller = ChunkLabeller(pos, starts, stops, frame_cuts, separation, sources, params_in)
+    # The result columns.  ``_alloc(name, dtype)`` lets the sharded path place them in a block all
+    # ranks share, so that the final gather copies nothing (parallel.py).
+    alloc = _alloc if _alloc is not None else (lambda name, dtype: np.empty(n, dtype=dtype))
+    csize = alloc('cluster_size', np.int64)
+    local_all = np.empty(n, dtype=np.int64)        # labels local to each frame
+    labeller = ChunkLabeller(pos, starts, stops, frame_cuts, separation, sources, params_in,
+                             device=getattr(frameset, "dev", None), size_out=csize, label_out=local_all)
     _LABELLERS.append(labeller)
     frame_cuts = labeller.frame_cuts
     t1 = time.perf_counter()
     out_params = _pinned_array("params", (n, P), np.float64)
     out_cost = _pinned_array("cost", (n,), np.float64)             # one entry per cluster (<= n)
     out_status = _pinned_array("status", (n,), np.int32)
-    # The result columns.  ``_alloc(name, dtype)`` lets the sharded path place them in a block all
-    # ranks share, so that the final gather copies nothing (parallel.py).
-    alloc = _alloc if _alloc is not None else (lambda name, dtype: np.empty(n, dtype=dtype))
     block = [alloc(col, np.float64) for col in ff.params]          # fitted columns, table order
     cost = alloc('cost', np.float64)
     cluster = alloc('cluster', np.int64)
-    csize = alloc('cluster_size', np.int64)
     threads = host_threads(8)
-    local_all = np.empty(n, dtype=np.int64)        # labels local to each frame
     frame_offset = np.zeros(n_frames, dtype=np.int64)                 # find.py:127-128
     chunks = []                                    # (a, b, rows by group (chunk-local), plan, pending, c0)
     totals = dict(h2d=0, d2h=0, launches=0, failed=0)
@@ -1191,31 +1192,59 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
     # (74 ms -> 190-240 ms per call), so one stream is the default.
     streams = _chunk_streams(frameset, int(os.environ.get('CTK_CHUNK_STREAMS', 1)))
     lap = dict(label_wait=0., index=0., launch=0., finish=0.)
-    for k, (fa, fb) in enumerate(zip(frame_cuts[:-1], frame_cuts[1:])):
-        a, b = int(starts[fa]), int(stops[fb - 1])
-        _ta = time.perf_counter()
-        local, size, by_cluster, spans, g_offset, g_frame = labeller.get(k)
-        _tb = time.perf_counter()
-        csize[a:b] = size
-        local_all[a:b] = local
-        frame_offset[fa:fb] = next_id + np.concatenate(([0], np.cumsum(spans)[:-1]))
-        next_id += int(np.sum(spans))
-        _tc = time.perf_counter()
-        plan = _plan_for(pre, by_cluster, g_offset, g_frame, params_in[a:b])
-        n_c = len(g_frame)
-        pending = launch_cuda(plan, frameset, out_params[a:b], out_cost[c0:c0 + n_c],
-                              out_status[c0:c0 + n_c], stream=streams[k % len(streams)])
-        chunks.append((a, b, by_cluster, plan, pending, c0))
-        c0 += n_c
-        _te = time.perf_counter()
-        if k > 0:
-            finish(chunks[k - 1])                  # while the device works on chunk k
-        _tf = time.perf_counter()
-        for name, dt in (("label_wait", _tb - _ta), ("index", _tc - _tb), ("launch", _te - _tc),
-                         ("finish", _tf - _te)):
-            lap[name] += 1e3 * dt
-    t2 = time.perf_counter()
-    finish(chunks[-1])
+    # The write-back of a chunk (wait for its results, scatter into the table columns: C code on
+    # host threads, no interpreter lock) runs on its own thread, so that the main thread goes
+    # straight on to the next chunk's launch and the device never waits for a scatter.
+    import queue
+    import threading
+    done_queue, finish_errors = queue.Queue(), []
+
+    def finisher():
+        while True:
+            chunk = done_queue.get()
+            if chunk is None:
+                return
+            if finish_errors:
+                continue
+            try:
+                _t = time.perf_counter()
+                finish(chunk)
+                lap['finish'] += 1e3 * (time.perf_counter() - _t)
+            except BaseException as exc:          # re-raised on the main thread
+                finish_errors.append(exc)
+
+    finish_thread = threading.Thread(target=finisher, daemon=True)
+    finish_thread.start()
+    try:
+        for k, (fa, fb) in enumerate(zip(frame_cuts[:-1], frame_cuts[1:])):
+            a, b = int(starts[fa]), int(stops[fb - 1])
+            _ta = time.perf_counter()
+            local, size, by_cluster, spans, g_offset, g_frame = labeller.get(k)
+            _tb = time.perf_counter()
+            if size is not csize:                  # (the native labeller writes both in place)
+                csize[a:b] = size
+                local_all[a:b] = local
+            frame_offset[fa:fb] = next_id + np.concatenate(([0], np.cumsum(spans)[:-1]))
+            next_id += int(np.sum(spans))
+            _tc = time.perf_counter()
+            plan = _plan_for(pre, by_cluster, g_offset, g_frame, params_in[a:b])
+            n_c = len(g_frame)
+            pending = launch_cuda(plan, frameset, out_params[a:b], out_cost[c0:c0 + n_c],
+                                  out_status[c0:c0 + n_c], stream=streams[k % len(streams)])
+            chunks.append((a, b, by_cluster, plan, pending, c0))
+            done_queue.put(chunks[-1])
+            c0 += n_c
+            _te = time.perf_counter()
+            for name, dt in (("label_wait", _tb - _ta), ("index", _tc - _tb), ("launch", _te - _tc)):
+                lap[name] += 1e3 * dt
+            if finish_errors:
+                break
+    finally:
+        done_queue.put(None)
+        t2 = time.perf_counter()
+        finish_thread.join()
+    if finish_errors:
+        raise finish_errors[0]
     _lib.apply_label_offsets(local_all, starts, stops, frame_offset, threads, cluster)
     for row, status in failures:
         logger.warning("RefineException: cluster %d: %s", int(cluster[row]),
@@ -1255,8 +1284,14 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
     out = pd.DataFrame(data, index=base.index, copy=False)
     t4 = time.perf_counter()
     LAST_CALL.clear()
-    LAST_CALL.update(h2d_bytes=totals['h2d'] + frameset.h2d_bytes, d2h_bytes=totals['d2h'],
-                     launches=totals['launches'] + frameset.launches, chunks=len(chunks),
+    dl = labeller.device_labels            # cluster labels from the GPU (ctk_label_frames): one launch
+    LAST_CALL.update(h2d_bytes=totals['h2d'] + frameset.h2d_bytes + (dl.h2d_bytes if dl else 0),
+                     d2h_bytes=totals['d2h'] + (dl.d2h_bytes if dl else 0),
+                     launches=totals['launches'] + frameset.launches + (1 if dl else 0),
+                     chunks=len(chunks),
+                     labelling=dict(where='device' if dl else 'host threads',
+                                    frames_relabelled_on_host=labeller.flagged_frames,
+                                    **(dl.ms if dl else {})),
                      phases_ms=dict(setup=1e3 * (t1 - t0), chunks=1e3 * (t2 - t1),
                                     last_chunk=1e3 * (t3 - t2), table=1e3 * (t4 - t3), **lap))
     return out

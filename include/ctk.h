@@ -289,6 +289,31 @@ int ctk_pairs_set_order(const int64_t* pairs, int64_t n_pairs, int64_t* order_ou
 int ctk_query_pairs(const double* data, int64_t n, int32_t ndim, int64_t* pairs_out,
                     int64_t capacity, int64_t* n_pairs_out);
 
+/* Device: the cluster labels of find_clusters for a whole video (find.py:72-93: cKDTree(pos /
+ * separation).query_pairs(1), the pairs visited in the iteration order of the python set, the union
+ * rule of Clusters.add), one warp per frame, label VALUES identical to the reference's (kd-tree,
+ * std::nth_element, CPython set order restated on the device; see csrc/ctk_label.cuh).
+ *   d_pos_cols [ndim]  HOST array of device pointers: table-order float64 columns, rows sorted by frame
+ *   d_starts, d_stops [n_frames] int64 (device): frame f owns rows d_starts[f] .. d_stops[f]-1
+ *   max_points         most rows of one frame;  separation [ndim] (host)
+ *   d_labels [rows] int32   label of every row, local to its frame (as ctk_cluster_frames)
+ *   d_flags  [n_frames] int32  0 = labelled; 1 = a scratch capacity was exceeded (label this frame
+ *                      with ctk_cluster_pack_labelled / ctk_cluster_frames on the host); 2 = non-finite
+ *   d_scratch          at least ctk_label_frames_scratch(...) bytes, 256-byte aligned
+ * Asynchronous on `stream`.  The columns, d_starts / d_stops, d_labels and d_flags may be MAPPED
+ * pinned host memory: a frame's labels are visible to the host before its flag is written
+ * (__threadfence_system), so a host thread that initialised the flags to -1 can consume the frames
+ * as they complete. */
+int ctk_label_frames_scratch(int64_t max_points, int32_t ndim, int64_t n_frames, int64_t* bytes_out);
+int ctk_label_frames(const double* const* d_pos_cols, int32_t ndim, const int64_t* d_starts,
+                     const int64_t* d_stops, int64_t n_frames, int64_t max_points,
+                     const double* separation, int32_t* d_labels, int32_t* d_flags,
+                     void* d_scratch, int64_t scratch_bytes, void* stream);
+
+/* Host helper: sleep until none of flags[0 .. n-1] (the mapped per-frame flags of ctk_label_frames,
+ * initialised to -1 by the caller) is negative, or timeout_us have passed (returns 1). */
+int ctk_wait_flags(const int32_t* flags, int64_t n, int64_t timeout_us);
+
 /* Host helper (no GPU): find_clusters for a whole video on host threads (find.py:72-129).
  *   pos [n, ndim] float64, rows sorted by frame; frame f owns rows starts[f] .. stops[f]-1
  *   separation [ndim]; n_threads worker threads (frames are independent)
@@ -327,6 +352,17 @@ int ctk_cluster_pack_columns(const double* pos, const double* const* pos_cols, i
                              int64_t* span_out, const double* const* columns, const double* scalars,
                              int32_t n_cols, int64_t row_base, double* params_out,
                              int32_t* group_count_out, int32_t* group_start_out);
+/* The same with the labels of the frames already computed on the device (ctk_label_frames):
+ * labels_in [n] int32 for this call's rows, frame_flags [n_frames]; frames whose flag is not 0 are
+ * labelled on the host as above. */
+int ctk_cluster_pack_labelled(const double* pos, const double* const* pos_cols, int64_t n,
+                              int32_t ndim, const int64_t* starts, const int64_t* stops,
+                              int64_t n_frames, const double* separation, int32_t n_threads,
+                              int64_t* cluster_out, int64_t* size_out, int64_t* by_cluster_out,
+                              int64_t* span_out, const double* const* columns, const double* scalars,
+                              int32_t n_cols, int64_t row_base, double* params_out,
+                              int32_t* group_count_out, int32_t* group_start_out,
+                              const int32_t* labels_in, const int32_t* frame_flags);
 int ctk_concat_groups(const int64_t* starts, const int64_t* stops, const int32_t* group_count,
                       const int32_t* group_start, int64_t n_frames, int32_t frame_base,
                       int32_t* group_offset_out, int32_t* group_frame_out, int64_t* n_groups_out);
