@@ -649,45 +649,56 @@ LBL_UNROLL
   }
 
   // All lanes: the pairs of leaf block (n1, n2) in (i, j) order; `checked`: test the distance.
+  // The lanes tile the block row-major (w lanes per row of b, 32 / w rows of a per step); the
+  // float64 tests of GROUP steps are issued together (they are independent; one test alone is a
+  // chain of dependent float64 operations), then the hits are written in order with ballots.
   LBL_DEV void leaf_block(int n1, int n2, bool checked, double upper, int& np) {
+    enum { GROUP = 4 };
     const int a0 = s.nodes[n1].start, na = s.nodes[n1].end - a0;
     const int b0 = s.nodes[n2].start, nb = s.nodes[n2].end - b0;
     const bool same = n1 == n2;
+    const double *c0 = s.c[0], *c1 = s.c[1], *c2 = s.c[2];
     int w = LBL_WARP;                           // lanes per row
     if (nb <= LBL_WARP / 2) { w = 1; while (w < nb) w <<= 1; }
     const int rows = LBL_WARP / w;
     const int r = lane / w, jj0 = lane % w;
-    for (int i0 = 0; i0 < na; i0 += rows) {
-      const int i = a0 + i0 + r;
-      const bool row_ok = i0 + r < na;
-      double u0 = 0., u1 = 0., u2 = 0.;
-      int ui = 0;
-      if (row_ok) {
-        u0 = s.c[0][i];
-        if (m > 1) u1 = s.c[1][i];
-        if (m > 2) u2 = s.c[2][i];
-        ui = s.idx[i];
-      }
+    // several column chunks (nb > 32): a row must finish all its chunks before the next row starts
+    const int group = nb > w ? 1 : GROUP;
+    for (int i0 = 0; i0 < na; i0 += rows * group) {
       for (int jb = 0; jb < nb; jb += w) {
         const int j = b0 + jb + jj0;
-        bool hit = row_ok && jb + jj0 < nb && (!same || j > i);
+        const bool col_ok = jb + jj0 < nb;
+        double v0 = 0., v1 = 0., v2 = 0.;
         int vi = 0;
-        if (hit) {
-          vi = s.idx[j];
-          if (checked) {
-            double d = dsub(u0, s.c[0][j]);
-            double q = dadd(0., dmul(d, d));
-            if (m > 1) { d = dsub(u1, s.c[1][j]); q = dadd(q, dmul(d, d)); }
-            if (m > 2) { d = dsub(u2, s.c[2][j]); q = dadd(q, dmul(d, d)); }
-            hit = q <= upper;
+        if (col_ok) { v0 = c0[j]; if (m > 1) v1 = c1[j]; if (m > 2) v2 = c2[j]; vi = s.idx[j]; }
+        bool hit[GROUP];
+        int ui[GROUP];
+        LBL_UNROLL
+        for (int g = 0; g < GROUP; ++g) {
+          const int i = a0 + i0 + g * rows + r;
+          hit[g] = g < group && col_ok && i0 + g * rows + r < na && (!same || j > i);
+          ui[g] = 0;
+          if (hit[g]) {
+            ui[g] = s.idx[i];
+            if (checked) {
+              double d = dsub(c0[i], v0);
+              double q = dadd(0., dmul(d, d));
+              if (m > 1) { d = dsub(c1[i], v1); q = dadd(q, dmul(d, d)); }
+              if (m > 2) { d = dsub(c2[i], v2); q = dadd(q, dmul(d, d)); }
+              hit[g] = q <= upper;
+            }
           }
         }
-        const uint32_t bits = ballot(hit);
-        if (hit) {
-          const int pos = np + popc(bits & lanemask_lt());
-          if (pos < caps.pairs) s.pairs[pos] = ui < vi ? Pair{ui, vi} : Pair{vi, ui};
+        LBL_UNROLL
+        for (int g = 0; g < GROUP; ++g) {
+          if (g >= group) continue;
+          const uint32_t bits = ballot(hit[g]);
+          if (hit[g]) {
+            const int pos = np + popc(bits & lanemask_lt());
+            if (pos < caps.pairs) s.pairs[pos] = ui[g] < vi ? Pair{ui[g], vi} : Pair{vi, ui[g]};
+          }
+          np += popc(bits);
         }
-        np += popc(bits);
       }
     }
   }
@@ -808,8 +819,8 @@ LBL_UNROLL
       int n1 = 0, n2 = 0, mode = 0;
       if (t < n_cur) { n1 = list[t].n1; n2 = list[t].n2; mode = list[t].mode; }
       const int count = n_cur - base < LBL_WARP ? n_cur - base : LBL_WARP;
-      for (int j = 0; j < count; ++j)
-        leaf_block(shfl(n1, j), shfl(n2, j), shfl(mode, j) == MODE_LEAVES, upper, np);
+      for (int k = 0; k < count; ++k)
+        leaf_block(shfl(n1, k), shfl(n2, k), shfl(mode, k) == MODE_LEAVES, upper, np);
       if (np > caps.pairs) { flag = FLAG_CAPACITY; break; }
     }
     warp_sync();
@@ -974,6 +985,8 @@ LBL_UNROLL
   int32_t* out_label_;
 
   // ---- driver ------------------------------------------------------------------------------------
+  int n_pairs_ = 0;        // pairs found by the last run (s.pairs holds them in scipy's order)
+
   // pos[k]: table-order column k; the frame owns rows a .. a + n - 1.  labels_out [rows] int32.
   LBL_DEV int run(const double* const* pos, int64_t a, int n_, int m_, const double* separation,
                   double r, int32_t* labels_out) {
@@ -1004,6 +1017,7 @@ LBL_UNROLL
     LBL_TICK(1);
     if (flag) return flag;
     const int np = query(r);
+    n_pairs_ = np;
     LBL_TICK(2);
     if (flag) return flag;
     label_union(np);

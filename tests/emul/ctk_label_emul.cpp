@@ -109,3 +109,30 @@ extern "C" int ctk_emul_nth_element_check(int32_t n, int32_t nth, int32_t random
   if (hit_heap_out) *hit_heap_out = heap_hits;
   return 0;
 }
+
+// The close pairs of ONE point set in the order the device code reports them (= the order
+// scipy's query_pairs(output_type='ndarray') reports them).  pairs_out [capacity, 2] int64.
+extern "C" int ctk_emul_query_pairs(const double* const* pos_cols, int32_t ndim, int64_t n,
+                                    int64_t pair_factor, int64_t window, int64_t* pairs_out,
+                                    int64_t capacity, int64_t* n_pairs_out) {
+  const ctk_label::Caps caps = ctk_label::make_caps(n, pair_factor);
+  const int64_t bytes = ctk_label::scratch_bytes(caps);
+  char* mem = static_cast<char*>(aligned_alloc(128, (size_t) bytes));
+  if (window < 0) window = ctk_label::window_bytes(n, ndim);
+  char* fast = window > 0 ? static_cast<char*>(aligned_alloc(128, (size_t) ctk_label::align_up(window, 128))) : nullptr;
+  memset(mem, 0xCD, (size_t) bytes);
+  ctk_label::FrameLabeller fl;
+  fl.s = ctk_label::carve(mem, caps);
+  fl.caps = caps;
+  if (fast) ctk_label::use_window(fl.s, fast, window, (int) n, ndim);
+  const ctk_label::Pair* pairs = fl.s.pairs;
+  const double ones[3] = {1., 1., 1.};
+  std::vector<int32_t> labels((size_t) n);
+  const int flag = fl.run(pos_cols, 0, (int) n, ndim, ones, 1.0, labels.data());
+  *n_pairs_out = fl.n_pairs_;
+  if (flag == 0 && fl.n_pairs_ <= capacity)
+    for (int k = 0; k < fl.n_pairs_; ++k) { pairs_out[2 * k] = pairs[k].i; pairs_out[2 * k + 1] = pairs[k].j; }
+  free(mem);
+  free(fast);
+  return flag;
+}

@@ -37,6 +37,7 @@ def lib():
         _handle = ctypes.CDLL(out)
         _handle.ctk_emul_label_frames.restype = ctypes.c_int
         _handle.ctk_emul_nth_element_check.restype = ctypes.c_int
+        _handle.ctk_emul_query_pairs.restype = ctypes.c_int
     return _handle
 
 
@@ -69,6 +70,24 @@ def test_emulated_device_labels_equal_host_labels(name, window):
         assert flags[f] == 0
         assert np.array_equal(got_l[a:b], want_l[a:b])
         assert np.array_equal(got_s[a:b], want_s[a:b])
+
+
+@pytest.mark.parametrize("name", sorted(label_cases()))
+def test_emulated_pairs_come_in_scipy_order(name):
+    """The pair LIST itself (the labels depend on its order only through hash collisions)."""
+    pos, starts, stops, separation = label_cases()[name]
+    data = np.ascontiguousarray(pos[starts[0]:stops[0]] / separation)
+    n, m = data.shape
+    want = _lib.query_pairs(data)
+    cols = [np.ascontiguousarray(data[:, k]) for k in range(m)]
+    ptrs = (ctypes.c_void_p * 3)(*([c.ctypes.data for c in cols] + [None] * (3 - m)))
+    got = np.empty((len(want) + 1, 2), np.int64)
+    count = ctypes.c_int64(0)
+    rc = lib().ctk_emul_query_pairs(ptrs, ctypes.c_int32(m), ctypes.c_int64(n), ctypes.c_int64(400),
+                                    ctypes.c_int64(-1), ctypes.c_void_p(got.ctypes.data),
+                                    ctypes.c_int64(len(got)), ctypes.byref(count))
+    assert rc == 0 and count.value == len(want)
+    assert np.array_equal(got[:len(want)], want)
 
 
 def test_capacity_is_flagged_not_mislabelled():
