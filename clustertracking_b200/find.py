@@ -363,9 +363,14 @@ class DeviceLabels(object):
         return self.labels, self.flags
 
 
-def device_labelling_enabled():
-    """CTK_LABEL_DEVICE=0 keeps the labelling on the host threads."""
-    return os.environ.get('CTK_LABEL_DEVICE', '1') != '0'
+def device_labelling_enabled(n_rows, n_frames):
+    """Where the cluster labels are computed.  CTK_LABEL_DEVICE=0: always on the host threads;
+    2: always on the GPU; default: on the GPU unless the table is so small (a few frames, a few
+    thousand features) that the launch would cost more than the host threads need."""
+    mode = os.environ.get('CTK_LABEL_DEVICE', '1')
+    if mode == '0':
+        return False
+    return mode == '2' or (n_frames >= 4 and n_rows >= 4096)
 
 
 class ChunkLabeller(object):
@@ -412,8 +417,8 @@ class ChunkLabeller(object):
             return
         workers = max(1, _pool_workers())
         self.cancelled = False
-        if (device is not None and device_labelling_enabled() and isinstance(pos, (list, tuple))
-                and len(starts) > 0 and len(pos[0]) > 0):
+        if (device is not None and isinstance(pos, (list, tuple)) and len(starts) > 0
+                and len(pos[0]) > 0 and device_labelling_enabled(len(pos[0]), len(starts))):
             # the labels themselves come from the GPU (one warp per frame); the host threads below
             # only count, order and pack
             self.device_labels = DeviceLabels(pos, self.starts, self.stops, separation, device)

@@ -54,8 +54,14 @@ def test_refine_leastsq_labels_do_not_depend_on_where_they_are_computed(monkeypa
     import pandas as pd
     f0 = pd.concat(f0, ignore_index=True)
     reader = artificial.FrameStack(np.stack(frames))
-    monkeypatch.setenv('CTK_LABEL_DEVICE', '1')
+    monkeypatch.setenv('CTK_LABEL_DEVICE', '2')            # forced: the table is below the automatic threshold
     on_device = ctb.refine_leastsq(f0.copy(), reader, 11)
     monkeypatch.setenv('CTK_LABEL_DEVICE', '0')
     on_host = ctb.refine_leastsq(f0.copy(), reader, 11)
+    from clustertracking_b200 import refine
     pd.testing.assert_frame_equal(on_device, on_host)
+    assert refine.LAST_CALL['labelling']['where'] == 'host threads'
+    monkeypatch.setenv('CTK_LABEL_DEVICE', '2')
+    ctb.refine_leastsq(f0.copy(), reader, 11)
+    assert refine.LAST_CALL['labelling']['where'] == 'device'
+    assert refine.LAST_CALL['labelling']['frames_relabelled_on_host'] == 0
