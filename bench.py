@@ -469,6 +469,8 @@ def run_ours(args):
         return parallel.refine_leastsq_sharded(table, rd, DIAMETER, presharded=True, gather='root',
                                                precision=args.precision)
 
+    step_log = []
+
     def time_api(table, rd, steps, warmup):
         times, out = [], None
         for step in range(warmup + steps):
@@ -480,9 +482,13 @@ def run_ours(args):
             dt = max_over_ranks(time.perf_counter() - t0)
             if step >= warmup:
                 times.append(dt)
+                step_log.append((round(1e3 * dt, 1), dict(ctb_refine.LAST_CALL).get("setup_ms")))
         return sum(times), out
 
     e2e_s, out = time_api(f0, reader, args.steps, args.warmup)
+    if rank == 0 and os.environ.get("CTK_BENCH_STEPS"):
+        for entry in step_log:
+            print("e2e step", entry, file=sys.stderr, flush=True)
     info = dict(ctb_refine.LAST_CALL)
     h2d, d2h = sum_over_ranks(info["h2d_bytes"]), sum_over_ranks(info["d2h_bytes"])
     api = ("clustertracking_b200.refine_leastsq(DataFrame, FrameStack(pinned host uint8), 11)" if world == 1 else

@@ -610,20 +610,22 @@ class FrameSet(object):
         cuts = list(range(0, self.n_frames, per_batch)) + [self.n_frames]
         self.recorded, self.thread, self.upload_error = None, None, None
         with torch.cuda.device(self.dev):
-            free, _ = torch.cuda.mem_get_info(self.dev)
-            need = self.n_frames * self.frame_bytes
-            if need > free + torch.cuda.memory_reserved(self.dev) - torch.cuda.memory_allocated(self.dev):
-                raise MemoryError("the %d frames of this call need %.1f GB of device memory, %.1f GB "
-                                  "are free: refine the video in blocks of frames"
-                                  % (self.n_frames, need / 1e9, free / 1e9))
             compute = torch.cuda.current_stream(self.dev)
             copy_stream = torch.cuda.Stream(device=self.dev)
             batches, ptrs = [], np.empty(self.n_frames, dtype=np.int64)
-            for f0, f1 in zip(cuts[:-1], cuts[1:]):
-                d_frames = torch.empty((f1 - f0,) + tuple(self.info.shape), dtype=self.torch_dtype,
-                                       device=self.dev)
-                ptrs[f0:f1] = d_frames.data_ptr() + self.frame_bytes * np.arange(f1 - f0, dtype=np.int64)
-                batches.append(d_frames)
+            try:
+                for f0, f1 in zip(cuts[:-1], cuts[1:]):
+                    d_frames = torch.empty((f1 - f0,) + tuple(self.info.shape), dtype=self.torch_dtype,
+                                           device=self.dev)
+                    ptrs[f0:f1] = d_frames.data_ptr() + self.frame_bytes * np.arange(f1 - f0, dtype=np.int64)
+                    batches.append(d_frames)
+            except torch.cuda.OutOfMemoryError:
+                # (asked only now: cudaMemGetInfo costs 3 ms per call and stalls behind other threads)
+                del batches
+                free, _ = torch.cuda.mem_get_info(self.dev)
+                raise MemoryError("the %d frames of this call need %.1f GB of device memory, %.1f GB "
+                                  "are free: refine the video in blocks of frames"
+                                  % (self.n_frames, self.n_frames * self.frame_bytes / 1e9, free / 1e9))
             self.d_ptrs.copy_(torch.from_numpy(ptrs))
             self.tensors.extend(batches)
             copy_stream.wait_stream(compute)
@@ -1112,6 +1114,7 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
     ff, info = pre.ff, pre.info
     frameset = started[0]
     P = len(ff.params)
+    _s1 = time.perf_counter()
 
     # ---- frame-sorted view of the table (find.py:122-129: the result is sorted by frame) ----------
     frames_col = f[t_column].values
@@ -1147,6 +1150,7 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
             sources.append(np.ascontiguousarray(base[col].values, dtype=np.float64))
         else:
             sources.append(float(ff.default[col]))
+    _s2 = time.perf_counter()
     params_in = _pinned_array("params_in", (n, P), np.float64)     # packed, group order
     # labelling, packing and the group tables run on host threads from here on
     # The result columns.  ``_alloc(name, dtype)`` lets the sharded path place them in a block all
@@ -1159,6 +1163,7 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
     _LABELLERS.append(labeller)
     frame_cuts = labeller.frame_cuts
     t1 = time.perf_counter()
+    setup_parts = dict(prepare=1e3 * (_s1 - t0), columns=1e3 * (_s2 - _s1), labeller=1e3 * (t1 - _s2))
     out_params = _pinned_array("params", (n, P), np.float64)
     out_cost = _pinned_array("cost", (n,), np.float64)             # one entry per cluster (<= n)
     out_status = _pinned_array("status", (n,), np.int32)
@@ -1292,6 +1297,7 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
                      labelling=dict(where='device' if dl else 'host threads',
                                     frames_relabelled_on_host=labeller.flagged_frames,
                                     **(dl.ms if dl else {})),
+                     setup_ms=setup_parts,
                      phases_ms=dict(setup=1e3 * (t1 - t0), chunks=1e3 * (t2 - t1),
                                     last_chunk=1e3 * (t3 - t2), table=1e3 * (t4 - t3), **lap))
     return out
