@@ -350,6 +350,31 @@ class DeviceLabels(object):
         self.t_launch = time.perf_counter()
         self.ms = dict(stage=1e3 * (t1 - t0), launch=1e3 * (self.t_launch - t1))
 
+    def start_async(self):
+        """``start()`` on a thread of its own (so that the caller's set-up goes on meanwhile)."""
+        import threading
+        self.error = None
+
+        def run():
+            try:
+                self.start()
+            except BaseException as exc:
+                self.error = exc
+
+        self.thread = threading.Thread(target=run, daemon=True)
+        self.thread.start()
+        return self
+
+    def join(self):
+        thread = getattr(self, 'thread', None)
+        if thread is not None:
+            thread.join()
+            self.thread = None
+        if getattr(self, 'error', None) is not None:
+            raise self.error
+
+    close = join
+
     def wait_frames(self, fa, fb):
         import time
         flags = self.flags[fa:fb]
@@ -387,7 +412,7 @@ class ChunkLabeller(object):
     labelled through scipy and packed with numpy."""
 
     def __init__(self, pos, starts, stops, frame_cuts, separation, sources, params_out, device=None,
-                 size_out=None, label_out=None):
+                 size_out=None, label_out=None, device_labels=None):
         import threading
         self.native = os.environ.get('CTK_FIND_NATIVE', '1') != '0' and _native_is_exact()
         self.device_labels = None
@@ -417,7 +442,10 @@ class ChunkLabeller(object):
             return
         workers = max(1, _pool_workers())
         self.cancelled = False
-        if (device is not None and isinstance(pos, (list, tuple)) and len(starts) > 0
+        early = device_labels is not None and np.array_equal(device_labels.starts, self.starts)
+        if early:
+            self.device_labels = device_labels            # launched by the caller during its set-up
+        elif (device is not None and isinstance(pos, (list, tuple)) and len(starts) > 0
                 and len(pos[0]) > 0 and device_labelling_enabled(len(pos[0]), len(starts))):
             # the labels themselves come from the GPU (one warp per frame); the host threads below
             # only count, order and pack
@@ -427,7 +455,10 @@ class ChunkLabeller(object):
             try:
                 labels = flags = None
                 if self.device_labels is not None:
-                    self.device_labels.start()
+                    if early:
+                        self.device_labels.join()
+                    else:
+                        self.device_labels.start()
                 for k, (fa, fb) in enumerate(zip(self.frame_cuts[:-1], self.frame_cuts[1:])):
                     if self.cancelled:
                         raise RuntimeError("labelling cancelled")

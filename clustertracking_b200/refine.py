@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 from . import constraints as _constraints
-from .find import ChunkLabeller, cluster_table
+from .find import ChunkLabeller, DeviceLabels, cluster_table, device_labelling_enabled
 from .fitfunc import FitFunctions
 from .utils import guess_pos_columns, host_threads, is_isotropic, validate_tuple
 
@@ -1106,11 +1106,27 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
                               max_iter, max_shift, max_rms_dev, residual_factor, compute_error,
                               **kwargs)
     started = []          # the uploads start as soon as the frames are known, before the clustering
+    early_labels = []     # ... and so does the cluster labelling on the GPU (frame-sorted tables)
+
+    def frames_known(info):
+        frameset = _track(FrameSet(info))
+        n_rows = len(f)
+        if info.run_starts is not None and device_labelling_enabled(n_rows, len(info.run_starts)):
+            cols = pos_columns if pos_columns is not None else guess_pos_columns(f)
+            sep = np.asarray(validate_tuple(diameter if separation is None else separation, len(cols)),
+                             dtype=np.float64)
+            first = info.run_starts.astype(np.int64)
+            last = np.concatenate((first[1:], [n_rows])).astype(np.int64)
+            columns = [np.ascontiguousarray(f[col].values, dtype=np.float64) for col in cols]
+            labels = DeviceLabels(columns, first, last, sep, frameset.dev)
+            _LABELLERS.append(labels)
+            early_labels.append(labels.start_async())
+        started.append(frameset.upload_async())
+
     pre = prepare_common(f, reader, diameter, separation, fit_function, param_mode, param_val,
                          constraints, bounds, pos_columns, t_column, noise_size, threshold,
                          max_iter, max_shift, max_rms_dev, residual_factor, compute_error,
-                         frames_hook=lambda info: started.append(_track(FrameSet(info)).upload_async()),
-                         **kwargs)
+                         frames_hook=frames_known, **kwargs)
     ff, info = pre.ff, pre.info
     frameset = started[0]
     P = len(ff.params)
@@ -1159,7 +1175,8 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
     csize = alloc('cluster_size', np.int64)
     local_all = np.empty(n, dtype=np.int64)        # labels local to each frame
     labeller = ChunkLabeller(pos, starts, stops, frame_cuts, separation, sources, params_in,
-                             device=getattr(frameset, "dev", None), size_out=csize, label_out=local_all)
+                             device=getattr(frameset, "dev", None), size_out=csize, label_out=local_all,
+                             device_labels=early_labels[0] if early_labels else None)
     _LABELLERS.append(labeller)
     frame_cuts = labeller.frame_cuts
     t1 = time.perf_counter()
@@ -1244,49 +1261,57 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
                 lap[name] += 1e3 * dt
             if finish_errors:
                 break
-    finally:
+    except BaseException:
         done_queue.put(None)
-        t2 = time.perf_counter()
+        finish_thread.join()
+        raise
+    done_queue.put(None)
+    t2 = time.perf_counter()
+
+    # ---- while the device works on the last chunks and the write-back thread drains: the running
+    # cluster ids (find.py:127-128) and the result table, a frame-sorted copy of f with the new
+    # columns (refine.py:296-305).  The fitted columns and the cost are the arrays the write-back
+    # thread fills in place; the table only references them.
+    try:
+        _lib.apply_label_offsets(local_all, starts, stops, frame_offset, threads, cluster)
+        data = {}
+        fitted = {col: block[j] for j, col in enumerate(ff.params)}
+
+        def filled(col, values):
+            """A result column holding ``values`` (array or scalar): an independent copy, like f.copy()."""
+            values = np.asarray(values)
+            dst = alloc(col, values.dtype)
+            dst[...] = values
+            return dst
+
+        for col in base.columns:
+            if col in fitted:
+                data[col] = fitted[col]
+            elif param_val is not None and col in param_val:
+                data[col] = filled(col, param_val[col])
+            else:
+                data[col] = filled(col, base[col].values)
+        data['cluster'] = cluster
+        data['cluster_size'] = csize
+        if param_val is not None:
+            for col in param_val:
+                if col not in data:
+                    data[col] = fitted[col] if col in fitted else filled(col, param_val[col])
+        for col in ff.params:
+            if col not in data:
+                data[col] = fitted[col]
+        data['cost'] = cost
+        out = pd.DataFrame(data, index=base.index, copy=False)
+    finally:
+        t3 = time.perf_counter()
         finish_thread.join()
     if finish_errors:
         raise finish_errors[0]
-    _lib.apply_label_offsets(local_all, starts, stops, frame_offset, threads, cluster)
     for row, status in failures:
         logger.warning("RefineException: cluster %d: %s", int(cluster[row]),
                        _lib.STATUS_NAMES.get(status, "status %d" % status))
     if totals['failed'] > 20:
         logger.warning("RefineException: ... and %d more clusters failed", totals['failed'] - 20)
-    t3 = time.perf_counter()
-
-    # ---- the result table: a frame-sorted copy of f with the new columns (refine.py:296-305) -------
-    data = {}
-    fitted = {col: block[j] for j, col in enumerate(ff.params)}
-
-    def filled(col, values):
-        """A result column holding ``values`` (array or scalar): an independent copy, like f.copy()."""
-        values = np.asarray(values)
-        dst = alloc(col, values.dtype)
-        dst[...] = values
-        return dst
-
-    for col in base.columns:
-        if col in fitted:
-            data[col] = fitted[col]
-        elif param_val is not None and col in param_val:
-            data[col] = filled(col, param_val[col])
-        else:
-            data[col] = filled(col, base[col].values)
-    data['cluster'] = cluster
-    data['cluster_size'] = csize
-    if param_val is not None:
-        for col in param_val:
-            if col not in data:
-                data[col] = fitted[col] if col in fitted else filled(col, param_val[col])
-    for col in ff.params:
-        if col not in data:
-            data[col] = fitted[col]
-    data['cost'] = cost
-    out = pd.DataFrame(data, index=base.index, copy=False)
     t4 = time.perf_counter()
     LAST_CALL.clear()
     dl = labeller.device_labels            # cluster labels from the GPU (ctk_label_frames): one launch
@@ -1299,7 +1324,7 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
                                     **(dl.ms if dl else {})),
                      setup_ms=setup_parts,
                      phases_ms=dict(setup=1e3 * (t1 - t0), chunks=1e3 * (t2 - t1),
-                                    last_chunk=1e3 * (t3 - t2), table=1e3 * (t4 - t3), **lap))
+                                    table=1e3 * (t3 - t2), last_chunk=1e3 * (t4 - t3), **lap))
     return out
 
 
