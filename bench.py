@@ -482,7 +482,9 @@ def run_ours(args):
             dt = max_over_ranks(time.perf_counter() - t0)
             if step >= warmup:
                 times.append(dt)
-                step_log.append((round(1e3 * dt, 1), dict(ctb_refine.LAST_CALL).get("setup_ms")))
+                step_log.append((round(1e3 * dt, 1), dict(ctb_refine.LAST_CALL).get("setup_ms"), dict(ctb_refine.LAST_CALL).get("launched_at_ms"),
+                                 dict(ctb_refine.LAST_CALL).get("returned_at_ms"), dict(ctb_refine.LAST_CALL).get("labelling"),
+                                 dict(ctb_refine.LAST_CALL).get("phases_ms")))
         return sum(times), out
 
     e2e_s, out = time_api(f0, reader, args.steps, args.warmup)

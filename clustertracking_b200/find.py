@@ -348,7 +348,7 @@ class DeviceLabels(object):
                                      scratch.data_ptr(), nbytes, self.stream.cuda_stream)
         self.keep = (stage, out, scratch)
         self.t_launch = time.perf_counter()
-        self.ms = dict(stage=1e3 * (t1 - t0), launch=1e3 * (self.t_launch - t1))
+        self.ms = dict(stage=1e3 * (t1 - t0), launch=1e3 * (self.t_launch - t1), launched_at=self.t_launch)
 
     def start_async(self):
         """``start()`` on a thread of its own (so that the caller's set-up goes on meanwhile)."""

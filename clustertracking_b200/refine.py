@@ -1220,6 +1220,7 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
     import queue
     import threading
     done_queue, finish_errors = queue.Queue(), []
+    timeline = []                                   # ms after the call began: launch of every chunk
 
     def finisher():
         while True:
@@ -1255,6 +1256,7 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
                                   out_status[c0:c0 + n_c], stream=streams[k % len(streams)])
             chunks.append((a, b, by_cluster, plan, pending, c0))
             done_queue.put(chunks[-1])
+            timeline.append(round(1e3 * (time.perf_counter() - t0), 1))
             c0 += n_c
             _te = time.perf_counter()
             for name, dt in (("label_wait", _tb - _ta), ("index", _tc - _tb), ("launch", _te - _tc)):
@@ -1322,7 +1324,8 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
                      labelling=dict(where='device' if dl else 'host threads',
                                     frames_relabelled_on_host=labeller.flagged_frames,
                                     **(dl.ms if dl else {})),
-                     setup_ms=setup_parts,
+                     setup_ms=setup_parts, launched_at_ms=timeline,
+                     returned_at_ms=round(1e3 * (time.perf_counter() - t0), 1),
                      phases_ms=dict(setup=1e3 * (t1 - t0), chunks=1e3 * (t2 - t1),
                                     table=1e3 * (t3 - t2), last_chunk=1e3 * (t4 - t3), **lap))
     return out
