@@ -253,14 +253,41 @@ class _SharedColumns(object):
     (its ``_alloc`` hook), so that "gathering" the table costs no copy at all."""
 
     def __init__(self, path, n_slots, total, a, b, create):
-        self.path, self.n_slots, self.total, self.a, self.b = path, n_slots, total, a, b
+        self.path, self.n_slots, self.total = path, n_slots, total
         self.nbytes = max(8, 8 * n_slots * total)
         if create:
             with open(path, 'wb') as fh:
                 fh.truncate(self.nbytes)
-        self.cells = np.memmap(path, dtype=np.int64, mode='r+', shape=(n_slots, total))
+        self.mapped = np.memmap(path, dtype=np.int64, mode='r+', shape=(n_slots, total))
+        self.private = None                        # copy-on-write mapping (readers other than rank 0)
+        self.fresh = True                          # pages not touched yet
+        self.begin(a, b)
+
+    def begin(self, a, b):
+        """Start a call: rows a..b are this rank's.  Every array handed out during the call derives
+        from ONE token object, so that "is any result of that call still alive?" is a weak
+        reference (the block is reused by the next call only when the answer is no)."""
+        import weakref
+        self.a, self.b = a, b
+        token = _Token(self.mapped)
+        self.cells = np.asarray(token)             # base chain: views -> this array -> token
+        self.alive = weakref.ref(token)
+        self.private_alive = None
         self.columns = []                          # (name, dtype) in allocation order
         self.spilled = False                       # a column did not fit the 8-byte cells
+        self.thread = None
+        if self.fresh:
+            self._start_populate()
+
+    def end(self):
+        """Drop this object's own references to the call's arrays."""
+        self.cells = None
+
+    def in_use(self):
+        return self.alive() is not None or (self.private_alive is not None and
+                                            self.private_alive() is not None)
+
+    def _start_populate(self):
         # Fresh tmpfs pages fault one 4 KB page at a time (no transparent huge pages): ~30 ms per
         # rank for a 2 M-row table if the faults happen where the columns are first written.  A
         # background thread populates the cells of every column as soon as it is allocated, while
@@ -269,10 +296,10 @@ class _SharedColumns(object):
         import queue
         import threading
         self.todo = queue.Queue()
-        self.thread = threading.Thread(target=self._populate, daemon=True)
+        self.thread = threading.Thread(target=self._populate, args=(self.cells,), daemon=True)
         self.thread.start()
 
-    def _populate(self):
+    def _populate(self, cells):
         import ctypes
         import mmap
         page = mmap.PAGESIZE
@@ -282,7 +309,7 @@ class _SharedColumns(object):
             libc.madvise.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
         except (OSError, AttributeError):
             libc = None
-        base = self.cells.ctypes.data
+        base = cells.ctypes.data
         while True:
             k = self.todo.get()
             if k is None:
@@ -293,13 +320,14 @@ class _SharedColumns(object):
             if libc is None or libc.madvise(base + lo, hi - lo, populate_write) != 0:
                 # fallback: READ one word per page (allocates and zeroes the page; a write here
                 # could land after refine_leastsq has filled the column)
-                int(np.asarray(self.cells[k, self.a:self.b:page // 8]).sum())
+                int(np.asarray(cells[k, self.a:self.b:page // 8]).sum())
 
     def ready(self):
         thread, self.thread = self.thread, None
         if thread is not None:
             self.todo.put(None)
             thread.join()
+        self.fresh = False
 
     def alloc(self, name, dtype):
         dtype = np.dtype(dtype)
@@ -308,15 +336,53 @@ class _SharedColumns(object):
             self.spilled = True
             return np.empty(self.b - self.a, dtype=dtype)
         self.columns.append((name, dtype.str))
-        self.todo.put(k)
-        return np.asarray(self.cells[k, self.a:self.b]).view(dtype)
+        if self.thread is not None:
+            self.todo.put(k)
+        return self.cells[k, self.a:self.b].view(dtype)
 
     def table(self, columns, private):
-        cells = self.cells if not private else np.memmap(self.path, dtype=np.int64, mode='c',
-                                                         shape=(self.n_slots, self.total))
-        data = {name: np.asarray(cells[k]).view(np.dtype(dt)) for k, (name, dt) in enumerate(columns)}
-        index = np.asarray(cells[self.n_slots - 1])
+        cells = self.cells
+        if private:
+            import weakref
+            if self.private is None:
+                self.private = np.memmap(self.path, dtype=np.int64, mode='c',
+                                         shape=(self.n_slots, self.total))
+            token = _Token(self.private)
+            cells = np.asarray(token)
+            self.private_alive = weakref.ref(token)
+        data = {name: cells[k].view(np.dtype(dt)) for k, (name, dt) in enumerate(columns)}
+        index = cells[self.n_slots - 1]
         return pd.DataFrame(data, index=index, copy=False)
+
+
+class _Token(object):
+    """Owner of the arrays of one call: exposes a mapping through the array interface and keeps it
+    alive; weakly referenceable, which numpy arrays viewed from a memmap are not usefully."""
+
+    def __init__(self, array):
+        self.__array_interface__ = dict(array.__array_interface__)
+        self._keep = array
+
+
+# The shared block of the previous call, kept mapped (and its file linked) so that the next call of
+# the same size writes into pages that are already resident: populating a fresh tmpfs mapping costs
+# ~1 ms per 2 MB and was the largest host cost of the sharded path at 8 ranks.  It is reused only
+# when NO array of the previous result is alive any more on any rank (weak references above).
+_CACHE = {}
+
+
+def _drop_cache(unlink):
+    block = _CACHE.pop('block', None)
+    if block is not None and unlink and os.path.exists(block.path):
+        os.unlink(block.path)
+
+
+def _cache_signature():
+    block = _CACHE.get('block')
+    if block is None:
+        return [0, 0, 0, 0]
+    tag = int.from_bytes(block.path.encode()[-7:], 'little')
+    return [0 if block.in_use() else 1, block.total, block.n_slots, tag]
 
 
 def _refine_into_shared(mine, reader, diameter, t_column, group, gather, kwargs):
@@ -328,20 +394,37 @@ def _refine_into_shared(mine, reader, diameter, t_column, group, gather, kwargs)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     index_ok = isinstance(mine.index, pd.RangeIndex) or mine.index.dtype.kind in 'iu'
     numeric = all(mine[c].dtype.kind in 'fiu' and mine[c].dtype.itemsize == 8 for c in mine.columns)
-    counts = _all_gather_ints([len(mine), 1 if (index_ok and numeric) else 0, len(mine.columns)], group)
+    counts = _all_gather_ints([len(mine), 1 if (index_ok and numeric) else 0, len(mine.columns)]
+                              + _cache_signature(), group)
     host_ok = _same_host(group)
     if not (host_ok and counts[:, 1].all()) or counts[:, 0].sum() == 0:
         return False, None
     row_off = np.concatenate(([0], np.cumsum(counts[:, 0])))
     total, a, b = int(row_off[-1]), int(row_off[rank]), int(row_off[rank + 1])
     n_slots = int(counts[:, 2].max()) + 24               # input columns + model columns + index
-    name = [None]
-    if rank == 0:
-        name[0] = os.path.join('/dev/shm', 'ctk_%s' % uuid.uuid4().hex)
-        shared = _SharedColumns(name[0], n_slots, total, a, b, create=True)
-    dist.broadcast_object_list(name, src=0, group=group)
-    if rank != 0:
-        shared = _SharedColumns(name[0], n_slots, total, a, b, create=False)
+    # every rank evaluates the same predicate on the gathered signatures: the cached block is free
+    # everywhere, has this call's shape and is the same file on all ranks
+    reuse = bool(counts[:, 3].all() and (counts[:, 4] == total).all() and (counts[:, 5] == n_slots).all()
+                 and (counts[:, 6] == counts[0, 6]).all() and os.environ.get('CTK_SHARED_CACHE', '1') != '0')
+    if reuse:
+        shared = _CACHE['block']
+        shared.begin(a, b)
+    else:
+        _drop_cache(unlink=rank == 0)
+        name = [None]
+        if rank == 0:
+            name[0] = os.path.join('/dev/shm', 'ctk_%d_%s' % (os.getpid(), uuid.uuid4().hex[:12]))
+            shared = _SharedColumns(name[0], n_slots, total, a, b, create=True)
+        dist.broadcast_object_list(name, src=0, group=group)
+        if rank != 0:
+            shared = _SharedColumns(name[0], n_slots, total, a, b, create=False)
+        _CACHE['block'] = shared
+        if rank == 0 and not _CACHE.get('atexit'):
+            import atexit
+            atexit.register(_drop_cache, True)
+            _CACHE['atexit'] = True
+    LAST_GATHER.clear()
+    LAST_GATHER['block_reused'] = reuse
     try:
         part = None
         lap.append(time.perf_counter())
@@ -381,14 +464,16 @@ def _refine_into_shared(mine, reader, diameter, t_column, group, gather, kwargs)
         lap.append(time.perf_counter())
         dist.barrier(group=group)                                  # every reader has mapped it
         lap.append(time.perf_counter())
-        LAST_GATHER.clear()
         if len(lap) == 6:
             LAST_GATHER.update(zip(("setup_ms", "refine_ms", "ids_and_wait_ms", "table_ms", "barrier_ms"),
                                    (1e3 * (y - x) for x, y in zip(lap[:-1], lap[1:]))))
         return True, out
+    except BaseException:
+        _drop_cache(unlink=rank == 0)              # whatever state the block is in: not reused
+        raise
     finally:
-        if rank == 0 and os.path.exists(name[0]):
-            os.unlink(name[0])
+        part = None
+        shared.end()
 
 
 def refine_leastsq_sharded(f, reader, diameter, t_column='frame', group=None, presharded=False,

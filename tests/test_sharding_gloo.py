@@ -67,6 +67,22 @@ def _worker(rank, world, port, out_dir):
                                           passes_factory=emul_backend.GlobalPasses)
     if out is not None:
         out.to_pickle(os.path.join(out_dir, "global.pkl"))
+    # (6) the shared result block is reused by the next call -- but only when no array of the
+    # previous result is alive on any rank
+    import json
+    keep = parallel.refine_leastsq_sharded(f0, reader, 11)
+    snapshot = keep.copy()
+    second = parallel.refine_leastsq_sharded(f0.assign(signal=f0['signal'] * 1.5), reader, 11)
+    reused_while_alive = bool(parallel.LAST_GATHER['block_reused'])
+    untouched = all(np.array_equal(keep[c].values, snapshot[c].values, equal_nan=True) for c in keep.columns)
+    del keep, second
+    third = parallel.refine_leastsq_sharded(f0, reader, 11)
+    reused_when_dead = bool(parallel.LAST_GATHER['block_reused'])
+    third.to_pickle(os.path.join(out_dir, "reused%d.pkl" % rank))
+    with open(os.path.join(out_dir, "reuse%d.json" % rank), "w") as fh:
+        json.dump(dict(reused_while_alive=reused_while_alive, untouched=untouched,
+                       reused_when_dead=reused_when_dead), fh)
+    del third
     # (4) no gather: every rank keeps its part, cluster ids already running on across ranks
     out = parallel.refine_leastsq_sharded(mine, reader, 11, presharded=True, gather='none')
     out.to_pickle(os.path.join(out_dir, "part%d.pkl" % rank))
@@ -119,6 +135,12 @@ def test_two_rank_sharding_matches_single_process(tmp_path):
     parts = [read("rank%d.pkl" % r) for r in range(2)] + [read("tensors%d.pkl" % r) for r in range(2)]
     parts += [read("root_shm.pkl"), read("root_copy.pkl"), read("root_tensors.pkl"),
               pd.concat([read("part%d.pkl" % r) for r in range(2)])]
+    parts += [read("reused%d.pkl" % r) for r in range(2)]
+    import json
+    for r in range(2):
+        with open(os.path.join(str(tmp_path), "reuse%d.json" % r)) as fh:
+            flags = json.load(fh)
+        assert flags == dict(reused_while_alive=False, untouched=True, reused_when_dead=True), flags
     reader, f0 = _video()
     single, _ = emul_backend.refine_leastsq(f0, reader, 11)
     for part in parts:                           # every variant: the full, identical result
