@@ -58,6 +58,18 @@ class Problem(ctypes.Structure):
 LIB_PATH = os.environ.get("CTK_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
                                                           "libctk.so")
 _lib = None
+_WORKSPACE = {}       # cached host scratch arrays (internal to one call at a time)
+
+
+def workspace(key, n, dtype):
+    """A reusable scratch array of at least ``n`` items: fresh multi-megabyte numpy arrays are new
+    mappings whose pages fault in one by one -- per call and per rank, at the same moment on every
+    rank of a box.  Only for arrays that never leave the call that uses them."""
+    arr = _WORKSPACE.get(key)
+    if arr is None or arr.dtype != np.dtype(dtype) or len(arr) < n:
+        arr = np.empty(max(int(n), 1), dtype=dtype)
+        _WORKSPACE[key] = arr
+    return arr[:n]
 
 _vp, _i32, _i64, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
 _PROTOTYPES = {
@@ -306,7 +318,8 @@ def label_frames_device(pos_ptrs, ndim, d_starts, d_stops, n_frames, max_points,
 
 
 def cluster_pack_frames(pos, starts, stops, separation, n_threads, sources, row_base, params_out,
-                        labels=None, flags=None, cluster_out=None, size_out=None):
+                        labels=None, flags=None, cluster_out=None, size_out=None, by_cluster_out=None,
+                        group_start_out=None):
     """``ctk_cluster_pack_columns`` -> (labels local to each frame, sizes, by_cluster, spans,
     group counts per frame, group starts); ``params_out`` [n, P] receives the packed rows.
     ``pos``: [n, ndim] array of this call's rows, or a list of ndim table-order float64 columns
@@ -329,10 +342,12 @@ def cluster_pack_frames(pos, starts, stops, separation, n_threads, sources, row_
     size = np.empty(n, dtype=np.int64) if size_out is None else size_out
     for arr in (cluster, size):                    # optional caller-owned outputs (views are fine)
         assert arr.dtype == np.int64 and arr.flags.c_contiguous and len(arr) == n
-    by_cluster = np.empty(n, dtype=np.int64)
+    by_cluster = np.empty(n, dtype=np.int64) if by_cluster_out is None else by_cluster_out
     spans = np.zeros(len(starts), dtype=np.int64)
     gcount = np.zeros(len(starts), dtype=np.int32)
-    gstart = np.empty(max(n, 1), dtype=np.int32)
+    gstart = np.empty(max(n, 1), dtype=np.int32) if group_start_out is None else group_start_out
+    assert by_cluster.dtype == np.int64 and len(by_cluster) == n and by_cluster.flags.c_contiguous
+    assert gstart.dtype == np.int32 and len(gstart) >= n and gstart.flags.c_contiguous
     ptrs, scalars = column_pointers(sources)
     assert params_out.flags.c_contiguous and params_out.dtype == np.float64
     if labels is not None:

@@ -399,7 +399,7 @@ struct PairQuery {
 
 // per-thread scratch of the frame labelling
 struct FrameScratch {
-  std::vector<int64_t> pairs, order, ordered, count;
+  std::vector<int64_t> pairs, order, ordered, count, sizes;
   KdTree tree;
   PairQuery query;
 };
@@ -517,19 +517,8 @@ static int cluster_pack_impl(const double* pos, const double* const* pos_cols, i
         if (group_count_out) group_count_out[f] = 0;
         continue;
       }
-      if (labels_in && frame_flags[f] == 0) {
-        // labels from the device; sizes by counting
-        s.count.assign((size_t) cnt, 0);
-        bool ok = true;
-        for (int i = 0; i < cnt; ++i) {
-          const int32_t id = labels_in[a + i];
-          if (id < 0 || id >= cnt) { ok = false; break; }
-          cluster_out[a + i] = id;
-          ++s.count[id];
-        }
-        if (!ok) { failed = 1; continue; }
-        for (int i = 0; i < cnt; ++i) size_out[a + i] = s.count[cluster_out[a + i]];
-      } else {
+      const bool given = labels_in && frame_flags[f] == 0;
+      if (!given) {
         if (labels_in && frame_flags[f] == 2) { failed = 2; continue; }
         s.tree.init(pos ? pos + a * ndim : nullptr, cnt, ndim, separation, pos_cols, row_base + a);
         if (!s.tree.finite) { failed = 2; continue; }
@@ -551,29 +540,39 @@ static int cluster_pack_impl(const double* pos, const double* const* pos_cols, i
           continue;
         }
       }
-      // stable argsort of the labels (counting sort: labels are point indices of the frame)
+      // Four passes over the frame (labels are point indices of the frame, so everything is a
+      // counting sort): (1) labels -> histogram; (2) prefix sums: where each label's rows start,
+      // its size, the group table; (3) stable scatter of the rows by label, the packed parameter
+      // row of every feature written on the way (columns read in table order); (4) sizes.
       s.count.assign((size_t) cnt + 1, 0);
+      int64_t* start = s.count.data();               // start[id + 1]: histogram, then offsets
       int64_t top = 0;
+      bool ok = true;
       for (int i = 0; i < cnt; ++i) {
-        const int64_t id = cluster_out[a + i];
-        ++s.count[id + 1];
+        const int64_t id = given ? (int64_t) labels_in[a + i] : cluster_out[a + i];
+        if (id < 0 || id >= cnt) { ok = false; break; }
+        if (given) cluster_out[a + i] = id;
+        ++start[id + 1];
         top = id > top ? id : top;
       }
-      for (int i = 0; i < cnt; ++i) s.count[i + 1] += s.count[i];
-      for (int i = 0; i < cnt; ++i) by_cluster_out[a + s.count[cluster_out[a + i]]++] = a + i;
+      if (!ok) { failed = 1; continue; }
       span_out[f] = top + 1;
-      if (group_count_out) {                       // group starts: where the label changes
-        int groups = 0;
-        int64_t prev = -1;
-        for (int64_t k = a; k < b; ++k) {
-          const int64_t label = cluster_out[by_cluster_out[k]];
-          if (label != prev) { group_start_out[a + groups++] = (int32_t) k; prev = label; }
-        }
-        group_count_out[f] = groups;
+      s.sizes.resize((size_t) cnt);
+      int groups = 0;
+      for (int id = 0; id < cnt; ++id) {
+        const int64_t size = start[id + 1];
+        s.sizes[id] = size;
+        if (size > 0 && group_count_out) group_start_out[a + groups++] = (int32_t) (a + start[id]);
+        start[id + 1] += start[id];
       }
-      if (columns) {                               // packed rows in (cluster, row) order
-        for (int64_t k = a; k < b; ++k) {
-          const int64_t row = row_base + by_cluster_out[k];
+      if (group_count_out) group_count_out[f] = groups;
+      for (int i = 0; i < cnt; ++i) {
+        const int64_t id = cluster_out[a + i];
+        const int64_t k = a + start[id]++;
+        by_cluster_out[k] = a + i;
+        size_out[a + i] = s.sizes[id];
+        if (columns) {                               // packed rows in (cluster, row) order
+          const int64_t row = row_base + a + i;
           double* dst = params_out + k * n_cols;
           for (int j = 0; j < n_cols; ++j) dst[j] = columns[j] ? columns[j][row] : scalars[j];
         }

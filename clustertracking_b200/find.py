@@ -451,6 +451,10 @@ class ChunkLabeller(object):
             # only count, order and pack
             self.device_labels = DeviceLabels(pos, self.starts, self.stops, separation, device)
 
+        n_rows = int(self.stops[-1]) if len(self.stops) else 0
+        order_all = _lib.workspace("by_cluster", n_rows, np.int64)
+        gstart_all = _lib.workspace("group_start", n_rows + 1, np.int32)
+
         def work():
             try:
                 labels = flags = None
@@ -474,7 +478,8 @@ class ChunkLabeller(object):
                         labels=None if labels is None else labels[a:b],
                         flags=None if flags is None else flags[fa:fb],
                         cluster_out=None if label_out is None else label_out[a:b],
-                        size_out=None if size_out is None else size_out[a:b])
+                        size_out=None if size_out is None else size_out[a:b],
+                        by_cluster_out=order_all[a:b], group_start_out=gstart_all[a:b + 1])
                     if size_out is not None:       # written in place: tell the caller not to copy
                         size, local = size_out, label_out
                     goff, gframe = _lib.concat_groups(st, sp, gcount, gstart, fa)

@@ -1173,7 +1173,7 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
     # ranks share, so that the final gather copies nothing (parallel.py).
     alloc = _alloc if _alloc is not None else (lambda name, dtype: np.empty(n, dtype=dtype))
     csize = alloc('cluster_size', np.int64)
-    local_all = np.empty(n, dtype=np.int64)        # labels local to each frame
+    local_all = _lib.workspace("local_labels", n, np.int64)        # labels local to each frame
     labeller = ChunkLabeller(pos, starts, stops, frame_cuts, separation, sources, params_in,
                              device=getattr(frameset, "dev", None), size_out=csize, label_out=local_all,
                              device_labels=early_labels[0] if early_labels else None)
