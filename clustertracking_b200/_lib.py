@@ -107,6 +107,7 @@ _PROTOTYPES = {
     "ctk_cluster_pack_labelled": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp,
                                                  _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp,
                                                  _vp, _vp]),
+    "ctk_frame_runs": (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "ctk_wait_flags": (ctypes.c_int, [_vp, _i64, _i64]),
     "ctk_label_frames_scratch": (ctypes.c_int, [_i64, _i32, _i64, _vp]),
     "ctk_label_frames": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
@@ -295,6 +296,20 @@ def column_pointers(sources):
             ptrs[j] = None
             scalars[j] = float(src)
     return ptrs, scalars
+
+
+def frame_runs(frames):
+    """``ctk_frame_runs`` for a contiguous int64 column -> (run starts int64, sorted?)."""
+    n = len(frames)
+    capacity = 1 << 16
+    while True:
+        starts = np.empty(capacity, dtype=np.int64)
+        runs, is_sorted = ctypes.c_int64(0), ctypes.c_int32(0)
+        check(load().ctk_frame_runs(frames.ctypes.data, n, starts.ctypes.data, capacity,
+                                    ctypes.byref(runs), ctypes.byref(is_sorted)), "ctk_frame_runs")
+        if runs.value <= capacity:
+            return starts[:runs.value].copy(), bool(is_sorted.value)
+        capacity = int(runs.value)
 
 
 def label_frames_scratch_bytes(max_points, ndim, n_frames):

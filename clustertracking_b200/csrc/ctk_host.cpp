@@ -871,3 +871,30 @@ extern "C" int ctk_wait_flags(const int32_t* flags, int64_t n, int64_t timeout_u
       return 1;
   }
 }
+
+// Rows at which a new frame starts in a frame column (find.py:122: groupby(frame)), in one pass.
+//   starts_out [capacity] receives the first row of every run of equal values;
+//   *n_runs_out the number of runs (may exceed capacity: then only the count is valid);
+//   *sorted_out 1 when every change is an increase (the table is sorted by frame)
+extern "C" int ctk_frame_runs(const int64_t* frames, int64_t n, int64_t* starts_out, int64_t capacity,
+                              int64_t* n_runs_out, int32_t* sorted_out) {
+  if (n < 0 || (n > 0 && !frames) || !n_runs_out || !sorted_out || capacity < 0 ||
+      (capacity > 0 && !starts_out))
+    return CTK_E_INVALID;
+  int64_t runs = 0;
+  int32_t sorted = 1;
+  if (n > 0) {
+    if (capacity > 0) starts_out[0] = 0;
+    runs = 1;
+    for (int64_t i = 1; i < n; ++i) {
+      if (frames[i] != frames[i - 1]) {
+        if (frames[i] < frames[i - 1]) sorted = 0;
+        if (runs < capacity) starts_out[runs] = i;
+        ++runs;
+      }
+    }
+  }
+  *n_runs_out = runs;
+  *sorted_out = sorted;
+  return 0;
+}

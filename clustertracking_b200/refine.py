@@ -331,7 +331,11 @@ class FrameInfo(object):
     def __init__(self, source, frame_column, ndim):
         frames = np.asarray(frame_column)
         self.run_starts = None                  # rows at which a new frame starts (sorted tables)
-        if len(frames) > 1:
+        if len(frames) > 1 and frames.dtype == np.int64 and frames.flags.c_contiguous:
+            starts, is_sorted = _lib.frame_runs(frames)             # one pass in C
+            if is_sorted:
+                self.run_starts = starts
+        elif len(frames) > 1:
             change = frames[1:] != frames[:-1]
             cuts = np.flatnonzero(change) + 1
             # sorted <=> every change is an increase

@@ -1,6 +1,5 @@
 #!/bin/bash
-# occupancy experiment: pad the dynamic shared memory so that fewer blocks fit an SM
-for pad in 0 26 63 160; do
-  echo "=== CTK_SMEM_PAD=$pad"
-  CTK_SMEM_PAD=$pad python profiles/tools/class_times.py 300 2>&1 | grep -E "main|total"
+for tag in base w2b9 w2b10 w3b6; do
+  echo "=== $tag"
+  if [ $tag = base ]; then python profiles/tools/class_times.py 300 2>&1 | grep -E "main|total"; else CTK_LIB_PATH=/root/repo/profiles/tools/_build/libctk_$tag.so python profiles/tools/class_times.py 300 2>&1 | grep -E "main|total"; fi
 done

@@ -310,6 +310,12 @@ int ctk_label_frames(const double* const* d_pos_cols, int32_t ndim, const int64_
                      const double* separation, int32_t* d_labels, int32_t* d_flags,
                      void* d_scratch, int64_t scratch_bytes, void* stream);
 
+/* Host helper: the rows at which a new frame starts in an int64 frame column (the groups of
+ * find.py:122), in one pass; *sorted_out = 1 when the column never decreases.  starts_out holds up to
+ * `capacity` entries, *n_runs_out the number of runs. */
+int ctk_frame_runs(const int64_t* frames, int64_t n, int64_t* starts_out, int64_t capacity,
+                   int64_t* n_runs_out, int32_t* sorted_out);
+
 /* Host helper: sleep until none of flags[0 .. n-1] (the mapped per-frame flags of ctk_label_frames,
  * initialised to -1 by the caller) is negative, or timeout_us have passed (returns 1). */
 int ctk_wait_flags(const int32_t* flags, int64_t n, int64_t timeout_us);
