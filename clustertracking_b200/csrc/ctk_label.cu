@@ -5,7 +5,6 @@
 // live in a per-block scratch in global memory (L1/L2 resident: ~100 KB per frame of config 2).
 #include <cuda_runtime.h>
 #include <stdio.h>
-#include <stdlib.h>
 
 #include "ctk.h"
 #include "ctk_label.cuh"
@@ -91,14 +90,8 @@ int make_plan(int64_t max_points, int32_t ndim, int64_t n_frames, LabelPlan* pla
   window = window / 16 * 16;
   plan->window = (int32_t) window;
   plan->smem_bytes = (int32_t) (window + 256);
-  int64_t per_sm = (228 * 1024) / (plan->smem_bytes + 1024);   // 228 KB per SM, 1 KB reserved per block
+  int64_t per_sm = (225 * 1024) / (plan->smem_bytes + 1024);
   if (per_sm > 16) per_sm = 16;
-  // Default: at most 3 frames per SM.  Alone the kernel is faster with 4 (8.4 against 10.1 ms for
-  // the config-2 video), but inside refine_leastsq the first chunk of frames is what the device
-  // waits for, and a frame finishes sooner with fewer warps per SM (e2e 53.9 against 56.3 ms).
-  int64_t cap = 3;
-  if (const char* env = getenv("CTK_LABEL_BLOCKS_PER_SM")) cap = atoi(env);
-  if (cap >= 1 && per_sm > cap) per_sm = cap;
   if (per_sm < 1) per_sm = 1;
   int64_t slots = (int64_t) sms * per_sm;
   if (slots > n_frames) slots = n_frames;

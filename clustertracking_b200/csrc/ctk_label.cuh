@@ -96,11 +96,12 @@ enum { FLAG_OK = 0, FLAG_CAPACITY = 1, FLAG_NONFINITE = 2 };
 enum { LEAF_SIZE = 16 };
 enum { MODE_CHECK = 0, MODE_NOCHECK = 1, MODE_LEAVES = 2, MODE_LEAVES_ALL = 3 };
 
-struct Node {                 // 24 bytes; the children of a node are adjacent: greater = less + 1
+struct Node {                 // 32 bytes
   double split;
   int32_t start, end;
-  int32_t less;               // first child (-1: none)
+  int32_t less, greater;
   int32_t split_dim;          // -1: leaf
+  int32_t pad_;
 };
 struct Box { double lo[3], hi[3]; };     // tight bounds of a node's points
 
@@ -207,7 +208,7 @@ Scratch carve(char* base, const Caps& c) {
 __host__ __device__
 #endif
 inline int64_t window_bytes(int64_t n, int m) {
-  return align_up(n * (8 * m + 4), 16) + (n / 4 + 8) * (int64_t) sizeof(Node) + 64;
+  return align_up(n * (8 * m + 4), 16) + (n / 4 + 64) * (int64_t) sizeof(Node) + 64;
 }
 
 // Point the frame's hot arrays into the fast window `w` (shared memory on the device) as far as
@@ -224,7 +225,7 @@ LBL_DEV void use_window(Scratch& s, char* w, int64_t bytes, int n, int m) {
     if (k < m) { s.c[k] = reinterpret_cast<double*>(p); p += (int64_t) n * 8; }
   s.idx = reinterpret_cast<int32_t*>(p);
   const int64_t nodes = (s.fast_bytes - pts) / (int64_t) sizeof(Node);
-  if (nodes >= n / 4 + 8) {
+  if (nodes >= n / 4 + 64) {
     s.nodes = reinterpret_cast<Node*>(w + pts);
     s.fast_nodes = (int32_t) nodes;
   }
@@ -498,8 +499,8 @@ LBL_UNROLL
       }
       if (lane == 0) {
         Node nd;
-        nd.split = split; nd.start = 0; nd.end = n; nd.split_dim = d;
-        nd.less = d >= 0 ? 1 : -1;
+        nd.split = split; nd.start = 0; nd.end = n; nd.split_dim = d; nd.pad_ = 0;
+        nd.less = d >= 0 ? 1 : -1; nd.greater = d >= 0 ? 2 : -1;
         s.nodes[0] = nd;
         Box bx;
         LBL_UNROLL
@@ -507,7 +508,7 @@ LBL_UNROLL
         s.boxes[0] = bx;
         if (d >= 0) {
           Node c;
-          c.split = 0.; c.split_dim = -1; c.less = -1;
+          c.split = 0.; c.split_dim = -1; c.less = -1; c.greater = -1; c.pad_ = 0;
           c.start = 0; c.end = p; s.nodes[1] = c;
           c.start = p; c.end = n; s.nodes[2] = c;
         }
@@ -560,8 +561,9 @@ LBL_UNROLL
           s.nodes[node].split = split;
           s.nodes[node].split_dim = d;
           s.nodes[node].less = child;
+          s.nodes[node].greater = child + 1;
           Node c;
-          c.split = 0.; c.split_dim = -1; c.less = -1;
+          c.split = 0.; c.split_dim = -1; c.less = -1; c.greater = -1; c.pad_ = 0;
           c.start = start; c.end = p; s.nodes[child] = c;
           c.start = p; c.end = end; s.nodes[child + 1] = c;
         }
@@ -757,14 +759,14 @@ LBL_UNROLL
             if (!desc_a && sa == 1) continue;
             Rect mid = parent;
             if (desc_a && mode == MODE_CHECK) track_push(mid, limit, 1, sa == 0, a_dim, a_split);
-            const int child1 = desc_a ? (sa == 0 ? a.less : a.less + 1) : n1;
+            const int child1 = desc_a ? (sa == 0 ? a.less : a.greater) : n1;
 LBL_UNROLL
             for (int sb = 0; sb < 2; ++sb) {
               if (!desc_b && sb == 1) continue;
               if (desc_a && desc_b && n1 == n2 && sa == 1 && sb == 0) continue;
               Rect child = mid;
               if (desc_b && mode == MODE_CHECK) track_push(child, limit, 2, sb == 0, b_dim, b_split);
-              const int child2 = desc_b ? (sb == 0 ? b.less : b.less + 1) : n2;
+              const int child2 = desc_b ? (sb == 0 ? b.less : b.greater) : n2;
               const int slot = 2 * sa + sb;
               c1[slot] = child1; c2[slot] = child2;
               cm[slot] = enter(child1, child2, mode, child, upper);
