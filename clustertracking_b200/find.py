@@ -373,7 +373,15 @@ class DeviceLabels(object):
         if getattr(self, 'error', None) is not None:
             raise self.error
 
-    close = join
+    def close(self):
+        """End of the call (also a failed one): the kernel writes into cached mapped buffers the
+        next call reuses, so it must have finished."""
+        try:
+            self.join()
+        finally:
+            stream = getattr(self, 'stream', None)
+            if stream is not None:
+                stream.synchronize()
 
     def wait_frames(self, fa, fb):
         import time

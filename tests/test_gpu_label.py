@@ -65,3 +65,29 @@ def test_refine_leastsq_labels_do_not_depend_on_where_they_are_computed(monkeypa
     ctb.refine_leastsq(f0.copy(), reader, 11)
     assert refine.LAST_CALL['labelling']['where'] == 'device'
     assert refine.LAST_CALL['labelling']['frames_relabelled_on_host'] == 0
+
+
+def test_non_finite_positions_raise_like_scipy(monkeypatch):
+    """cKDTree refuses non-finite data (ValueError); so does the labelling on either side."""
+    import clustertracking_b200 as ctb
+    from clustertracking_b200 import artificial
+    import pandas as pd
+    frames, f0 = [], []
+    for k in range(6):
+        frame, f, _ = artificial.clustered_frame((128, 128), 44, 2.75, 8, seed=70 + k)
+        f['frame'] = k
+        frames.append(frame)
+        f0.append(f)
+    f0 = pd.concat(f0, ignore_index=True)
+    f0.loc[len(f0) // 2, 'x'] = np.nan
+    reader = artificial.FrameStack(np.stack(frames))
+    for mode in ('2', '0'):
+        monkeypatch.setenv('CTK_LABEL_DEVICE', mode)
+        with pytest.raises(ValueError):
+            ctb.refine_leastsq(f0.copy(), reader, 11)
+    # ... and the next call is not disturbed by the failed one
+    monkeypatch.setenv('CTK_LABEL_DEVICE', '2')
+    good = f0.dropna()
+    out = ctb.refine_leastsq(good.copy(), reader, 11)
+    monkeypatch.setenv('CTK_LABEL_DEVICE', '0')
+    pd.testing.assert_frame_equal(out, ctb.refine_leastsq(good.copy(), reader, 11))
