@@ -91,3 +91,24 @@ def test_non_finite_positions_raise_like_scipy(monkeypatch):
     out = ctb.refine_leastsq(good.copy(), reader, 11)
     monkeypatch.setenv('CTK_LABEL_DEVICE', '0')
     pd.testing.assert_frame_equal(out, ctb.refine_leastsq(good.copy(), reader, 11))
+
+
+def test_config2_video_labels_equal_host_labels():
+    """64 frames of the bench's config-2 geometry (~2100 features per frame in clusters of 2-6, the
+    case where the label VALUES depend on the pair order): every label identical, nothing flagged."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    n_frames = 64
+    _, frame, _, start = bench.video_geometry(n_frames, seed=11)
+    starts = np.searchsorted(frame, np.arange(n_frames)).astype(np.int64)
+    stops = np.concatenate((starts[1:], [len(frame)])).astype(np.int64)
+    separation = np.array([float(bench.DIAMETER)] * 2)
+    start = np.ascontiguousarray(start)
+    want, _, _, _ = _lib.cluster_frames(start, starts, stops, separation, 4)
+    got, flags = device_labels(start, starts, stops, separation)
+    assert not flags.any()
+    assert np.array_equal(got, want)
+    sizes = np.bincount(np.bincount(want[starts[0]:stops[0]]))      # components of 3+ exist
+    assert len(sizes) > 3
