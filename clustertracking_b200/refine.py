@@ -1124,7 +1124,8 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
             columns = [np.ascontiguousarray(f[col].values, dtype=np.float64) for col in cols]
             labels = DeviceLabels(columns, first, last, sep, frameset.dev)
             _LABELLERS.append(labels)
-            early_labels.append(labels.start_async())
+            labels.start()         # stages + enqueues its 34 MB ahead of the gigabyte of frames
+            early_labels.append(labels)
         started.append(frameset.upload_async())
 
     pre = prepare_common(f, reader, diameter, separation, fit_function, param_mode, param_val,

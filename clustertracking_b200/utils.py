@@ -50,4 +50,7 @@ def host_threads(cap=16):
     except (AttributeError, OSError):
         cores = os.cpu_count() or 1
     local_ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1') or 1))
-    return int(min(cap, max(1, cores // local_ranks)))
+    share = max(1, cores // local_ranks)
+    if os.environ.get('CTK_HOST_THREADS'):               # explicit budget per process
+        share = max(1, int(os.environ['CTK_HOST_THREADS']))
+    return int(min(cap, share))
