@@ -291,6 +291,36 @@ def _pinned(torch, key, nbytes):
     return buf[:nbytes]
 
 
+class Prestaged(object):
+    """The position columns on their way into the pinned staging buffer, on threads, started the
+    moment ``refine_leastsq`` is entered (the copy needs nothing the argument handling computes)."""
+
+    def __init__(self, columns):
+        import threading
+        import torch
+        from concurrent.futures import ThreadPoolExecutor
+        from .utils import host_threads
+        self.columns = columns
+        ndim, n = len(columns), len(columns[0])
+        # room for the frame bounds behind the columns (at most one frame per row)
+        self.stage = _pinned(torch, "pos", (ndim * n + 2 * n) * 8)
+        cols = self.stage.numpy()[:ndim * n * 8].view(np.float64).reshape(ndim, n)
+        pieces = [(k, a, min(n, a + (1 << 20))) for k in range(ndim) for a in range(0, n, 1 << 20)]
+        workers = max(1, min(4, host_threads(4), len(pieces)))
+
+        def run():
+            with ThreadPoolExecutor(workers) as pool:
+                list(pool.map(lambda p: np.copyto(cols[p[0], p[1]:p[2]], columns[p[0]][p[1]:p[2]]), pieces))
+
+        self.thread = threading.Thread(target=run, daemon=True)
+        self.thread.start()
+
+    def close(self):
+        thread, self.thread = self.thread, None
+        if thread is not None:
+            thread.join()
+
+
 class DeviceLabels(object):
     """Labels of all frames of a frame-sorted table from ``ctk_label_frames`` (one warp per frame on
     the GPU, label values identical to the reference's).  Both directions go through MAPPED pinned
@@ -304,7 +334,8 @@ class DeviceLabels(object):
     Frames whose flag is 1 exceeded a scratch capacity on the device and are labelled by the host
     path."""
 
-    def __init__(self, pos, starts, stops, separation, device):
+    def __init__(self, pos, starts, stops, separation, device, prestaged=None):
+        self.prestaged = prestaged if prestaged is not None and prestaged.columns is pos else None
         self.pos, self.starts, self.stops = pos, starts, stops
         self.separation, self.device = separation, device
         n, n_frames, ndim = len(pos[0]), len(starts), len(pos)
@@ -321,13 +352,18 @@ class DeviceLabels(object):
         n, n_frames, ndim = len(pos[0]), len(self.starts), len(pos)
         t0 = time.perf_counter()
         max_points = int((self.stops - self.starts).max())
-        stage = _pinned(torch, "pos", (ndim * n + 2 * n_frames) * 8)
-        host = stage.numpy()
-        cols = host[:ndim * n * 8].view(np.float64).reshape(ndim, n)
-        pieces = [(k, a, min(n, a + (1 << 20))) for k in range(ndim) for a in range(0, n, 1 << 20)]
-        with ThreadPoolExecutor(max(1, min(4, host_threads(4), len(pieces)))) as pool:
-            list(pool.map(lambda p: np.copyto(cols[p[0], p[1]:p[2]], pos[p[0]][p[1]:p[2]]), pieces))
-        bounds = host[ndim * n * 8:].view(np.int64).reshape(2, n_frames)
+        if self.prestaged is not None:                     # copied while the arguments were handled
+            self.prestaged.close()
+            stage = self.prestaged.stage[:(ndim * n + 2 * n_frames) * 8]
+            host = stage.numpy()
+        else:
+            stage = _pinned(torch, "pos", (ndim * n + 2 * n_frames) * 8)
+            host = stage.numpy()
+            cols = host[:ndim * n * 8].view(np.float64).reshape(ndim, n)
+            pieces = [(k, a, min(n, a + (1 << 20))) for k in range(ndim) for a in range(0, n, 1 << 20)]
+            with ThreadPoolExecutor(max(1, min(4, host_threads(4), len(pieces)))) as pool:
+                list(pool.map(lambda p: np.copyto(cols[p[0], p[1]:p[2]], pos[p[0]][p[1]:p[2]]), pieces))
+        bounds = host[ndim * n * 8:(ndim * n + 2 * n_frames) * 8].view(np.int64).reshape(2, n_frames)
         bounds[0], bounds[1] = self.starts, self.stops
         out = _pinned(torch, "labels", (n + n_frames) * 4)
         result = out.numpy().view(np.int32)

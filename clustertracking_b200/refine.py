@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 from . import constraints as _constraints
-from .find import ChunkLabeller, DeviceLabels, cluster_table, device_labelling_enabled
+from .find import ChunkLabeller, DeviceLabels, Prestaged, cluster_table, device_labelling_enabled
 from .fitfunc import FitFunctions
 from .utils import guess_pos_columns, host_threads, is_isotropic, validate_tuple
 
@@ -1073,6 +1073,11 @@ def _refine_global(f, reader, diameter, separation, fit_function, param_mode, pa
     return global_fit.write_back(plan, ok, params, rms_dev)
 
 
+def _cuda_present():
+    import torch
+    return torch.cuda.is_available()
+
+
 def _track(frameset):
     _FRAMESETS.append(frameset)
     return frameset
@@ -1112,17 +1117,26 @@ def _refine_leastsq(f, reader, diameter, separation=None, fit_function='gauss', 
     started = []          # the uploads start as soon as the frames are known, before the clustering
     early_labels = []     # ... and so does the cluster labelling on the GPU (frame-sorted tables)
 
+    # the position columns start towards the pinned staging buffer right away (threads)
+    prestaged = None
+    label_cols = pos_columns if pos_columns is not None else guess_pos_columns(f)
+    if (len(f) >= 4096 and all(col in f for col in label_cols) and device_labelling_enabled(len(f), 4)
+            and _cuda_present()):
+        prestaged = Prestaged([np.ascontiguousarray(f[col].values, dtype=np.float64) for col in label_cols])
+        _LABELLERS.append(prestaged)
+
     def frames_known(info):
         frameset = _track(FrameSet(info))
         n_rows = len(f)
         if info.run_starts is not None and device_labelling_enabled(n_rows, len(info.run_starts)):
-            cols = pos_columns if pos_columns is not None else guess_pos_columns(f)
+            cols = label_cols
             sep = np.asarray(validate_tuple(diameter if separation is None else separation, len(cols)),
                              dtype=np.float64)
             first = info.run_starts.astype(np.int64)
             last = np.concatenate((first[1:], [n_rows])).astype(np.int64)
-            columns = [np.ascontiguousarray(f[col].values, dtype=np.float64) for col in cols]
-            labels = DeviceLabels(columns, first, last, sep, frameset.dev)
+            columns = (prestaged.columns if prestaged is not None else
+                       [np.ascontiguousarray(f[col].values, dtype=np.float64) for col in cols])
+            labels = DeviceLabels(columns, first, last, sep, frameset.dev, prestaged=prestaged)
             _LABELLERS.append(labels)
             labels.start()         # stages + enqueues its 34 MB ahead of the gigabyte of frames
             early_labels.append(labels)
