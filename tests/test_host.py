@@ -364,3 +364,18 @@ def test_drop_close_frames_matches_oracle():
             want = np.ones(counts[f], bool)
             want[list(find_oracle.where_close(pos, sep, values[f, :counts[f]]))] = False
             assert_array_equal(keep[f, :counts[f]], want)
+
+
+def test_frame_runs_helper():
+    """ctk_frame_runs: first rows of the frame groups (find.py:122) and sortedness, in one pass."""
+    from clustertracking_b200 import _lib
+    frames = np.array([3, 3, 3, 5, 5, 9, 10, 10], dtype=np.int64)
+    starts, is_sorted = _lib.frame_runs(frames)
+    assert is_sorted and starts.tolist() == [0, 3, 5, 6]
+    starts, is_sorted = _lib.frame_runs(np.array([4, 4, 2, 2, 7], dtype=np.int64))
+    assert not is_sorted and starts.tolist() == [0, 2, 4]
+    starts, is_sorted = _lib.frame_runs(np.zeros(0, dtype=np.int64))
+    assert is_sorted and len(starts) == 0
+    many = np.arange(200000, dtype=np.int64)                 # more runs than the first capacity
+    starts, is_sorted = _lib.frame_runs(many)
+    assert is_sorted and np.array_equal(starts, many)
